@@ -1,0 +1,226 @@
+"""Host-side mirror of the reference's call surface for the registration hot path.
+
+The reference is a C++ library (fast_limo::Mapper / fast_limo::Localizer, singletons; see
+INTEGRATION.md for the C++ binding).  This module exposes the same operations, with the same
+names and argument meaning, over the C ABI in ``include/flimo.h`` so that the parity tests and
+``bench.py`` read like calls into the reference:
+
+    Mapper.set_config / exists / size / last_time / add / match      (Modules/Mapper.hpp:49-60)
+    Localizer-side iterated update: ``Registration.update``           (Localizer.cpp:326-353 ->
+                                                                       esekfom.hpp:1620-1823)
+
+No computation happens in Python and nothing here falls back to a CPU path.
+"""
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _lib
+from ._lib import FlimoCfg, FlimoError, FlimoStats
+
+
+@dataclass
+class MappingConfig:
+    """fast_limo::Config::iKFoM::Mapping (+ the two iKFoM flags the path reads)."""
+    NUM_MATCH_POINTS: int = 5
+    MAX_NUM_MATCHES: int = 2000
+    MAX_NUM_PC2MATCH: int = 10000
+    MAX_DIST_PLANE: float = 2.0
+    PLANE_THRESHOLD: float = 5.0e-2
+    estimate_extrinsics: bool = True
+    octree_bucket_size: int = 2          # ignored, exactly like the reference
+    octree_min_extent: float = 0.2
+    octree_downsampling: bool = True
+    knn_cell: float = 0.0                # extension: device grid cell (0 = auto)
+    sort_scan: bool = False              # extension: Morton-sort the scan on upload
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _fp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+@dataclass
+class PassResult:
+    HTH: np.ndarray
+    HTh: np.ndarray
+    n_valid: int
+    n_rows: int
+    sum_sq_res: float
+
+
+class Mapper:
+    """fast_limo::Mapper over one GPU (the reference's is a process-wide singleton)."""
+
+    def __init__(self, config: MappingConfig = None, device: int = 0):
+        self._L = _lib.load()
+        self._h = C.c_void_p()
+        self.device = device
+        self.set_config(config or MappingConfig())
+
+    # -- lifecycle ---------------------------------------------------------------------------
+    def set_config(self, cfg: MappingConfig):
+        c = FlimoCfg()
+        self._L.flimo_cfg_default(C.byref(c))
+        c.NUM_MATCH_POINTS = int(cfg.NUM_MATCH_POINTS)
+        c.MAX_NUM_MATCHES = int(cfg.MAX_NUM_MATCHES)
+        c.MAX_NUM_PC2MATCH = int(cfg.MAX_NUM_PC2MATCH)
+        c.MAX_DIST_PLANE = float(cfg.MAX_DIST_PLANE)
+        c.PLANE_THRESHOLD = float(cfg.PLANE_THRESHOLD)
+        c.estimate_extrinsics = int(bool(cfg.estimate_extrinsics))
+        c.octree_bucket_size = int(cfg.octree_bucket_size)
+        c.octree_min_extent = float(cfg.octree_min_extent)
+        c.octree_downsampling = int(bool(cfg.octree_downsampling))
+        c.knn_cell = float(cfg.knn_cell)
+        c.sort_scan = int(bool(cfg.sort_scan))
+        if self._h:
+            self._L.flimo_destroy(self._h)
+            self._h = C.c_void_p()
+        rc = self._L.flimo_create(C.byref(c), int(self.device), C.byref(self._h))
+        if rc != 0:
+            raise FlimoError(f"flimo_create failed ({rc}): {self._L.flimo_last_error(None).decode()}")
+        self.config = cfg
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h:
+            self._L.flimo_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise FlimoError(f"libflimo_cuda error {rc}: {self._L.flimo_last_error(self._h).decode()}")
+
+    # -- Mapper API --------------------------------------------------------------------------
+    def exists(self):
+        return bool(self._L.flimo_map_exists(self._h))
+
+    def size(self):
+        n = C.c_size_t(0)
+        self._ck(self._L.flimo_map_size(self._h, C.byref(n)))
+        return int(n.value)
+
+    def last_time(self):
+        return float(self._L.flimo_map_last_time(self._h))
+
+    def add(self, points, time=0.0):
+        """Mapper::add(pc, time): world-frame points, (n, >=3) float32 (row stride = itemsize*cols)."""
+        pts = np.ascontiguousarray(points, dtype=np.float32)
+        self._ck(self._L.flimo_map_add(self._h, pts.ctypes.data, pts.shape[0], pts.strides[0], float(time)))
+
+    def add_device(self, dptr, n, stride_bytes, time=0.0):
+        self._ck(self._L.flimo_map_add_device(self._h, C.c_void_p(dptr), n, stride_bytes, float(time)))
+
+    def points(self):
+        n = self.size()
+        out = np.empty((max(n, 1), 3), np.float32)
+        got = C.c_size_t(0)
+        self._ck(self._L.flimo_map_get_points(self._h, _fp(out), n, C.byref(got)))
+        return out[:n]
+
+    def set_scan(self, scan):
+        """Binds Localizer::pc2match (body-frame points of the current scan)."""
+        sc = np.ascontiguousarray(scan, dtype=np.float32)
+        self._ck(self._L.flimo_scan_set(self._h, sc.ctypes.data, sc.shape[0], sc.strides[0]))
+        self._scan_n = min(sc.shape[0], self.config.MAX_NUM_PC2MATCH)
+
+    def set_scan_device(self, dptr, n, stride_bytes):
+        self._ck(self._L.flimo_scan_set_device(self._h, C.c_void_p(dptr), n, stride_bytes))
+        self._scan_n = min(n, self.config.MAX_NUM_PC2MATCH)
+
+    def shard(self, begin, end):
+        self._ck(self._L.flimo_scan_shard(self._h, begin, end))
+
+    def match(self, state, scan=None) -> PassResult:
+        """Mapper::match(State, pc) + Localizer::calculate_H + H^T H / H^T h, reduced form."""
+        if scan is not None:
+            self.set_scan(scan)
+        st = np.ascontiguousarray(np.asarray(state, np.float64)[:14])
+        HTH = np.zeros((12, 12), np.float64)
+        HTh = np.zeros(12, np.float64)
+        nv, nr, ss = C.c_int64(0), C.c_int64(0), C.c_double(0)
+        self._ck(self._L.flimo_match_reduce(self._h, _dp(st), _dp(HTH), _dp(HTh), C.byref(nv), C.byref(nr), C.byref(ss)))
+        return PassResult(HTH, HTh, int(nv.value), int(nr.value), float(ss.value))
+
+    def match_async(self, state, d_out_ptr, stream=None):
+        st = np.ascontiguousarray(np.asarray(state, np.float64)[:14])
+        self._ck(self._L.flimo_match_reduce_async(self._h, _dp(st), C.c_void_p(d_out_ptr), C.c_void_p(stream or 0)))
+
+    def match_debug(self, state):
+        """Per-point records of one pass: dict of arrays in original scan order."""
+        st = np.ascontiguousarray(np.asarray(state, np.float64)[:14])
+        n = self._scan_n
+        out = np.zeros((max(n, 1), 16), np.float32)
+        got = C.c_size_t(0)
+        self._ck(self._L.flimo_match_debug(self._h, _dp(st), _fp(out), n, C.byref(got)))
+        out = out[:n]
+        return dict(world=out[:, 0:3], plane=out[:, 3:7], dist=out[:, 7], good=out[:, 8] > 0.5, nn_d2=out[:, 9:14])
+
+    def scan_to_world(self, state):
+        st = np.ascontiguousarray(np.asarray(state, np.float64)[:14])
+        n = self._scan_n
+        out = np.zeros((max(n, 1), 3), np.float32)
+        got = C.c_size_t(0)
+        self._ck(self._L.flimo_scan_to_world(self._h, _dp(st), _fp(out), n, C.byref(got)))
+        return out[:n]
+
+    def stats(self):
+        s = FlimoStats()
+        self._ck(self._L.flimo_get_stats(self._h, C.byref(s)))
+        return {f: getattr(s, f) for f, _ in s._fields_}
+
+    def stream(self):
+        return int(self._L.flimo_stream(self._h) or 0)
+
+    # -- iterated update ---------------------------------------------------------------------
+    def update(self, state26, P, max_iter, limits, R=0.001, D=5.0):
+        """esekf::update_iterated_dyn_share_modified on the bound scan.  Returns (x, P, passes)."""
+        x = np.array(state26, np.float64).copy()
+        Pm = np.array(P, np.float64).reshape(23, 23).copy()
+        lim = np.ascontiguousarray(np.broadcast_to(np.asarray(limits, np.float64), (23,)))
+        passes = C.c_int(0)
+        self._ck(self._L.flimo_update(self._h, _dp(x), _dp(Pm), int(max_iter), _dp(lim), float(R), float(D), C.byref(passes)))
+        return x, Pm, int(passes.value)
+
+    def ekf_begin(self, state26, P, max_iter, limits, R=0.001, D=5.0):
+        x = np.ascontiguousarray(state26, np.float64)
+        Pm = np.ascontiguousarray(np.asarray(P, np.float64).reshape(23, 23))
+        lim = np.ascontiguousarray(np.broadcast_to(np.asarray(limits, np.float64), (23,)))
+        self._ck(self._L.flimo_ekf_begin(self._h, _dp(x), _dp(Pm), int(max_iter), _dp(lim), float(R), float(D)))
+
+    def ekf_state(self):
+        x = np.zeros(26, np.float64)
+        self._ck(self._L.flimo_ekf_state(self._h, _dp(x)))
+        return x
+
+    def ekf_step(self, HTH, HTh, n_rows):
+        HTH = np.ascontiguousarray(HTH, np.float64)
+        HTh = np.ascontiguousarray(HTh, np.float64)
+        done = C.c_int(0)
+        self._ck(self._L.flimo_ekf_step(self._h, _dp(HTH), _dp(HTh), int(n_rows), C.byref(done)))
+        return bool(done.value)
+
+    def ekf_end(self):
+        x = np.zeros(26, np.float64)
+        Pm = np.zeros((23, 23), np.float64)
+        self._ck(self._L.flimo_ekf_end(self._h, _dp(x), _dp(Pm)))
+        return x, Pm
+
+
+def unpack96(packed):
+    L = _lib.load()
+    p = np.ascontiguousarray(packed, np.float64)
+    HTH = np.zeros((12, 12), np.float64)
+    HTh = np.zeros(12, np.float64)
+    nv, nr, ss = C.c_int64(0), C.c_int64(0), C.c_double(0)
+    L.flimo_unpack96(_dp(p), _dp(HTH), _dp(HTh), C.byref(nv), C.byref(nr), C.byref(ss))
+    return PassResult(HTH, HTh, int(nv.value), int(nr.value), float(ss.value))

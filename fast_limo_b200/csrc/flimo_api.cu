@@ -1,0 +1,578 @@
+// C ABI of libflimo_cuda.so (declared in include/flimo.h).  Host-side plumbing only: device
+// buffers, streams, pose constants, launch sequencing, the MAX_NUM_MATCHES first-N rule, and the
+// host IKFoM update (ekf_host.hpp).  No CPU fallback exists: without a working CUDA device every
+// entry point fails with a negative status.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/flimo.h"
+#include "ekf_host.hpp"
+#include "flimo_dev.cuh"
+
+using namespace flimo;
+
+struct flimo_ctx {
+  flimo_cfg cfg{};
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::string err;
+
+  MapIndex map;
+  bool map_exists = false;
+  double last_time = -1.0;       // Mapper::last_map_time (Mapper.cpp:23)
+
+  float4* scan = nullptr;        // packed scan (w = original index)
+  float4* scan_tmp = nullptr;
+  size_t scan_cap = 0, scan_n = 0;
+  size_t shard_begin = 0, shard_end = 0;
+  uint32_t* scan_keys = nullptr;
+  size_t scan_keys_cap = 0;
+  void* scan_cub = nullptr;
+  size_t scan_cub_bytes = 0;
+
+  void* stage = nullptr;         // raw strided uploads
+  size_t stage_cap = 0;
+  unsigned int* d_count = nullptr;
+
+  double* partials = nullptr;
+  size_t partials_cap = 0;       // in doubles
+  unsigned int* ticket = nullptr;
+  size_t ticket_cap = 0;
+  double* out96 = nullptr;       // device
+  double* h_out96 = nullptr;     // pinned host
+  float* dbg16 = nullptr;
+  size_t dbg_cap = 0;
+  uint8_t* valid_flags = nullptr;
+  size_t valid_cap = 0;
+  float* xyz_out = nullptr;
+  size_t xyz_cap = 0;
+
+  ekf::IteratedUpdate upd;
+  bool upd_active = false;
+
+  flimo_stats stats{};
+};
+
+namespace {
+
+thread_local std::string g_err;   // for errors without a handle
+
+int fail(flimo_handle h, int code, const std::string& msg) {
+  if (h) h->err = msg;
+  else g_err = msg;
+  return code;
+}
+
+#define CU(h, call)                                                                           \
+  do {                                                                                        \
+    cudaError_t e__ = (call);                                                                 \
+    if (e__ != cudaSuccess)                                                                   \
+      return fail(h, e__ == cudaErrorMemoryAllocation ? FLIMO_ERR_NOMEM : FLIMO_ERR_CUDA,     \
+                  std::string(#call) + ": " + cudaGetErrorString(e__));                       \
+  } while (0)
+
+#define NEED_GPU(h)                                                                            \
+  do {                                                                                        \
+    if ((h)->device < 0) return fail(h, FLIMO_ERR_NO_DEVICE, "host-only handle: no GPU bound"); \
+    CU(h, cudaSetDevice((h)->device));                                                        \
+  } while (0)
+
+template <typename T>
+cudaError_t grow(T** p, size_t* cap, size_t need) {
+  if (*cap >= need) return cudaSuccess;
+  if (*p) cudaFree(*p);
+  *p = nullptr;
+  *cap = 0;
+  size_t want = need + need / 4 + 256;
+  cudaError_t e = cudaMalloc(reinterpret_cast<void**>(p), want * sizeof(T));
+  if (e != cudaSuccess) return e;
+  *cap = want;
+  return cudaSuccess;
+}
+
+// --- pose constants, float32 exactly as the reference builds them -----------------------------
+template <typename T>
+void quat_matrix(const T q[4], T R[9]) {   // Eigen QuaternionBase::toRotationMatrix
+  const T tx = T(2) * q[0], ty = T(2) * q[1], tz = T(2) * q[2];
+  const T twx = tx * q[3], twy = ty * q[3], twz = tz * q[3];
+  const T txx = tx * q[0], txy = ty * q[0], txz = tz * q[0];
+  const T tyy = ty * q[1], tyz = tz * q[1], tzz = tz * q[2];
+  R[0] = T(1) - (tyy + tzz); R[1] = txy - twz;          R[2] = txz + twy;
+  R[3] = txy + twz;          R[4] = T(1) - (txx + tzz); R[5] = tyz - twx;
+  R[6] = txz - twy;          R[7] = tyz + twx;          R[8] = T(1) - (txx + tyy);
+}
+
+// [R|t]^-1 = [R^T | -R^T t] with Eigen's fixed-size evaluation order (State.cpp:145-153)
+void rigid_inverse(const float R[9], const float t[3], float Ri[9], float ti[3]) {
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) Ri[3 * r + c] = R[3 * c + r];
+  for (int r = 0; r < 3; ++r) {
+    const volatile float a = (-Ri[3 * r]) * t[0], b = (-Ri[3 * r + 1]) * t[1], c = (-Ri[3 * r + 2]) * t[2];
+    const volatile float bc = b + c;
+    ti[r] = a + bc;
+  }
+}
+
+void make_pose(const double s[14], PoseConsts& pc) {
+  // State::State(const state_ikfom&) casts (State.cpp:38-55)
+  float q[4], qLI[4], p[3], pLI[3];
+  for (int i = 0; i < 3; ++i) p[i] = (float)s[i];
+  for (int i = 0; i < 4; ++i) q[i] = (float)s[3 + i];
+  for (int i = 0; i < 4; ++i) qLI[i] = (float)s[7 + i];
+  for (int i = 0; i < 3; ++i) pLI[i] = (float)s[11 + i];
+  quat_matrix<float>(q, pc.R_wb);
+  for (int i = 0; i < 3; ++i) pc.t_wb[i] = p[i];
+  rigid_inverse(pc.R_wb, p, pc.Rinv_wb, pc.tinv_wb);
+  float R_LI[9];
+  quat_matrix<float>(qLI, R_LI);
+  rigid_inverse(R_LI, pLI, pc.Rinv_LI, pc.tinv_LI);
+  // Localizer.cpp:554-555: conjugate of the DOUBLE quaternion -> matrix -> cast<float>
+  double qc[4] = {-s[3], -s[4], -s[5], s[6]}, Rd[9];
+  quat_matrix<double>(qc, Rd);
+  for (int i = 0; i < 9; ++i) pc.Rd_wb_inv[i] = (float)Rd[i];
+  double qc2[4] = {-s[7], -s[8], -s[9], s[10]};
+  quat_matrix<double>(qc2, Rd);
+  for (int i = 0; i < 9; ++i) pc.Rd_LI_inv[i] = (float)Rd[i];
+}
+
+// smallest float f with (double)f >= D:  (double)x < D  <=>  x < f  for every float x
+float ceil_to_float(double D) {
+  float f = (float)D;
+  if ((double)f < D) f = std::nextafterf(f, INFINITY);
+  return f;
+}
+
+int upload(flimo_handle h, const void* host, size_t bytes) {
+  if (bytes > h->stage_cap) {
+    if (h->stage) cudaFree(h->stage);
+    h->stage = nullptr;
+    h->stage_cap = 0;
+    CU(h, cudaMalloc(&h->stage, bytes + bytes / 4 + 4096));
+    h->stage_cap = bytes + bytes / 4 + 4096;
+  }
+  CU(h, cudaMemcpyAsync(h->stage, host, bytes, cudaMemcpyHostToDevice, h->stream));
+  return FLIMO_OK;
+}
+
+int fill_params(flimo_handle h, const double state14[14], MatchParams& P, double* d_out, uint32_t orig_limit,
+                float* dbg, uint8_t* valid) {
+  const size_t n = h->shard_end - h->shard_begin;
+  const int tiles = match_num_tiles((int)n);
+  const int groups = (tiles + 31) / 32;
+  const size_t need_part = (size_t)(tiles + groups) * kPartialStride;
+  CU(h, grow(&h->partials, &h->partials_cap, need_part));
+  if ((size_t)groups + 1 > h->ticket_cap) {
+    CU(h, grow(&h->ticket, &h->ticket_cap, (size_t)groups + 1));
+    CU(h, cudaMemsetAsync(h->ticket, 0, h->ticket_cap * sizeof(unsigned int), h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+  }
+  P.scan = h->scan;
+  P.map = h->map.pts;
+  P.cell_start = h->map.cell_start;
+  P.g = h->map.g;
+  make_pose(state14, P.pc);
+  P.q_begin = (int)h->shard_begin;
+  P.q_end = (int)h->shard_end;
+  P.max_dist_f = ceil_to_float(h->cfg.MAX_DIST_PLANE);
+  P.plane_thr = (float)h->cfg.PLANE_THRESHOLD;
+  P.estimate_extrinsics = h->cfg.estimate_extrinsics;
+  P.orig_limit = orig_limit;
+  P.partials = h->partials;
+  P.ticket = h->ticket;
+  P.out96 = d_out;
+  P.dbg16 = dbg;
+  P.valid_by_orig = valid;
+  return FLIMO_OK;
+}
+
+int run_pass_blocking(flimo_handle h, const double state14[14], uint32_t orig_limit, float* dbg, uint8_t* valid,
+                      double packed[96]) {
+  MatchParams P;
+  int rc = fill_params(h, state14, P, h->out96, orig_limit, dbg, valid);
+  if (rc) return rc;
+  CU(h, cudaEventRecord(h->ev0, h->stream));
+  CU(h, launch_match(P, h->stream));
+  CU(h, cudaEventRecord(h->ev1, h->stream));
+  CU(h, cudaMemcpyAsync(h->h_out96, h->out96, 96 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CU(h, cudaStreamSynchronize(h->stream));
+  h->stats.kernel_launches++;
+  h->stats.match_launches++;
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+  h->stats.last_match_ms = ms;
+  std::memcpy(packed, h->h_out96, 96 * sizeof(double));
+  return FLIMO_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* flimo_version(void) { return "fast_limo_b200 0.1 (sm_100a)"; }
+
+void flimo_cfg_default(flimo_cfg* c) {
+  std::memset(c, 0, sizeof(*c));
+  c->NUM_MATCH_POINTS = 5;
+  c->MAX_NUM_MATCHES = 2000;        // src/main.cpp:149
+  c->MAX_NUM_PC2MATCH = 10000;      // Mapper.cpp:27
+  c->estimate_extrinsics = 1;
+  c->MAX_DIST_PLANE = 2.0;
+  c->PLANE_THRESHOLD = 5.e-2;
+  c->octree_bucket_size = 2;        // YAML value; ignored like the reference ignores it
+  c->octree_downsampling = 1;
+  c->octree_min_extent = 0.2f;
+  c->knn_cell = 0.f;
+  c->sort_scan = 0;
+}
+
+const char* flimo_last_error(flimo_handle h) { return h ? h->err.c_str() : g_err.c_str(); }
+
+int flimo_create(const flimo_cfg* cfg, int device, flimo_handle* out) {
+  if (!cfg || !out) return fail(nullptr, FLIMO_ERR_INVALID, "null argument");
+  *out = nullptr;
+  if (cfg->NUM_MATCH_POINTS != 5)
+    return fail(nullptr, FLIMO_ERR_INVALID, "NUM_MATCH_POINTS != 5 is not compiled in (all shipped configs use 5)");
+  if (device == -1) {
+    // Host-only handle: ONLY the flimo_ekf_* state machine works (pure host algebra, used by the
+    // CPU unit tests and by drivers that run the measurement pass elsewhere).  Every entry point
+    // that needs the GPU fails with FLIMO_ERR_NO_DEVICE; there is no CPU measurement path.
+    flimo_ctx* hh = new (std::nothrow) flimo_ctx;
+    if (!hh) return fail(nullptr, FLIMO_ERR_NOMEM, "host allocation failed");
+    hh->cfg = *cfg;
+    hh->device = -1;
+    *out = hh;
+    return FLIMO_OK;
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(nullptr, FLIMO_ERR_NO_DEVICE, "no CUDA device: libflimo_cuda has no CPU path");
+  if (device < 0 || device >= ndev) return fail(nullptr, FLIMO_ERR_INVALID, "device ordinal out of range");
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major < 10)
+    return fail(nullptr, FLIMO_ERR_NO_DEVICE, "device is not sm_100 class; this library ships sm_100a code only");
+  flimo_ctx* h = new (std::nothrow) flimo_ctx;
+  if (!h) return fail(nullptr, FLIMO_ERR_NOMEM, "host allocation failed");
+  h->cfg = *cfg;
+  h->device = device;
+  CU(h, cudaSetDevice(device));
+  CU(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  CU(h, cudaEventCreate(&h->ev0));
+  CU(h, cudaEventCreate(&h->ev1));
+  CU(h, cudaMalloc(&h->out96, 96 * sizeof(double)));
+  CU(h, cudaMemset(h->out96, 0, 96 * sizeof(double)));
+  CU(h, cudaMallocHost(&h->h_out96, 96 * sizeof(double)));
+  CU(h, cudaMalloc(&h->d_count, sizeof(unsigned int)));
+  *out = h;
+  return FLIMO_OK;
+}
+
+void flimo_destroy(flimo_handle h) {
+  if (!h) return;
+  if (h->device < 0) {
+    delete h;
+    return;
+  }
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  map_index_free(h->map);
+  cudaFree(h->scan);
+  cudaFree(h->scan_tmp);
+  cudaFree(h->scan_keys);
+  cudaFree(h->scan_cub);
+  cudaFree(h->stage);
+  cudaFree(h->d_count);
+  cudaFree(h->partials);
+  cudaFree(h->ticket);
+  cudaFree(h->out96);
+  cudaFreeHost(h->h_out96);
+  cudaFree(h->dbg16);
+  cudaFree(h->valid_flags);
+  cudaFree(h->xyz_out);
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+void* flimo_stream(flimo_handle h) { return h ? (void*)h->stream : nullptr; }
+
+int flimo_get_stats(flimo_handle h, flimo_stats* out) {
+  if (!h || !out) return FLIMO_ERR_INVALID;
+  h->stats.knn_cell = h->map.g.cell;
+  h->stats.grid_nx = h->map.g.nx;
+  h->stats.grid_ny = h->map.g.ny;
+  h->stats.grid_nz = h->map.g.nz;
+  h->stats.table_bytes = (h->map.n_cells + 1) * sizeof(uint32_t);
+  h->stats.map_bytes = h->map.n_pts * sizeof(float4);
+  *out = h->stats;
+  return FLIMO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+int flimo_map_add_device(flimo_handle h, const void* d_xyz, size_t n, size_t stride_bytes, double stamp) {
+  if (!h || (!d_xyz && n)) return fail(h, FLIMO_ERR_INVALID, "null argument");
+  if (stride_bytes < 12 || stride_bytes % 4) return fail(h, FLIMO_ERR_INVALID, "stride must be a multiple of 4 and >= 12");
+  if (n < 1) return FLIMO_OK;                                   // Mapper::add: size < 1 -> return
+  NEED_GPU(h);
+  const size_t old_n = h->map_exists ? h->map.n_pts : 0;
+  if (h->map_exists && h->cfg.octree_downsampling)
+    return fail(h, FLIMO_ERR_INVALID, "incremental insert with down-sampling is not built yet (K3)");
+  CU(h, map_index_reserve(h->map, old_n + n));
+  if (old_n) CU(h, cudaMemcpyAsync(h->map.pts_alt, h->map.pts, old_n * sizeof(float4), cudaMemcpyDeviceToDevice, h->stream));
+  CU(h, cudaMemsetAsync(h->d_count, 0, sizeof(unsigned int), h->stream));
+  CU(h, pack_points(d_xyz, n, stride_bytes, h->map.pts_alt + old_n, h->d_count, h->stream));
+  unsigned int kept = 0;
+  CU(h, cudaMemcpyAsync(&kept, h->d_count, sizeof(kept), cudaMemcpyDeviceToHost, h->stream));
+  CU(h, cudaStreamSynchronize(h->stream));
+  h->stats.kernel_launches += 1;
+  const size_t total = old_n + kept;
+  if (total == 0) return FLIMO_OK;                              // Octree::initialize: empty -> no root
+  const size_t max_cells = (size_t)1 << 30;
+  CU(h, map_index_build(h->map, total, h->cfg.knn_cell, max_cells, h->stream, &h->stats.kernel_launches));
+  CU(h, cudaStreamSynchronize(h->stream));
+  h->map_exists = true;
+  h->last_time = stamp;
+  return FLIMO_OK;
+}
+
+int flimo_map_add(flimo_handle h, const float* xyz, size_t n, size_t stride_bytes, double stamp) {
+  if (!h || (!xyz && n)) return fail(h, FLIMO_ERR_INVALID, "null argument");
+  if (n < 1) return FLIMO_OK;
+  NEED_GPU(h);
+  int rc = upload(h, xyz, n * stride_bytes);
+  if (rc) return rc;
+  return flimo_map_add_device(h, h->stage, n, stride_bytes, stamp);
+}
+
+int flimo_map_size(flimo_handle h, size_t* n_points) {
+  if (!h || !n_points) return FLIMO_ERR_INVALID;
+  *n_points = h->map_exists ? h->map.n_pts : 0;
+  return FLIMO_OK;
+}
+int flimo_map_exists(flimo_handle h) { return (h && h->map_exists && h->map.n_pts > 0) ? 1 : 0; }
+double flimo_map_last_time(flimo_handle h) { return h ? h->last_time : -1.0; }
+
+int flimo_map_get_points(flimo_handle h, float* out_xyz, size_t cap_points, size_t* n_points) {
+  if (!h || !n_points) return fail(h, FLIMO_ERR_INVALID, "null argument");
+  const size_t n = h->map_exists ? h->map.n_pts : 0;
+  *n_points = n;
+  if (!out_xyz || n == 0) return FLIMO_OK;
+  NEED_GPU(h);
+  const size_t m = n < cap_points ? n : cap_points;
+  std::vector<float4> tmp(m);
+  CU(h, cudaMemcpyAsync(tmp.data(), h->map.pts, m * sizeof(float4), cudaMemcpyDeviceToHost, h->stream));
+  CU(h, cudaStreamSynchronize(h->stream));
+  for (size_t i = 0; i < m; ++i) {
+    out_xyz[3 * i] = tmp[i].x;
+    out_xyz[3 * i + 1] = tmp[i].y;
+    out_xyz[3 * i + 2] = tmp[i].z;
+  }
+  return FLIMO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+int flimo_scan_set_device(flimo_handle h, const void* d_xyz, size_t n, size_t stride_bytes) {
+  if (!h || (!d_xyz && n)) return fail(h, FLIMO_ERR_INVALID, "null argument");
+  if (stride_bytes < 12 || stride_bytes % 4) return fail(h, FLIMO_ERR_INVALID, "stride must be a multiple of 4 and >= 12");
+  NEED_GPU(h);
+  const size_t cap = h->cfg.MAX_NUM_PC2MATCH > 0 ? (size_t)h->cfg.MAX_NUM_PC2MATCH : 0;
+  const size_t nq = n > cap ? cap : n;                           // first-N rule (Mapper.cpp:63-69)
+  if (nq > h->scan_cap) {
+    cudaFree(h->scan);
+    cudaFree(h->scan_tmp);
+    h->scan = h->scan_tmp = nullptr;
+    h->scan_cap = 0;
+    const size_t want = nq + nq / 4 + 1024;
+    CU(h, cudaMalloc(&h->scan, want * sizeof(float4)));
+    CU(h, cudaMalloc(&h->scan_tmp, want * sizeof(float4)));
+    h->scan_cap = want;
+  }
+  CU(h, pack_scan(d_xyz, nq, stride_bytes, h->scan, h->stream));
+  h->stats.kernel_launches += nq ? 1 : 0;
+  if (h->cfg.sort_scan && nq > 1)
+    CU(h, sort_scan_morton(h->scan, h->scan_tmp, nq, &h->scan_cub, &h->scan_cub_bytes, &h->scan_keys, &h->scan_keys_cap,
+                           h->stream, &h->stats.kernel_launches));
+  h->scan_n = nq;
+  h->shard_begin = 0;
+  h->shard_end = nq;
+  return FLIMO_OK;
+}
+
+int flimo_scan_set(flimo_handle h, const float* xyz_body, size_t n, size_t stride_bytes) {
+  if (!h || (!xyz_body && n)) return fail(h, FLIMO_ERR_INVALID, "null argument");
+  NEED_GPU(h);
+  const size_t cap = h->cfg.MAX_NUM_PC2MATCH > 0 ? (size_t)h->cfg.MAX_NUM_PC2MATCH : 0;
+  const size_t nq = n > cap ? cap : n;
+  if (nq) {
+    int rc = upload(h, xyz_body, nq * stride_bytes);
+    if (rc) return rc;
+  }
+  return flimo_scan_set_device(h, h->stage, nq, stride_bytes);
+}
+
+int flimo_scan_shard(flimo_handle h, size_t begin, size_t end) {
+  if (!h) return FLIMO_ERR_INVALID;
+  if (begin > end || end > h->scan_n) return fail(h, FLIMO_ERR_INVALID, "shard out of range");
+  h->shard_begin = begin;
+  h->shard_end = end;
+  return FLIMO_OK;
+}
+
+void flimo_unpack96(const double p[96], double HTH[144], double HTh[12], int64_t* n_valid, int64_t* n_rows,
+                    double* sum_sq_res) {
+  int e = 0;
+  for (int i = 0; i < 12; ++i)
+    for (int j = i; j < 12; ++j) {
+      HTH[i * 12 + j] = p[e];
+      HTH[j * 12 + i] = p[e];
+      ++e;
+    }
+  for (int i = 0; i < 12; ++i) HTh[i] = p[78 + i];
+  if (n_rows) *n_rows = (int64_t)std::llround(p[90]);
+  if (sum_sq_res) *sum_sq_res = p[91];
+  if (n_valid) *n_valid = (int64_t)std::llround(p[92]);
+}
+
+int flimo_match_reduce_async(flimo_handle h, const double state14[14], double* d_out96, void* cuda_stream) {
+  if (!h || !state14 || !d_out96) return fail(h, FLIMO_ERR_INVALID, "null argument");
+  NEED_GPU(h);
+  cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : h->stream;
+  if (!flimo_map_exists(h) || h->shard_end == h->shard_begin) {   // Mapper::match on an empty map -> no matches
+    CU(h, cudaMemsetAsync(d_out96, 0, 96 * sizeof(double), st));
+    return FLIMO_OK;
+  }
+  MatchParams P;
+  int rc = fill_params(h, state14, P, d_out96, 0xFFFFFFFFu, nullptr, nullptr);
+  if (rc) return rc;
+  CU(h, launch_match(P, st));
+  h->stats.kernel_launches++;
+  h->stats.match_launches++;
+  return FLIMO_OK;
+}
+
+int flimo_match_reduce(flimo_handle h, const double state14[14], double HTH[144], double HTh[12], int64_t* n_valid,
+                       int64_t* n_rows, double* sum_sq_res) {
+  if (!h || !state14 || !HTH || !HTh) return fail(h, FLIMO_ERR_INVALID, "null argument");
+  NEED_GPU(h);
+  double packed[96];
+  std::memset(packed, 0, sizeof(packed));
+  if (flimo_map_exists(h) && h->shard_end > h->shard_begin) {
+    int rc = run_pass_blocking(h, state14, 0xFFFFFFFFu, nullptr, nullptr, packed);
+    if (rc) return rc;
+    const int64_t nv = (int64_t)std::llround(packed[92]);
+    const int64_t cap = h->cfg.MAX_NUM_MATCHES;
+    if (nv > cap) {
+      // Localizer::calculate_H keeps the FIRST MAX_NUM_MATCHES accepted matches in scan order
+      // (Localizer.cpp:539,547-548).  Find the original index after which rows stop counting.
+      const size_t nq = h->scan_n;
+      CU(h, grow(&h->valid_flags, &h->valid_cap, nq));
+      CU(h, cudaMemsetAsync(h->valid_flags, 0, nq, h->stream));
+      rc = run_pass_blocking(h, state14, 0xFFFFFFFFu, nullptr, h->valid_flags, packed);
+      if (rc) return rc;
+      std::vector<uint8_t> flags(nq);
+      CU(h, cudaMemcpyAsync(flags.data(), h->valid_flags, nq, cudaMemcpyDeviceToHost, h->stream));
+      CU(h, cudaStreamSynchronize(h->stream));
+      int64_t seen = 0;
+      uint32_t limit = (uint32_t)nq;
+      for (size_t i = 0; i < nq; ++i) {
+        if (flags[i] && ++seen == cap) {
+          limit = (uint32_t)(i + 1);
+          break;
+        }
+      }
+      if (cap <= 0) limit = 0;
+      rc = run_pass_blocking(h, state14, limit, nullptr, nullptr, packed);
+      if (rc) return rc;
+    }
+  }
+  flimo_unpack96(packed, HTH, HTh, n_valid, n_rows, sum_sq_res);
+  return FLIMO_OK;
+}
+
+int flimo_match_debug(flimo_handle h, const double state14[14], float* out16, size_t cap_points, size_t* n_points) {
+  if (!h || !state14 || !n_points) return fail(h, FLIMO_ERR_INVALID, "null argument");
+  NEED_GPU(h);
+  const size_t nq = h->scan_n;
+  *n_points = nq;
+  if (!out16 || nq == 0) return FLIMO_OK;
+  CU(h, grow(&h->dbg16, &h->dbg_cap, nq * 16));
+  CU(h, cudaMemsetAsync(h->dbg16, 0, nq * 16 * sizeof(float), h->stream));
+  if (flimo_map_exists(h) && h->shard_end > h->shard_begin) {
+    double packed[96];
+    int rc = run_pass_blocking(h, state14, 0xFFFFFFFFu, h->dbg16, nullptr, packed);
+    if (rc) return rc;
+  }
+  const size_t m = nq < cap_points ? nq : cap_points;
+  CU(h, cudaMemcpyAsync(out16, h->dbg16, m * 16 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  CU(h, cudaStreamSynchronize(h->stream));
+  return FLIMO_OK;
+}
+
+int flimo_scan_to_world(flimo_handle h, const double state14[14], float* out_xyz, size_t cap_points, size_t* n_points) {
+  if (!h || !state14 || !n_points) return fail(h, FLIMO_ERR_INVALID, "null argument");
+  NEED_GPU(h);
+  const size_t nq = h->scan_n;
+  *n_points = nq;
+  if (!out_xyz || nq == 0) return FLIMO_OK;
+  CU(h, grow(&h->xyz_out, &h->xyz_cap, nq * 3));
+  PoseConsts pc;
+  make_pose(state14, pc);
+  CU(h, transform_scan(h->scan, nq, pc, h->xyz_out, h->stream));
+  h->stats.kernel_launches++;
+  const size_t m = nq < cap_points ? nq : cap_points;
+  CU(h, cudaMemcpyAsync(out_xyz, h->xyz_out, m * 3 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  CU(h, cudaStreamSynchronize(h->stream));
+  return FLIMO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+int flimo_ekf_begin(flimo_handle h, const double state26[26], const double P529[529], int max_iter,
+                    const double limit23[23], double R_noise, double D_degeneracy) {
+  if (!h || !state26 || !P529 || !limit23) return fail(h, FLIMO_ERR_INVALID, "null argument");
+  h->upd.begin(state26, P529, max_iter, limit23, R_noise, D_degeneracy);
+  h->upd_active = true;
+  return FLIMO_OK;
+}
+int flimo_ekf_state(flimo_handle h, double state26[26]) {
+  if (!h || !state26 || !h->upd_active) return fail(h, FLIMO_ERR_STATE, "flimo_ekf_begin not called");
+  h->upd.state(state26);
+  return FLIMO_OK;
+}
+int flimo_ekf_step(flimo_handle h, const double HTH[144], const double HTh[12], int64_t n_rows, int* done) {
+  if (!h || !HTH || !HTh || !h->upd_active) return fail(h, FLIMO_ERR_STATE, "flimo_ekf_begin not called");
+  const bool d = h->upd.step(HTH, HTh, n_rows);
+  if (done) *done = d ? 1 : 0;
+  return FLIMO_OK;
+}
+int flimo_ekf_end(flimo_handle h, double state26[26], double P529[529]) {
+  if (!h || !state26 || !P529 || !h->upd_active) return fail(h, FLIMO_ERR_STATE, "flimo_ekf_begin not called");
+  h->upd.end(state26, P529);
+  h->upd_active = false;
+  return FLIMO_OK;
+}
+
+int flimo_update(flimo_handle h, double state26[26], double P529[529], int max_iter, const double limit23[23],
+                 double R_noise, double D_degeneracy, int* passes_out) {
+  if (!h || !state26 || !P529 || !limit23) return fail(h, FLIMO_ERR_INVALID, "null argument");
+  ekf::IteratedUpdate& u = h->upd;
+  u.begin(state26, P529, max_iter, limit23, R_noise, D_degeneracy);
+  double x[26], HTH[144], HTh[12];
+  while (!u.done()) {
+    u.state(x);
+    int64_t nv = 0, nr = 0;
+    double ss = 0;
+    int rc = flimo_match_reduce(h, x, HTH, HTh, &nv, &nr, &ss);
+    if (rc) return rc;
+    u.step(HTH, HTh, nr);
+  }
+  u.end(state26, P529);
+  if (passes_out) *passes_out = u.passes();
+  return FLIMO_OK;
+}
+
+}  // extern "C"

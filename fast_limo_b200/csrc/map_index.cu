@@ -1,0 +1,331 @@
+// Device-resident map index of the registration hot path (B200 / sm_100a).
+//
+// Replaces the pointer-based i-Octree container of the reference
+// (fast_limo/Objects/Octree.hpp:103-132, built by createOctant :301-338) with a layout made for
+// HBM3e: map points live in ONE float4 array sorted by uniform-grid cell (x fastest), plus a dense
+// prefix table cell_start[] over the map's bounding box.  kNN is exact for any cell size (the
+// search in match_kernel.cu expands rings until the k-th distance is inside the explored block),
+// so the grid is a performance choice only — it does not have to be the octree's lattice.
+//
+// Build = bounding box -> cell keys -> radix sort (CUB, 32-bit keys, only the bits needed) ->
+// gather -> boundary scatter + suffix-min scan for the prefix table.  All on the device; one
+// small D2H (6 floats) to size the grid.  The build is off the per-pass hot path (once per
+// Mapper::add).
+#include <cfloat>
+#include <cmath>
+#include <cstdio>
+
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+#include <thrust/iterator/reverse_iterator.h>
+
+#include "flimo_dev.cuh"
+#include "grid_math.cuh"
+
+namespace flimo {
+
+#define FL_TRY(x)                     \
+  do {                                \
+    cudaError_t e_ = (x);             \
+    if (e_ != cudaSuccess) return e_; \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// order-preserving float <-> uint encoding for atomicMin/Max
+__device__ __forceinline__ unsigned int f2ord(float f) {
+  unsigned int u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__host__ __device__ __forceinline__ float ord2f(unsigned int u) {
+  unsigned int v = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
+#ifdef __CUDA_ARCH__
+  return __uint_as_float(v);
+#else
+  float f;
+  memcpy(&f, &v, 4);
+  return f;
+#endif
+}
+
+__global__ void bbox_init_kernel(unsigned int* bb) {
+  if (threadIdx.x < 3) bb[threadIdx.x] = 0xFFFFFFFFu;       // mins
+  else if (threadIdx.x < 6) bb[threadIdx.x] = 0u;            // maxs
+}
+
+__global__ void __launch_bounds__(256) bbox_kernel(const float4* __restrict__ p, size_t n, unsigned int* bb) {
+  float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float4 v = p[i];
+    lo[0] = fminf(lo[0], v.x); hi[0] = fmaxf(hi[0], v.x);
+    lo[1] = fminf(lo[1], v.y); hi[1] = fmaxf(hi[1], v.y);
+    lo[2] = fminf(lo[2], v.z); hi[2] = fmaxf(hi[2], v.z);
+  }
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      lo[a] = fminf(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o));
+      hi[a] = fmaxf(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o));
+    }
+  }
+  if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      atomicMin(&bb[a], f2ord(lo[a]));
+      atomicMax(&bb[3 + a], f2ord(hi[a]));
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) keys_kernel(const float4* __restrict__ p, size_t n, GridDesc g,
+                                                   uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 v = p[i];
+  const int ix = cell_coord(v.x, g.ox, g.inv_cell, g.nx);
+  const int iy = cell_coord(v.y, g.oy, g.inv_cell, g.ny);
+  const int iz = cell_coord(v.z, g.oz, g.inv_cell, g.nz);
+  keys[i] = (uint32_t)((iz * g.ny + iy) * g.nx + ix);
+  vals[i] = (uint32_t)i;
+}
+
+__global__ void __launch_bounds__(256) gather_kernel(const float4* __restrict__ src, const uint32_t* __restrict__ order,
+                                                     size_t n, float4* __restrict__ dst) {
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[order[i]];
+}
+
+// cell_start[c] = first sorted position whose key is >= c.  Occupied cells get their start here,
+// empty cells are filled by the suffix-min scan that follows.
+__global__ void __launch_bounds__(256) boundaries_kernel(const uint32_t* __restrict__ keys, size_t n, size_t n_cells,
+                                                         uint32_t* __restrict__ cell_start) {
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i == 0) cell_start[n_cells] = (uint32_t)n;
+  if (i >= n) return;
+  const uint32_t k = keys[i];
+  if (i == 0 || keys[i - 1] != k) cell_start[k] = (uint32_t)i;
+}
+
+__global__ void __launch_bounds__(256) pack_points_kernel(const unsigned char* __restrict__ src, size_t n, size_t stride,
+                                                          float4* __restrict__ dst, unsigned int* __restrict__ count) {
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  bool keep = false;
+  float x = 0, y = 0, z = 0;
+  if (i < n) {
+    const float* p = reinterpret_cast<const float*>(src + i * stride);
+    x = p[0]; y = p[1]; z = p[2];
+    keep = !(isnan(x) || isnan(y) || isnan(z));      // Octree::processPoints (Octree.hpp:243)
+  }
+  // warp-aggregated append (order inside the map array is irrelevant: it is re-sorted by cell)
+  const unsigned int m = __ballot_sync(0xffffffffu, keep);
+  if (m == 0) return;
+  const int lane = threadIdx.x & 31;
+  unsigned int base = 0;
+  if (lane == __ffs(m) - 1) base = atomicAdd(count, __popc(m));
+  base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+  if (keep) dst[base + __popc(m & ((1u << lane) - 1))] = make_float4(x, y, z, 0.f);
+}
+
+__global__ void __launch_bounds__(256) pack_scan_kernel(const unsigned char* __restrict__ src, size_t n, size_t stride,
+                                                        float4* __restrict__ dst) {
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float* p = reinterpret_cast<const float*>(src + i * stride);
+  dst[i] = make_float4(p[0], p[1], p[2], __uint_as_float((unsigned int)i));
+}
+
+__device__ __forceinline__ uint32_t spread10(uint32_t v) {
+  v &= 0x3ffu;
+  v = (v | (v << 16)) & 0x030000FFu;
+  v = (v | (v << 8)) & 0x0300F00Fu;
+  v = (v | (v << 4)) & 0x030C30C3u;
+  v = (v | (v << 2)) & 0x09249249u;
+  return v;
+}
+
+// Morton key of the body-frame position at 0.25 m resolution in a +-128 m cube (pose independent,
+// so one sort per scan serves every pass).
+__global__ void __launch_bounds__(256) scan_keys_kernel(const float4* __restrict__ scan, size_t n, uint32_t* keys,
+                                                        uint32_t* vals) {
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 v = scan[i];
+  auto q = [](float c) {
+    float u = (c + 128.0f) * 4.0f;
+    u = isnan(u) ? 0.f : fminf(fmaxf(u, 0.f), 1023.f);
+    return (uint32_t)u;
+  };
+  keys[i] = spread10(q(v.x)) | (spread10(q(v.y)) << 1) | (spread10(q(v.z)) << 2);
+  vals[i] = (uint32_t)i;
+}
+
+__global__ void __launch_bounds__(256) transform_kernel(const float4* __restrict__ scan, size_t n, PoseConsts pc,
+                                                        float* __restrict__ out) {
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 v = scan[i];
+  const unsigned int orig = __float_as_uint(v.w);
+  float g[3];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    float acc = __fmul_rn(pc.R_wb[3 * r], v.x);
+    acc = __fadd_rn(__fmul_rn(pc.R_wb[3 * r + 1], v.y), acc);
+    acc = __fadd_rn(__fmul_rn(pc.R_wb[3 * r + 2], v.z), acc);
+    g[r] = __fadd_rn(pc.t_wb[r], acc);
+  }
+  out[3 * (size_t)orig] = g[0];
+  out[3 * (size_t)orig + 1] = g[1];
+  out[3 * (size_t)orig + 2] = g[2];
+}
+
+// ---------------------------------------------------------------------------------------------
+static inline unsigned int nblk(size_t n, int t = 256) { return (unsigned int)((n + t - 1) / t); }
+
+cudaError_t pack_points(const void* d_src, size_t n, size_t stride_bytes, float4* dst, unsigned int* d_count,
+                        cudaStream_t st) {
+  if (n == 0) return cudaSuccess;
+  pack_points_kernel<<<nblk(n), 256, 0, st>>>(static_cast<const unsigned char*>(d_src), n, stride_bytes, dst, d_count);
+  return cudaGetLastError();
+}
+
+cudaError_t pack_scan(const void* d_src, size_t n, size_t stride_bytes, float4* dst, cudaStream_t st) {
+  if (n == 0) return cudaSuccess;
+  pack_scan_kernel<<<nblk(n), 256, 0, st>>>(static_cast<const unsigned char*>(d_src), n, stride_bytes, dst);
+  return cudaGetLastError();
+}
+
+cudaError_t transform_scan(const float4* scan, size_t n, const PoseConsts& pc, float* d_out_xyz, cudaStream_t st) {
+  if (n == 0) return cudaSuccess;
+  transform_kernel<<<nblk(n), 256, 0, st>>>(scan, n, pc, d_out_xyz);
+  return cudaGetLastError();
+}
+
+static cudaError_t ensure(void** p, size_t* cap, size_t need) {
+  if (*cap >= need) return cudaSuccess;
+  if (*p) cudaFree(*p);
+  *p = nullptr;
+  *cap = 0;
+  FL_TRY(cudaMalloc(p, need));
+  *cap = need;
+  return cudaSuccess;
+}
+
+cudaError_t sort_scan_morton(float4* scan, float4* tmp, size_t n, void** cub_tmp, size_t* cub_tmp_bytes, uint32_t** keys,
+                             size_t* keys_cap, cudaStream_t st, uint64_t* launches) {
+  if (n < 2) return cudaSuccess;
+  size_t need_keys = 4 * n * sizeof(uint32_t);
+  FL_TRY(ensure(reinterpret_cast<void**>(keys), keys_cap, need_keys));
+  uint32_t *k0 = *keys, *k1 = k0 + n, *v0 = k1 + n, *v1 = v0 + n;
+  scan_keys_kernel<<<nblk(n), 256, 0, st>>>(scan, n, k0, v0);
+  cub::DoubleBuffer<uint32_t> dk(k0, k1), dv(v0, v1);
+  size_t bytes = 0;
+  FL_TRY(cub::DeviceRadixSort::SortPairs(nullptr, bytes, dk, dv, (int)n, 0, 30, st));
+  FL_TRY(ensure(cub_tmp, cub_tmp_bytes, bytes));
+  FL_TRY(cub::DeviceRadixSort::SortPairs(*cub_tmp, bytes, dk, dv, (int)n, 0, 30, st));
+  FL_TRY(cudaMemcpyAsync(tmp, scan, n * sizeof(float4), cudaMemcpyDeviceToDevice, st));
+  gather_kernel<<<nblk(n), 256, 0, st>>>(tmp, dv.Current(), n, scan);
+  if (launches) *launches += 6;
+  return cudaGetLastError();
+}
+
+cudaError_t map_index_reserve(MapIndex& idx, size_t n) {
+  if (n <= idx.cap_pts) return cudaSuccess;
+  size_t cap = idx.cap_pts ? idx.cap_pts : 1024;
+  while (cap < n) cap += cap / 2 + 1024;
+  float4 *np = nullptr, *na = nullptr;
+  FL_TRY(cudaMalloc(&np, cap * sizeof(float4)));
+  FL_TRY(cudaMalloc(&na, cap * sizeof(float4)));
+  if (idx.pts) {
+    if (idx.n_pts) FL_TRY(cudaMemcpy(np, idx.pts, idx.n_pts * sizeof(float4), cudaMemcpyDeviceToDevice));
+    cudaFree(idx.pts);
+  }
+  if (idx.pts_alt) cudaFree(idx.pts_alt);
+  idx.pts = np;
+  idx.pts_alt = na;
+  idx.cap_pts = cap;
+  if (idx.keys) cudaFree(idx.keys);
+  idx.keys = nullptr;
+  FL_TRY(cudaMalloc(&idx.keys, 4 * cap * sizeof(uint32_t)));
+  idx.keys_alt = idx.keys + cap;
+  idx.vals = idx.keys_alt + cap;
+  idx.vals_alt = idx.vals + cap;
+  idx.cap_scratch = cap;
+  if (!idx.bbox) FL_TRY(cudaMalloc(&idx.bbox, 8 * sizeof(float)));
+  return cudaSuccess;
+}
+
+void map_index_free(MapIndex& idx) {
+  cudaFree(idx.pts);
+  cudaFree(idx.pts_alt);
+  cudaFree(idx.cell_start);
+  cudaFree(idx.keys);
+  cudaFree(idx.cub_tmp);
+  cudaFree(idx.bbox);
+  idx = MapIndex{};
+}
+
+cudaError_t map_index_build(MapIndex& idx, size_t n, float cell, size_t max_cells, cudaStream_t st, uint64_t* launches) {
+  if (n == 0 || n > 0xFFFFFFF0ull) return cudaErrorInvalidValue;
+  if (n > idx.cap_pts || n > idx.cap_scratch) return cudaErrorInvalidValue;   // caller reserves
+  unsigned int* bb = reinterpret_cast<unsigned int*>(idx.bbox);
+  bbox_init_kernel<<<1, 32, 0, st>>>(bb);
+  bbox_kernel<<<min(nblk(n), 148u * 8u), 256, 0, st>>>(idx.pts_alt, n, bb);
+  unsigned int hb[6];
+  FL_TRY(cudaMemcpyAsync(hb, bb, sizeof(hb), cudaMemcpyDeviceToHost, st));
+  FL_TRY(cudaStreamSynchronize(st));
+  float lo[3], hi[3];
+  for (int a = 0; a < 3; ++a) {
+    lo[a] = ord2f(hb[a]);
+    hi[a] = ord2f(hb[3 + a]);
+  }
+  if (!(cell > 0.f)) cell = 0.25f;
+  GridDesc g{};
+  for (;;) {
+    g.cell = cell;
+    g.inv_cell = 1.0f / cell;
+    g.ox = lo[0] - 0.5f * cell;
+    g.oy = lo[1] - 0.5f * cell;
+    g.oz = lo[2] - 0.5f * cell;
+    const double ex = (double)hi[0] - g.ox, ey = (double)hi[1] - g.oy, ez = (double)hi[2] - g.oz;
+    const double fx = std::floor(ex / cell) + 2, fy = std::floor(ey / cell) + 2, fz = std::floor(ez / cell) + 2;
+    if (fx * fy * fz <= (double)max_cells && fx < 2e9 && fy < 2e9 && fz < 2e9) {
+      g.nx = (int)fx;
+      g.ny = (int)fy;
+      g.nz = (int)fz;
+      break;
+    }
+    cell *= 1.25992105f;   // halve the cell count and retry
+  }
+  const size_t n_cells = (size_t)g.nx * g.ny * g.nz;
+  if (n_cells + 1 > idx.cap_cells) {
+    if (idx.cell_start) cudaFree(idx.cell_start);
+    idx.cell_start = nullptr;
+    idx.cap_cells = 0;
+    const size_t cap = n_cells + n_cells / 4 + 1024;
+    FL_TRY(cudaMalloc(&idx.cell_start, cap * sizeof(uint32_t)));
+    idx.cap_cells = cap;
+  }
+  idx.g = g;
+  idx.n_cells = n_cells;
+  idx.n_pts = n;
+
+  keys_kernel<<<nblk(n), 256, 0, st>>>(idx.pts_alt, n, g, idx.keys, idx.vals);
+  int bits = 1;
+  while (bits < 32 && ((size_t)1 << bits) < n_cells) ++bits;
+  cub::DoubleBuffer<uint32_t> dk(idx.keys, idx.keys_alt), dv(idx.vals, idx.vals_alt);
+  size_t bytes = 0, bytes2 = 0;
+  FL_TRY(cub::DeviceRadixSort::SortPairs(nullptr, bytes, dk, dv, (int)n, 0, bits, st));
+  auto rb = thrust::make_reverse_iterator(idx.cell_start + n_cells + 1);
+  FL_TRY(cub::DeviceScan::InclusiveScan(nullptr, bytes2, rb, rb, cub::Min(), (int)(n_cells + 1), st));
+  if (bytes2 > bytes) bytes = bytes2;
+  FL_TRY(ensure(&idx.cub_tmp, &idx.cub_tmp_bytes, bytes));
+  FL_TRY(cub::DeviceRadixSort::SortPairs(idx.cub_tmp, bytes, dk, dv, (int)n, 0, bits, st));
+  gather_kernel<<<nblk(n), 256, 0, st>>>(idx.pts_alt, dv.Current(), n, idx.pts);
+  FL_TRY(cudaMemsetAsync(idx.cell_start, 0xFF, (n_cells + 1) * sizeof(uint32_t), st));
+  boundaries_kernel<<<nblk(n), 256, 0, st>>>(dk.Current(), n, n_cells, idx.cell_start);
+  FL_TRY(cub::DeviceScan::InclusiveScan(idx.cub_tmp, bytes, rb, rb, cub::Min(), (int)(n_cells + 1), st));
+  if (launches) *launches += 12;
+  return cudaGetLastError();
+}
+
+}  // namespace flimo

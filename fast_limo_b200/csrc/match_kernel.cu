@@ -1,0 +1,525 @@
+// K1 — the fused registration measurement pass on B200 (sm_100a).
+//
+// One launch = one IKFoM::h_share_model evaluation (use-ikfom.cpp:10-31) fused with the two
+// products that consume it (esekfom.hpp:1723 HTH = H^T H, :1727 H^T h):
+//
+//   per scan point (one thread each, reference loop Mapper.cpp:68-76):
+//     g      = T_wb * p                              Mapper.cpp:71-72, State.cpp:136-143
+//     5-NN   = exact nearest map points to g         Mapper.cpp:106-109, Octree.hpp:526-599
+//     gates  : 5 found, d2_5 < MAX_DIST_PLANE        Plane.cpp:41-48
+//     plane  : column-pivoted Householder QR of the 5x3 system A x = -1 (float32),
+//              n = x/|x|, d = 1/|x|                  Plane.cpp:80-105 (Eigen ColPivHouseholderQR)
+//     gate   : all |n.q_j + d| <= PLANE_THRESHOLD    Plane.cpp:107-114
+//     dist   = n.g + d                               Plane.cpp:50-52, Match.cpp:27
+//     row    = [n, p_imu x C, p_lid x (R_LI^T C), C], z = -dist      Localizer.cpp:549-572
+//   reduction (float64): sum over accepted points of [row,z]^T [row,z]  (13x13 upper triangle =
+//     78 HTH + 12 HTh + sum z^2), warp-cooperative, then a deterministic two-level
+//     last-CTA-done tree over tiles.  H is never written to memory.
+//
+// This translation unit is compiled with --fmad=false: every float32 operation is an individually
+// rounded IEEE add/mul/div/sqrt in the order the reference's x86-64 (no-FMA) build evaluates them,
+// so per-point results are bit-identical to the CPU restatement in oracle/ (tests/ check that).
+//
+// Data layout: see map_index.cu.  The search reads map points as 16-byte float4 through the
+// read-only path; neighbouring threads handle neighbouring scan points (ring order or Morton
+// order), so the cell rows a warp touches overlap and are served from L1/L2.
+#include <cfloat>
+
+#include "flimo_dev.cuh"
+#include "grid_math.cuh"
+
+namespace flimo {
+
+namespace {
+
+constexpr int kGroupTiles = 32;   // tiles per first-level reduction group
+
+struct Top5 {
+  float d[5];
+  uint32_t i[5];
+};
+
+// Sorted insertion; on equal distance the earlier candidate stays in front and a candidate equal
+// to the current worst is rejected (Octree.hpp:72-87).  Branch free; NaN is never inserted.
+__device__ __forceinline__ void top5_offer(Top5& t, float d, uint32_t idx) {
+  const bool c0 = d < t.d[0], c1 = d < t.d[1], c2 = d < t.d[2], c3 = d < t.d[3], c4 = d < t.d[4];
+  t.i[4] = c3 ? t.i[3] : (c4 ? idx : t.i[4]);
+  t.d[4] = c3 ? t.d[3] : (c4 ? d : t.d[4]);
+  t.i[3] = c2 ? t.i[2] : (c3 ? idx : t.i[3]);
+  t.d[3] = c2 ? t.d[2] : (c3 ? d : t.d[3]);
+  t.i[2] = c1 ? t.i[1] : (c2 ? idx : t.i[2]);
+  t.d[2] = c1 ? t.d[1] : (c2 ? d : t.d[2]);
+  t.i[1] = c0 ? t.i[0] : (c1 ? idx : t.i[1]);
+  t.d[1] = c0 ? t.d[0] : (c1 ? d : t.d[1]);
+  t.i[0] = c0 ? idx : t.i[0];
+  t.d[0] = c0 ? d : t.d[0];
+}
+
+__device__ __forceinline__ void scan_run(const float4* __restrict__ map, uint32_t s, uint32_t e, float qx, float qy,
+                                         float qz, Top5& t) {
+#pragma unroll 2
+  for (uint32_t i = s; i < e; ++i) {
+    const float4 p = __ldg(&map[i]);
+    const float dx = qx - p.x, dy = qy - p.y, dz = qz - p.z;
+    const float d = dx * dx + (dy * dy + dz * dz);     // Eigen Vector3f::squaredNorm order
+    top5_offer(t, d, i);
+  }
+}
+
+// Exact 5-NN of q over the grid-sorted map, outcome-equivalent to an unbounded search for every
+// query the reference would accept: rings of cells are added until either the 5th distance lies
+// inside the explored block, or the block already covers radius^2 >= MAX_DIST_PLANE (any further
+// point is rejected by Plane::close_enough anyway), or the whole grid has been visited.
+__device__ __forceinline__ void knn_search(const MatchParams& P, float qx, float qy, float qz, Top5& t) {
+  const GridDesc& G = P.g;
+  const float ux = cell_units(qx, G.ox, G.inv_cell), uy = cell_units(qy, G.oy, G.inv_cell),
+              uz = cell_units(qz, G.oz, G.inv_cell);
+  const int hx = cell_coord(qx, G.ox, G.inv_cell, G.nx), hy = cell_coord(qy, G.oy, G.inv_cell, G.ny),
+            hz = cell_coord(qz, G.oz, G.inv_cell, G.nz);
+  const float fx = ux - (float)hx, fy = uy - (float)hy, fz = uz - (float)hz;
+  // Binning slack: a point and the query are binned with ~1 ulp(u) error each.
+  const float slack = 6.0e-7f * fmaxf(fmaxf(fabsf(ux), fabsf(uy)), fabsf(uz)) + 1.0e-6f;
+  const uint32_t* __restrict__ cs = P.cell_start;
+
+  // block k = 1 : 3x3x3, nine x-runs
+#pragma unroll 1
+  for (int dz = -1; dz <= 1; ++dz) {
+    const int z = hz + dz;
+    if (z < 0 || z >= G.nz) continue;
+#pragma unroll 1
+    for (int dy = -1; dy <= 1; ++dy) {
+      const int y = hy + dy;
+      if (y < 0 || y >= G.ny) continue;
+      const int row = (z * G.ny + y) * G.nx;
+      const int x0 = max(hx - 1, 0), x1 = min(hx + 1, G.nx - 1);
+      scan_run(P.map, __ldg(&cs[row + x0]), __ldg(&cs[row + x1 + 1]), qx, qy, qz, t);
+    }
+  }
+  int k = 1;
+#pragma unroll 1
+  for (;;) {
+    // distance (in cells) from q to each face of the explored block; faces on the grid boundary
+    // do not count (nothing lies beyond them)
+    float m = FLT_MAX;
+    if (hx - k > 0) m = fminf(m, fx + (float)k);
+    if (hx + k < G.nx - 1) m = fminf(m, (1.0f - fx) + (float)k);
+    if (hy - k > 0) m = fminf(m, fy + (float)k);
+    if (hy + k < G.ny - 1) m = fminf(m, (1.0f - fy) + (float)k);
+    if (hz - k > 0) m = fminf(m, fz + (float)k);
+    if (hz + k < G.nz - 1) m = fminf(m, (1.0f - fz) + (float)k);
+    if (m == FLT_MAX) break;                                  // whole grid visited
+    const float me = (m - slack) * G.cell * 0.999999f;
+    const float gr2 = me > 0.f ? me * me : 0.f;
+    if (t.d[4] <= gr2) break;                                 // exact: nothing closer can be outside
+    if (gr2 >= P.max_dist_f) break;                           // outside points fail close_enough
+    ++k;
+    // shell k
+#pragma unroll 1
+    for (int dz = -k; dz <= k; ++dz) {
+      const int z = hz + dz;
+      if (z < 0 || z >= G.nz) continue;
+#pragma unroll 1
+      for (int dy = -k; dy <= k; ++dy) {
+        const int y = hy + dy;
+        if (y < 0 || y >= G.ny) continue;
+        const int row = (z * G.ny + y) * G.nx;
+        if (max(abs(dy), abs(dz)) == k) {
+          const int x0 = max(hx - k, 0), x1 = min(hx + k, G.nx - 1);
+          scan_run(P.map, __ldg(&cs[row + x0]), __ldg(&cs[row + x1 + 1]), qx, qy, qz, t);
+        } else {
+          const int xa = hx - k, xb = hx + k;
+          if (xa >= 0) scan_run(P.map, __ldg(&cs[row + xa]), __ldg(&cs[row + xa + 1]), qx, qy, qz, t);
+          if (xb < G.nx) scan_run(P.map, __ldg(&cs[row + xb]), __ldg(&cs[row + xb + 1]), qx, qy, qz, t);
+        }
+      }
+    }
+  }
+}
+
+// Column swap helper with static register indexing.
+__device__ __forceinline__ void cswap(bool c, float& a, float& b) {
+  const float ta = c ? b : a, tb = c ? a : b;
+  a = ta;
+  b = tb;
+}
+
+// Least-squares solve of the 5x3 system A x = -1 by column-pivoted Householder QR, float32, same
+// operation order as Eigen 3.3's ColPivHouseholderQR::computeInPlace + _solve_impl restated in
+// oracle/plane_match.hpp (reference call site Plane.cpp:95).  A[r][c] is destroyed.
+__device__ __forceinline__ void plane_qr_solve(float (&A)[5][3], float (&x)[3]) {
+  constexpr int R = 5;
+  const float eps = 1.1920929e-07f;
+  float nu[3], nd[3], hc[3];
+  int perm[3] = {0, 1, 2};
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    float s = 0.f;
+#pragma unroll
+    for (int r = 0; r < R; ++r) s = s + A[r][c] * A[r][c];
+    nd[c] = sqrtf(s);
+    nu[c] = nd[c];
+  }
+  float maxn = nu[0];
+  if (nu[1] > maxn) maxn = nu[1];
+  if (nu[2] > maxn) maxn = nu[2];
+  const float th = maxn * eps;
+  const float threshold_helper = (th * th) / 5.0f;
+  const float downdate_thr = sqrtf(eps);
+  int nonzero = 3;
+
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    // pivot: first column of maximal updated norm among k..2
+    int big = k;
+    float bign = nu[k];
+#pragma unroll
+    for (int c = k + 1; c < 3; ++c)
+      if (nu[c] > bign) {
+        bign = nu[c];
+        big = c;
+      }
+    const float big_sq = bign * bign;
+    if (nonzero == 3 && big_sq < threshold_helper * (float)(R - k)) nonzero = k;
+#pragma unroll
+    for (int c = k + 1; c < 3; ++c) {
+      const bool sw = (big == c);
+#pragma unroll
+      for (int r = 0; r < R; ++r) cswap(sw, A[r][k], A[r][c]);
+      cswap(sw, nu[k], nu[c]);
+      cswap(sw, nd[k], nd[c]);
+      const int pk = sw ? perm[c] : perm[k], pc = sw ? perm[k] : perm[c];
+      perm[k] = pk;
+      perm[c] = pc;
+    }
+    // Householder vector of column k
+    float tail = 0.f;
+#pragma unroll
+    for (int r = k + 1; r < R; ++r) tail = tail + A[r][k] * A[r][k];
+    const float c0 = A[k][k];
+    float tau, beta;
+    if (tail <= FLT_MIN) {
+      tau = 0.f;
+      beta = c0;
+#pragma unroll
+      for (int r = k + 1; r < R; ++r) A[r][k] = 0.f;
+    } else {
+      beta = sqrtf(c0 * c0 + tail);
+      if (c0 >= 0.f) beta = -beta;
+      const float den = c0 - beta;
+#pragma unroll
+      for (int r = k + 1; r < R; ++r) A[r][k] = A[r][k] / den;
+      tau = (beta - c0) / beta;
+    }
+    A[k][k] = beta;
+    hc[k] = tau;
+    if (tau != 0.f) {
+#pragma unroll
+      for (int c = k + 1; c < 3; ++c) {
+        float tmp = 0.f;
+#pragma unroll
+        for (int r = k + 1; r < R; ++r) tmp = tmp + A[r][k] * A[r][c];
+        tmp = tmp + A[k][c];
+        A[k][c] = A[k][c] - tau * tmp;
+#pragma unroll
+        for (int r = k + 1; r < R; ++r) A[r][c] = A[r][c] - tmp * (tau * A[r][k]);
+      }
+    }
+    // column-norm downdate (LAWN 176)
+#pragma unroll
+    for (int c = k + 1; c < 3; ++c) {
+      if (nu[c] != 0.f) {
+        float temp = fabsf(A[k][c]) / nu[c];
+        temp = (1.f + temp) * (1.f - temp);
+        temp = temp < 0.f ? 0.f : temp;
+        const float ratio = nu[c] / nd[c];
+        const float temp2 = temp * (ratio * ratio);
+        if (temp2 <= downdate_thr) {
+          float s = 0.f;
+#pragma unroll
+          for (int r = k + 1; r < R; ++r) s = s + A[r][c] * A[r][c];
+          nd[c] = sqrtf(s);
+          nu[c] = nd[c];
+        } else {
+          nu[c] = nu[c] * sqrtf(temp);
+        }
+      }
+    }
+  }
+
+  float cv[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) cv[r] = -1.0f;
+  x[0] = x[1] = x[2] = 0.f;
+  if (nonzero == 0) return;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    if (k < nonzero) {
+      const float tau = hc[k];
+      if (tau != 0.f) {
+        float tmp = 0.f;
+#pragma unroll
+        for (int r = k + 1; r < R; ++r) tmp = tmp + A[r][k] * cv[r];
+        tmp = tmp + cv[k];
+        cv[k] = cv[k] - tau * tmp;
+#pragma unroll
+        for (int r = k + 1; r < R; ++r) cv[r] = cv[r] - tmp * (tau * A[r][k]);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 2; i >= 0; --i) {
+    if (i < nonzero) {
+      cv[i] = cv[i] / A[i][i];
+#pragma unroll
+      for (int j = 0; j < i; ++j) cv[j] = cv[j] - cv[i] * A[j][i];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    if (i < nonzero) {
+#pragma unroll
+      for (int j = 0; j < 3; ++j)
+        if (perm[i] == j) x[j] = cv[i];
+    }
+  }
+}
+
+__device__ __forceinline__ void affine_apply(const float* __restrict__ Rm, const float* __restrict__ tv, float px,
+                                             float py, float pz, float (&o)[3]) {
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    float acc = Rm[3 * r] * px;
+    acc = Rm[3 * r + 1] * py + acc;
+    acc = Rm[3 * r + 2] * pz + acc;
+    o[r] = tv[r] * 1.0f + acc;
+  }
+}
+__device__ __forceinline__ void mat3_vec(const float* __restrict__ M, const float (&v)[3], float (&o)[3]) {
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    const float a = M[3 * r] * v[0], b = M[3 * r + 1] * v[1], c = M[3 * r + 2] * v[2];
+    o[r] = a + (b + c);
+  }
+}
+
+// (i,j) of the e-th entry of the row-major upper triangle of a 13x13 matrix.
+__device__ __forceinline__ void tri13(int e, int& i, int& j) {
+  int r = 0, base = 0;
+  bool go = true;
+#pragma unroll
+  for (int q = 0; q < 12; ++q) {
+    const int len = 13 - q;
+    if (go && e >= base + len) {
+      base += len;
+      r = q + 1;
+    } else {
+      go = false;
+    }
+  }
+  i = r;
+  j = r + (e - base);
+}
+
+__global__ void __launch_bounds__(kTileQueries) match_reduce_kernel(const __grid_constant__ MatchParams P) {
+  __shared__ double tile[kTileQueries / 32][32][13];
+  __shared__ double wsum[kTileQueries / 32][kPartialStride];
+  __shared__ int s_last;
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int q = P.q_begin + blockIdx.x * kTileQueries + threadIdx.x;
+  const bool in_range = q < P.q_end;
+
+  float v13[13];
+#pragma unroll
+  for (int c = 0; c < 13; ++c) v13[c] = 0.f;
+  bool accepted = false;   // Match::lisanAlGaib()
+  uint32_t orig = 0;
+
+  if (in_range) {
+    const float4 sp = __ldg(&P.scan[q]);
+    orig = __float_as_uint(sp.w);
+    float g[3];
+    affine_apply(P.pc.R_wb, P.pc.t_wb, sp.x, sp.y, sp.z, g);
+
+    Top5 t;
+#pragma unroll
+    for (int s = 0; s < 5; ++s) {
+      t.d[s] = __int_as_float(0x7f800000);   // +inf == empty slot
+      t.i[s] = 0;
+    }
+    knn_search(P, g[0], g[1], g[2], t);
+
+    float n4[4] = {0.f, 0.f, 0.f, 0.f};
+    float dist = 0.f;
+    // Plane::enough_points + close_enough: an empty slot is +inf and fails the strict '<'.
+    if (t.d[4] < P.max_dist_f) {
+      float A[5][3];
+      float4 nb[5];
+#pragma unroll
+      for (int j = 0; j < 5; ++j) {
+        nb[j] = __ldg(&P.map[t.i[j]]);
+        A[j][0] = nb[j].x;
+        A[j][1] = nb[j].y;
+        A[j][2] = nb[j].z;
+      }
+      float x[3];
+      plane_qr_solve(A, x);
+      const float nrm = sqrtf(x[0] * x[0] + (x[1] * x[1] + x[2] * x[2]));
+      n4[0] = x[0] / nrm;
+      n4[1] = x[1] / nrm;
+      n4[2] = x[2] / nrm;
+      n4[3] = 1.0f / nrm;   // == float(1.0 / double(nrm)): double rounding is innocuous for division
+      bool ok = true;
+#pragma unroll
+      for (int j = 0; j < 5; ++j) {
+        const float res = ((n4[0] * nb[j].x + n4[1] * nb[j].y) + n4[2] * nb[j].z) + n4[3];
+        if (fabsf(res) > P.plane_thr) ok = false;
+      }
+      accepted = ok;
+      dist = ((n4[0] * g[0] + n4[1] * g[1]) + n4[2] * g[2]) + n4[3];
+    }
+
+    if (accepted) {
+      float p_imu[3], p_lid[3], C[3], RC[3];
+      affine_apply(P.pc.Rinv_wb, P.pc.tinv_wb, g[0], g[1], g[2], p_imu);
+      affine_apply(P.pc.Rinv_LI, P.pc.tinv_LI, p_imu[0], p_imu[1], p_imu[2], p_lid);
+      const float nv[3] = {n4[0], n4[1], n4[2]};
+      mat3_vec(P.pc.Rd_wb_inv, nv, C);
+      mat3_vec(P.pc.Rd_LI_inv, C, RC);
+      v13[0] = n4[0];
+      v13[1] = n4[1];
+      v13[2] = n4[2];
+      v13[3] = p_imu[1] * C[2] - p_imu[2] * C[1];
+      v13[4] = p_imu[2] * C[0] - p_imu[0] * C[2];
+      v13[5] = p_imu[0] * C[1] - p_imu[1] * C[0];
+      if (P.estimate_extrinsics) {
+        v13[6] = p_lid[1] * RC[2] - p_lid[2] * RC[1];
+        v13[7] = p_lid[2] * RC[0] - p_lid[0] * RC[2];
+        v13[8] = p_lid[0] * RC[1] - p_lid[1] * RC[0];
+        v13[9] = C[0];
+        v13[10] = C[1];
+        v13[11] = C[2];
+      }
+      v13[12] = -dist;
+    }
+
+    if (P.dbg16 != nullptr) {
+      float4* o = reinterpret_cast<float4*>(P.dbg16 + (size_t)orig * 16);
+      o[0] = make_float4(g[0], g[1], g[2], n4[0]);
+      o[1] = make_float4(n4[1], n4[2], n4[3], dist);
+      o[2] = make_float4(accepted ? 1.f : 0.f, t.d[0], t.d[1], t.d[2]);
+      o[3] = make_float4(t.d[3], t.d[4], 0.f, 0.f);
+    }
+    if (P.valid_by_orig != nullptr) P.valid_by_orig[orig] = accepted ? 1 : 0;
+  }
+
+  // ---- warp-cooperative float64 accumulation of [row,z]^T [row,z] -------------------------------
+  const bool contributes = accepted && (orig < P.orig_limit);
+  const unsigned int m_all = __ballot_sync(0xffffffffu, accepted);
+  unsigned int m_rows = __ballot_sync(0xffffffffu, contributes);
+  if (contributes) {
+#pragma unroll
+    for (int c = 0; c < 13; ++c) tile[warp][lane][c] = (double)v13[c];
+  }
+  __syncwarp();
+  int ei[3], ej[3];
+#pragma unroll
+  for (int s = 0; s < 3; ++s) {
+    const int e = lane + 32 * s;
+    tri13(e < kTriEntries ? e : 0, ei[s], ej[s]);
+  }
+  double acc[3] = {0.0, 0.0, 0.0};
+  unsigned int m = m_rows;
+  while (m) {
+    const int r = __ffs(m) - 1;
+    m &= m - 1;
+    const double* rowp = tile[warp][r];
+#pragma unroll
+    for (int s = 0; s < 3; ++s) acc[s] = fma(rowp[ei[s]], rowp[ej[s]], acc[s]);
+  }
+#pragma unroll
+  for (int s = 0; s < 3; ++s) {
+    const int e = lane + 32 * s;
+    if (e < kPartialStride) wsum[warp][e] = (e < kTriEntries) ? acc[s] : 0.0;
+  }
+  __syncwarp();
+  if (lane == 0) {
+    wsum[warp][91] = (double)__popc(m_all);    // n_valid
+    wsum[warp][92] = (double)__popc(m_rows);   // n_rows
+  }
+  __syncthreads();
+
+  // ---- CTA partial, then a deterministic two-level tree over tiles ----------------------------------
+  const int n_tiles = gridDim.x;
+  const int n_groups = (n_tiles + kGroupTiles - 1) / kGroupTiles;
+  const int group = blockIdx.x / kGroupTiles;
+  double* tile_part = P.partials;                                   // [n_tiles][96]
+  double* group_part = P.partials + (size_t)n_tiles * kPartialStride;   // [n_groups][96]
+  if (threadIdx.x < kPartialStride) {
+    double s = 0.0;
+#pragma unroll
+    for (int w = 0; w < kTileQueries / 32; ++w) s += wsum[w][threadIdx.x];
+    __stcg(&tile_part[(size_t)blockIdx.x * kPartialStride + threadIdx.x], s);
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int g_first = group * kGroupTiles;
+    const int g_count = min(kGroupTiles, n_tiles - g_first);
+    const unsigned int prev = atomicAdd(&P.ticket[1 + group], 1u);
+    s_last = (prev == (unsigned int)(g_count - 1)) ? 1 : 0;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  {
+    const int g_first = group * kGroupTiles;
+    const int g_count = min(kGroupTiles, n_tiles - g_first);
+    if (threadIdx.x < kPartialStride) {
+      double s = 0.0;
+      for (int t = 0; t < g_count; ++t) s += __ldcg(&tile_part[(size_t)(g_first + t) * kPartialStride + threadIdx.x]);
+      __stcg(&group_part[(size_t)group * kPartialStride + threadIdx.x], s);
+    }
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    P.ticket[1 + group] = 0u;   // self reset for the next launch
+    const unsigned int prev = atomicAdd(&P.ticket[0], 1u);
+    s_last = (prev == (unsigned int)(n_groups - 1)) ? 1 : 0;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  if (threadIdx.x < kPartialStride) {
+    double s = 0.0;
+    for (int gi = 0; gi < n_groups; ++gi) s += __ldcg(&group_part[(size_t)gi * kPartialStride + threadIdx.x]);
+    // pack: 13x13 triangle entry e=(i,j) -> [0..77] HTH tri (12x12), [78..89] HTh, [91] sum z^2
+    int out_idx;
+    const int e = threadIdx.x;
+    if (e < kTriEntries) {
+      int i, j;
+      tri13(e, i, j);
+      if (j < 12) out_idx = i * 12 - (i * (i - 1)) / 2 + (j - i);
+      else if (i < 12) out_idx = 78 + i;
+      else out_idx = 91;
+    } else if (e == 91) out_idx = 92;     // n_valid
+    else if (e == 92) out_idx = 90;       // n_rows
+    else out_idx = e;                     // 93,94,95 reserved (zero)
+    P.out96[out_idx] = s;
+  }
+  if (threadIdx.x == 0) P.ticket[0] = 0u;
+}
+
+}  // namespace
+
+int match_num_tiles(int n_queries) { return (n_queries + kTileQueries - 1) / kTileQueries; }
+
+cudaError_t launch_match(const MatchParams& p, cudaStream_t st) {
+  const int n = p.q_end - p.q_begin;
+  if (n <= 0) return cudaErrorInvalidValue;
+  match_reduce_kernel<<<match_num_tiles(n), kTileQueries, 0, st>>>(p);
+  return cudaGetLastError();
+}
+
+}  // namespace flimo

@@ -1,0 +1,236 @@
+"""Seeded synthetic worlds, maps and LiDAR scans for the parity tests and bench.py.
+
+SURVEY.md section 8(d): the world is made of planes (ground, an enclosure of four walls,
+axis-aligned boxes) so that the reference's plane gate (``Plane.cpp:107-114``, 0.05 m)
+passes; map samples carry sigma = 0.01 m Gaussian noise along the surface normal and a
+small uniform jitter on every coordinate so that no two kNN candidates tie
+(``Octree.hpp:73,80`` keeps the earlier-visited point on ties — order dependent).
+
+Everything is generated with ``numpy.random.default_rng(seed)`` (PCG64): identical on the
+dev container and on the GPU box (same image).  Nothing here reads /root/reference.
+"""
+from dataclasses import dataclass, field
+
+import numpy as np
+
+
+@dataclass
+class World:
+    half: float                    # ground plane spans [-half, half]^2 at z = 0
+    wall: float                    # enclosure walls at x = +-wall, y = +-wall
+    wall_h: float
+    boxes: np.ndarray              # (B, 6) xmin ymin zmin xmax ymax zmax
+    rects: list = field(default_factory=list)   # (origin3, u3, v3, normal3, area)
+
+
+def make_world(seed, half=120.0, wall=70.0, wall_h=25.0, n_boxes=60):
+    rng = np.random.default_rng(seed)
+    boxes = []
+    tries = 0
+    while len(boxes) < n_boxes and tries < 100000:
+        tries += 1
+        cx, cy = rng.uniform(-half + 12, half - 12, 2)
+        sx, sy = rng.uniform(3.0, 18.0, 2)
+        h = rng.uniform(2.0, 20.0)
+        if abs(cx) < 6 + sx / 2 and abs(cy) < 6 + sy / 2:
+            continue                      # keep the sensor neighbourhood free
+        if abs(abs(cx) - wall) < sx / 2 + 1 or abs(abs(cy) - wall) < sy / 2 + 1:
+            continue                      # do not straddle the enclosure
+        boxes.append([cx - sx / 2, cy - sy / 2, 0.0, cx + sx / 2, cy + sy / 2, h])
+    w = World(half, wall, wall_h, np.asarray(boxes, np.float64).reshape(-1, 6))
+    R = w.rects
+
+    def rect(o, u, v):
+        o, u, v = (np.asarray(a, np.float64) for a in (o, u, v))
+        n = np.cross(u, v)
+        area = np.linalg.norm(n)
+        R.append((o, u, v, n / area, area))
+
+    rect([-half, -half, 0], [2 * half, 0, 0], [0, 2 * half, 0])                       # ground
+    for s in (-1, 1):
+        rect([s * wall, -wall, 0], [0, 2 * wall, 0], [0, 0, wall_h])                  # x = +-wall
+        rect([-wall, s * wall, 0], [2 * wall, 0, 0], [0, 0, wall_h])                  # y = +-wall
+    for b in w.boxes:
+        x0, y0, z0, x1, y1, z1 = b
+        rect([x0, y0, z1], [x1 - x0, 0, 0], [0, y1 - y0, 0])                          # roof
+        rect([x0, y0, z0], [x1 - x0, 0, 0], [0, 0, z1 - z0])
+        rect([x0, y1, z0], [x1 - x0, 0, 0], [0, 0, z1 - z0])
+        rect([x0, y0, z0], [0, y1 - y0, 0], [0, 0, z1 - z0])
+        rect([x1, y0, z0], [0, y1 - y0, 0], [0, 0, z1 - z0])
+    return w
+
+
+def sample_map(world, n_points, seed, sigma=0.01, jitter=1e-3):
+    """Area-proportional surface samples (float32, shape (n, 3))."""
+    rng = np.random.default_rng(seed)
+    areas = np.array([r[4] for r in world.rects])
+    counts = rng.multinomial(n_points, areas / areas.sum())
+    out = np.empty((n_points, 3), np.float64)
+    k = 0
+    for (o, u, v, n, _), c in zip(world.rects, counts):
+        if c == 0:
+            continue
+        a = rng.random((c, 1))
+        b = rng.random((c, 1))
+        out[k:k + c] = o + a * u + b * v + rng.normal(0.0, sigma, (c, 1)) * n
+        k += c
+    out += rng.uniform(-jitter, jitter, out.shape)
+    rng.shuffle(out, axis=0)
+    return out.astype(np.float32)
+
+
+def _raycast(world, origin, dirs):
+    """Nearest positive hit distance of rays (origin + t*dirs) with the world surfaces."""
+    t_best = np.full(dirs.shape[0], np.inf)
+    ox, oy, oz = origin
+    dx, dy, dz = dirs[:, 0], dirs[:, 1], dirs[:, 2]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        t = -oz / dz                                                     # ground
+        hx, hy = ox + t * dx, oy + t * dy
+        ok = (t > 1e-6) & (np.abs(hx) <= world.half) & (np.abs(hy) <= world.half)
+        t_best = np.where(ok & (t < t_best), t, t_best)
+        for s in (-1.0, 1.0):                                            # enclosure, seen from inside
+            t = (s * world.wall - ox) / dx
+            hy, hz = oy + t * dy, oz + t * dz
+            ok = (t > 1e-6) & (np.abs(hy) <= world.wall) & (hz >= 0) & (hz <= world.wall_h)
+            t_best = np.where(ok & (t < t_best), t, t_best)
+            t = (s * world.wall - oy) / dy
+            hx, hz = ox + t * dx, oz + t * dz
+            ok = (t > 1e-6) & (np.abs(hx) <= world.wall) & (hz >= 0) & (hz <= world.wall_h)
+            t_best = np.where(ok & (t < t_best), t, t_best)
+        for b in world.boxes:                                            # slabs
+            t0x, t1x = (b[0] - ox) / dx, (b[3] - ox) / dx
+            t0y, t1y = (b[1] - oy) / dy, (b[4] - oy) / dy
+            t0z, t1z = (b[2] - oz) / dz, (b[5] - oz) / dz
+            tn = np.maximum(np.maximum(np.minimum(t0x, t1x), np.minimum(t0y, t1y)), np.minimum(t0z, t1z))
+            tf = np.minimum(np.minimum(np.maximum(t0x, t1x), np.maximum(t0y, t1y)), np.maximum(t0z, t1z))
+            ok = (tn <= tf) & (tn > 1e-6)
+            t_best = np.where(ok & (tn < t_best), tn, t_best)
+    return t_best
+
+
+def quat_from_rpy(roll, pitch, yaw):
+    cr, sr = np.cos(roll / 2), np.sin(roll / 2)
+    cp, sp = np.cos(pitch / 2), np.sin(pitch / 2)
+    cy, sy = np.cos(yaw / 2), np.sin(yaw / 2)
+    return np.array([sr * cp * cy - cr * sp * sy, cr * sp * cy + sr * cp * sy, cr * cp * sy - sr * sp * cy,
+                     cr * cp * cy + sr * sp * sy])            # x, y, z, w
+
+
+def quat_to_R(q):
+    x, y, z, w = q
+    return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                     [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                     [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+
+
+def spinning_scan(world, pos, quat, rings, azimuths, seed, fov_up_deg=2.0, fov_down_deg=-24.8, sigma=0.01,
+                  max_range=150.0):
+    """Ring-major spinning-LiDAR scan in the BODY frame (float32, (rings*azimuths, 3)).
+
+    Rays that hit nothing (sky) are replaced by the previous valid return so the scan always
+    has exactly rings*azimuths points (a real driver would drop them; the benchmark wants a
+    fixed N).  Range noise sigma along the ray.
+    """
+    rng = np.random.default_rng(seed)
+    el = np.deg2rad(np.linspace(fov_up_deg, fov_down_deg, rings))
+    az = np.linspace(0.0, 2 * np.pi, azimuths, endpoint=False)
+    ce, se = np.cos(el)[:, None], np.sin(el)[:, None]
+    d_body = np.stack([ce * np.cos(az)[None, :], ce * np.sin(az)[None, :], np.broadcast_to(se, (rings, azimuths))], -1)
+    d_body = d_body.reshape(-1, 3)
+    Rwb = quat_to_R(np.asarray(quat, np.float64))
+    d_world = d_body @ Rwb.T
+    t = _raycast(world, np.asarray(pos, np.float64), d_world)
+    bad = ~np.isfinite(t) | (t > max_range)
+    if bad.all():
+        raise ValueError("no ray hits the world")
+    idx = np.where(~bad, np.arange(t.size), 0)
+    np.maximum.accumulate(idx, out=idx)
+    first_ok = int(np.argmax(~bad))
+    idx[:first_ok] = first_ok
+    t = t[idx] + rng.normal(0.0, sigma, t.size)
+    pts = d_body[idx] * t[:, None]
+    pts += rng.uniform(-1e-4, 1e-4, pts.shape)
+    return pts.astype(np.float32)
+
+
+def rosette_scan(world, pos, quat, n_points, seed, cone_deg=70.0, sigma=0.01):
+    """Livox-style non-repetitive pattern: golden-angle spiral inside a forward cone."""
+    rng = np.random.default_rng(seed)
+    i = np.arange(n_points) + 0.5
+    half = np.deg2rad(cone_deg / 2)
+    r = half * np.sqrt(i / n_points)
+    th = i * np.pi * (3 - np.sqrt(5))
+    d_body = np.stack([np.cos(r), np.sin(r) * np.cos(th), np.sin(r) * np.sin(th) - 0.15], -1)
+    d_body /= np.linalg.norm(d_body, axis=1, keepdims=True)
+    Rwb = quat_to_R(np.asarray(quat, np.float64))
+    t = _raycast(world, np.asarray(pos, np.float64), d_body @ Rwb.T)
+    bad = ~np.isfinite(t)
+    idx = np.where(~bad, np.arange(t.size), 0)
+    np.maximum.accumulate(idx, out=idx)
+    idx[:int(np.argmax(~bad))] = int(np.argmax(~bad))
+    t = t[idx] + rng.normal(0.0, sigma, t.size)
+    return (d_body[idx] * t[:, None]).astype(np.float32)
+
+
+def make_state(pos, quat, offR=(0, 0, 0, 1), offT=(0, 0, 0), vel=(0, 0, 0), bg=(0, 0, 0), ba=(0, 0, 0),
+               grav=(0, 0, -9.809)):
+    """Flat 26-double state_ikfom: pos rot(xyzw) offset_R_L_I(xyzw) offset_T_L_I vel bg ba grav."""
+    return np.concatenate([np.asarray(a, np.float64) for a in (pos, quat, offR, offT, vel, bg, ba, grav)])
+
+
+def default_P0():
+    """init_iKFoM_state covariance (Localizer.cpp:685-693)."""
+    d = np.ones(23)
+    d[6:12] = 1e-6
+    d[15:18] = 1e-5
+    d[18:21] = 1e-4
+    d[21:23] = 1e-6
+    return np.diag(d)
+
+
+@dataclass
+class Case:
+    name: str
+    map_pts: np.ndarray
+    scan: np.ndarray
+    truth: np.ndarray       # state26 at the true pose
+    init: np.ndarray        # state26 at the perturbed (predicted) pose
+    passes: int
+
+
+_CFG = {
+    # name: (seed, half, wall, boxes, map points, rings, azimuths, passes)
+    "tiny": (1000, 30.0, 20.0, 6, 20_000, 8, 256, 3),
+    "c1": (1001, 40.0, 30.0, 10, 100_000, 16, 1024, 1),
+    "c2": (1002, 120.0, 70.0, 60, 5_000_000, 64, 2048, 3),
+    "c5": (1005, 100.0, 60.0, 40, 2_000_000, 32, 1024, 3),
+}
+
+
+def make_case(name, map_points=None):
+    """BASELINE.json configs as seeded synthetic cases: truth + (0.05 m, 0.5 deg)."""
+    if name == "c4":
+        seed, half, wall, nb, m = 1004, 160.0, 90.0, 90, 20_000_000
+        world = make_world(seed, half, wall, 25.0, nb)
+        pos = np.array([0.3, -0.2, 1.8])
+        quat = quat_from_rpy(0.01, -0.02, 0.4)
+        scan = rosette_scan(world, pos, quat, 300_000, seed + 2)
+        passes = 3
+    else:
+        seed, half, wall, nb, m, rings, az, passes = _CFG[name]
+        world = make_world(seed, half, wall, 25.0, nb)
+        pos = np.array([0.3, -0.2, 1.8])
+        quat = quat_from_rpy(0.01, -0.02, 0.4)
+        scan = spinning_scan(world, pos, quat, rings, az, seed + 2)
+    if map_points is not None:
+        m = int(map_points)
+    mp = sample_map(world, m, seed + 1)
+    truth = make_state(pos, quat)
+    dq = quat_from_rpy(np.deg2rad(0.3), np.deg2rad(-0.25), np.deg2rad(0.3))      # ~0.5 deg total
+    x, y, z, w = quat
+    a, b, c, d = dq
+    q2 = np.array([w * a + x * d + y * c - z * b, w * b - x * c + y * d + z * a, w * c + x * b - y * a + z * d,
+                   w * d - x * a - y * b - z * c])
+    init = make_state(pos + np.array([0.03, -0.03, 0.025]), q2 / np.linalg.norm(q2))
+    return Case(name, mp, scan, truth, init, passes)

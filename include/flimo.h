@@ -1,0 +1,166 @@
+/*
+ * flimo.h — C ABI of libflimo_cuda.so: the B200 (sm_100a) registration hot path of fast_LIMO.
+ *
+ * The reference (fetty31/fast_LIMO) has no FFI: its boundary for this path is the C++ class
+ * surface fast_limo::Mapper / fast_limo::Localizer plus the IKFoM measurement-model hook.
+ * Each entry point below names the reference interface it replaces (paths relative to the
+ * reference's include/ directory).  INTEGRATION.md shows the few lines a maintainer adds to
+ * Mapper.cpp / use-ikfom.cpp / Localizer.cpp to bind them.
+ *
+ * Conventions
+ *   - opaque handle; the caller owns every host buffer, the library owns all device memory;
+ *   - every function returns 0 on success or a negative flimo_status; it never throws and never
+ *     falls back to a CPU implementation (a missing GPU / CUDA error is an error);
+ *   - one caller at a time per handle (the reference calls this path under Localizer::mtx_ikfom,
+ *     fast_limo/Modules/Localizer.cpp:326-353); different handles are independent;
+ *   - quaternions are (x, y, z, w); matrices are row-major; points are float32 xyz with a caller
+ *     supplied stride in BYTES (16 for float4, 32 for fast_limo::Point, fast_limo/Common.hpp:100-113).
+ *   - state26 = state_ikfom flattened in declaration order (IKFoM/use-ikfom.hpp:12-21):
+ *       pos[3] rot[4] offset_R_L_I[4] offset_T_L_I[3] vel[3] bg[3] ba[3] grav[3]
+ *     state14 = its first 14 doubles (all the measurement model reads).
+ *     Covariances are 23x23 row-major in the error-state order pos rot offR offT vel bg ba grav(2).
+ */
+#ifndef FLIMO_H_
+#define FLIMO_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct flimo_ctx* flimo_handle;
+
+typedef enum {
+  FLIMO_OK = 0,
+  FLIMO_ERR_INVALID = -1,      /* bad argument / unsupported configuration */
+  FLIMO_ERR_CUDA = -2,         /* CUDA runtime error (see flimo_last_error) */
+  FLIMO_ERR_NO_DEVICE = -3,    /* no usable sm_100 device */
+  FLIMO_ERR_STATE = -4,        /* call sequence error (e.g. match before scan_set) */
+  FLIMO_ERR_NOMEM = -5
+} flimo_status;
+
+/* Mirrors fast_limo::Config::iKFoM::Mapping (fast_limo/Utils/Config.hpp:59-72) and the two
+ * iKFoM flags the hot path reads (Config.hpp:74-77).  Set by flimo_cfg_default() to the values of
+ * Mapper::Mapper() (fast_limo/Modules/Mapper.cpp:23-32) / src/main.cpp:148-156. */
+typedef struct {
+  int32_t NUM_MATCH_POINTS;     /* only 5 is compiled in (every shipped YAML uses 5) */
+  int32_t MAX_NUM_MATCHES;      /* first-N cap on Jacobian rows (Localizer.cpp:539) */
+  int32_t MAX_NUM_PC2MATCH;     /* first-N cap on queried points (Mapper.cpp:63-69) */
+  int32_t estimate_extrinsics;  /* Localizer.cpp:569 */
+  double MAX_DIST_PLANE;        /* compared with the 5th SQUARED distance (Plane.cpp:45-48) */
+  double PLANE_THRESHOLD;       /* Plane.cpp:107-114 */
+  /* Octree block (Config.hpp:65-69).  bucket_size is accepted and IGNORED exactly as the
+   * reference ignores it (Octree.hpp:178-180 is a self-assignment; effective bucket = 32). */
+  int32_t octree_bucket_size;
+  int32_t octree_downsampling;
+  float octree_min_extent;
+  /* Extensions (defaults keep reference behaviour): */
+  float knn_cell;               /* side of the device search grid in metres; 0 = choose automatically */
+  int32_t sort_scan;            /* 1 = Morton-sort the scan on upload for locality (results are order independent) */
+  int32_t reserved;
+} flimo_cfg;
+
+void flimo_cfg_default(flimo_cfg* cfg);
+
+/* Mapper::getInstance()/set_config (Mapper.cpp:38-45).  `device` is a CUDA ordinal. */
+int flimo_create(const flimo_cfg* cfg, int device, flimo_handle* out);
+void flimo_destroy(flimo_handle h);
+const char* flimo_last_error(flimo_handle h);   /* valid until the next call on h; h may be NULL */
+const char* flimo_version(void);
+
+/* ---- map (fast_limo::Mapper) -------------------------------------------------------------- */
+
+/* Mapper::add (Mapper.cpp:88-96) -> Octree::initialize / Octree::update (Octree.hpp:282-432):
+ * world-frame points; the first non-empty call builds the map and never down-samples, later calls
+ * apply the reference's leaf-split / drop-batch rule.  NaN points are skipped (Octree.hpp:243). */
+int flimo_map_add(flimo_handle h, const float* xyz, size_t n, size_t stride_bytes, double stamp);
+/* Same, points already in device memory (bench / pipelines that keep the scan on the GPU). */
+int flimo_map_add_device(flimo_handle h, const void* d_xyz, size_t n, size_t stride_bytes, double stamp);
+/* Mapper::size / exists / last_time (Mapper.cpp:47-57). */
+int flimo_map_size(flimo_handle h, size_t* n_points);
+int flimo_map_exists(flimo_handle h);
+double flimo_map_last_time(flimo_handle h);
+/* Copy the map points out (any order); for tests and for saving benchmark maps. */
+int flimo_map_get_points(flimo_handle h, float* out_xyz, size_t cap_points, size_t* n_points);
+
+/* ---- scan + one measurement pass ------------------------------------------------------------ */
+
+/* Binds Localizer::pc2match (use-ikfom.cpp:18): body-frame points of the current scan.  Only the
+ * first min(n, MAX_NUM_PC2MATCH) points are kept (Mapper.cpp:63-69).  One H2D copy per scan. */
+int flimo_scan_set(flimo_handle h, const float* xyz_body, size_t n, size_t stride_bytes);
+int flimo_scan_set_device(flimo_handle h, const void* d_xyz_body, size_t n, size_t stride_bytes);
+/* Multi-GPU: restrict this handle to the contiguous slice [begin, end) of the (capped) scan. */
+int flimo_scan_shard(flimo_handle h, size_t begin, size_t end);
+
+/* One IKFoM::h_share_model evaluation (use-ikfom.cpp:10-31 = Mapper::match, Mapper.cpp:59-86 +
+ * Localizer::calculate_H, Localizer.cpp:537-577) fused with the two products that consume its
+ * output in esekf::update_iterated_dyn_share_modified (esekfom.hpp:1723 HTH = H^T H, :1727 H^T h).
+ * H itself is never materialised.  Blocking.
+ *   HTH[144] row-major 12x12, HTh[12];
+ *   n_valid  = accepted matches (Mapper::match result size),
+ *   n_rows   = min(n_valid, MAX_NUM_MATCHES) rows that contributed (calculate_H's N),
+ *   sum_sq_res = sum of dist^2 over those rows.                                              */
+int flimo_match_reduce(flimo_handle h, const double state14[14], double HTH[144], double HTh[12],
+                       int64_t* n_valid, int64_t* n_rows, double* sum_sq_res);
+
+/* Asynchronous form for pipelines / multi-GPU: launches on `cuda_stream` (a cudaStream_t, NULL =
+ * the handle's stream) and leaves 96 doubles in DEVICE memory at d_out:
+ *   [0..77]  upper triangle of HTH, row by row (i<=j)   [78..89] HTh
+ *   [90] n_rows  [91] sum_sq_res  [92] n_valid  [93..95] reserved (0)
+ * With FLIMO sharding, summing d_out over ranks (ncclAllReduce, ncclDouble, 96) gives the
+ * whole-scan normal equations.  MAX_NUM_MATCHES truncation is NOT applied in this form unless
+ * n_valid <= MAX_NUM_MATCHES on every shard (the blocking form handles the general case). */
+int flimo_match_reduce_async(flimo_handle h, const double state14[14], double* d_out96, void* cuda_stream);
+/* Expands the 96-double packed form into HTH/HTh/... on the host. */
+void flimo_unpack96(const double packed[96], double HTH[144], double HTh[12], int64_t* n_valid,
+                    int64_t* n_rows, double* sum_sq_res);
+
+/* Per-point results of the LAST pass, for Localizer::get_matches (Localizer.cpp:139-141,575-576),
+ * RViz markers (ROSutils.hpp:216-252) and the parity tests.  Record layout (16 floats per queried
+ * point, original scan order): world xyz[3], plane ABCD[4], dist, valid (0/1), nn_d2[5], pad[2].
+ * Re-runs the pass with the per-point output enabled (debug path, not timed). */
+int flimo_match_debug(flimo_handle h, const double state14[14], float* out16, size_t cap_points,
+                      size_t* n_points);
+
+/* ---- iterated update (IKFoM) ---------------------------------------------------------------- */
+
+/* esekf::update_iterated_dyn_share_modified (esekfom.hpp:1620-1823) with the measurement pass
+ * above as h_dyn_share.  state26 / P529 in: x_ and P_ after prediction; out: updated.
+ * max_iter = Config::iKFoM::MAX_NUM_ITERS (passes <= max_iter + 1), limit23 = LIMITS,
+ * R_noise / D_degeneracy = the literals at Localizer.cpp:333 (0.001, 5.0).
+ * passes_out (may be NULL) receives the number of measurement passes executed. */
+int flimo_update(flimo_handle h, double state26[26], double P529[529], int max_iter,
+                 const double limit23[23], double R_noise, double D_degeneracy, int* passes_out);
+
+/* The same update as a pass-wise state machine, so a driver can put a collective between the
+ * measurement pass and the filter algebra (multi-GPU) or supply its own normal equations:
+ *   begin -> { ekf_state -> [measurement pass] -> ekf_step } until *done -> ekf_end            */
+int flimo_ekf_begin(flimo_handle h, const double state26[26], const double P529[529], int max_iter,
+                    const double limit23[23], double R_noise, double D_degeneracy);
+int flimo_ekf_state(flimo_handle h, double state26[26]);
+int flimo_ekf_step(flimo_handle h, const double HTH[144], const double HTh[12], int64_t n_rows, int* done);
+int flimo_ekf_end(flimo_handle h, double state26[26], double P529[529]);
+
+/* pcl::transformPointCloud(pc2match -> world) of Localizer.cpp:361-374 on the device copy of the
+ * scan, using State::get_RT() of state14; optional convenience so final_scan can come from the GPU. */
+int flimo_scan_to_world(flimo_handle h, const double state14[14], float* out_xyz, size_t cap_points,
+                        size_t* n_points);
+
+/* ---- introspection (bench / profiles) ------------------------------------------------------- */
+typedef struct {
+  uint64_t kernel_launches;     /* CUDA kernels launched by this handle so far */
+  uint64_t match_launches;      /* of which the fused match+reduce kernel */
+  float last_match_ms;          /* device time of the last blocking match pass (CUDA events) */
+  float knn_cell;               /* grid cell in use */
+  int32_t grid_nx, grid_ny, grid_nz;
+  uint64_t table_bytes, map_bytes;
+} flimo_stats;
+int flimo_get_stats(flimo_handle h, flimo_stats* out);
+void* flimo_stream(flimo_handle h);   /* the handle's cudaStream_t */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FLIMO_H_ */

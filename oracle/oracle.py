@@ -1,0 +1,222 @@
+"""ORACLE — TEST INFRASTRUCTURE ONLY.
+
+ctypes wrapper over ``liboracle.so`` (the CPU restatement of the reference's registration
+path: i-Octree kNN, plane fit, Jacobian, HtH, IKFoM iterated update).  Only ``tests/``,
+``__graft_entry__.smoke()`` and the ``cpu_baseline`` / ``--impl reference`` legs of
+``bench.py`` may import this module; the product package never does.
+
+Parity status: UNPINNED — the reference ships no tests/golden vectors and cannot be compiled
+here (Eigen3/PCL/Boost absent); see the headers of ioctree.hpp / plane_match.hpp / ekf.hpp
+for the reference file:line each function follows.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+TRACE_STRIDE = 26 + 23 + 1 + 144 + 12
+
+
+class OrcCfg(C.Structure):
+    _fields_ = [
+        ("k", C.c_int32),
+        ("estimate_extrinsics", C.c_int32),
+        ("num_threads", C.c_int32),
+        ("_pad", C.c_int32),
+        ("max_pc2match", C.c_int64),
+        ("max_matches", C.c_int64),
+        ("max_dist_plane", C.c_double),
+        ("plane_threshold", C.c_double),
+    ]
+
+
+def build(force=False):
+    """Compile liboracle.so from the sources in this directory (g++, a few seconds)."""
+    so = os.path.join(_HERE, "liboracle.so")
+    srcs = [os.path.join(_HERE, f) for f in ("oracle_capi.cpp", "ioctree.hpp", "plane_match.hpp", "ekf.hpp", "Makefile")]
+    stale = (not os.path.exists(so)) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs)
+    if force or stale:
+        subprocess.run(["make", "-C", _HERE, "-B" if force else "-s"], check=True, stdout=subprocess.DEVNULL)
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        L = C.CDLL(build())
+        f32p, f64p, u8p, i32p, i64p = (C.POINTER(t) for t in (C.c_float, C.c_double, C.c_uint8, C.c_int32, C.c_int64))
+        L.orc_max_threads.restype = C.c_int
+        L.orc_map_new.restype = C.c_void_p
+        L.orc_map_new.argtypes = [C.c_int, C.c_float, C.c_int]
+        L.orc_map_free.argtypes = [C.c_void_p]
+        L.orc_map_add.argtypes = [C.c_void_p, f32p, C.c_size_t, C.c_size_t]
+        L.orc_map_size.restype = C.c_size_t
+        L.orc_map_size.argtypes = [C.c_void_p]
+        L.orc_map_dump.restype = C.c_size_t
+        L.orc_map_dump.argtypes = [C.c_void_p, f32p, C.c_size_t]
+        L.orc_knn.argtypes = [C.c_void_p, f32p, C.c_size_t, C.c_size_t, C.c_int, C.c_int, f32p, f32p, i32p]
+        L.orc_plane_fit.argtypes = [f32p, C.c_int, f32p]
+        L.orc_match.restype = C.c_long
+        L.orc_match.argtypes = [C.c_void_p, C.POINTER(OrcCfg), f64p, f32p, C.c_size_t, C.c_size_t,
+                                u8p, f32p, f32p, f32p, f32p, f64p, f64p, f64p, f64p, i64p]
+        L.orc_update.restype = C.c_int
+        L.orc_update.argtypes = [C.c_void_p, C.POINTER(OrcCfg), f64p, f64p, C.c_int, f64p, C.c_double, C.c_double,
+                                 f32p, C.c_size_t, C.c_size_t, f64p, C.c_int]
+        L.orc_update_fixed.restype = C.c_int
+        L.orc_update_fixed.argtypes = [f64p, f64p, C.c_int, f64p, C.c_double, C.c_double, f64p, f64p, C.c_long, f64p, C.c_int]
+        L.orc_boxplus.argtypes = [f64p, f64p]
+        L.orc_boxminus.argtypes = [f64p, f64p, f64p]
+        L.orc_invert.restype = C.c_int
+        L.orc_invert.argtypes = [f64p, C.c_int]
+        _LIB = L
+    return _LIB
+
+
+def _p(a, t):
+    return None if a is None else a.ctypes.data_as(C.POINTER(t))
+
+
+def max_threads():
+    return int(lib().orc_max_threads())
+
+
+def make_cfg(k=5, max_pc2match=10000, max_matches=2000, max_dist_plane=2.0, plane_threshold=0.05,
+             estimate_extrinsics=True, num_threads=1):
+    return OrcCfg(k, int(bool(estimate_extrinsics)), int(num_threads), 0, int(max_pc2match), int(max_matches),
+                  float(max_dist_plane), float(plane_threshold))
+
+
+def _xyz(a):
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    assert a.ndim == 2 and a.shape[1] >= 3
+    return a
+
+
+class OracleMap:
+    """The reference's Mapper + i-Octree (bucket 32 effective)."""
+
+    def __init__(self, min_extent=0.2, downsample=True, bucket=32):
+        self._h = lib().orc_map_new(int(bucket), float(min_extent), int(bool(downsample)))
+
+    def __del__(self):
+        try:
+            if self._h:
+                lib().orc_map_free(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def add(self, pts):
+        pts = _xyz(pts)
+        lib().orc_map_add(self._h, _p(pts, C.c_float), pts.shape[0], pts.shape[1])
+
+    def size(self):
+        return int(lib().orc_map_size(self._h))
+
+    def points(self):
+        n = self.size()
+        out = np.empty((max(n, 1), 3), np.float32)
+        got = lib().orc_map_dump(self._h, _p(out, C.c_float), out.shape[0])
+        return out[:got].copy()
+
+    def knn(self, q, k=5, threads=1):
+        q = _xyz(q)
+        nq = q.shape[0]
+        d2 = np.empty((nq, k), np.float32)
+        nb = np.empty((nq, k, 3), np.float32)
+        cnt = np.empty(nq, np.int32)
+        lib().orc_knn(self._h, _p(q, C.c_float), nq, q.shape[1], k, threads, _p(d2, C.c_float), _p(nb, C.c_float), _p(cnt, C.c_int32))
+        return d2, nb, cnt
+
+    def match(self, cfg, state14, scan, want_rows=False):
+        """One h_share_model pass.  Returns dict with per-query arrays, HTH, HTh, n_valid, rows."""
+        scan = _xyz(scan)
+        n = scan.shape[0]
+        nq = min(n, cfg.max_pc2match)
+        st = np.ascontiguousarray(state14, np.float64)
+        good = np.zeros(nq, np.uint8)
+        plane = np.zeros((nq, 4), np.float32)
+        dist = np.zeros(nq, np.float32)
+        world = np.zeros((nq, 3), np.float32)
+        nn = np.zeros((nq, cfg.k), np.float32)
+        HTH = np.zeros((12, 12), np.float64)
+        HTh = np.zeros(12, np.float64)
+        nv = C.c_int64(0)
+        H = h = None
+        if want_rows:
+            cap = min(nq, cfg.max_matches)
+            H = np.zeros((cap + 1, 12), np.float64)
+            h = np.zeros(cap + 1, np.float64)
+        rows = lib().orc_match(self._h, C.byref(cfg), _p(st, C.c_double), _p(scan, C.c_float), n, scan.shape[1],
+                               _p(good, C.c_uint8), _p(plane, C.c_float), _p(dist, C.c_float), _p(world, C.c_float),
+                               _p(nn, C.c_float), _p(H, C.c_double), _p(h, C.c_double), _p(HTH, C.c_double),
+                               _p(HTh, C.c_double), C.byref(nv))
+        out = dict(good=good.astype(bool), plane=plane, dist=dist, world=world, nn_d2=nn, HTH=HTH, HTh=HTh,
+                   n_valid=int(nv.value), rows=int(rows))
+        if want_rows:
+            out["H"] = H[:rows]
+            out["h"] = h[:rows]
+        return out
+
+    def update(self, cfg, state26, P, max_iter, limits, scan, R=0.001, D=5.0):
+        """esekf::update_iterated_dyn_share_modified with the reference measurement model."""
+        scan = _xyz(scan)
+        st = np.array(state26, np.float64).copy()
+        Pm = np.array(P, np.float64).reshape(23, 23).copy()
+        lim = np.ascontiguousarray(np.broadcast_to(np.asarray(limits, np.float64), (23,)))
+        trace = np.zeros((max_iter + 2, TRACE_STRIDE), np.float64)
+        passes = lib().orc_update(self._h, C.byref(cfg), _p(st, C.c_double), _p(Pm, C.c_double), int(max_iter),
+                                  _p(lim, C.c_double), float(R), float(D), _p(scan, C.c_float), scan.shape[0],
+                                  scan.shape[1], _p(trace, C.c_double), trace.shape[0])
+        return st, Pm, unpack_trace(trace[:passes])
+
+
+def unpack_trace(tr):
+    return [dict(state=t[:26].copy(), dx=t[26:49].copy(), rows=int(t[49]), HTH=t[50:194].reshape(12, 12).copy(),
+                 HTh=t[194:206].copy()) for t in tr]
+
+
+def update_fixed(state26, P, max_iter, limits, H, h, R=0.001, D=5.0):
+    st = np.array(state26, np.float64).copy()
+    Pm = np.array(P, np.float64).reshape(23, 23).copy()
+    lim = np.ascontiguousarray(np.broadcast_to(np.asarray(limits, np.float64), (23,)))
+    H = np.ascontiguousarray(H, np.float64).reshape(-1, 12)
+    h = np.ascontiguousarray(h, np.float64)
+    trace = np.zeros((max_iter + 2, TRACE_STRIDE), np.float64)
+    passes = lib().orc_update_fixed(_p(st, C.c_double), _p(Pm, C.c_double), int(max_iter), _p(lim, C.c_double), float(R),
+                                    float(D), _p(H, C.c_double), _p(h, C.c_double), H.shape[0], _p(trace, C.c_double),
+                                    trace.shape[0])
+    return st, Pm, unpack_trace(trace[:passes])
+
+
+def plane_fit(pts):
+    pts = np.ascontiguousarray(pts, np.float32)
+    out = np.zeros(4, np.float32)
+    lib().orc_plane_fit(_p(pts, C.c_float), pts.shape[0], _p(out, C.c_float))
+    return out
+
+
+def boxplus(state26, d23):
+    st = np.array(state26, np.float64).copy()
+    d = np.ascontiguousarray(d23, np.float64)
+    lib().orc_boxplus(_p(st, C.c_double), _p(d, C.c_double))
+    return st
+
+
+def boxminus(a26, b26):
+    a = np.ascontiguousarray(a26, np.float64)
+    b = np.ascontiguousarray(b26, np.float64)
+    d = np.zeros(23, np.float64)
+    lib().orc_boxminus(_p(a, C.c_double), _p(b, C.c_double), _p(d, C.c_double))
+    return d
+
+
+def invert(A):
+    A = np.array(A, np.float64).copy()
+    rc = lib().orc_invert(_p(A, C.c_double), A.shape[0])
+    assert rc == 0
+    return A
