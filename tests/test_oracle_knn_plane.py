@@ -1,0 +1,133 @@
+"""CPU: the oracle (restated i-Octree + plane fit) against independent numpy computations."""
+import numpy as np
+import pytest
+
+from fast_limo_b200 import synth
+
+
+def _bf_d2(q, pts):
+    d = (q[:, None, :] - pts[None, :, :]).astype(np.float32)
+    xx, yy, zz = d[..., 0] * d[..., 0], d[..., 1] * d[..., 1], d[..., 2] * d[..., 2]
+    return (xx + (yy + zz)).astype(np.float32)
+
+
+@pytest.mark.parametrize("n,seed", [(5, 0), (33, 1), (2000, 2), (40000, 3)])
+def test_knn_matches_bruteforce(oracle, n, seed):
+    rng = np.random.default_rng(seed)
+    pts = rng.uniform(-20, 20, (n, 3)).astype(np.float32)
+    q = rng.uniform(-22, 22, (300, 3)).astype(np.float32)
+    m = oracle.OracleMap()
+    m.add(pts)
+    assert m.size() == n
+    d2, nb, cnt = m.knn(q, 5)
+    ref = np.sort(_bf_d2(q, pts), axis=1)[:, :5]
+    k = min(5, n)
+    assert (cnt == k).all()
+    assert np.array_equal(d2[:, :k], ref[:, :k])
+    # returned neighbours really are at those distances
+    again = ((q[:, None, :] - nb[:, :k, :]) ** 2).sum(-1)
+    assert np.allclose(again, d2[:, :k], rtol=1e-5, atol=1e-9)
+
+
+def test_knn_after_incremental_inserts(oracle):
+    rng = np.random.default_rng(7)
+    m = oracle.OracleMap(downsample=False)
+    allp = []
+    for b in range(6):
+        pts = (rng.uniform(-10, 10, (3000, 3)) + np.array([4.0 * b, 0, 0])).astype(np.float32)
+        m.add(pts)
+        allp.append(pts)
+    allp = np.concatenate(allp)
+    assert m.size() == allp.shape[0]
+    q = rng.uniform(-10, 30, (200, 3)).astype(np.float32)
+    d2, _, _ = m.knn(q, 5)
+    assert np.array_equal(d2, np.sort(_bf_d2(q, allp), axis=1)[:, :5])
+    dumped = m.points()
+    assert sorted(map(tuple, dumped.tolist())) == sorted(map(tuple, allp.tolist()))
+
+
+def test_downsampling_rule_closed_form(oracle):
+    """with down-sampling a point is dropped iff its min-level cell already holds > 4
+    points and is a leaf at min level; the map can only grow and never exceeds the no-downsample map."""
+    rng = np.random.default_rng(11)
+    m_ds, m_all = oracle.OracleMap(downsample=True), oracle.OracleMap(downsample=False)
+    def batch():
+        return np.c_[rng.uniform(-3, 3, (4000, 2)), rng.normal(0, 0.01, 4000)].astype(np.float32)
+    first = batch()
+    m_ds.add(first)
+    m_all.add(first)
+    assert m_ds.size() == m_all.size() == 4000          # Octree::initialize never down-samples
+    prev = 4000
+    for b in range(8):
+        pts = batch()
+        m_ds.add(pts)
+        m_all.add(pts)
+        assert prev <= m_ds.size() <= m_all.size()
+        prev = m_ds.size()
+    assert m_ds.size() < m_all.size()
+    kept = set(map(tuple, m_ds.points().tolist()))
+    assert set(map(tuple, first.tolist())) <= kept
+
+
+def test_plane_fit_against_lstsq(oracle):
+    rng = np.random.default_rng(5)
+    for trial in range(200):
+        n = rng.normal(size=3)
+        n /= np.linalg.norm(n)
+        off = rng.uniform(2, 30)
+        basis = np.linalg.svd(n[None, :])[2][1:]
+        uv = rng.uniform(-0.3, 0.3, (5, 2))
+        centre = -off * n + rng.uniform(-0.2, 0.2, 3)
+        pts = (centre + uv @ basis + rng.normal(0, 0.004, (5, 1)) * n).astype(np.float32)
+        got = oracle.plane_fit(pts)
+        x = np.linalg.lstsq(pts.astype(np.float64), -np.ones(5), rcond=None)[0]
+        ref = np.append(x / np.linalg.norm(x), 1 / np.linalg.norm(x))
+        assert np.allclose(got, ref, rtol=0, atol=5e-3 * max(1.0, abs(ref[3])) * 1e-2 + 2e-3)
+        assert abs(np.linalg.norm(got[:3]) - 1) < 1e-6
+
+
+def test_match_gates(oracle):
+    """Plane.cpp:41-48,107-114: >= 5 neighbours, d2_5 < MAX_DIST_PLANE (squared metres), 0.05 m planarity."""
+    rng = np.random.default_rng(9)
+    # a dense noisy plane z = 0 and an isolated sparse cluster
+    plane = np.c_[rng.uniform(-5, 5, (6000, 2)), 2.0 + rng.normal(0, 0.005, 6000)].astype(np.float32)   # z = 2 (a plane through the origin is singular for A x = -1)
+    blob = (rng.normal(0, 0.5, (40, 3)) + np.array([30, 0, 5])).astype(np.float32)   # not planar
+    m = oracle.OracleMap()
+    m.add(np.r_[plane, blob])
+    st = synth.make_state([0, 0, 0], [0, 0, 0, 1])
+    cfg = oracle.make_cfg(max_pc2match=10 ** 6, max_matches=10 ** 6)
+    scan = np.array([[0.5, 0.5, 2.3], [30, 0, 5.0], [0, 0, 5.0], [100, 100, 100]], np.float32)
+    r = m.match(cfg, st[:14], scan)
+    assert r["good"].tolist() == [True, False, False, False]
+    assert abs(abs(r["dist"][0]) - 0.3) < 0.01
+    assert r["nn_d2"][2, 4] >= 2.0 and r["nn_d2"][0, 4] < 2.0
+    # MAX_NUM_PC2MATCH keeps the first N points, MAX_NUM_MATCHES the first N accepted (H4)
+    scan2 = np.c_[rng.uniform(-4, 4, (500, 2)), 2.0 + rng.uniform(0.05, 0.4, 500)].astype(np.float32)
+    full = m.match(cfg, st[:14], scan2, want_rows=True)
+    cut = m.match(oracle.make_cfg(max_pc2match=100, max_matches=10 ** 6), st[:14], scan2, want_rows=True)
+    assert cut["good"].shape[0] == 100 and np.array_equal(cut["good"], full["good"][:100])
+    capped = m.match(oracle.make_cfg(max_pc2match=10 ** 6, max_matches=37), st[:14], scan2, want_rows=True)
+    assert capped["rows"] == 37 and np.array_equal(capped["H"], full["H"][:37])
+    assert np.allclose(capped["HTH"], full["H"][:37].T @ full["H"][:37])
+
+
+def test_jacobian_is_derivative_of_residual(oracle):
+    """H row = d(dist)/d(pos, rot) for a fixed plane (finite differences of the oracle's own residual)."""
+    case = synth.make_case("tiny")
+    m = oracle.OracleMap()
+    m.add(case.map_pts)
+    cfg = oracle.make_cfg(max_pc2match=10 ** 6, max_matches=10 ** 6)
+    r0 = m.match(cfg, case.truth[:14], case.scan, want_rows=True)
+    idx = np.flatnonzero(r0["good"])[:50]
+    H = r0["H"][:50]
+    eps = 1e-3
+    for a in range(3):
+        st = case.truth.copy()
+        st[a] += eps
+        r1 = m.match(cfg, st[:14], case.scan)
+        num = (r1["dist"][idx].astype(np.float64) - r0["dist"][idx]) / eps
+        both = r1["good"][idx]
+        # plane may change between passes; compare only where the same plane was fitted
+        same = both & (np.abs(r1["plane"][idx] - r0["plane"][idx]).max(1) < 1e-6)
+        assert same.sum() > 20
+        assert np.allclose(num[same], H[same, a], atol=5e-3)
