@@ -33,7 +33,7 @@ class FlimoCfg(C.Structure):
         ("octree_min_extent", C.c_float),
         ("knn_cell", C.c_float),
         ("sort_scan", C.c_int32),
-        ("reserved", C.c_int32),
+        ("knn_level_ratio", C.c_float),
     ]
 
 
@@ -46,6 +46,7 @@ class FlimoStats(C.Structure):
         ("grid_nx", C.c_int32),
         ("grid_ny", C.c_int32),
         ("grid_nz", C.c_int32),
+        ("n_levels", C.c_int32),
         ("table_bytes", C.c_uint64),
         ("map_bytes", C.c_uint64),
     ]

@@ -34,6 +34,7 @@ class MappingConfig:
     octree_downsampling: bool = True
     knn_cell: float = 0.0                # extension: device grid cell (0 = auto)
     sort_scan: bool = False              # extension: Morton-sort the scan on upload
+    knn_level_ratio: float = 0.0         # extension: cell growth between index levels (0 = 1.5)
 
 
 def _dp(a):
@@ -77,6 +78,7 @@ class Mapper:
         c.octree_downsampling = int(bool(cfg.octree_downsampling))
         c.knn_cell = float(cfg.knn_cell)
         c.sort_scan = int(bool(cfg.sort_scan))
+        c.knn_level_ratio = float(cfg.knn_level_ratio)
         if self._h:
             self._L.flimo_destroy(self._h)
             self._h = C.c_void_p()

@@ -2,6 +2,7 @@
 // buffers, streams, pose constants, launch sequencing, the MAX_NUM_MATCHES first-N rule, and the
 // host IKFoM update (ekf_host.hpp).  No CPU fallback exists: without a working CUDA device every
 // entry point fails with a negative status.
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -172,9 +173,12 @@ int fill_params(flimo_handle h, const double state14[14], MatchParams& P, double
     CU(h, cudaStreamSynchronize(h->stream));
   }
   P.scan = h->scan;
-  P.map = h->map.pts;
-  P.cell_start = h->map.cell_start;
-  P.g = h->map.g;
+  P.n_levels = h->map.n_levels;
+  for (int l = 0; l < kMaxLevels; ++l) {
+    P.lv[l].pts = h->map.lv[l].pts;
+    P.lv[l].cell_start = h->map.lv[l].cell_start;
+    P.lv[l].g = h->map.lv[l].g;
+  }
   make_pose(state14, P.pc);
   P.q_begin = (int)h->shard_begin;
   P.q_end = (int)h->shard_end;
@@ -228,6 +232,7 @@ void flimo_cfg_default(flimo_cfg* c) {
   c->octree_min_extent = 0.2f;
   c->knn_cell = 0.f;
   c->sort_scan = 0;
+  c->knn_level_ratio = 0.f;
 }
 
 const char* flimo_last_error(flimo_handle h) { return h ? h->err.c_str() : g_err.c_str(); }
@@ -303,12 +308,17 @@ void* flimo_stream(flimo_handle h) { return h ? (void*)h->stream : nullptr; }
 
 int flimo_get_stats(flimo_handle h, flimo_stats* out) {
   if (!h || !out) return FLIMO_ERR_INVALID;
-  h->stats.knn_cell = h->map.g.cell;
-  h->stats.grid_nx = h->map.g.nx;
-  h->stats.grid_ny = h->map.g.ny;
-  h->stats.grid_nz = h->map.g.nz;
-  h->stats.table_bytes = (h->map.n_cells + 1) * sizeof(uint32_t);
+  h->stats.knn_cell = h->map.lv[0].g.cell;
+  h->stats.grid_nx = h->map.lv[0].g.nx;
+  h->stats.grid_ny = h->map.lv[0].g.ny;
+  h->stats.grid_nz = h->map.lv[0].g.nz;
+  h->stats.n_levels = h->map.n_levels;
+  h->stats.table_bytes = 0;
   h->stats.map_bytes = h->map.n_pts * sizeof(float4);
+  for (int l = 0; l < h->map.n_levels; ++l) {
+    h->stats.table_bytes += (h->map.lv[l].n_cells + 2) * sizeof(uint32_t);
+    h->stats.map_bytes += h->map.lv[l].n_entries * sizeof(float4);
+  }
   *out = h->stats;
   return FLIMO_OK;
 }
@@ -323,17 +333,20 @@ int flimo_map_add_device(flimo_handle h, const void* d_xyz, size_t n, size_t str
   if (h->map_exists && h->cfg.octree_downsampling)
     return fail(h, FLIMO_ERR_INVALID, "incremental insert with down-sampling is not built yet (K3)");
   CU(h, map_index_reserve(h->map, old_n + n));
-  if (old_n) CU(h, cudaMemcpyAsync(h->map.pts_alt, h->map.pts, old_n * sizeof(float4), cudaMemcpyDeviceToDevice, h->stream));
   CU(h, cudaMemsetAsync(h->d_count, 0, sizeof(unsigned int), h->stream));
-  CU(h, pack_points(d_xyz, n, stride_bytes, h->map.pts_alt + old_n, h->d_count, h->stream));
+  CU(h, pack_points(d_xyz, n, stride_bytes, h->map.pts + old_n, h->d_count, h->stream));
   unsigned int kept = 0;
   CU(h, cudaMemcpyAsync(&kept, h->d_count, sizeof(kept), cudaMemcpyDeviceToHost, h->stream));
   CU(h, cudaStreamSynchronize(h->stream));
   h->stats.kernel_launches += 1;
   const size_t total = old_n + kept;
   if (total == 0) return FLIMO_OK;                              // Octree::initialize: empty -> no root
+  h->map.n_pts = total;
   const size_t max_cells = (size_t)1 << 30;
-  CU(h, map_index_build(h->map, total, h->cfg.knn_cell, max_cells, h->stream, &h->stats.kernel_launches));
+  // coarsest level: cell >= sqrt(MAX_DIST_PLANE) so its 3x3x3 block covers the close_enough radius
+  const float coarsest = (float)(std::sqrt(std::max(h->cfg.MAX_DIST_PLANE, 1e-6)) * 1.0001 + 1e-4);
+  CU(h, map_index_build(h->map, h->cfg.knn_cell, h->cfg.knn_level_ratio, coarsest, max_cells, h->stream,
+                        &h->stats.kernel_launches));
   CU(h, cudaStreamSynchronize(h->stream));
   h->map_exists = true;
   h->last_time = stamp;

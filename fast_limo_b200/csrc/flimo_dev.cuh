@@ -5,15 +5,30 @@
 
 namespace flimo {
 
-// Uniform search grid over the map's bounding box.  Cell (ix,iy,iz) has linear index
-// (iz*ny + iy)*nx + ix; map points are stored sorted by that index (x fastest), so the cells
-// [ix0..ix1] of one (iy,iz) row are ONE contiguous run of points:
-//   [cell_start[row + ix0], cell_start[row + ix1 + 1]).
+// One level of the device map index.
+//
+// A level is a uniform grid (cell side `cell`) over the map's bounding box.  Cell (ix,iy,iz) has
+// linear index (iz*ny + iy)*nx + ix.  For every grid row (iy,iz) the level stores a SUPER-ROW: all
+// map points whose cell lies in rows (iy-1..iy+1, iz-1..iz+1), sorted by ix.  Each point therefore
+// appears in (up to) nine super-rows — HBM capacity is traded for access shape: the 3x3x3 cell
+// neighbourhood of a query is ONE contiguous run
+//     [cell_start[row + ix-1], cell_start[row + ix+2])        of float4 points,
+// found with two table reads and streamed with perfectly predictable addresses.
+// Levels grow geometrically in cell size; a query whose 5th neighbour is not provably inside the
+// 3x3x3 block of level l simply rescans the (larger) block of level l+1 from scratch.
 struct GridDesc {
   float ox, oy, oz;   // lower corner
   float inv_cell;     // 1 / cell (float)
   float cell;         // cell side in metres
   int nx, ny, nz;
+};
+
+constexpr int kMaxLevels = 8;
+
+struct LevelView {
+  const float4* pts;           // super-row storage (9x duplicated), sorted by (row, ix)
+  const uint32_t* cell_start;  // nx*ny*nz + 1 prefix offsets into pts
+  GridDesc g;
 };
 
 // Constants of one measurement pass.  Built on the host from the double filter state exactly the
@@ -32,9 +47,8 @@ constexpr int kPartialStride = 96;    // doubles per partial record
 
 struct MatchParams {
   const float4* scan;          // body-frame points; .w carries the original scan index (bit pattern)
-  const float4* map;           // world-frame map points sorted by cell
-  const uint32_t* cell_start;  // nx*ny*nz + 1 prefix offsets
-  GridDesc g;
+  LevelView lv[kMaxLevels];    // finest first
+  int n_levels;
   PoseConsts pc;
   int q_begin, q_end;          // slice of the scan handled by this launch
   float max_dist_f;            // smallest float >= MAX_DIST_PLANE  (d2_5 < MAX_DIST_PLANE test)
@@ -49,26 +63,33 @@ struct MatchParams {
 };
 
 // map_index.cu
-struct MapIndex {
-  float4* pts = nullptr;        // sorted map points
+struct LevelIndex {
+  float4* pts = nullptr;        // duplicated, sorted
   uint32_t* cell_start = nullptr;
-  size_t n_pts = 0, cap_pts = 0;
+  size_t n_entries = 0, cap_entries = 0;
   size_t n_cells = 0, cap_cells = 0;
   GridDesc g{};
+};
+
+struct MapIndex {
+  float4* pts = nullptr;        // canonical map points (each once, insertion order)
+  size_t n_pts = 0, cap_pts = 0;
+  LevelIndex lv[kMaxLevels];
+  int n_levels = 0;
+  float lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};   // bounding box of the map
   // scratch
   uint32_t *keys = nullptr, *keys_alt = nullptr, *vals = nullptr, *vals_alt = nullptr;
-  float4* pts_alt = nullptr;
-  size_t cap_scratch = 0;
+  size_t cap_scratch = 0;       // entries (9 per point)
   void* cub_tmp = nullptr;
   size_t cub_tmp_bytes = 0;
   float* bbox = nullptr;        // 6 floats on device
 };
 
-// Rebuilds the index from `n` device points (float4, any order) stored in idx.pts_alt[0..n):
-// computes the bounding box, picks the grid, sorts by cell, builds cell_start.
-// cell <= 0 selects the side automatically from the point density.  Returns cudaError_t.
-cudaError_t map_index_build(MapIndex& idx, size_t n, float cell, size_t max_cells, cudaStream_t st,
-                            uint64_t* launches);
+// Rebuilds every level from the canonical points idx.pts[0..idx.n_pts).  cell0 <= 0 picks the
+// finest cell automatically; levels grow by `ratio` until one cell >= coarsest_min (the level whose
+// 3x3x3 block is guaranteed to cover the reference's MAX_DIST_PLANE ball).
+cudaError_t map_index_build(MapIndex& idx, float cell0, float ratio, float coarsest_min, size_t max_cells,
+                            cudaStream_t st, uint64_t* launches);
 cudaError_t map_index_reserve(MapIndex& idx, size_t n_pts);
 void map_index_free(MapIndex& idx);
 

@@ -2,15 +2,16 @@
 //
 // Replaces the pointer-based i-Octree container of the reference
 // (fast_limo/Objects/Octree.hpp:103-132, built by createOctant :301-338) with a layout made for
-// HBM3e: map points live in ONE float4 array sorted by uniform-grid cell (x fastest), plus a dense
-// prefix table cell_start[] over the map's bounding box.  kNN is exact for any cell size (the
-// search in match_kernel.cu expands rings until the k-th distance is inside the explored block),
-// so the grid is a performance choice only — it does not have to be the octree's lattice.
+// HBM3e capacity and streaming access (see LevelView in flimo_dev.cuh): per level, every grid row
+// owns a SUPER-ROW holding the points of its 3x3 neighbouring rows sorted by x cell, so that a
+// query's 3x3x3 neighbourhood is one contiguous float4 run.  kNN stays exact for any cell size
+// (match_kernel.cu escalates to the next, coarser level until the 5th distance is provably inside
+// the scanned block), so the grids are a performance choice only and need not be the octree lattice.
 //
-// Build = bounding box -> cell keys -> radix sort (CUB, 32-bit keys, only the bits needed) ->
-// gather -> boundary scatter + suffix-min scan for the prefix table.  All on the device; one
-// small D2H (6 floats) to size the grid.  The build is off the per-pass hot path (once per
-// Mapper::add).
+// Build (per level) = 9 (row key, point id) pairs per point -> radix sort (CUB, 32-bit keys, only
+// the bits needed) -> gather -> boundary scatter + suffix-min scan for the prefix table.
+// All on the device; one small D2H (6 floats) sizes the grids.  Off the per-pass hot path
+// (once per Mapper::add).
 #include <cfloat>
 #include <cmath>
 #include <cstdio>
@@ -77,16 +78,21 @@ __global__ void __launch_bounds__(256) bbox_kernel(const float4* __restrict__ p,
   }
 }
 
-__global__ void __launch_bounds__(256) keys_kernel(const float4* __restrict__ p, size_t n, GridDesc g,
-                                                   uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
-  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-  if (i >= n) return;
+// Nine (super-row key, point id) pairs per point: the point's cell column ix in each of the 3x3
+// rows around its own row.  Rows outside the grid get the sentinel key n_cells (sorted to the end).
+__global__ void __launch_bounds__(256) keys9_kernel(const float4* __restrict__ p, size_t n, GridDesc g, uint32_t n_cells,
+                                                    uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+  const size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (e >= 9 * n) return;
+  const size_t i = e / 9;
+  const int c = (int)(e - 9 * i);
   const float4 v = p[i];
   const int ix = cell_coord(v.x, g.ox, g.inv_cell, g.nx);
-  const int iy = cell_coord(v.y, g.oy, g.inv_cell, g.ny);
-  const int iz = cell_coord(v.z, g.oz, g.inv_cell, g.nz);
-  keys[i] = (uint32_t)((iz * g.ny + iy) * g.nx + ix);
-  vals[i] = (uint32_t)i;
+  const int iy = cell_coord(v.y, g.oy, g.inv_cell, g.ny) + (c % 3 - 1);
+  const int iz = cell_coord(v.z, g.oz, g.inv_cell, g.nz) + (c / 3 - 1);
+  const bool ok = iy >= 0 && iy < g.ny && iz >= 0 && iz < g.nz;
+  keys[e] = ok ? (uint32_t)((iz * g.ny + iy) * g.nx + ix) : n_cells;
+  vals[e] = (uint32_t)i;
 }
 
 __global__ void __launch_bounds__(256) gather_kernel(const float4* __restrict__ src, const uint32_t* __restrict__ order,
@@ -95,12 +101,22 @@ __global__ void __launch_bounds__(256) gather_kernel(const float4* __restrict__ 
   if (i < n) dst[i] = src[order[i]];
 }
 
+// Super-row entry = point coordinates + its canonical map index in .w (bit pattern).
+__global__ void __launch_bounds__(256) gather_tag_kernel(const float4* __restrict__ src, const uint32_t* __restrict__ order,
+                                                         size_t n, float4* __restrict__ dst) {
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t id = order[i];
+  const float4 v = src[id];
+  dst[i] = make_float4(v.x, v.y, v.z, __uint_as_float(id));
+}
+
 // cell_start[c] = first sorted position whose key is >= c.  Occupied cells get their start here,
 // empty cells are filled by the suffix-min scan that follows.
 __global__ void __launch_bounds__(256) boundaries_kernel(const uint32_t* __restrict__ keys, size_t n, size_t n_cells,
                                                          uint32_t* __restrict__ cell_start) {
   const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-  if (i == 0) cell_start[n_cells] = (uint32_t)n;
+  if (i == 0) cell_start[n_cells + 1] = (uint32_t)n;   // slot n_cells = start of the sentinel entries
   if (i >= n) return;
   const uint32_t k = keys[i];
   if (i == 0 || keys[i - 1] != k) cell_start[k] = (uint32_t)i;
@@ -229,103 +245,133 @@ cudaError_t sort_scan_morton(float4* scan, float4* tmp, size_t n, void** cub_tmp
 }
 
 cudaError_t map_index_reserve(MapIndex& idx, size_t n) {
-  if (n <= idx.cap_pts) return cudaSuccess;
-  size_t cap = idx.cap_pts ? idx.cap_pts : 1024;
-  while (cap < n) cap += cap / 2 + 1024;
-  float4 *np = nullptr, *na = nullptr;
-  FL_TRY(cudaMalloc(&np, cap * sizeof(float4)));
-  FL_TRY(cudaMalloc(&na, cap * sizeof(float4)));
-  if (idx.pts) {
-    if (idx.n_pts) FL_TRY(cudaMemcpy(np, idx.pts, idx.n_pts * sizeof(float4), cudaMemcpyDeviceToDevice));
-    cudaFree(idx.pts);
+  if (n > idx.cap_pts) {
+    size_t cap = idx.cap_pts ? idx.cap_pts : 1024;
+    while (cap < n) cap += cap / 2 + 1024;
+    float4* np = nullptr;
+    FL_TRY(cudaMalloc(&np, cap * sizeof(float4)));
+    if (idx.pts) {
+      if (idx.n_pts) FL_TRY(cudaMemcpy(np, idx.pts, idx.n_pts * sizeof(float4), cudaMemcpyDeviceToDevice));
+      cudaFree(idx.pts);
+    }
+    idx.pts = np;
+    idx.cap_pts = cap;
   }
-  if (idx.pts_alt) cudaFree(idx.pts_alt);
-  idx.pts = np;
-  idx.pts_alt = na;
-  idx.cap_pts = cap;
-  if (idx.keys) cudaFree(idx.keys);
-  idx.keys = nullptr;
-  FL_TRY(cudaMalloc(&idx.keys, 4 * cap * sizeof(uint32_t)));
-  idx.keys_alt = idx.keys + cap;
-  idx.vals = idx.keys_alt + cap;
-  idx.vals_alt = idx.vals + cap;
-  idx.cap_scratch = cap;
+  if (9 * idx.cap_pts > idx.cap_scratch) {
+    if (idx.keys) cudaFree(idx.keys);
+    idx.keys = nullptr;
+    idx.cap_scratch = 0;
+    const size_t cap = 9 * idx.cap_pts;
+    FL_TRY(cudaMalloc(&idx.keys, 4 * cap * sizeof(uint32_t)));
+    idx.keys_alt = idx.keys + cap;
+    idx.vals = idx.keys_alt + cap;
+    idx.vals_alt = idx.vals + cap;
+    idx.cap_scratch = cap;
+  }
   if (!idx.bbox) FL_TRY(cudaMalloc(&idx.bbox, 8 * sizeof(float)));
   return cudaSuccess;
 }
 
 void map_index_free(MapIndex& idx) {
   cudaFree(idx.pts);
-  cudaFree(idx.pts_alt);
-  cudaFree(idx.cell_start);
+  for (auto& l : idx.lv) {
+    cudaFree(l.pts);
+    cudaFree(l.cell_start);
+  }
   cudaFree(idx.keys);
   cudaFree(idx.cub_tmp);
   cudaFree(idx.bbox);
   idx = MapIndex{};
 }
 
-cudaError_t map_index_build(MapIndex& idx, size_t n, float cell, size_t max_cells, cudaStream_t st, uint64_t* launches) {
-  if (n == 0 || n > 0xFFFFFFF0ull) return cudaErrorInvalidValue;
-  if (n > idx.cap_pts || n > idx.cap_scratch) return cudaErrorInvalidValue;   // caller reserves
+static GridDesc make_grid(const float lo[3], const float hi[3], float cell) {
+  GridDesc g{};
+  g.cell = cell;
+  g.inv_cell = 1.0f / cell;
+  g.ox = lo[0] - 0.5f * cell;
+  g.oy = lo[1] - 0.5f * cell;
+  g.oz = lo[2] - 0.5f * cell;
+  g.nx = (int)std::min(2.0e9, std::floor(((double)hi[0] - g.ox) / cell) + 2);
+  g.ny = (int)std::min(2.0e9, std::floor(((double)hi[1] - g.oy) / cell) + 2);
+  g.nz = (int)std::min(2.0e9, std::floor(((double)hi[2] - g.oz) / cell) + 2);
+  return g;
+}
+
+static cudaError_t build_level(MapIndex& idx, LevelIndex& L, const GridDesc& g, cudaStream_t st, uint64_t* launches) {
+  const size_t n = idx.n_pts, n9 = 9 * n;
+  const size_t n_cells = (size_t)g.nx * g.ny * g.nz;
+  if (n_cells + 2 > L.cap_cells) {
+    if (L.cell_start) cudaFree(L.cell_start);
+    L.cell_start = nullptr;
+    L.cap_cells = 0;
+    const size_t cap = n_cells + n_cells / 8 + 1024;
+    FL_TRY(cudaMalloc(&L.cell_start, cap * sizeof(uint32_t)));
+    L.cap_cells = cap;
+  }
+  if (n9 > L.cap_entries) {
+    if (L.pts) cudaFree(L.pts);
+    L.pts = nullptr;
+    L.cap_entries = 0;
+    const size_t cap = 9 * idx.cap_pts;
+    FL_TRY(cudaMalloc(&L.pts, cap * sizeof(float4)));
+    L.cap_entries = cap;
+  }
+  L.g = g;
+  L.n_cells = n_cells;
+  keys9_kernel<<<nblk(n9), 256, 0, st>>>(idx.pts, n, g, (uint32_t)n_cells, idx.keys, idx.vals);
+  int bits = 1;
+  while (bits < 32 && ((size_t)1 << bits) <= n_cells) ++bits;      // keys go up to n_cells inclusive
+  cub::DoubleBuffer<uint32_t> dk(idx.keys, idx.keys_alt), dv(idx.vals, idx.vals_alt);
+  size_t bytes = 0, bytes2 = 0;
+  FL_TRY(cub::DeviceRadixSort::SortPairs(nullptr, bytes, dk, dv, (int)n9, 0, bits, st));
+  auto rb = thrust::make_reverse_iterator(L.cell_start + n_cells + 2);
+  FL_TRY(cub::DeviceScan::InclusiveScan(nullptr, bytes2, rb, rb, cub::Min(), (int)(n_cells + 2), st));
+  if (bytes2 > bytes) bytes = bytes2;
+  FL_TRY(ensure(&idx.cub_tmp, &idx.cub_tmp_bytes, bytes));
+  FL_TRY(cub::DeviceRadixSort::SortPairs(idx.cub_tmp, bytes, dk, dv, (int)n9, 0, bits, st));
+  gather_tag_kernel<<<nblk(n9), 256, 0, st>>>(idx.pts, dv.Current(), n9, L.pts);
+  FL_TRY(cudaMemsetAsync(L.cell_start, 0xFF, (n_cells + 2) * sizeof(uint32_t), st));
+  boundaries_kernel<<<nblk(n9), 256, 0, st>>>(dk.Current(), n9, n_cells, L.cell_start);
+  FL_TRY(cub::DeviceScan::InclusiveScan(idx.cub_tmp, bytes, rb, rb, cub::Min(), (int)(n_cells + 2), st));
+  L.n_entries = n9;
+  if (launches) *launches += 10;
+  return cudaGetLastError();
+}
+
+cudaError_t map_index_build(MapIndex& idx, float cell0, float ratio, float coarsest_min, size_t max_cells, cudaStream_t st,
+                            uint64_t* launches) {
+  const size_t n = idx.n_pts;
+  if (n == 0 || 9 * n > 0x7FFFFFF0ull) return cudaErrorInvalidValue;
+  if (n > idx.cap_pts || 9 * n > idx.cap_scratch) return cudaErrorInvalidValue;   // caller reserves
   unsigned int* bb = reinterpret_cast<unsigned int*>(idx.bbox);
   bbox_init_kernel<<<1, 32, 0, st>>>(bb);
-  bbox_kernel<<<min(nblk(n), 148u * 8u), 256, 0, st>>>(idx.pts_alt, n, bb);
+  bbox_kernel<<<min(nblk(n), 148u * 8u), 256, 0, st>>>(idx.pts, n, bb);
   unsigned int hb[6];
   FL_TRY(cudaMemcpyAsync(hb, bb, sizeof(hb), cudaMemcpyDeviceToHost, st));
   FL_TRY(cudaStreamSynchronize(st));
-  float lo[3], hi[3];
+  if (launches) *launches += 2;
   for (int a = 0; a < 3; ++a) {
-    lo[a] = ord2f(hb[a]);
-    hi[a] = ord2f(hb[3 + a]);
+    idx.lo[a] = ord2f(hb[a]);
+    idx.hi[a] = ord2f(hb[3 + a]);
   }
-  if (!(cell > 0.f)) cell = 0.25f;
-  GridDesc g{};
+  if (!(cell0 > 0.f)) cell0 = 0.25f;
+  if (!(ratio > 1.05f)) ratio = 1.5f;
+  for (;;) {   // finest level must fit the table budget
+    const GridDesc g = make_grid(idx.lo, idx.hi, cell0);
+    if ((double)g.nx * g.ny * g.nz <= (double)max_cells) break;
+    cell0 *= 1.25992105f;
+  }
+  int nl = 0;
+  float cell = cell0;
   for (;;) {
-    g.cell = cell;
-    g.inv_cell = 1.0f / cell;
-    g.ox = lo[0] - 0.5f * cell;
-    g.oy = lo[1] - 0.5f * cell;
-    g.oz = lo[2] - 0.5f * cell;
-    const double ex = (double)hi[0] - g.ox, ey = (double)hi[1] - g.oy, ez = (double)hi[2] - g.oz;
-    const double fx = std::floor(ex / cell) + 2, fy = std::floor(ey / cell) + 2, fz = std::floor(ez / cell) + 2;
-    if (fx * fy * fz <= (double)max_cells && fx < 2e9 && fy < 2e9 && fz < 2e9) {
-      g.nx = (int)fx;
-      g.ny = (int)fy;
-      g.nz = (int)fz;
-      break;
-    }
-    cell *= 1.25992105f;   // halve the cell count and retry
+    if (nl == kMaxLevels - 1 && cell < coarsest_min) cell = coarsest_min;   // force termination
+    FL_TRY(build_level(idx, idx.lv[nl], make_grid(idx.lo, idx.hi, cell), st, launches));
+    ++nl;
+    if (cell >= coarsest_min || nl == kMaxLevels) break;
+    cell *= ratio;
   }
-  const size_t n_cells = (size_t)g.nx * g.ny * g.nz;
-  if (n_cells + 1 > idx.cap_cells) {
-    if (idx.cell_start) cudaFree(idx.cell_start);
-    idx.cell_start = nullptr;
-    idx.cap_cells = 0;
-    const size_t cap = n_cells + n_cells / 4 + 1024;
-    FL_TRY(cudaMalloc(&idx.cell_start, cap * sizeof(uint32_t)));
-    idx.cap_cells = cap;
-  }
-  idx.g = g;
-  idx.n_cells = n_cells;
-  idx.n_pts = n;
-
-  keys_kernel<<<nblk(n), 256, 0, st>>>(idx.pts_alt, n, g, idx.keys, idx.vals);
-  int bits = 1;
-  while (bits < 32 && ((size_t)1 << bits) < n_cells) ++bits;
-  cub::DoubleBuffer<uint32_t> dk(idx.keys, idx.keys_alt), dv(idx.vals, idx.vals_alt);
-  size_t bytes = 0, bytes2 = 0;
-  FL_TRY(cub::DeviceRadixSort::SortPairs(nullptr, bytes, dk, dv, (int)n, 0, bits, st));
-  auto rb = thrust::make_reverse_iterator(idx.cell_start + n_cells + 1);
-  FL_TRY(cub::DeviceScan::InclusiveScan(nullptr, bytes2, rb, rb, cub::Min(), (int)(n_cells + 1), st));
-  if (bytes2 > bytes) bytes = bytes2;
-  FL_TRY(ensure(&idx.cub_tmp, &idx.cub_tmp_bytes, bytes));
-  FL_TRY(cub::DeviceRadixSort::SortPairs(idx.cub_tmp, bytes, dk, dv, (int)n, 0, bits, st));
-  gather_kernel<<<nblk(n), 256, 0, st>>>(idx.pts_alt, dv.Current(), n, idx.pts);
-  FL_TRY(cudaMemsetAsync(idx.cell_start, 0xFF, (n_cells + 1) * sizeof(uint32_t), st));
-  boundaries_kernel<<<nblk(n), 256, 0, st>>>(dk.Current(), n, n_cells, idx.cell_start);
-  FL_TRY(cub::DeviceScan::InclusiveScan(idx.cub_tmp, bytes, rb, rb, cub::Min(), (int)(n_cells + 1), st));
-  if (launches) *launches += 12;
-  return cudaGetLastError();
+  idx.n_levels = nl;
+  return cudaSuccess;
 }
 
 }  // namespace flimo

@@ -55,37 +55,23 @@ __device__ __forceinline__ void top5_offer(Top5& t, float d, uint32_t idx) {
   t.d[0] = c0 ? d : t.d[0];
 }
 
-__device__ __forceinline__ void scan_run(const float4* __restrict__ map, uint32_t s, uint32_t e, float qx, float qy,
-                                         float qz, Top5& t) {
-#pragma unroll 2
-  for (uint32_t i = s; i < e; ++i) {
-    const float4 p = __ldg(&map[i]);
-    const float dx = qx - p.x, dy = qy - p.y, dz = qz - p.z;
-    const float d = dx * dx + (dy * dy + dz * dz);     // Eigen Vector3f::squaredNorm order
-    top5_offer(t, d, i);
-  }
-}
-
 // ---------------------------------------------------------------------------------------------------
-// Fast path for the first 3x3x3 block (nine x-runs): branch-free selection on PACKED keys.
+// Block scan: exact top-5 of the 3x3x3 cell block around the query's home cell at one level.
+// The block is one contiguous run of the level's super-row (flimo_dev.cuh), streamed four points at
+// a time.  Selection is branch-free on PACKED keys:
 //
-//   key = (float_bits(d2) & ~low) | tag        tag = (run << Bo) | offset_in_run   (unique per candidate)
+//   key = (float_bits(d2) & ~low) | n            n = position in the run (unique per candidate)
 //
 // Squared distances are non-negative floats, so their bit patterns order like unsigned integers; the
-// low B = Bo+4 mantissa bits are replaced by the candidate's tag, which makes every key unique and
-// lets a 6-slot sorted list be maintained with 11 integer min/max per candidate and no branch, no
-// index bookkeeping.  Truncation can only reorder candidates whose distances agree in all but the
-// low B bits, so the six smallest KEYS are re-ranked with exact arithmetic afterwards, and the
-// result is accepted only if provably identical to the exact search:
-//   every candidate not kept has key > k5  =>  bucket(d) >= bucket(k5);
-//   if bucket(k5) > bucket(d2_5 exact) then all of them have d2 > d2_5.          (else: slow path)
-// Ties in d2 keep visiting order (tag order), as the reference's heap does (Octree.hpp:72-87).
+// low B mantissa bits are replaced by the candidate's ordinal, which makes every key unique and lets a
+// 6-slot sorted list be maintained with 11 integer min/max per candidate — no branch, no index
+// bookkeeping.  Truncation can only reorder candidates whose distances agree in all but the low B
+// bits, so the six smallest KEYS are re-ranked with exact arithmetic afterwards, and the result is
+// accepted only if provably identical to the exact search:
+//   every candidate not kept has key > k5  =>  bucket(d2) >= bucket(k5);
+//   if bucket(k5) > bucket(exact 5th d2) then all of them have d2 > that 5th d2.     (else: exact path)
+// Ties in d2 are ordered by position in the run (x cell, then map index).
 // ---------------------------------------------------------------------------------------------------
-struct RunTable {               // per-thread run bounds, one column per thread (bank-conflict free)
-  uint32_t s[9][kTileQueries];
-  uint32_t e[9][kTileQueries];
-};
-
 __device__ __forceinline__ void keys6_insert(uint32_t (&k)[6], uint32_t x) {
   k[5] = min(k[5], max(x, k[4]));
   k[4] = min(k[4], max(x, k[3]));
@@ -95,236 +81,133 @@ __device__ __forceinline__ void keys6_insert(uint32_t (&k)[6], uint32_t x) {
   k[0] = min(k[0], x);
 }
 
-__device__ __forceinline__ void cmpswap64(unsigned long long& a, unsigned long long& b, uint32_t& ia, uint32_t& ib) {
+__device__ __forceinline__ void cmpswap64(unsigned long long& a, unsigned long long& b) {
   const bool sw = a > b;
   const unsigned long long ta = sw ? b : a, tb = sw ? a : b;
-  const uint32_t ua = sw ? ib : ia, ub = sw ? ia : ib;
-  a = ta; b = tb; ia = ua; ib = ub;
+  a = ta;
+  b = tb;
 }
 
-// Slow exact scan of the nine runs (also the fallback of the fast path).
-__device__ __noinline__ void block1_exact(const float4* __restrict__ map, const RunTable& rt, int tid, float qx, float qy,
-                                          float qz, Top5& t) {
+__device__ __forceinline__ float sqdist(float qx, float qy, float qz, const float4& p) {
+  const float dx = qx - p.x, dy = qy - p.y, dz = qz - p.z;
+  return dx * dx + (dy * dy + dz * dz);               // Eigen Vector3f::squaredNorm order
+}
+
+// Exact (slow, branchy) scan of a run; positions are recorded relative to `s`.
+__device__ __noinline__ void run_exact(const float4* __restrict__ pts, uint32_t s, uint32_t e, float qx, float qy, float qz,
+                                       Top5& t) {
+#pragma unroll
+  for (int j = 0; j < 5; ++j) {
+    t.d[j] = __int_as_float(0x7f800000);
+    t.i[j] = 0;
+  }
 #pragma unroll 1
-  for (int r = 0; r < 9; ++r) scan_run(map, rt.s[r][tid], rt.e[r][tid], qx, qy, qz, t);
+  for (uint32_t i = s; i < e; ++i) top5_offer(t, sqdist(qx, qy, qz, __ldg(&pts[i])), i);
 }
 
-// Returns true when t holds the exact result for the block, false when the caller must run
-// block1_exact (never observed to exceed a few queries per 10^5 on the benchmark maps).
-__device__ __forceinline__ bool block1_fast(const MatchParams& P, RunTable& rt, int tid, int hx, int hy, int hz, float qx,
-                                            float qy, float qz, Top5& t) {
-  const GridDesc& G = P.g;
-  const uint32_t* __restrict__ cs = P.cell_start;
-  const int x0 = max(hx - 1, 0), x1 = min(hx + 1, G.nx - 1);
-  uint32_t total = 0, max_len = 0;
-  uint32_t sv[9], ev[9];
+// On return t.d[] holds the exact ascending squared distances of the block's five nearest points and
+// t.i[] their positions in L.pts (+inf / 0 for missing ones).
+__device__ __forceinline__ void block_scan(const LevelView& L, int hx, int hy, int hz, float qx, float qy, float qz, Top5& t) {
+  const GridDesc& G = L.g;
+  const int row = (hz * G.ny + hy) * G.nx;
+  const uint32_t s = __ldg(&L.cell_start[row + max(hx - 1, 0)]);
+  const uint32_t e = __ldg(&L.cell_start[row + min(hx + 1, G.nx - 1) + 1]);
+  const uint32_t total = e - s;
 #pragma unroll
-  for (int r = 0; r < 9; ++r) {
-    const int z = hz + r / 3 - 1, y = hy + r % 3 - 1;
-    const bool ok = (z >= 0) && (z < G.nz) && (y >= 0) && (y < G.ny);
-    const int row = ok ? (z * G.ny + y) * G.nx : 0;
-    sv[r] = ok ? __ldg(&cs[row + x0]) : 0u;
-    ev[r] = ok ? __ldg(&cs[row + x1 + 1]) : 0u;
+  for (int j = 0; j < 5; ++j) {
+    t.d[j] = __int_as_float(0x7f800000);
+    t.i[j] = 0;
   }
-#pragma unroll
-  for (int r = 0; r < 9; ++r) {
-    rt.s[r][tid] = sv[r];
-    rt.e[r][tid] = ev[r];
-    const uint32_t len = ev[r] - sv[r];
-    total += len;
-    max_len = max(max_len, len);
+  if (total == 0) return;
+  const int B = 32 - __clz(total);               // ordinals 0..total-1 fit in B bits
+  const float4* __restrict__ pts = L.pts + s;
+  if (B > 14) {                                  // > 16k candidates in one block: exact path
+    run_exact(L.pts, s, e, qx, qy, qz, t);
+    return;
   }
-  if (total == 0) return true;
-  const int Bo = 32 - __clz(max_len);          // offsets 0..max_len-1 need Bo bits (max_len >= 1)
-  if (Bo > 10) return false;                   // >= 1024 points in one run: use the exact path
-  const int B = Bo + 4;
   const uint32_t low = (1u << B) - 1u;
-
   uint32_t k[6];
 #pragma unroll
   for (int j = 0; j < 6; ++j) k[j] = 0xFFFFFFFFu;
 
-  int r = 0;
-  uint32_t i = sv[0], e = ev[0], tag = 0;
-  while (i == e) {                             // total > 0 guarantees termination with r <= 8
-    ++r;
-    i = rt.s[r][tid];
-    e = rt.e[r][tid];
-    tag = (uint32_t)r << Bo;
-  }
-  const float4* __restrict__ map = P.map;
-  float4 pn = __ldg(&map[i]);
+  uint32_t n = 0;
 #pragma unroll 1
-  for (uint32_t n = 0; n < total; ++n) {
-    const float4 p = pn;
-    const uint32_t mytag = tag;
-    ++i;
-    ++tag;
-    if (n + 1 < total) {
-      while (i == e) {
-        ++r;
-        i = rt.s[r][tid];
-        e = rt.e[r][tid];
-        tag = (uint32_t)r << Bo;
-      }
-      pn = __ldg(&map[i]);
-    }
-    const float dx = qx - p.x, dy = qy - p.y, dz = qz - p.z;
-    const float d = dx * dx + (dy * dy + dz * dz);
-    keys6_insert(k, (__float_as_uint(d) & ~low) | mytag);
+  for (; n + 4 <= total; n += 4) {
+    const float4 p0 = __ldg(&pts[n]), p1 = __ldg(&pts[n + 1]), p2 = __ldg(&pts[n + 2]), p3 = __ldg(&pts[n + 3]);
+    const float d0 = sqdist(qx, qy, qz, p0), d1 = sqdist(qx, qy, qz, p1), d2 = sqdist(qx, qy, qz, p2),
+                d3 = sqdist(qx, qy, qz, p3);
+    keys6_insert(k, (__float_as_uint(d0) & ~low) | n);
+    keys6_insert(k, (__float_as_uint(d1) & ~low) | (n + 1));
+    keys6_insert(k, (__float_as_uint(d2) & ~low) | (n + 2));
+    keys6_insert(k, (__float_as_uint(d3) & ~low) | (n + 3));
   }
+#pragma unroll 1
+  for (; n < total; ++n) keys6_insert(k, (__float_as_uint(sqdist(qx, qy, qz, __ldg(&pts[n]))) & ~low) | n);
 
-  // exact re-ranking of the (up to) six kept candidates
+  // exact re-ranking of the (up to) six kept candidates: sort (exact d2 bits, ordinal) pairs
   unsigned long long ek[6];
-  uint32_t ei[6];
 #pragma unroll
   for (int j = 0; j < 6; ++j) {
     const bool have = k[j] != 0xFFFFFFFFu;
-    const uint32_t tg = k[j] & low;
-    const uint32_t rr = have ? (tg >> Bo) : 0u;
-    const uint32_t idx = rt.s[rr][tid] + (tg & ((1u << Bo) - 1u));
+    const uint32_t ord = k[j] & low;
     float d = __int_as_float(0x7f800000);
-    if (have) {
-      const float4 p = __ldg(&map[idx]);
-      const float dx = qx - p.x, dy = qy - p.y, dz = qz - p.z;
-      d = dx * dx + (dy * dy + dz * dz);
-    }
-    ek[j] = ((unsigned long long)__float_as_uint(d) << 32) | (have ? tg : 0xFFFFFFFFu);
-    ei[j] = idx;
+    if (have) d = sqdist(qx, qy, qz, __ldg(&pts[ord]));
+    ek[j] = ((unsigned long long)__float_as_uint(d) << 32) | (have ? ord : 0xFFFFFFFFu);
   }
-  cmpswap64(ek[0], ek[5], ei[0], ei[5]); cmpswap64(ek[1], ek[3], ei[1], ei[3]); cmpswap64(ek[2], ek[4], ei[2], ei[4]);
-  cmpswap64(ek[1], ek[2], ei[1], ei[2]); cmpswap64(ek[3], ek[4], ei[3], ei[4]);
-  cmpswap64(ek[0], ek[3], ei[0], ei[3]); cmpswap64(ek[2], ek[5], ei[2], ei[5]);
-  cmpswap64(ek[0], ek[1], ei[0], ei[1]); cmpswap64(ek[2], ek[3], ei[2], ei[3]); cmpswap64(ek[4], ek[5], ei[4], ei[5]);
-  cmpswap64(ek[1], ek[2], ei[1], ei[2]); cmpswap64(ek[3], ek[4], ei[3], ei[4]);
+  cmpswap64(ek[0], ek[5]); cmpswap64(ek[1], ek[3]); cmpswap64(ek[2], ek[4]);
+  cmpswap64(ek[1], ek[2]); cmpswap64(ek[3], ek[4]);
+  cmpswap64(ek[0], ek[3]); cmpswap64(ek[2], ek[5]);
+  cmpswap64(ek[0], ek[1]); cmpswap64(ek[2], ek[3]); cmpswap64(ek[4], ek[5]);
+  cmpswap64(ek[1], ek[2]); cmpswap64(ek[3], ek[4]);
+  const bool safe = (k[5] == 0xFFFFFFFFu) || ((k[5] & ~low) > ((uint32_t)(ek[4] >> 32) & ~low));
+  if (!safe) {
+    run_exact(L.pts, s, e, qx, qy, qz, t);
+    return;
+  }
 #pragma unroll
   for (int j = 0; j < 5; ++j) {
     t.d[j] = __uint_as_float((uint32_t)(ek[j] >> 32));
-    t.i[j] = ei[j];
+    t.i[j] = s + (uint32_t)(ek[j] & 0xFFFFFFFFu);
   }
-  if (k[5] == 0xFFFFFFFFu) return true;                        // fewer than six candidates: all ranked exactly
-  return (k[5] & ~low) > ((uint32_t)(ek[4] >> 32) & ~low);
 }
 
-// Ring bookkeeping: has the search around home cell (hx,hy,hz), explored out to ring k, provably
-// found the reference's answer?  Faces of the explored block that coincide with the grid boundary
-// do not count (nothing lies beyond them).  `slack` covers the ~1 ulp binning error of point and query.
-__device__ __forceinline__ bool ring_needs_more(const MatchParams& P, int hx, int hy, int hz, float fx, float fy, float fz,
-                                                float slack, int k, float d5) {
-  const GridDesc& G = P.g;
-  float m = FLT_MAX;
-  if (hx - k > 0) m = fminf(m, fx + (float)k);
-  if (hx + k < G.nx - 1) m = fminf(m, (1.0f - fx) + (float)k);
-  if (hy - k > 0) m = fminf(m, fy + (float)k);
-  if (hy + k < G.ny - 1) m = fminf(m, (1.0f - fy) + (float)k);
-  if (hz - k > 0) m = fminf(m, fz + (float)k);
-  if (hz + k < G.nz - 1) m = fminf(m, (1.0f - fz) + (float)k);
-  if (m == FLT_MAX) return false;                             // whole grid visited
-  const float me = (m - slack) * G.cell * 0.999999f;
-  const float gr2 = me > 0.f ? me * me : 0.f;
-  if (d5 <= gr2) return false;                                // exact: nothing closer can be outside
-  if (gr2 >= P.max_dist_f) return false;                      // outside points fail Plane::close_enough
-  return true;
-}
-
-// Exact 5-NN of q over the grid-sorted map (ties: smaller map index first), outcome-equivalent to
-// the reference's unbounded search for every query it would accept.
-//   ring 1 (3x3x3 cells) : one thread per query, packed-key fast path (block1_fast).
-//   rings >= 2           : the few queries that need them are handled by the WHOLE WARP, one query at a
-//                          time: lanes split the shell's x-runs, keep private exact top-5 lists, and the
-//                          lists are merged with five rounds of warp-wide (d2, index) arg-min (REDUX).
-//                          This keeps the rare long searches from serialising behind one lane.
-// Must be called by all 32 lanes of the warp (inactive lanes pass active = false).
-__device__ __forceinline__ void knn_search(const MatchParams& P, RunTable& rt, int tid, bool active, float qx, float qy,
-                                           float qz, Top5& t) {
-  const GridDesc& G = P.g;
-  const unsigned int full = 0xffffffffu;
-  const int lane = tid & 31;
+// Is the block's answer provably the answer of an unbounded search (or irrelevant for the reference's
+// outcome)?  m = distance, in cells, from q to the nearest face of the 3x3x3 block that is not on the
+// grid boundary (nothing lies beyond boundary faces); `slack` covers the ~1 ulp binning error of the
+// point and of the query.
+__device__ __forceinline__ bool block_is_final(const GridDesc& G, float max_dist_f, float qx, float qy, float qz, int hx,
+                                               int hy, int hz, float d5) {
   const float ux = cell_units(qx, G.ox, G.inv_cell), uy = cell_units(qy, G.oy, G.inv_cell),
               uz = cell_units(qz, G.oz, G.inv_cell);
-  const int hx = cell_coord(qx, G.ox, G.inv_cell, G.nx), hy = cell_coord(qy, G.oy, G.inv_cell, G.ny),
-            hz = cell_coord(qz, G.oz, G.inv_cell, G.nz);
   const float fx = ux - (float)hx, fy = uy - (float)hy, fz = uz - (float)hz;
   const float slack = 6.0e-7f * fmaxf(fmaxf(fabsf(ux), fabsf(uy)), fabsf(uz)) + 1.0e-6f;
-  const uint32_t* __restrict__ cs = P.cell_start;
+  float m = FLT_MAX;
+  if (hx - 1 > 0) m = fminf(m, fx + 1.0f);
+  if (hx + 1 < G.nx - 1) m = fminf(m, (1.0f - fx) + 1.0f);
+  if (hy - 1 > 0) m = fminf(m, fy + 1.0f);
+  if (hy + 1 < G.ny - 1) m = fminf(m, (1.0f - fy) + 1.0f);
+  if (hz - 1 > 0) m = fminf(m, fz + 1.0f);
+  if (hz + 1 < G.nz - 1) m = fminf(m, (1.0f - fz) + 1.0f);
+  if (m == FLT_MAX) return true;                              // the block is the whole grid
+  const float me = (m - slack) * G.cell * 0.999999f;
+  const float gr2 = me > 0.f ? me * me : 0.f;
+  if (d5 <= gr2) return true;                                 // exact: nothing closer can be outside
+  return gr2 >= max_dist_f;                                   // outside points fail Plane::close_enough
+}
 
-  if (active) {
-    if (!block1_fast(P, rt, tid, hx, hy, hz, qx, qy, qz, t)) {
-#pragma unroll
-      for (int s = 0; s < 5; ++s) {
-        t.d[s] = __int_as_float(0x7f800000);
-        t.i[s] = 0;
-      }
-      block1_exact(P.map, rt, tid, qx, qy, qz, t);
-    }
-  }
-  int k = 1;
-  bool more = active && ring_needs_more(P, hx, hy, hz, fx, fy, fz, slack, k, t.d[4]);
-
+// Exact 5-NN of q, outcome-equivalent to the reference's unbounded octree search
+// (Octree.hpp:526-599) for every query the reference would accept: the finest level whose 3x3x3
+// block provably contains the 5th neighbour answers; the coarsest level's cell is >= sqrt(MAX_DIST_PLANE),
+// so its block always covers the radius beyond which Plane::close_enough rejects the match anyway.
+__device__ __forceinline__ void knn_search(const MatchParams& P, float qx, float qy, float qz, Top5& t, const float4*& src) {
 #pragma unroll 1
-  for (;;) {
-    const unsigned int pending = __ballot_sync(full, more);
-    if (pending == 0) break;
-    const int L = __ffs(pending) - 1;                         // the query the warp works on now
-    const float bqx = __shfl_sync(full, qx, L), bqy = __shfl_sync(full, qy, L), bqz = __shfl_sync(full, qz, L);
-    const int bhx = __shfl_sync(full, hx, L), bhy = __shfl_sync(full, hy, L), bhz = __shfl_sync(full, hz, L);
-    const int bk = __shfl_sync(full, k, L) + 1;
-    Top5 mine;
-#pragma unroll
-    for (int s = 0; s < 5; ++s) {
-      mine.d[s] = (lane == L) ? t.d[s] : __int_as_float(0x7f800000);
-      mine.i[s] = (lane == L) ? t.i[s] : 0u;
-    }
-    // shell bk: rows (dy,dz) in [-bk,bk]^2; border rows are one run [hx-bk, hx+bk], inner rows two cells
-    const int side = 2 * bk + 1;
-    const int items = 2 * side * side;
-#pragma unroll 1
-    for (int w = lane; w < items; w += 32) {
-      const int j = w >> 1, which = w & 1;
-      const int dy = j % side - bk, dz = j / side - bk;
-      const int y = bhy + dy, z = bhz + dz;
-      if (y < 0 || y >= G.ny || z < 0 || z >= G.nz) continue;
-      const int row = (z * G.ny + y) * G.nx;
-      int xa, xb;
-      if (max(abs(dy), abs(dz)) == bk) {
-        if (which) continue;
-        xa = max(bhx - bk, 0);
-        xb = min(bhx + bk, G.nx - 1);
-      } else {
-        xa = xb = which ? bhx + bk : bhx - bk;
-        if (xa < 0 || xa >= G.nx) continue;
-      }
-      scan_run(P.map, __ldg(&cs[row + xa]), __ldg(&cs[row + xb + 1]), bqx, bqy, bqz, mine);
-    }
-    // merge: five rounds of warp arg-min over (d2 bits, map index)
-    float rd[5];
-    uint32_t ri[5];
-#pragma unroll
-    for (int round = 0; round < 5; ++round) {
-      const uint32_t db = __float_as_uint(mine.d[0]);
-      const uint32_t mb = __reduce_min_sync(full, db);
-      const uint32_t mi = __reduce_min_sync(full, db == mb ? mine.i[0] : 0xFFFFFFFFu);
-      if (db == mb && mine.i[0] == mi) {                      // winner pops its head
-#pragma unroll
-        for (int s = 0; s < 4; ++s) {
-          mine.d[s] = mine.d[s + 1];
-          mine.i[s] = mine.i[s + 1];
-        }
-        mine.d[4] = __int_as_float(0x7f800000);
-        mine.i[4] = 0u;
-      }
-      rd[round] = __uint_as_float(mb);
-      ri[round] = mi;
-    }
-    if (lane == L) {
-#pragma unroll
-      for (int s = 0; s < 5; ++s) {
-        t.d[s] = rd[s];
-        t.i[s] = ri[s];
-      }
-      k = bk;
-      more = ring_needs_more(P, hx, hy, hz, fx, fy, fz, slack, k, t.d[4]);
-    }
+  for (int l = 0; l < P.n_levels; ++l) {
+    const LevelView& L = P.lv[l];
+    const int hx = cell_coord(qx, L.g.ox, L.g.inv_cell, L.g.nx), hy = cell_coord(qy, L.g.oy, L.g.inv_cell, L.g.ny),
+              hz = cell_coord(qz, L.g.oz, L.g.inv_cell, L.g.nz);
+    block_scan(L, hx, hy, hz, qx, qy, qz, t);
+    src = L.pts;
+    if (block_is_final(L.g, P.max_dist_f, qx, qy, qz, hx, hy, hz, t.d[4])) return;
   }
 }
 
@@ -513,7 +396,6 @@ __device__ __forceinline__ void tri13(int e, int& i, int& j) {
 }
 
 __global__ void __launch_bounds__(kTileQueries) match_reduce_kernel(const __grid_constant__ MatchParams P) {
-  __shared__ RunTable rt;
   __shared__ double tile[kTileQueries / 32][32][13];
   __shared__ double wsum[kTileQueries / 32][kPartialStride];
   __shared__ int s_last;
@@ -528,21 +410,15 @@ __global__ void __launch_bounds__(kTileQueries) match_reduce_kernel(const __grid
   bool accepted = false;   // Match::lisanAlGaib()
   uint32_t orig = 0;
 
-  float g[3] = {0.f, 0.f, 0.f};
   if (in_range) {
     const float4 sp = __ldg(&P.scan[q]);
     orig = __float_as_uint(sp.w);
+    float g[3];
     affine_apply(P.pc.R_wb, P.pc.t_wb, sp.x, sp.y, sp.z, g);
-  }
-  Top5 t;
-#pragma unroll
-  for (int s = 0; s < 5; ++s) {
-    t.d[s] = __int_as_float(0x7f800000);   // +inf == empty slot
-    t.i[s] = 0;
-  }
-  knn_search(P, rt, threadIdx.x, in_range, g[0], g[1], g[2], t);   // warp-converged call
+    Top5 t;
+    const float4* src = nullptr;           // level storage t.i[] indexes into
+    knn_search(P, g[0], g[1], g[2], t, src);
 
-  if (in_range) {
     float n4[4] = {0.f, 0.f, 0.f, 0.f};
     float dist = 0.f;
     // Plane::enough_points + close_enough: an empty slot is +inf and fails the strict '<'.
@@ -551,7 +427,7 @@ __global__ void __launch_bounds__(kTileQueries) match_reduce_kernel(const __grid
       float4 nb[5];
 #pragma unroll
       for (int j = 0; j < 5; ++j) {
-        nb[j] = __ldg(&P.map[t.i[j]]);
+        nb[j] = __ldg(&src[t.i[j]]);
         A[j][0] = nb[j].x;
         A[j][1] = nb[j].y;
         A[j][2] = nb[j].z;

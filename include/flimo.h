@@ -59,7 +59,7 @@ typedef struct {
   /* Extensions (defaults keep reference behaviour): */
   float knn_cell;               /* side of the device search grid in metres; 0 = choose automatically */
   int32_t sort_scan;            /* 1 = Morton-sort the scan on upload for locality (results are order independent) */
-  int32_t reserved;
+  float knn_level_ratio;        /* cell growth between index levels; 0 = default (1.5) */
 } flimo_cfg;
 
 void flimo_cfg_default(flimo_cfg* cfg);
@@ -153,8 +153,9 @@ typedef struct {
   uint64_t kernel_launches;     /* CUDA kernels launched by this handle so far */
   uint64_t match_launches;      /* of which the fused match+reduce kernel */
   float last_match_ms;          /* device time of the last blocking match pass (CUDA events) */
-  float knn_cell;               /* grid cell in use */
+  float knn_cell;               /* finest grid cell in use */
   int32_t grid_nx, grid_ny, grid_nz;
+  int32_t n_levels;
   uint64_t table_bytes, map_bytes;
 } flimo_stats;
 int flimo_get_stats(flimo_handle h, flimo_stats* out);
