@@ -42,6 +42,8 @@ class FlimoStats(C.Structure):
         ("kernel_launches", C.c_uint64),
         ("match_launches", C.c_uint64),
         ("last_match_ms", C.c_float),
+        ("match_ms_total", C.c_double),
+        ("match_timed", C.c_uint64),
         ("knn_cell", C.c_float),
         ("grid_nx", C.c_int32),
         ("grid_ny", C.c_int32),

@@ -33,7 +33,7 @@ class MappingConfig:
     octree_min_extent: float = 0.2
     octree_downsampling: bool = True
     knn_cell: float = 0.0                # extension: device grid cell (0 = auto)
-    sort_scan: bool = False              # extension: Morton-sort the scan on upload
+    sort_scan: bool = True               # extension: Morton-sort the scan on upload (results are order independent)
     knn_level_ratio: float = 0.0         # extension: cell growth between index levels (0 = 1.5)
 
 
@@ -116,8 +116,8 @@ class Mapper:
 
     def add(self, points, time=0.0):
         """Mapper::add(pc, time): world-frame points, (n, >=3) float32 (row stride = itemsize*cols)."""
-        pts = np.ascontiguousarray(points, dtype=np.float32)
-        self._ck(self._L.flimo_map_add(self._h, pts.ctypes.data, pts.shape[0], pts.strides[0], float(time)))
+        pts = np.ascontiguousarray(points, dtype=np.float32).reshape(-1, np.shape(points)[-1] if np.ndim(points) == 2 else 3)
+        self._ck(self._L.flimo_map_add(self._h, pts.ctypes.data, pts.shape[0], 4 * pts.shape[1], float(time)))
 
     def add_device(self, dptr, n, stride_bytes, time=0.0):
         self._ck(self._L.flimo_map_add_device(self._h, C.c_void_p(dptr), n, stride_bytes, float(time)))
@@ -131,8 +131,8 @@ class Mapper:
 
     def set_scan(self, scan):
         """Binds Localizer::pc2match (body-frame points of the current scan)."""
-        sc = np.ascontiguousarray(scan, dtype=np.float32)
-        self._ck(self._L.flimo_scan_set(self._h, sc.ctypes.data, sc.shape[0], sc.strides[0]))
+        sc = np.ascontiguousarray(scan, dtype=np.float32).reshape(-1, np.shape(scan)[-1] if np.ndim(scan) == 2 else 3)
+        self._ck(self._L.flimo_scan_set(self._h, sc.ctypes.data, sc.shape[0], 4 * sc.shape[1]))
         self._scan_n = min(sc.shape[0], self.config.MAX_NUM_PC2MATCH)
 
     def set_scan_device(self, dptr, n, stride_bytes):

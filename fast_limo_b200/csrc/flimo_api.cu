@@ -51,12 +51,14 @@ struct flimo_ctx {
   uint8_t* valid_flags = nullptr;
   size_t valid_cap = 0;
   float* xyz_out = nullptr;
+  unsigned long long* timing = nullptr;   // tools/warp_timing.py only
   size_t xyz_cap = 0;
 
   ekf::IteratedUpdate upd;
   bool upd_active = false;
 
   flimo_stats stats{};
+  std::vector<cudaEvent_t> ev_pending, ev_pool;   // async match launches awaiting timing
 };
 
 namespace {
@@ -191,6 +193,7 @@ int fill_params(flimo_handle h, const double state14[14], MatchParams& P, double
   P.out96 = d_out;
   P.dbg16 = dbg;
   P.valid_by_orig = valid;
+  P.timing = h->timing;
   return FLIMO_OK;
 }
 
@@ -209,6 +212,8 @@ int run_pass_blocking(flimo_handle h, const double state14[14], uint32_t orig_li
   float ms = 0.f;
   cudaEventElapsedTime(&ms, h->ev0, h->ev1);
   h->stats.last_match_ms = ms;
+  h->stats.match_ms_total += ms;
+  h->stats.match_timed++;
   std::memcpy(packed, h->h_out96, 96 * sizeof(double));
   return FLIMO_OK;
 }
@@ -231,7 +236,7 @@ void flimo_cfg_default(flimo_cfg* c) {
   c->octree_downsampling = 1;
   c->octree_min_extent = 0.2f;
   c->knn_cell = 0.f;
-  c->sort_scan = 0;
+  c->sort_scan = 1;
   c->knn_level_ratio = 0.f;
 }
 
@@ -298,6 +303,8 @@ void flimo_destroy(flimo_handle h) {
   cudaFree(h->dbg16);
   cudaFree(h->valid_flags);
   cudaFree(h->xyz_out);
+  for (auto e : h->ev_pending) cudaEventDestroy(e);
+  for (auto e : h->ev_pool) cudaEventDestroy(e);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -306,8 +313,40 @@ void flimo_destroy(flimo_handle h) {
 
 void* flimo_stream(flimo_handle h) { return h ? (void*)h->stream : nullptr; }
 
+// Profiling aid (not part of flimo.h): per-warp timestamps of the next passes are written to a
+// device buffer of 6 u64 per warp; returns it to the host.  Pass enable=0 to switch off.
+int flimo_debug_timing(flimo_handle h, int enable, unsigned long long* host_out, size_t n_warps) {
+  if (!h || h->device < 0) return FLIMO_ERR_INVALID;
+  cudaSetDevice(h->device);
+  if (enable && !h->timing) {
+    if (cudaMalloc(&h->timing, n_warps * 6 * sizeof(unsigned long long)) != cudaSuccess) return FLIMO_ERR_NOMEM;
+    cudaMemset(h->timing, 0, n_warps * 6 * sizeof(unsigned long long));
+  }
+  if (host_out && h->timing) {
+    cudaStreamSynchronize(h->stream);
+    cudaMemcpy(host_out, h->timing, n_warps * 6 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+  }
+  if (!enable && h->timing) {
+    cudaFree(h->timing);
+    h->timing = nullptr;
+  }
+  return FLIMO_OK;
+}
+
 int flimo_get_stats(flimo_handle h, flimo_stats* out) {
   if (!h || !out) return FLIMO_ERR_INVALID;
+  for (size_t i = 0; i + 1 < h->ev_pending.size(); i += 2) {
+    float ms = 0.f;
+    if (cudaEventSynchronize(h->ev_pending[i + 1]) == cudaSuccess &&
+        cudaEventElapsedTime(&ms, h->ev_pending[i], h->ev_pending[i + 1]) == cudaSuccess) {
+      h->stats.match_ms_total += ms;
+      h->stats.match_timed++;
+      h->stats.last_match_ms = ms;
+    }
+    h->ev_pool.push_back(h->ev_pending[i]);
+    h->ev_pool.push_back(h->ev_pending[i + 1]);
+  }
+  h->ev_pending.clear();
   h->stats.knn_cell = h->map.lv[0].g.cell;
   h->stats.grid_nx = h->map.lv[0].g.nx;
   h->stats.grid_ny = h->map.lv[0].g.ny;
@@ -462,7 +501,20 @@ int flimo_match_reduce_async(flimo_handle h, const double state14[14], double* d
   MatchParams P;
   int rc = fill_params(h, state14, P, d_out96, 0xFFFFFFFFu, nullptr, nullptr);
   if (rc) return rc;
+  // device-time bookkeeping for bench.py: event pairs are resolved lazily in flimo_get_stats
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (h->ev_pool.size() >= 2) {
+    e0 = h->ev_pool.back(); h->ev_pool.pop_back();
+    e1 = h->ev_pool.back(); h->ev_pool.pop_back();
+  } else {
+    CU(h, cudaEventCreate(&e0));
+    CU(h, cudaEventCreate(&e1));
+  }
+  CU(h, cudaEventRecord(e0, st));
   CU(h, launch_match(P, st));
+  CU(h, cudaEventRecord(e1, st));
+  h->ev_pending.push_back(e0);
+  h->ev_pending.push_back(e1);
   h->stats.kernel_launches++;
   h->stats.match_launches++;
   return FLIMO_OK;

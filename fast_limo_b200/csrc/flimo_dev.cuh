@@ -60,6 +60,7 @@ struct MatchParams {
   double* out96;               // packed result (see flimo.h)
   float* dbg16;                // optional per-point record [n][16], indexed by original index
   uint8_t* valid_by_orig;      // optional accepted flag per original index
+  unsigned long long* timing;  // optional per-warp timestamps (profiling builds of the tools only)
 };
 
 // map_index.cu

@@ -72,13 +72,19 @@ __device__ __forceinline__ void top5_offer(Top5& t, float d, uint32_t idx) {
 //   if bucket(k5) > bucket(exact 5th d2) then all of them have d2 > that 5th d2.     (else: exact path)
 // Ties in d2 are ordered by position in the run (x cell, then map index).
 // ---------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void keys6_insert(uint32_t (&k)[6], uint32_t x) {
-  k[5] = min(k[5], max(x, k[4]));
-  k[4] = min(k[4], max(x, k[3]));
-  k[3] = min(k[3], max(x, k[2]));
-  k[2] = min(k[2], max(x, k[1]));
-  k[1] = min(k[1], max(x, k[0]));
-  k[0] = min(k[0], x);
+// Keys are bit patterns of non-negative, non-NaN floats, so they are ranked with FLOAT min/max
+// (FMNMX, full-rate ALU pipe) — the ordering equals the unsigned-integer ordering of the bits.
+// Empty slot = +inf.  A NaN key (NaN query) is never inserted because fminf/fmaxf drop NaN operands.
+__device__ __forceinline__ void keys6_insert(float (&k)[6], float x) {
+  k[5] = fminf(k[5], fmaxf(x, k[4]));
+  k[4] = fminf(k[4], fmaxf(x, k[3]));
+  k[3] = fminf(k[3], fmaxf(x, k[2]));
+  k[2] = fminf(k[2], fmaxf(x, k[1]));
+  k[1] = fminf(k[1], fmaxf(x, k[0]));
+  k[0] = fminf(k[0], x);
+}
+__device__ __forceinline__ float pack_key(float d, uint32_t low, uint32_t ord) {
+  return __uint_as_float((__float_as_uint(d) & ~low) | ord);
 }
 
 __device__ __forceinline__ void cmpswap64(unsigned long long& a, unsigned long long& b) {
@@ -93,21 +99,14 @@ __device__ __forceinline__ float sqdist(float qx, float qy, float qz, const floa
   return dx * dx + (dy * dy + dz * dz);               // Eigen Vector3f::squaredNorm order
 }
 
-// Exact (slow, branchy) scan of a run; positions are recorded relative to `s`.
-__device__ __noinline__ void run_exact(const float4* __restrict__ pts, uint32_t s, uint32_t e, float qx, float qy, float qz,
-                                       Top5& t) {
-#pragma unroll
-  for (int j = 0; j < 5; ++j) {
-    t.d[j] = __int_as_float(0x7f800000);
-    t.i[j] = 0;
-  }
-#pragma unroll 1
-  for (uint32_t i = s; i < e; ++i) top5_offer(t, sqdist(qx, qy, qz, __ldg(&pts[i])), i);
-}
+constexpr uint32_t kPrivateCap = 96;   // longest run a single thread scans by itself
 
-// On return t.d[] holds the exact ascending squared distances of the block's five nearest points and
-// t.i[] their positions in L.pts (+inf / 0 for missing ones).
-__device__ __forceinline__ void block_scan(const LevelView& L, int hx, int hy, int hz, float qx, float qy, float qz, Top5& t) {
+// Thread-private scan of a short run (level 0, <= kPrivateCap candidates).  Returns false when the
+// packed selection cannot be proven exact (or the run is too long): the caller then hands the query
+// to the warp-cooperative exact scan below.  On success t.d[] holds the exact ascending squared
+// distances of the block's five nearest points and t.i[] their positions in L.pts (+inf / 0 if missing).
+__device__ __forceinline__ bool block_scan_private(const LevelView& L, int hx, int hy, int hz, float qx, float qy, float qz,
+                                                   Top5& t) {
   const GridDesc& G = L.g;
   const int row = (hz * G.ny + hy) * G.nx;
   const uint32_t s = __ldg(&L.cell_start[row + max(hx - 1, 0)]);
@@ -118,38 +117,45 @@ __device__ __forceinline__ void block_scan(const LevelView& L, int hx, int hy, i
     t.d[j] = __int_as_float(0x7f800000);
     t.i[j] = 0;
   }
-  if (total == 0) return;
-  const int B = 32 - __clz(total);               // ordinals 0..total-1 fit in B bits
+  if (total == 0) return true;
+  if (total > kPrivateCap) return false;
+  const int B = 32 - __clz(total);               // ordinals 0..total-1 fit in B bits (B <= 7)
   const float4* __restrict__ pts = L.pts + s;
-  if (B > 14) {                                  // > 16k candidates in one block: exact path
-    run_exact(L.pts, s, e, qx, qy, qz, t);
-    return;
-  }
   const uint32_t low = (1u << B) - 1u;
-  uint32_t k[6];
+  float k[6];
 #pragma unroll
-  for (int j = 0; j < 6; ++j) k[j] = 0xFFFFFFFFu;
+  for (int j = 0; j < 6; ++j) k[j] = __int_as_float(0x7f800000);
 
+  // software-pipelined: the next four points are in flight while the current four are ranked
+  const uint32_t last = total - 1;
+  float4 a0 = __ldg(&pts[0]), a1 = __ldg(&pts[min(1u, last)]), a2 = __ldg(&pts[min(2u, last)]), a3 = __ldg(&pts[min(3u, last)]);
   uint32_t n = 0;
 #pragma unroll 1
   for (; n + 4 <= total; n += 4) {
-    const float4 p0 = __ldg(&pts[n]), p1 = __ldg(&pts[n + 1]), p2 = __ldg(&pts[n + 2]), p3 = __ldg(&pts[n + 3]);
+    const float4 p0 = a0, p1 = a1, p2 = a2, p3 = a3;
+    a0 = __ldg(&pts[min(n + 4, last)]);
+    a1 = __ldg(&pts[min(n + 5, last)]);
+    a2 = __ldg(&pts[min(n + 6, last)]);
+    a3 = __ldg(&pts[min(n + 7, last)]);
     const float d0 = sqdist(qx, qy, qz, p0), d1 = sqdist(qx, qy, qz, p1), d2 = sqdist(qx, qy, qz, p2),
                 d3 = sqdist(qx, qy, qz, p3);
-    keys6_insert(k, (__float_as_uint(d0) & ~low) | n);
-    keys6_insert(k, (__float_as_uint(d1) & ~low) | (n + 1));
-    keys6_insert(k, (__float_as_uint(d2) & ~low) | (n + 2));
-    keys6_insert(k, (__float_as_uint(d3) & ~low) | (n + 3));
+    keys6_insert(k, pack_key(d0, low, n));
+    keys6_insert(k, pack_key(d1, low, n + 1));
+    keys6_insert(k, pack_key(d2, low, n + 2));
+    keys6_insert(k, pack_key(d3, low, n + 3));
   }
-#pragma unroll 1
-  for (; n < total; ++n) keys6_insert(k, (__float_as_uint(sqdist(qx, qy, qz, __ldg(&pts[n]))) & ~low) | n);
+  // tail (< 4 candidates): a0..a2 already hold pts[n], pts[n+1], pts[n+2] (clamped)
+  if (n < total) keys6_insert(k, pack_key(sqdist(qx, qy, qz, a0), low, n));
+  if (n + 1 < total) keys6_insert(k, pack_key(sqdist(qx, qy, qz, a1), low, n + 1));
+  if (n + 2 < total) keys6_insert(k, pack_key(sqdist(qx, qy, qz, a2), low, n + 2));
 
   // exact re-ranking of the (up to) six kept candidates: sort (exact d2 bits, ordinal) pairs
   unsigned long long ek[6];
 #pragma unroll
   for (int j = 0; j < 6; ++j) {
-    const bool have = k[j] != 0xFFFFFFFFu;
-    const uint32_t ord = k[j] & low;
+    const uint32_t kb = __float_as_uint(k[j]);
+    const bool have = kb < 0x7f800000u;
+    const uint32_t ord = kb & low;
     float d = __int_as_float(0x7f800000);
     if (have) d = sqdist(qx, qy, qz, __ldg(&pts[ord]));
     ek[j] = ((unsigned long long)__float_as_uint(d) << 32) | (have ? ord : 0xFFFFFFFFu);
@@ -159,15 +165,65 @@ __device__ __forceinline__ void block_scan(const LevelView& L, int hx, int hy, i
   cmpswap64(ek[0], ek[3]); cmpswap64(ek[2], ek[5]);
   cmpswap64(ek[0], ek[1]); cmpswap64(ek[2], ek[3]); cmpswap64(ek[4], ek[5]);
   cmpswap64(ek[1], ek[2]); cmpswap64(ek[3], ek[4]);
-  const bool safe = (k[5] == 0xFFFFFFFFu) || ((k[5] & ~low) > ((uint32_t)(ek[4] >> 32) & ~low));
-  if (!safe) {
-    run_exact(L.pts, s, e, qx, qy, qz, t);
-    return;
-  }
 #pragma unroll
   for (int j = 0; j < 5; ++j) {
     t.d[j] = __uint_as_float((uint32_t)(ek[j] >> 32));
     t.i[j] = s + (uint32_t)(ek[j] & 0xFFFFFFFFu);
+  }
+  const uint32_t k5 = __float_as_uint(k[5]);
+  return (k5 >= 0x7f800000u) || ((k5 & ~low) > ((uint32_t)(ek[4] >> 32) & ~low));
+}
+
+// TEAM scan: exact top-5 of one query's block at level L by a team of T consecutive lanes
+// (T a power of two, 1..32; every lane of the warp calls this, teams work on different queries).
+// Team lanes stride through the contiguous run (coalesced reads), keep private exact top-5 lists,
+// and the lists are merged inside the team by five rounds of (d2 bits, position) arg-min built from
+// xor-shuffles of width T.  Results are identical in all lanes of a team.  A team with nothing to do
+// passes valid = false.
+__device__ __forceinline__ void block_scan_team(const LevelView& L, int T, int tl, bool valid, float qx, float qy, float qz,
+                                                float (&rd)[5], uint32_t (&ri)[5]) {
+  const unsigned int full = 0xffffffffu;
+  const GridDesc& G = L.g;
+  uint32_t s = 0, e = 0;
+  if (valid) {
+    const int hx = cell_coord(qx, G.ox, G.inv_cell, G.nx), hy = cell_coord(qy, G.oy, G.inv_cell, G.ny),
+              hz = cell_coord(qz, G.oz, G.inv_cell, G.nz);
+    const int row = (hz * G.ny + hy) * G.nx;
+    s = __ldg(&L.cell_start[row + max(hx - 1, 0)]);
+    e = __ldg(&L.cell_start[row + min(hx + 1, G.nx - 1) + 1]);
+  }
+  Top5 mine;
+#pragma unroll
+  for (int j = 0; j < 5; ++j) {
+    mine.d[j] = __int_as_float(0x7f800000);
+    mine.i[j] = 0xFFFFFFFFu;
+  }
+  const float4* __restrict__ pts = L.pts;
+#pragma unroll 1
+  for (uint32_t i = s + tl; i < e; i += T) top5_offer(mine, sqdist(qx, qy, qz, __ldg(&pts[i])), i);
+#pragma unroll
+  for (int round = 0; round < 5; ++round) {
+    const uint32_t db = __float_as_uint(mine.d[0]);
+    uint32_t mb = db;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1)
+      if (o < T) mb = min(mb, __shfl_xor_sync(full, mb, o));
+    const uint32_t cand = (db == mb) ? mine.i[0] : 0xFFFFFFFFu;
+    uint32_t mi = cand;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1)
+      if (o < T) mi = min(mi, __shfl_xor_sync(full, mi, o));
+    if (db == mb && mine.i[0] == mi) {                        // the winner pops its head
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        mine.d[j] = mine.d[j + 1];
+        mine.i[j] = mine.i[j + 1];
+      }
+      mine.d[4] = __int_as_float(0x7f800000);
+      mine.i[4] = 0xFFFFFFFFu;
+    }
+    rd[round] = __uint_as_float(mb);
+    ri[round] = (mi == 0xFFFFFFFFu) ? 0u : mi;
   }
 }
 
@@ -199,15 +255,66 @@ __device__ __forceinline__ bool block_is_final(const GridDesc& G, float max_dist
 // (Octree.hpp:526-599) for every query the reference would accept: the finest level whose 3x3x3
 // block provably contains the 5th neighbour answers; the coarsest level's cell is >= sqrt(MAX_DIST_PLANE),
 // so its block always covers the radius beyond which Plane::close_enough rejects the match anyway.
-__device__ __forceinline__ void knn_search(const MatchParams& P, float qx, float qy, float qz, Top5& t, const float4*& src) {
-#pragma unroll 1
-  for (int l = 0; l < P.n_levels; ++l) {
-    const LevelView& L = P.lv[l];
+//   level 0  : one thread per query (block_scan_private);
+//   the rest : the queries that are not settled are shared out among TEAMS of lanes
+//              (block_scan_team), one level per round, until every query is settled.
+// Must be called by all 32 lanes (inactive lanes pass active = false).  `lvl` returns the level whose
+// storage t.i[] indexes into.
+__device__ __forceinline__ void knn_search(const MatchParams& P, int lane, bool active, float qx, float qy, float qz, Top5& t,
+                                           int& lvl) {
+  const unsigned int full = 0xffffffffu;
+  lvl = 0;
+  bool exact_here = true;      // does t hold the exact block answer of level `lvl`?
+  bool pending = false;
+  if (active) {
+    const LevelView& L = P.lv[0];
     const int hx = cell_coord(qx, L.g.ox, L.g.inv_cell, L.g.nx), hy = cell_coord(qy, L.g.oy, L.g.inv_cell, L.g.ny),
               hz = cell_coord(qz, L.g.oz, L.g.inv_cell, L.g.nz);
-    block_scan(L, hx, hy, hz, qx, qy, qz, t);
-    src = L.pts;
-    if (block_is_final(L.g, P.max_dist_f, qx, qy, qz, hx, hy, hz, t.d[4])) return;
+    exact_here = block_scan_private(L, hx, hy, hz, qx, qy, qz, t);
+    if (!exact_here) {
+      pending = true;                                          // redo level 0 cooperatively
+    } else if (!block_is_final(L.g, P.max_dist_f, qx, qy, qz, hx, hy, hz, t.d[4])) {
+      pending = P.n_levels > 1;
+      lvl = pending ? 1 : 0;
+    }
+  }
+#pragma unroll 1
+  for (;;) {
+    const unsigned int todo = __ballot_sync(full, pending);
+    if (todo == 0) break;
+    // Split the warp into G = pow2ceil(#pending) teams of T = 32/G lanes; team g serves the pending
+    // lane of rank g.  Few stragglers => wide teams (short, parallel scans); many => T = 1, which is
+    // the thread-per-query regime with every lane busy.
+    const int n_pend = __popc(todo);
+    const int G = (n_pend <= 1) ? 1 : (1 << (32 - __clz(n_pend - 1)));
+    const int T = 32 / G;
+    const int team = lane / T, tl = lane - team * T;
+    const bool valid = team < n_pend;
+    const int src_lane = valid ? (int)__fns(todo, 0, team + 1) : 0;
+    const float bx = __shfl_sync(full, qx, src_lane), by = __shfl_sync(full, qy, src_lane), bz = __shfl_sync(full, qz, src_lane);
+    const int bl = __shfl_sync(full, lvl, src_lane);
+    float rd[5];
+    uint32_t ri[5];
+    block_scan_team(P.lv[bl], T, tl, valid, bx, by, bz, rd, ri);
+    // hand the results back: pending lane of rank r reads from the first lane of team r
+    const int my_rank = __popc(todo & ((1u << lane) - 1u));
+    const int from = pending ? my_rank * T : lane;
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+      const float dj = __shfl_sync(full, rd[j], from);
+      const uint32_t ij = __shfl_sync(full, ri[j], from);
+      if (pending) {
+        t.d[j] = dj;
+        t.i[j] = ij;
+      }
+    }
+    if (pending) {
+      const LevelView& L = P.lv[lvl];
+      const int hx = cell_coord(qx, L.g.ox, L.g.inv_cell, L.g.nx), hy = cell_coord(qy, L.g.oy, L.g.inv_cell, L.g.ny),
+                hz = cell_coord(qz, L.g.oz, L.g.inv_cell, L.g.nz);
+      if (block_is_final(L.g, P.max_dist_f, qx, qy, qz, hx, hy, hz, t.d[4]) || lvl + 1 >= P.n_levels) pending = false;
+      else ++lvl;
+    }
   }
 }
 
@@ -395,13 +502,16 @@ __device__ __forceinline__ void tri13(int e, int& i, int& j) {
   j = r + (e - base);
 }
 
-__global__ void __launch_bounds__(kTileQueries) match_reduce_kernel(const __grid_constant__ MatchParams P) {
+__global__ void __launch_bounds__(kTileQueries, 7) match_reduce_kernel(const __grid_constant__ MatchParams P) {
   __shared__ double tile[kTileQueries / 32][32][13];
   __shared__ double wsum[kTileQueries / 32][kPartialStride];
   __shared__ int s_last;
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int q = P.q_begin + blockIdx.x * kTileQueries + threadIdx.x;
+  // Interleaved assignment: slot s of tile t handles query s*n_tiles + t, so consecutive scan points
+  // (which share sparse / dense regions of the map and therefore search cost) are spread over all
+  // tiles instead of piling up in one warp.  Results do not depend on the assignment.
+  const int q = P.q_begin + (int)threadIdx.x * (int)gridDim.x + (int)blockIdx.x;
   const bool in_range = q < P.q_end;
 
   float v13[13];
@@ -410,15 +520,26 @@ __global__ void __launch_bounds__(kTileQueries) match_reduce_kernel(const __grid
   bool accepted = false;   // Match::lisanAlGaib()
   uint32_t orig = 0;
 
+  float g[3] = {0.f, 0.f, 0.f};
   if (in_range) {
     const float4 sp = __ldg(&P.scan[q]);
     orig = __float_as_uint(sp.w);
-    float g[3];
     affine_apply(P.pc.R_wb, P.pc.t_wb, sp.x, sp.y, sp.z, g);
-    Top5 t;
-    const float4* src = nullptr;           // level storage t.i[] indexes into
-    knn_search(P, g[0], g[1], g[2], t, src);
+  }
+  Top5 t;
+#pragma unroll
+  for (int j = 0; j < 5; ++j) {
+    t.d[j] = __int_as_float(0x7f800000);
+    t.i[j] = 0;
+  }
+  int lvl = 0;
+  unsigned long long tm0 = 0, tm1 = 0, tm2 = 0;
+  if (P.timing) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tm0));
+  knn_search(P, lane, in_range, g[0], g[1], g[2], t, lvl);      // warp-converged call
+  if (P.timing) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tm1));
 
+  if (in_range) {
+    const float4* __restrict__ src = P.lv[lvl].pts;             // storage t.i[] indexes into
     float n4[4] = {0.f, 0.f, 0.f, 0.f};
     float dist = 0.f;
     // Plane::enough_points + close_enough: an empty slot is +inf and fails the strict '<'.
@@ -483,6 +604,10 @@ __global__ void __launch_bounds__(kTileQueries) match_reduce_kernel(const __grid
     if (P.valid_by_orig != nullptr) P.valid_by_orig[orig] = accepted ? 1 : 0;
   }
 
+  if (P.timing) {
+    __syncwarp();
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tm2));
+  }
   // ---- warp-cooperative float64 accumulation of [row,z]^T [row,z] -------------------------------
   const bool contributes = accepted && (orig < P.orig_limit);
   const unsigned int m_all = __ballot_sync(0xffffffffu, accepted);
@@ -519,6 +644,17 @@ __global__ void __launch_bounds__(kTileQueries) match_reduce_kernel(const __grid
   }
   __syncthreads();
 
+  if (P.timing && lane == 0) {
+    unsigned long long tm3;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tm3));
+    unsigned int smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    unsigned long long* o = P.timing + ((size_t)blockIdx.x * (kTileQueries / 32) + warp) * 6;
+    o[0] = smid; o[1] = tm0; o[2] = tm1; o[3] = tm2; o[4] = tm3;
+    o[5] = (unsigned long long)__popc(__ballot_sync(0xffffffffu, lvl > 0) );
+  } else if (P.timing) {
+    (void)__ballot_sync(0xffffffffu, lvl > 0);
+  }
   // ---- CTA partial, then a deterministic two-level tree over tiles ----------------------------------
   const int n_tiles = gridDim.x;
   const int n_groups = (n_tiles + kGroupTiles - 1) / kGroupTiles;

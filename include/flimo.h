@@ -152,7 +152,9 @@ int flimo_scan_to_world(flimo_handle h, const double state14[14], float* out_xyz
 typedef struct {
   uint64_t kernel_launches;     /* CUDA kernels launched by this handle so far */
   uint64_t match_launches;      /* of which the fused match+reduce kernel */
-  float last_match_ms;          /* device time of the last blocking match pass (CUDA events) */
+  float last_match_ms;          /* device time of the last timed match launch (CUDA events) */
+  double match_ms_total;        /* sum of device times of all match launches (events on the launch stream) */
+  uint64_t match_timed;         /* number of launches in that sum */
   float knn_cell;               /* finest grid cell in use */
   int32_t grid_nx, grid_ny, grid_nz;
   int32_t n_levels;

@@ -1,0 +1,36 @@
+"""CPU: the oracle reproduces the committed golden fixtures (tests/golden/make_golden.py)."""
+import os
+
+import numpy as np
+import pytest
+
+from fast_limo_b200 import synth
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+CASES = [("tiny", 1 << 18, 1 << 18), ("tiny", 1500, 400), ("c1", 1 << 18, 1 << 18)]
+
+
+def load(name, mm):
+    return np.load(os.path.join(G, f"{name}_m{mm}.npz"))
+
+
+@pytest.mark.parametrize("name,pc2,mm", CASES)
+def test_oracle_matches_golden(oracle, name, pc2, mm):
+    g = load(name, mm)
+    case = synth.make_case(name)
+    assert case.scan.astype(np.float64).sum() == float(g["scan_checksum"])      # generators are seed-stable
+    assert case.map_pts.astype(np.float64).sum() == float(g["map_checksum"])
+    om = oracle.OracleMap()
+    om.add(case.map_pts)
+    cfg = oracle.make_cfg(max_pc2match=pc2, max_matches=mm, num_threads=2)
+    r = om.match(cfg, case.init[:14], case.scan)
+    good = np.unpackbits(g["good"])[: int(g["n_q"])].astype(bool)
+    assert np.array_equal(r["good"], good)
+    assert np.array_equal(r["plane"][good], g["plane"]) and np.array_equal(r["dist"][good], g["dist"])
+    assert np.array_equal(r["nn_d2"], g["nn_d2"])
+    assert r["n_valid"] == int(g["n_valid"]) and r["rows"] == int(g["rows"])
+    assert np.allclose(r["HTH"], g["HTH"], rtol=1e-13, atol=1e-12)
+    x, P, tr = om.update(cfg, case.init, synth.default_P0(), int(g["max_iter"]), 0.0, case.scan)
+    assert np.allclose(x, g["x_final"], rtol=0, atol=1e-12)
+    assert np.allclose(P, g["P_final"], rtol=1e-9, atol=1e-13)
+    assert [t["rows"] for t in tr] == g["trace_rows"].tolist()
