@@ -152,6 +152,7 @@ def main():
     import torch
     import torch.distributed as dist
     from fast_limo_b200 import api, synth
+    from fast_limo_b200.dist import shard_bounds, sharded_update
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -176,7 +177,7 @@ def main():
         s4[:, :3] = s
         d_scans.append(torch.from_numpy(s4).cuda())
         h_scans.append(torch.from_numpy(s4).pin_memory())
-    lo, hi = (n_pts * rank) // world, (n_pts * (rank + 1)) // world
+    lo, hi = shard_bounds(n_pts, rank, world)
     red = torch.zeros(96, dtype=torch.float64, device="cuda")
     h_stream = torch.cuda.ExternalStream(m.stream())
     cur = torch.cuda.current_stream()
@@ -193,16 +194,17 @@ def main():
             x, P, passes = m.update(inits[k], P0, MAX_ITER, lim)
             return x, passes
         m.shard(lo, hi)
-        m.ekf_begin(inits[k], P0, MAX_ITER, lim)
-        passes, done = 0, False
         cur.wait_stream(h_stream)                      # scan upload / sort ran on the handle's stream
-        while not done:
-            m.match_async(m.ekf_state(), red.data_ptr(), cur.cuda_stream)
-            dist.all_reduce(red)                       # 96 doubles: HTH tri + HTh + counters
-            r = api.unpack96(red.cpu().numpy())
-            done = m.ekf_step(r.HTH, r.HTh, r.n_rows)
-            passes += 1
-        x, P = m.ekf_end()
+
+        def local_pass(state):
+            m.match_async(state, red.data_ptr(), cur.cuda_stream)
+            return red
+
+        def all_reduce(t):
+            dist.all_reduce(t)                         # 96 doubles: HTH tri + HTh + counters (NCCL)
+            return t.cpu().numpy()
+
+        x, P, passes = sharded_update(m, inits[k], P0, MAX_ITER, lim, local_pass, all_reduce)
         return x, passes
 
     def timed(steps, from_host):
