@@ -194,17 +194,19 @@ def main():
             x, P, passes = m.update(inits[k], P0, MAX_ITER, lim)
             return x, passes
         m.shard(lo, hi)
-        cur.wait_stream(h_stream)                      # scan upload / sort ran on the handle's stream
+        # Everything of the pass is ordered on the HANDLE's stream: the kernel is launched there
+        # (stream NULL in the ABI = the handle's stream; the legacy default stream cannot be named) and
+        # torch enqueues the NCCL all-reduce relative to the current stream, which we make that stream.
+        with torch.cuda.stream(h_stream):
+            def local_pass(state):
+                m.match_async(state, red.data_ptr(), None)
+                return red
 
-        def local_pass(state):
-            m.match_async(state, red.data_ptr(), cur.cuda_stream)
-            return red
+            def all_reduce(t):
+                dist.all_reduce(t)                     # 96 doubles: HTH tri + HTh + counters (NCCL)
+                return t.cpu().numpy()
 
-        def all_reduce(t):
-            dist.all_reduce(t)                         # 96 doubles: HTH tri + HTh + counters (NCCL)
-            return t.cpu().numpy()
-
-        x, P, passes = sharded_update(m, inits[k], P0, MAX_ITER, lim, local_pass, all_reduce)
+            x, P, passes = sharded_update(m, inits[k], P0, MAX_ITER, lim, local_pass, all_reduce)
         return x, passes
 
     def timed(steps, from_host):

@@ -39,6 +39,12 @@ struct flimo_ctx {
   void* stage = nullptr;         // raw strided uploads
   size_t stage_cap = 0;
   unsigned int* d_count = nullptr;
+  float4* batch = nullptr;                // packed incoming batch
+  size_t batch_cap = 0;
+  unsigned long long* batch_keys = nullptr;
+  uint8_t* batch_accept = nullptr;
+  OctreeLattice lattice;                  // the reference octree's cell lattice (insert rule)
+  CountTable counts;
 
   double* partials = nullptr;
   size_t partials_cap = 0;       // in doubles
@@ -296,6 +302,10 @@ void flimo_destroy(flimo_handle h) {
   cudaFree(h->scan_cub);
   cudaFree(h->stage);
   cudaFree(h->d_count);
+  cudaFree(h->batch);
+  cudaFree(h->batch_keys);
+  cudaFree(h->batch_accept);
+  table_free(h->counts);
   cudaFree(h->partials);
   cudaFree(h->ticket);
   cudaFree(h->out96);
@@ -369,17 +379,50 @@ int flimo_map_add_device(flimo_handle h, const void* d_xyz, size_t n, size_t str
   if (n < 1) return FLIMO_OK;                                   // Mapper::add: size < 1 -> return
   NEED_GPU(h);
   const size_t old_n = h->map_exists ? h->map.n_pts : 0;
-  if (h->map_exists && h->cfg.octree_downsampling)
-    return fail(h, FLIMO_ERR_INVALID, "incremental insert with down-sampling is not built yet (K3)");
-  CU(h, map_index_reserve(h->map, old_n + n));
+  // 1. pack the batch (drops NaN points, Octree::processPoints :243) and take its bounding box
+  if (n > h->batch_cap) {
+    cudaFree(h->batch);
+    cudaFree(h->batch_keys);
+    cudaFree(h->batch_accept);
+    h->batch = nullptr;
+    h->batch_keys = nullptr;
+    h->batch_accept = nullptr;
+    h->batch_cap = 0;
+    const size_t want = n + n / 4 + 1024;
+    CU(h, cudaMalloc(&h->batch, want * sizeof(float4)));
+    CU(h, cudaMalloc(&h->batch_keys, want * sizeof(unsigned long long)));
+    CU(h, cudaMalloc(&h->batch_accept, want));
+    h->batch_cap = want;
+  }
   CU(h, cudaMemsetAsync(h->d_count, 0, sizeof(unsigned int), h->stream));
-  CU(h, pack_points(d_xyz, n, stride_bytes, h->map.pts + old_n, h->d_count, h->stream));
+  CU(h, pack_points(d_xyz, n, stride_bytes, h->batch, h->d_count, h->stream));
   unsigned int kept = 0;
   CU(h, cudaMemcpyAsync(&kept, h->d_count, sizeof(kept), cudaMemcpyDeviceToHost, h->stream));
   CU(h, cudaStreamSynchronize(h->stream));
   h->stats.kernel_launches += 1;
-  const size_t total = old_n + kept;
-  if (total == 0) return FLIMO_OK;                              // Octree::initialize: empty -> no root
+  if (kept == 0) return FLIMO_OK;                               // Octree::initialize: empty -> no root
+  CU(h, map_index_reserve(h->map, old_n + kept));
+  float lo[3], hi[3];
+  CU(h, points_bbox(h->batch, kept, h->map.bbox, lo, hi, h->stream));
+  h->stats.kernel_launches += 2;
+  // 2. the octree lattice: first batch defines it (Octree::initialize), later ones may double the root
+  const bool first = !h->map_exists;
+  if (first) {
+    lattice_init(h->lattice, lo, hi, h->cfg.octree_min_extent);
+    table_free(h->counts);
+  } else {
+    lattice_grow(h->lattice, hi);                               // expandTree(max) then expandTree(min), Octree.hpp:373-374
+    lattice_grow(h->lattice, lo);
+  }
+  // 3. accept / drop per point, append the accepted ones to the canonical list, update the counts
+  unsigned int accepted = 0;
+  CU(h, map_insert_batch(h->lattice, h->counts, h->batch, kept, h->cfg.octree_downsampling, first, h->map.pts + old_n,
+                         h->d_count, h->batch_keys, h->batch_accept, &accepted, h->stream, &h->stats.kernel_launches));
+  const size_t total = old_n + accepted;
+  h->map_exists = true;                                         // the tree exists even if this batch was dropped entirely
+  h->last_time = stamp;
+  if (accepted == 0) return FLIMO_OK;
+  // 4. rebuild the search index over all map points
   h->map.n_pts = total;
   const size_t max_cells = (size_t)1 << 30;
   // coarsest level: cell >= sqrt(MAX_DIST_PLANE) so its 3x3x3 block covers the close_enough radius
@@ -387,8 +430,6 @@ int flimo_map_add_device(flimo_handle h, const void* d_xyz, size_t n, size_t str
   CU(h, map_index_build(h->map, h->cfg.knn_cell, h->cfg.knn_level_ratio, coarsest, max_cells, h->stream,
                         &h->stats.kernel_launches));
   CU(h, cudaStreamSynchronize(h->stream));
-  h->map_exists = true;
-  h->last_time = stamp;
   return FLIMO_OK;
 }
 

@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <vector>
+
 namespace flimo {
 
 // One level of the device map index.
@@ -103,6 +105,47 @@ cudaError_t pack_scan(const void* d_src, size_t n, size_t stride_bytes, float4* 
 cudaError_t sort_scan_morton(float4* scan, float4* tmp, size_t n, void** cub_tmp, size_t* cub_tmp_bytes,
                              uint32_t** keys, size_t* keys_cap, cudaStream_t st, uint64_t* launches);
 cudaError_t transform_scan(const float4* scan, size_t n, const PoseConsts& pc, float* d_out_xyz, cudaStream_t st);
+
+// map_insert.cu — the reference's incremental insert rule (Octree::update, Octree.hpp:341-432)
+constexpr int kMaxChain = 24;          // root doublings tracked (2^23 x the first scan's extent)
+
+struct LatticeDesc {                   // kernel-parameter view of the octree lattice
+  int n_chain;                         // chain[0] = original root ... chain[n_chain-1] = current root
+  int min_depth;                       // depth of the min-level cells below the original root
+  int off[3];                          // integer offset of the current root's lower corner (min-level cells)
+  float chain_c[kMaxChain][3];
+  float chain_ext[kMaxChain];
+  int chain_slot[kMaxChain];           // child slot of chain[k-1] inside chain[k]
+};
+
+struct OctreeLattice {                 // host-side state, built with the reference's float arithmetic
+  struct Root {
+    float c[3];
+    float ext;
+    int slot;
+  };
+  std::vector<Root> chain;
+  int min_depth = 0;
+  int off[3] = {0, 0, 0};
+  float min_extent = 0.2f;
+  bool initialised = false;
+};
+
+struct CountTable {                    // open-addressing hash: cell key -> number of map points
+  unsigned long long* keys = nullptr;
+  uint32_t* vals = nullptr;
+  size_t cap = 0;
+  size_t used_bound = 0;               // upper bound on occupied slots
+};
+
+void lattice_init(OctreeLattice& L, const float lo[3], const float hi[3], float min_extent);
+void lattice_grow(OctreeLattice& L, const float boundary[3]);
+void table_free(CountTable& T);
+cudaError_t map_insert_batch(OctreeLattice& L, CountTable& T, const float4* d_batch, size_t n, int downsample, bool first_batch,
+                             float4* d_dst, unsigned int* d_counter, unsigned long long* d_cell_keys, uint8_t* d_accept,
+                             unsigned int* n_accepted, cudaStream_t st, uint64_t* launches);
+// bounding box (lo[3], hi[3]) of n float4 points on the device -> host (synchronises the stream)
+cudaError_t points_bbox(const float4* d_pts, size_t n, float* d_scratch8, float lo[3], float hi[3], cudaStream_t st);
 
 // match_kernel.cu
 cudaError_t launch_match(const MatchParams& p, cudaStream_t st);

@@ -284,6 +284,20 @@ void map_index_free(MapIndex& idx) {
   idx = MapIndex{};
 }
 
+cudaError_t points_bbox(const float4* d_pts, size_t n, float* d_scratch8, float lo[3], float hi[3], cudaStream_t st) {
+  unsigned int* bb = reinterpret_cast<unsigned int*>(d_scratch8);
+  bbox_init_kernel<<<1, 32, 0, st>>>(bb);
+  bbox_kernel<<<min(nblk(n), 148u * 8u), 256, 0, st>>>(d_pts, n, bb);
+  unsigned int hb[6];
+  FL_TRY(cudaMemcpyAsync(hb, bb, sizeof(hb), cudaMemcpyDeviceToHost, st));
+  FL_TRY(cudaStreamSynchronize(st));
+  for (int a = 0; a < 3; ++a) {
+    lo[a] = ord2f(hb[a]);
+    hi[a] = ord2f(hb[3 + a]);
+  }
+  return cudaGetLastError();
+}
+
 static GridDesc make_grid(const float lo[3], const float hi[3], float cell) {
   GridDesc g{};
   g.cell = cell;

@@ -105,8 +105,8 @@ int flimo_scan_shard(flimo_handle h, size_t begin, size_t end);
 int flimo_match_reduce(flimo_handle h, const double state14[14], double HTH[144], double HTh[12],
                        int64_t* n_valid, int64_t* n_rows, double* sum_sq_res);
 
-/* Asynchronous form for pipelines / multi-GPU: launches on `cuda_stream` (a cudaStream_t, NULL =
- * the handle's stream) and leaves 96 doubles in DEVICE memory at d_out:
+/* Asynchronous form for pipelines / multi-GPU: launches on `cuda_stream` (a cudaStream_t; NULL =
+ * the handle's own stream, flimo_stream(h) — the legacy default stream cannot be selected) and leaves 96 doubles in DEVICE memory at d_out:
  *   [0..77]  upper triangle of HTH, row by row (i<=j)   [78..89] HTh
  *   [90] n_rows  [91] sum_sq_res  [92] n_valid  [93..95] reserved (0)
  * With FLIMO sharding, summing d_out over ranks (ncclAllReduce, ncclDouble, 96) gives the

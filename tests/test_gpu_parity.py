@@ -240,3 +240,61 @@ def test_headline_config_properties(oracle, flimo_lib):
     assert passes == 3 and np.abs(x[:3] - case.truth[:3]).max() < 5e-3
     w = m.scan_to_world(x)
     assert w.shape == case.scan.shape and np.isfinite(w).all()
+
+
+def _batches(seed, n_batches=10, n=6000):
+    """A vehicle driving along +x over a noisy ground plane with a wall: dense re-observation (drops),
+    new terrain (root doubling in several directions) and a few NaN points."""
+    rng = np.random.default_rng(seed)
+    out = []
+    for b in range(n_batches):
+        cx = 6.0 * b - (25.0 if b == 7 else 0.0)          # one jump backwards: expansion towards -x
+        ground = np.c_[rng.uniform(cx - 12, cx + 12, n), rng.uniform(-10, 10 + b, n), 0.3 + rng.normal(0, 0.01, n)]
+        wall = np.c_[rng.uniform(cx - 12, cx + 12, n // 3), np.full(n // 3, 10.0 + b) + rng.normal(0, 0.01, n // 3),
+                     rng.uniform(0.3, 4.0 + 3 * b, n // 3)]
+        pts = np.r_[ground, wall].astype(np.float32)
+        pts[rng.integers(0, len(pts), 5)] = np.nan
+        out.append(pts)
+    return out
+
+
+@pytest.mark.parametrize("downsample", [True, False])
+@pytest.mark.parametrize("min_extent", [0.2, 0.35])
+def test_incremental_insert_matches_octree(oracle, flimo_lib, downsample, min_extent):
+    """Mapper::add / Octree::update (Octree.hpp:341-432): identical map CONTENTS after every batch."""
+    om = oracle.OracleMap(min_extent=min_extent, downsample=downsample)
+    m = mapper(octree_downsampling=downsample, octree_min_extent=min_extent)
+    prev = 0
+    for b, pts in enumerate(_batches(5)):
+        om.add(pts)
+        m.add(pts, float(b))
+        assert m.size() == om.size(), (b, m.size(), om.size())
+        assert m.last_time() == float(b)
+        prev = m.size()
+    a = m.points()
+    r = om.points()
+    key = lambda p: p[np.lexsort((p[:, 2], p[:, 1], p[:, 0]))]
+    assert np.array_equal(key(a), key(r))
+    if downsample:
+        assert m.size() < sum(int((~np.isnan(p[:, 0])).sum()) for p in _batches(5))
+    # and the grown map still answers queries like the octree
+    st = synth.make_state([20.0, 0.0, 1.8], [0, 0, 0, 1])
+    scan = np.c_[np.random.default_rng(1).uniform(-10, 10, (2000, 2)), np.full(2000, -1.5)].astype(np.float32)
+    ref = om.match(oracle.make_cfg(max_pc2match=BIG, max_matches=BIG), st[:14], scan)
+    m.set_scan(scan)
+    check_per_point(m.match_debug(st), ref)
+    assert ref["good"].sum() > 500
+
+
+def test_insert_tiny_first_scan(oracle, flimo_lib):
+    """First scan smaller than a min-level cell (root itself is the min level) and an all-NaN batch."""
+    rng = np.random.default_rng(2)
+    om = oracle.OracleMap()
+    m = mapper()
+    first = rng.uniform(-0.15, 0.15, (20, 3)).astype(np.float32)
+    for pts in (first, first + 0.01, rng.uniform(-3, 3, (500, 3)).astype(np.float32), first - 0.02):
+        om.add(pts)
+        m.add(pts)
+        assert m.size() == om.size()
+    m.add(np.full((4, 3), np.nan, np.float32))
+    assert m.size() == om.size()
