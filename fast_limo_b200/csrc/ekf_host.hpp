@@ -262,46 +262,63 @@ inline void boxminus(const State& x, const State& y, double* d) {
   s2_minus(x.grav, y.grav, d[21], d[22]);
 }
 
-// LU (partial pivoting) inverse of an n x n row-major matrix, in place.
+// Inverse of an n x n row-major matrix by Gauss-Jordan elimination with partial (row) pivoting on the
+// augmented system [A | I]; every inner loop runs over a contiguous row, so the host compiler
+// vectorises it (the 23x23 case takes a few microseconds).  Returns false on an exactly singular pivot.
 template <int n>
 inline bool invert(Mat<n, n>& M) {
-  double lu[n][n];
-  int piv[n];
-  for (int r = 0; r < n; ++r)
-    for (int c = 0; c < n; ++c) lu[r][c] = M(r, c);
-  for (int i = 0; i < n; ++i) piv[i] = i;
-  for (int c = 0; c < n; ++c) {
-    int p = c;
-    double best = std::fabs(lu[c][c]);
-    for (int r = c + 1; r < n; ++r)
-      if (std::fabs(lu[r][c]) > best) {
-        best = std::fabs(lu[r][c]);
-        p = r;
-      }
-    if (best == 0.0) return false;
-    if (p != c) {
-      for (int k = 0; k < n; ++k) std::swap(lu[c][k], lu[p][k]);
-      std::swap(piv[c], piv[p]);
-    }
-    for (int r = c + 1; r < n; ++r) {
-      lu[r][c] /= lu[c][c];
-      const double f = lu[r][c];
-      for (int k = c + 1; k < n; ++k) lu[r][k] -= f * lu[c][k];
+  alignas(32) double w[n][2 * n];
+  for (int r = 0; r < n; ++r) {
+    for (int c = 0; c < n; ++c) {
+      w[r][c] = M(r, c);
+      w[r][n + c] = (r == c) ? 1.0 : 0.0;
     }
   }
-  for (int col = 0; col < n; ++col) {   // solve A x = e_col
-    double y[n];
+  for (int c = 0; c < n; ++c) {
+    int p = c;
+    double best = std::fabs(w[c][c]);
+    for (int r = c + 1; r < n; ++r) {
+      const double v = std::fabs(w[r][c]);
+      if (v > best) {
+        best = v;
+        p = r;
+      }
+    }
+    if (best == 0.0) return false;
+    if (p != c)
+      for (int k = 0; k < 2 * n; ++k) std::swap(w[c][k], w[p][k]);
+    const double inv = 1.0 / w[c][c];
+    for (int k = 0; k < 2 * n; ++k) w[c][k] *= inv;
     for (int r = 0; r < n; ++r) {
-      double s = (piv[r] == col) ? 1.0 : 0.0;
-      for (int k = 0; k < r; ++k) s -= lu[r][k] * y[k];
-      y[r] = s;
+      if (r == c) continue;
+      const double f = w[r][c];
+      if (f == 0.0) continue;
+      for (int k = 0; k < 2 * n; ++k) w[r][k] -= f * w[c][k];
     }
-    for (int r = n - 1; r >= 0; --r) {
-      double s = y[r];
-      for (int k = r + 1; k < n; ++k) s -= lu[r][k] * y[k];
-      y[r] = s / lu[r][r];
+  }
+  for (int r = 0; r < n; ++r)
+    for (int c = 0; c < n; ++c) M(r, c) = w[r][n + c];
+  return true;
+}
+
+// true when every eigenvalue of the symmetric 6x6 S exceeds `floor` by a safe margin: S - floor*I has
+// a Cholesky factorisation whose pivots are all comfortably positive.
+inline bool all_eigs_above(const Mat<6, 6>& S, double floor) {
+  double L[6][6];
+  double scale = 0.0;
+  for (int i = 0; i < 6; ++i) scale = std::fmax(scale, std::fabs(S(i, i)));
+  const double tiny = 1e-9 * (scale + std::fabs(floor)) + 1e-300;
+  for (int j = 0; j < 6; ++j) {
+    double d = S(j, j) - floor;
+    for (int k = 0; k < j; ++k) d -= L[j][k] * L[j][k];
+    if (!(d > tiny)) return false;
+    const double dj = std::sqrt(d);
+    L[j][j] = dj;
+    for (int i = j + 1; i < 6; ++i) {
+      double v = S(i, j);
+      for (int k = 0; k < j; ++k) v -= L[i][k] * L[j][k];
+      L[i][j] = v / dj;
     }
-    for (int r = 0; r < n; ++r) M(r, col) = y[r];
   }
   return true;
 }
@@ -452,6 +469,10 @@ class IteratedUpdate {
           for (int c = 0; c < 6; ++c) S6(r, c) = HTH144[r * 12 + c];
       double w[6];
       Mat<6, 6> V;
+      // Fast exit: if every eigenvalue is safely above both thresholds of the filter (D and, for the
+      // product test, 1e-20^(1/6)), the reference computes V^-1 * V * dx = dx; skip the decomposition.
+      const bool clear = n_rows >= N && all_eigs_above(S6, std::fmax(D_, 1e-3));
+      if (clear) goto filter_done;
       sym_eig6(S6, w, V);
       double prod = 1;
       for (double v : w) prod *= v;
@@ -469,6 +490,7 @@ class IteratedUpdate {
         dxn[r] = s;
       }
     }
+  filter_done:
 
     boxplus(x_, dxn);
     bool converge = true;
