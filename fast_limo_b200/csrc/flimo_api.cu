@@ -3,6 +3,7 @@
 // host IKFoM update (ekf_host.hpp).  No CPU fallback exists: without a working CUDA device every
 // entry point fails with a negative status.
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -51,7 +52,16 @@ struct flimo_ctx {
   unsigned int* ticket = nullptr;
   size_t ticket_cap = 0;
   double* out96 = nullptr;       // device
-  double* h_out96 = nullptr;     // pinned host
+  double* h_out96 = nullptr;     // pinned + mapped host copy: 96 doubles + [96] sequence word
+  double* d_h_out96 = nullptr;   // device alias of h_out96
+  unsigned long long seq = 0;    // sequence number of the last blocking pass
+  struct ScanGraph {
+    const void* src;
+    size_t n, stride;
+    int sort;
+    cudaGraphExec_t exec;
+  };
+  std::vector<ScanGraph> scan_graphs;   // captured upload pipelines (pack + sort + gather)
   float* dbg16 = nullptr;
   size_t dbg_cap = 0;
   uint8_t* valid_flags = nullptr;
@@ -200,27 +210,55 @@ int fill_params(flimo_handle h, const double state14[14], MatchParams& P, double
   P.dbg16 = dbg;
   P.valid_by_orig = valid;
   P.timing = h->timing;
+  P.host_out96 = nullptr;
+  P.seq = 0;
   return FLIMO_OK;
 }
 
+// Blocking pass.  The last CTA of the kernel also writes the 96 result doubles and then a sequence
+// word into MAPPED pinned host memory; the host spins on that word instead of issuing a D2H copy and
+// a stream synchronise (saves ~10 us of launch/sync latency per pass).  Device time is taken from a
+// pair of events that is resolved lazily in flimo_get_stats.
 int run_pass_blocking(flimo_handle h, const double state14[14], uint32_t orig_limit, float* dbg, uint8_t* valid,
                       double packed[96]) {
   MatchParams P;
   int rc = fill_params(h, state14, P, h->out96, orig_limit, dbg, valid);
   if (rc) return rc;
-  CU(h, cudaEventRecord(h->ev0, h->stream));
+  P.host_out96 = h->d_h_out96;
+  P.seq = ++h->seq;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (h->ev_pool.size() >= 2) {
+    e0 = h->ev_pool.back(); h->ev_pool.pop_back();
+    e1 = h->ev_pool.back(); h->ev_pool.pop_back();
+  } else {
+    CU(h, cudaEventCreate(&e0));
+    CU(h, cudaEventCreate(&e1));
+  }
+  CU(h, cudaEventRecord(e0, h->stream));
   CU(h, launch_match(P, h->stream));
-  CU(h, cudaEventRecord(h->ev1, h->stream));
-  CU(h, cudaMemcpyAsync(h->h_out96, h->out96, 96 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-  CU(h, cudaStreamSynchronize(h->stream));
+  CU(h, cudaEventRecord(e1, h->stream));
+  h->ev_pending.push_back(e0);
+  h->ev_pending.push_back(e1);
   h->stats.kernel_launches++;
   h->stats.match_launches++;
-  float ms = 0.f;
-  cudaEventElapsedTime(&ms, h->ev0, h->ev1);
-  h->stats.last_match_ms = ms;
-  h->stats.match_ms_total += ms;
-  h->stats.match_timed++;
+  volatile unsigned long long* flag = reinterpret_cast<volatile unsigned long long*>(h->h_out96 + 96);
+  unsigned long long spins = 0;
+  while (*flag != P.seq) {
+    if ((++spins & 0xFFFFF) == 0) {                       // every ~1M polls: has the kernel died?
+      const cudaError_t q = cudaStreamQuery(h->stream);
+      if (q != cudaSuccess && q != cudaErrorNotReady) return fail(h, FLIMO_ERR_CUDA, std::string("match kernel: ") + cudaGetErrorString(q));
+      if (q == cudaSuccess && *flag != P.seq) {           // finished without the flag: treat as failure
+        CU(h, cudaMemcpy(h->h_out96, h->out96, 96 * sizeof(double), cudaMemcpyDeviceToHost));
+        break;
+      }
+    }
+  }
+  std::atomic_thread_fence(std::memory_order_acquire);
   std::memcpy(packed, h->h_out96, 96 * sizeof(double));
+  if (h->ev_pending.size() > 64) {                         // keep the lazy list short
+    flimo_stats tmp;
+    flimo_get_stats(h, &tmp);
+  }
   return FLIMO_OK;
 }
 
@@ -281,7 +319,9 @@ int flimo_create(const flimo_cfg* cfg, int device, flimo_handle* out) {
   CU(h, cudaEventCreate(&h->ev1));
   CU(h, cudaMalloc(&h->out96, 96 * sizeof(double)));
   CU(h, cudaMemset(h->out96, 0, 96 * sizeof(double)));
-  CU(h, cudaMallocHost(&h->h_out96, 96 * sizeof(double)));
+  CU(h, cudaHostAlloc(&h->h_out96, 104 * sizeof(double), cudaHostAllocMapped));
+  std::memset(h->h_out96, 0, 104 * sizeof(double));
+  CU(h, cudaHostGetDevicePointer(reinterpret_cast<void**>(&h->d_h_out96), h->h_out96, 0));
   CU(h, cudaMalloc(&h->d_count, sizeof(unsigned int)));
   *out = h;
   return FLIMO_OK;
@@ -309,6 +349,7 @@ void flimo_destroy(flimo_handle h) {
   cudaFree(h->partials);
   cudaFree(h->ticket);
   cudaFree(h->out96);
+  for (auto& g : h->scan_graphs) cudaGraphExecDestroy(g.exec);
   cudaFreeHost(h->h_out96);
   cudaFree(h->dbg16);
   cudaFree(h->valid_flags);
@@ -484,15 +525,53 @@ int flimo_scan_set_device(flimo_handle h, const void* d_xyz, size_t n, size_t st
     CU(h, cudaMalloc(&h->scan, want * sizeof(float4)));
     CU(h, cudaMalloc(&h->scan_tmp, want * sizeof(float4)));
     h->scan_cap = want;
+    for (auto& g : h->scan_graphs) cudaGraphExecDestroy(g.exec);   // captured pointers are stale
+    h->scan_graphs.clear();
   }
-  CU(h, pack_scan(d_xyz, nq, stride_bytes, h->scan, h->stream));
-  h->stats.kernel_launches += nq ? 1 : 0;
-  if (h->cfg.sort_scan && nq > 1)
-    CU(h, sort_scan_morton(h->scan, h->scan_tmp, nq, &h->scan_cub, &h->scan_cub_bytes, &h->scan_keys, &h->scan_keys_cap,
-                           h->stream, &h->stats.kernel_launches));
   h->scan_n = nq;
   h->shard_begin = 0;
   h->shard_end = nq;
+  if (nq == 0) return FLIMO_OK;
+  const int sort = (h->cfg.sort_scan && nq > 1) ? 1 : 0;
+  // The upload pipeline (pack + Morton keys, radix sort, gather: 7 launches) is captured once per
+  // (source pointer, size) into a CUDA graph and replayed with a single launch afterwards.
+  for (auto& g : h->scan_graphs) {
+    if (g.src == d_xyz && g.n == nq && g.stride == stride_bytes && g.sort == sort) {
+      CU(h, cudaGraphLaunch(g.exec, h->stream));
+      h->stats.kernel_launches += sort ? 7 : 1;
+      return FLIMO_OK;
+    }
+  }
+  const size_t old_keys_cap = h->scan_keys_cap;
+  if (sort) CU(h, scan_prepare_reserve(nq, &h->scan_cub, &h->scan_cub_bytes, &h->scan_keys, &h->scan_keys_cap));
+  if (h->scan_keys_cap != old_keys_cap) {                        // scratch moved: drop graphs that point at the old one
+    for (auto& g : h->scan_graphs) cudaGraphExecDestroy(g.exec);
+    h->scan_graphs.clear();
+  }
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  uint64_t dummy = 0;
+  CU(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+  const cudaError_t ce = scan_prepare(d_xyz, nq, stride_bytes, sort != 0, h->scan, h->scan_tmp, &h->scan_cub, &h->scan_cub_bytes,
+                                      &h->scan_keys, &h->scan_keys_cap, h->stream, &dummy);
+  const cudaError_t ee = cudaStreamEndCapture(h->stream, &graph);
+  if (ce != cudaSuccess || ee != cudaSuccess || graph == nullptr) {
+    if (graph) cudaGraphDestroy(graph);
+    cudaGetLastError();
+    // capture unavailable: run the pipeline directly
+    CU(h, scan_prepare(d_xyz, nq, stride_bytes, sort != 0, h->scan, h->scan_tmp, &h->scan_cub, &h->scan_cub_bytes, &h->scan_keys,
+                       &h->scan_keys_cap, h->stream, &h->stats.kernel_launches));
+    return FLIMO_OK;
+  }
+  CU(h, cudaGraphInstantiate(&exec, graph, 0));
+  cudaGraphDestroy(graph);
+  if (h->scan_graphs.size() >= 8) {
+    cudaGraphExecDestroy(h->scan_graphs.front().exec);
+    h->scan_graphs.erase(h->scan_graphs.begin());
+  }
+  h->scan_graphs.push_back({d_xyz, nq, stride_bytes, sort, exec});
+  CU(h, cudaGraphLaunch(exec, h->stream));
+  h->stats.kernel_launches += sort ? 7 : 1;
   return FLIMO_OK;
 }
 

@@ -62,6 +62,8 @@ struct MatchParams {
   double* out96;               // packed result (see flimo.h)
   float* dbg16;                // optional per-point record [n][16], indexed by original index
   uint8_t* valid_by_orig;      // optional accepted flag per original index
+  double* host_out96;          // optional mapped pinned copy of the result (+ [96] = sequence number)
+  unsigned long long seq;      // value written to host_out96[96] when the result is complete
   unsigned long long* timing;  // optional per-warp timestamps (profiling builds of the tools only)
 };
 
@@ -102,8 +104,9 @@ cudaError_t pack_points(const void* d_src, size_t n, size_t stride_bytes, float4
 // Packs a scan: float4 with w = original index bits (no NaN filtering: the reference matches them
 // and they simply fail the kNN gate).
 cudaError_t pack_scan(const void* d_src, size_t n, size_t stride_bytes, float4* dst, cudaStream_t st);
-cudaError_t sort_scan_morton(float4* scan, float4* tmp, size_t n, void** cub_tmp, size_t* cub_tmp_bytes,
-                             uint32_t** keys, size_t* keys_cap, cudaStream_t st, uint64_t* launches);
+cudaError_t scan_prepare(const void* d_src, size_t n, size_t stride_bytes, bool sort, float4* scan, float4* tmp, void** cub_tmp,
+                         size_t* cub_tmp_bytes, uint32_t** keys, size_t* keys_cap, cudaStream_t st, uint64_t* launches);
+cudaError_t scan_prepare_reserve(size_t n, void** cub_tmp, size_t* cub_tmp_bytes, uint32_t** keys, size_t* keys_cap);
 cudaError_t transform_scan(const float4* scan, size_t n, const PoseConsts& pc, float* d_out_xyz, cudaStream_t st);
 
 // map_insert.cu — the reference's incremental insert rule (Octree::update, Octree.hpp:341-432)

@@ -159,22 +159,6 @@ __device__ __forceinline__ uint32_t spread10(uint32_t v) {
   return v;
 }
 
-// Morton key of the body-frame position at 0.25 m resolution in a +-128 m cube (pose independent,
-// so one sort per scan serves every pass).
-__global__ void __launch_bounds__(256) scan_keys_kernel(const float4* __restrict__ scan, size_t n, uint32_t* keys,
-                                                        uint32_t* vals) {
-  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const float4 v = scan[i];
-  auto q = [](float c) {
-    float u = (c + 128.0f) * 4.0f;
-    u = isnan(u) ? 0.f : fminf(fmaxf(u, 0.f), 1023.f);
-    return (uint32_t)u;
-  };
-  keys[i] = spread10(q(v.x)) | (spread10(q(v.y)) << 1) | (spread10(q(v.z)) << 2);
-  vals[i] = (uint32_t)i;
-}
-
 __global__ void __launch_bounds__(256) transform_kernel(const float4* __restrict__ scan, size_t n, PoseConsts pc,
                                                         float* __restrict__ out) {
   const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
@@ -226,22 +210,54 @@ static cudaError_t ensure(void** p, size_t* cap, size_t need) {
   return cudaSuccess;
 }
 
-cudaError_t sort_scan_morton(float4* scan, float4* tmp, size_t n, void** cub_tmp, size_t* cub_tmp_bytes, uint32_t** keys,
-                             size_t* keys_cap, cudaStream_t st, uint64_t* launches) {
-  if (n < 2) return cudaSuccess;
-  size_t need_keys = 4 * n * sizeof(uint32_t);
-  FL_TRY(ensure(reinterpret_cast<void**>(keys), keys_cap, need_keys));
+// Scan upload pipeline (all launches on `st`, capturable into a CUDA graph):
+//   pack (+ Morton key of the body-frame position) -> radix sort of (key, index) -> gather.
+// The key has 9 bits per axis at 0.5 m resolution in a +-128 m cube: neighbouring scan points end up in
+// neighbouring tiles, which is all the ordering is for (results do not depend on it).
+__global__ void __launch_bounds__(256) pack_scan_keys_kernel(const unsigned char* __restrict__ src, size_t n, size_t stride,
+                                                             float4* __restrict__ dst, uint32_t* __restrict__ keys,
+                                                             uint32_t* __restrict__ vals) {
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float* p = reinterpret_cast<const float*>(src + i * stride);
+  const float x = p[0], y = p[1], z = p[2];
+  dst[i] = make_float4(x, y, z, __uint_as_float((unsigned int)i));
+  auto q = [](float c) {
+    float u = (c + 128.0f) * 2.0f;
+    u = isnan(u) ? 0.f : fminf(fmaxf(u, 0.f), 511.f);
+    return (uint32_t)u;
+  };
+  keys[i] = spread10(q(x)) | (spread10(q(y)) << 1) | (spread10(q(z)) << 2);
+  vals[i] = (uint32_t)i;
+}
+
+cudaError_t scan_prepare(const void* d_src, size_t n, size_t stride_bytes, bool sort, float4* scan, float4* tmp, void** cub_tmp,
+                         size_t* cub_tmp_bytes, uint32_t** keys, size_t* keys_cap, cudaStream_t st, uint64_t* launches) {
+  if (n == 0) return cudaSuccess;
+  if (!sort || n < 2) {
+    pack_scan_kernel<<<nblk(n), 256, 0, st>>>(static_cast<const unsigned char*>(d_src), n, stride_bytes, scan);
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+  }
   uint32_t *k0 = *keys, *k1 = k0 + n, *v0 = k1 + n, *v1 = v0 + n;
-  scan_keys_kernel<<<nblk(n), 256, 0, st>>>(scan, n, k0, v0);
+  pack_scan_keys_kernel<<<nblk(n), 256, 0, st>>>(static_cast<const unsigned char*>(d_src), n, stride_bytes, tmp, k0, v0);
   cub::DoubleBuffer<uint32_t> dk(k0, k1), dv(v0, v1);
-  size_t bytes = 0;
-  FL_TRY(cub::DeviceRadixSort::SortPairs(nullptr, bytes, dk, dv, (int)n, 0, 30, st));
-  FL_TRY(ensure(cub_tmp, cub_tmp_bytes, bytes));
-  FL_TRY(cub::DeviceRadixSort::SortPairs(*cub_tmp, bytes, dk, dv, (int)n, 0, 30, st));
-  FL_TRY(cudaMemcpyAsync(tmp, scan, n * sizeof(float4), cudaMemcpyDeviceToDevice, st));
+  size_t bytes = *cub_tmp_bytes;
+  FL_TRY(cub::DeviceRadixSort::SortPairs(*cub_tmp, bytes, dk, dv, (int)n, 0, 27, st));
   gather_kernel<<<nblk(n), 256, 0, st>>>(tmp, dv.Current(), n, scan);
-  if (launches) *launches += 6;
+  if (launches) *launches += 7;
   return cudaGetLastError();
+}
+
+// Sizes the scratch buffers of scan_prepare for n points (allocation must not happen during capture).
+cudaError_t scan_prepare_reserve(size_t n, void** cub_tmp, size_t* cub_tmp_bytes, uint32_t** keys, size_t* keys_cap) {
+  if (n < 2) return cudaSuccess;
+  FL_TRY(ensure(reinterpret_cast<void**>(keys), keys_cap, 4 * n * sizeof(uint32_t)));
+  cub::DoubleBuffer<uint32_t> dk(*keys, *keys + n), dv(*keys + 2 * n, *keys + 3 * n);
+  size_t bytes = 0;
+  FL_TRY(cub::DeviceRadixSort::SortPairs(nullptr, bytes, dk, dv, (int)n, 0, 27, (cudaStream_t)0));
+  FL_TRY(ensure(cub_tmp, cub_tmp_bytes, bytes));
+  return cudaSuccess;
 }
 
 cudaError_t map_index_reserve(MapIndex& idx, size_t n) {

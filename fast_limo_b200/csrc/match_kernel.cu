@@ -735,6 +735,15 @@ __global__ void __launch_bounds__(kTileQueries, 7) match_reduce_kernel(const __g
     else if (e == 92) out_idx = 90;       // n_rows
     else out_idx = e;                     // 93,94,95 reserved (zero)
     P.out96[out_idx] = s;
+    if (P.host_out96 != nullptr) P.host_out96[out_idx] = s;      // mapped pinned host copy
+  }
+  if (P.host_out96 != nullptr) {
+    __threadfence_system();                                      // result words before the sequence word
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      *reinterpret_cast<volatile unsigned long long*>(P.host_out96 + 96) = P.seq;
+      __threadfence_system();
+    }
   }
   if (threadIdx.x == 0) P.ticket[0] = 0u;
 }
