@@ -33,7 +33,7 @@ class MappingConfig:
     octree_min_extent: float = 0.2
     octree_downsampling: bool = True
     knn_cell: float = 0.0                # extension: device grid cell (0 = auto)
-    sort_scan: bool = True               # extension: Morton-sort the scan on upload (results are order independent)
+    sort_scan: bool = False              # extension: Morton-sort the scan on upload (default: in-kernel scatter instead)
     knn_level_ratio: float = 0.0         # extension: cell growth between index levels (0 = 1.5)
 
 

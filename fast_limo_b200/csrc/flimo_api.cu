@@ -159,6 +159,22 @@ void make_pose(const double s[14], PoseConsts& pc) {
   for (int i = 0; i < 9; ++i) pc.Rd_LI_inv[i] = (float)Rd[i];
 }
 
+// stride ~ 0.618 n that is co-prime with n: i -> (i * stride) mod n is a permutation of [0, n)
+uint32_t coprime_stride(uint32_t n) {
+  if (n < 3) return 1;
+  uint32_t s = (uint32_t)(0.6180339887 * n) | 1u;
+  auto gcd = [](uint32_t a, uint32_t b) {
+    while (b) {
+      const uint32_t t = a % b;
+      a = b;
+      b = t;
+    }
+    return a;
+  };
+  while (gcd(s, n) != 1) s += 2;
+  return s % n ? s % n : 1;
+}
+
 // smallest float f with (double)f >= D:  (double)x < D  <=>  x < f  for every float x
 float ceil_to_float(double D) {
   float f = (float)D;
@@ -199,6 +215,7 @@ int fill_params(flimo_handle h, const double state14[14], MatchParams& P, double
   }
   make_pose(state14, P.pc);
   P.q_begin = (int)h->shard_begin;
+  P.perm_stride = h->cfg.sort_scan ? 0u : coprime_stride((uint32_t)n);   // unsorted scans are scattered instead
   P.q_end = (int)h->shard_end;
   P.max_dist_f = ceil_to_float(h->cfg.MAX_DIST_PLANE);
   P.plane_thr = (float)h->cfg.PLANE_THRESHOLD;
@@ -280,7 +297,7 @@ void flimo_cfg_default(flimo_cfg* c) {
   c->octree_downsampling = 1;
   c->octree_min_extent = 0.2f;
   c->knn_cell = 0.f;
-  c->sort_scan = 1;
+  c->sort_scan = 0;
   c->knn_level_ratio = 0.f;
 }
 

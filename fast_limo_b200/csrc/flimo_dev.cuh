@@ -53,6 +53,7 @@ struct MatchParams {
   int n_levels;
   PoseConsts pc;
   int q_begin, q_end;          // slice of the scan handled by this launch
+  unsigned int perm_stride;    // multiplicative scatter of the query order (co-prime with the slice length; 0 = off)
   float max_dist_f;            // smallest float >= MAX_DIST_PLANE  (d2_5 < MAX_DIST_PLANE test)
   float plane_thr;             // (float)PLANE_THRESHOLD
   int estimate_extrinsics;

@@ -508,10 +508,15 @@ __global__ void __launch_bounds__(kTileQueries, 7) match_reduce_kernel(const __g
   __shared__ int s_last;
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  // Interleaved assignment: slot s of tile t handles query s*n_tiles + t, so consecutive scan points
-  // (which share sparse / dense regions of the map and therefore search cost) are spread over all
-  // tiles instead of piling up in one warp.  Results do not depend on the assignment.
-  const int q = P.q_begin + (int)threadIdx.x * (int)gridDim.x + (int)blockIdx.x;
+  // Query assignment.  Slot s of tile t takes index i = s*n_tiles + t (consecutive scan points are
+  // spread over all tiles), and i is then scattered by a multiplicative permutation of [0, n)
+  // (stride co-prime with n, ~0.618 n): neighbouring scan points share sparse / dense regions of the map
+  // and therefore search cost, and must not pile up in one warp.  Results do not depend on the assignment.
+  const int n_queries = P.q_end - P.q_begin;
+  const int i_lin = (int)threadIdx.x * (int)gridDim.x + (int)blockIdx.x;
+  const int q = i_lin < n_queries
+                    ? P.q_begin + (P.perm_stride ? (int)(((unsigned long long)i_lin * P.perm_stride) % (unsigned long long)n_queries) : i_lin)
+                    : P.q_end;
   const bool in_range = q < P.q_end;
 
   float v13[13];

@@ -58,7 +58,7 @@ typedef struct {
   float octree_min_extent;
   /* Extensions (defaults keep reference behaviour): */
   float knn_cell;               /* side of the device search grid in metres; 0 = choose automatically */
-  int32_t sort_scan;            /* 1 = Morton-sort the scan on upload for locality (results are order independent) */
+  int32_t sort_scan;            /* 1 = Morton-sort the scan on upload; 0 (default) = the kernel scatters the query order itself */
   float knn_level_ratio;        /* cell growth between index levels; 0 = default (1.5) */
 } flimo_cfg;
 
