@@ -145,6 +145,8 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--cell", type=float, default=0.0)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--exchange", choices=["shm", "nccl"], default="shm",
+                    help="N>1: how the 96 doubles per pass are summed over ranks (fused host-segment exchange | NCCL all-reduce)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -152,7 +154,7 @@ def main():
     import torch
     import torch.distributed as dist
     from fast_limo_b200 import api, synth
-    from fast_limo_b200.dist import shard_bounds, sharded_update
+    from fast_limo_b200.dist import attach_exchange, shard_bounds, sharded_update, sharded_update_exchange
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -179,6 +181,14 @@ def main():
         h_scans.append(torch.from_numpy(s4).pin_memory())
     lo, hi = shard_bounds(n_pts, rank, world)
     red = torch.zeros(96, dtype=torch.float64, device="cuda")
+    shm = None
+    if world > 1 and args.exchange == "shm":
+        def bcast(obj):
+            box = [obj]
+            dist.broadcast_object_list(box, src=0)
+            return box[0]
+        shm = attach_exchange(m, rank, world, bcast)
+        dist.barrier()
     h_stream = torch.cuda.ExternalStream(m.stream())
     cur = torch.cuda.current_stream()
 
@@ -194,6 +204,9 @@ def main():
             x, P, passes = m.update(inits[k], P0, MAX_ITER, lim)
             return x, passes
         m.shard(lo, hi)
+        if shm is not None:
+            x, P, passes = m.update_exchange(inits[k], P0, MAX_ITER, lim)
+            return x, passes
         # Everything of the pass is ordered on the HANDLE's stream: the kernel is launched there
         # (stream NULL in the ABI = the handle's stream; the legacy default stream cannot be named) and
         # torch enqueues the NCCL all-reduce relative to the current stream, which we make that stream.
@@ -251,7 +264,8 @@ def main():
             "metric": METRIC, "value": value, "unit": "scans/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32 per-point / f64 reduction", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "parallelism": "scan-shard x%d (replicated map, 96-double all-reduce per pass)" % world,
+            "config": {"workload": WORKLOAD, "parallelism": "scan-shard x%d (replicated map, 96 doubles summed per pass via %s)"
+                       % (world, "fused host-segment exchange" if (world > 1 and args.exchange == "shm") else ("NCCL all-reduce" if world > 1 else "no exchange")),
                        "passes_per_scan": passes, "l2_policy": "inputs larger than L2 (multi-level map index %.1f GB, 4 rotating scans)"
                        % (st1["map_bytes"] / 1e9), "pose_err_m": pose_err, "knn_cell": st1["knn_cell"], "levels": st1["n_levels"]},
             "e2e": {"value": args.steps / (ms_e2e / 1e3), "unit": "scans/s", "h2d_bytes_per_step": n_pts * 16,
@@ -266,6 +280,12 @@ def main():
             out["cpu_baseline"] = cpu_baseline(case, scans, inits)
         print(json.dumps(out))
     if world > 1:
+        dist.barrier()
+        m.close()
+        if shm is not None:
+            shm.close()
+            if rank == 0:
+                shm.unlink()
         dist.destroy_process_group()
 
 

@@ -16,7 +16,7 @@ SYMBOLS = [
     "flimo_map_get_points", "flimo_scan_set", "flimo_scan_set_device", "flimo_scan_shard",
     "flimo_match_reduce", "flimo_match_reduce_async", "flimo_unpack96", "flimo_match_debug",
     "flimo_update", "flimo_ekf_begin", "flimo_ekf_state", "flimo_ekf_step", "flimo_ekf_end",
-    "flimo_scan_to_world", "flimo_get_stats", "flimo_stream",
+    "flimo_scan_to_world", "flimo_get_stats", "flimo_stream", "flimo_exchange_attach", "flimo_match_reduce_exchange", "flimo_update_exchange",
 ]
 
 
@@ -92,10 +92,13 @@ def load():
     L.flimo_scan_shard.argtypes = [vp, sz, sz]
     L.flimo_match_reduce.argtypes = [vp, pd, pd, pd, C.POINTER(i64), C.POINTER(i64), pd]
     L.flimo_match_reduce_async.argtypes = [vp, pd, vp, vp]
+    L.flimo_exchange_attach.argtypes = [vp, vp, sz, C.c_int, C.c_int]
+    L.flimo_match_reduce_exchange.argtypes = [vp, pd, pd, pd, C.POINTER(i64), C.POINTER(i64), pd]
     L.flimo_unpack96.argtypes = [pd, pd, pd, C.POINTER(i64), C.POINTER(i64), pd]
     L.flimo_unpack96.restype = None
     L.flimo_match_debug.argtypes = [vp, pd, pf, sz, C.POINTER(sz)]
     L.flimo_update.argtypes = [vp, pd, pd, C.c_int, pd, dbl, dbl, C.POINTER(C.c_int)]
+    L.flimo_update_exchange.argtypes = [vp, pd, pd, C.c_int, pd, dbl, dbl, C.POINTER(C.c_int)]
     L.flimo_ekf_begin.argtypes = [vp, pd, pd, C.c_int, pd, dbl, dbl]
     L.flimo_ekf_state.argtypes = [vp, pd]
     L.flimo_ekf_step.argtypes = [vp, pd, pd, i64, C.POINTER(C.c_int)]

@@ -153,6 +153,21 @@ class Mapper:
         self._ck(self._L.flimo_match_reduce(self._h, _dp(st), _dp(HTH), _dp(HTh), C.byref(nv), C.byref(nr), C.byref(ss)))
         return PassResult(HTH, HTh, int(nv.value), int(nr.value), float(ss.value))
 
+    def exchange_attach(self, buf, rank, world):
+        """Attach a host segment shared by all ranks (flimo_exchange_attach); `buf` is a writable buffer."""
+        self._xch_keep = buf
+        addr = C.addressof(C.c_char.from_buffer(buf))
+        self._ck(self._L.flimo_exchange_attach(self._h, C.c_void_p(addr), len(buf), int(rank), int(world)))
+
+    def match_exchange(self, state) -> PassResult:
+        """One pass on this rank's shard, summed over all ranks through the shared segment."""
+        st = np.ascontiguousarray(np.asarray(state, np.float64)[:14])
+        HTH = np.zeros((12, 12), np.float64)
+        HTh = np.zeros(12, np.float64)
+        nv, nr, ss = C.c_int64(0), C.c_int64(0), C.c_double(0)
+        self._ck(self._L.flimo_match_reduce_exchange(self._h, _dp(st), _dp(HTH), _dp(HTh), C.byref(nv), C.byref(nr), C.byref(ss)))
+        return PassResult(HTH, HTh, int(nv.value), int(nr.value), float(ss.value))
+
     def match_async(self, state, d_out_ptr, stream=None):
         st = np.ascontiguousarray(np.asarray(state, np.float64)[:14])
         self._ck(self._L.flimo_match_reduce_async(self._h, _dp(st), C.c_void_p(d_out_ptr), C.c_void_p(stream or 0)))
@@ -191,6 +206,15 @@ class Mapper:
         lim = np.ascontiguousarray(np.broadcast_to(np.asarray(limits, np.float64), (23,)))
         passes = C.c_int(0)
         self._ck(self._L.flimo_update(self._h, _dp(x), _dp(Pm), int(max_iter), _dp(lim), float(R), float(D), C.byref(passes)))
+        return x, Pm, int(passes.value)
+
+    def update_exchange(self, state26, P, max_iter, limits, R=0.001, D=5.0):
+        """`update` with every pass summed over all ranks through the attached exchange segment."""
+        x = np.array(state26, np.float64).copy()
+        Pm = np.array(P, np.float64).reshape(23, 23).copy()
+        lim = np.ascontiguousarray(np.broadcast_to(np.asarray(limits, np.float64), (23,)))
+        passes = C.c_int(0)
+        self._ck(self._L.flimo_update_exchange(self._h, _dp(x), _dp(Pm), int(max_iter), _dp(lim), float(R), float(D), C.byref(passes)))
         return x, Pm, int(passes.value)
 
     def ekf_begin(self, state26, P, max_iter, limits, R=0.001, D=5.0):

@@ -55,6 +55,11 @@ struct flimo_ctx {
   double* h_out96 = nullptr;     // pinned + mapped host copy: 96 doubles + [96] sequence word
   double* d_h_out96 = nullptr;   // device alias of h_out96
   unsigned long long seq = 0;    // sequence number of the last blocking pass
+  // multi-process exchange segment (flimo_exchange_attach)
+  double* xch_host = nullptr;
+  double* xch_dev = nullptr;
+  int xch_rank = 0, xch_world = 0;
+  unsigned long long xch_seq = 0;
   struct ScanGraph {
     const void* src;
     size_t n, stride;
@@ -367,6 +372,7 @@ void flimo_destroy(flimo_handle h) {
   cudaFree(h->ticket);
   cudaFree(h->out96);
   for (auto& g : h->scan_graphs) cudaGraphExecDestroy(g.exec);
+  if (h->xch_host) cudaHostUnregister(h->xch_host);
   cudaFreeHost(h->h_out96);
   cudaFree(h->dbg16);
   cudaFree(h->valid_flags);
@@ -612,6 +618,85 @@ int flimo_scan_shard(flimo_handle h, size_t begin, size_t end) {
   return FLIMO_OK;
 }
 
+int flimo_exchange_attach(flimo_handle h, void* shared_host_mem, size_t bytes, int rank, int world) {
+  if (!h || !shared_host_mem || world < 1 || rank < 0 || rank >= world) return fail(h, FLIMO_ERR_INVALID, "bad exchange arguments");
+  if (bytes < (size_t)world * FLIMO_EXCHANGE_BYTES_PER_RANK) return fail(h, FLIMO_ERR_INVALID, "exchange segment too small");
+  NEED_GPU(h);
+  if (h->xch_host) {
+    cudaHostUnregister(h->xch_host);
+    h->xch_host = nullptr;
+  }
+  CU(h, cudaHostRegister(shared_host_mem, bytes, cudaHostRegisterMapped | cudaHostRegisterPortable));
+  CU(h, cudaHostGetDevicePointer(reinterpret_cast<void**>(&h->xch_dev), shared_host_mem, 0));
+  h->xch_host = static_cast<double*>(shared_host_mem);
+  h->xch_rank = rank;
+  h->xch_world = world;
+  h->xch_seq = 0;
+  return FLIMO_OK;
+}
+
+int flimo_match_reduce_exchange(flimo_handle h, const double state14[14], double HTH[144], double HTh[12], int64_t* n_valid,
+                                int64_t* n_rows, double* sum_sq_res) {
+  if (!h || !state14 || !HTH || !HTh) return fail(h, FLIMO_ERR_INVALID, "null argument");
+  NEED_GPU(h);
+  if (!h->xch_host) return fail(h, FLIMO_ERR_STATE, "flimo_exchange_attach not called");
+  const unsigned long long seq = ++h->xch_seq;
+  // two buffers per rank, alternating by sequence parity: a rank can be at most one pass ahead of a peer
+  // that is still reading (it needs that peer's data of the current pass to advance)
+  const size_t slot_doubles = FLIMO_EXCHANGE_BYTES_PER_RANK / sizeof(double);      // 256
+  const size_t buf_doubles = slot_doubles / 2;                                      // 128 (96 + flag + pad)
+  const size_t my_off = (size_t)h->xch_rank * slot_doubles + (seq & 1) * buf_doubles;
+  if (flimo_map_exists(h) && h->shard_end > h->shard_begin) {
+    MatchParams P;
+    int rc = fill_params(h, state14, P, h->out96, 0xFFFFFFFFu, nullptr, nullptr);
+    if (rc) return rc;
+    P.host_out96 = h->xch_dev + my_off;
+    P.seq = seq;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (h->ev_pool.size() >= 2) {
+      e0 = h->ev_pool.back(); h->ev_pool.pop_back();
+      e1 = h->ev_pool.back(); h->ev_pool.pop_back();
+    } else {
+      CU(h, cudaEventCreate(&e0));
+      CU(h, cudaEventCreate(&e1));
+    }
+    CU(h, cudaEventRecord(e0, h->stream));
+    CU(h, launch_match(P, h->stream));
+    CU(h, cudaEventRecord(e1, h->stream));
+    h->ev_pending.push_back(e0);
+    h->ev_pending.push_back(e1);
+    h->stats.kernel_launches++;
+    h->stats.match_launches++;
+  } else {                                         // nothing to match on this rank: publish zeros
+    double* mine = h->xch_host + my_off;
+    for (int i = 0; i < 96; ++i) mine[i] = 0.0;
+    std::atomic_thread_fence(std::memory_order_release);
+    *reinterpret_cast<volatile unsigned long long*>(mine + 96) = seq;
+  }
+  double packed[96];
+  for (int i = 0; i < 96; ++i) packed[i] = 0.0;
+  for (int r = 0; r < h->xch_world; ++r) {          // fixed rank order => identical sums on every rank
+    const double* slot = h->xch_host + (size_t)r * slot_doubles + (seq & 1) * buf_doubles;
+    volatile const unsigned long long* flag = reinterpret_cast<volatile const unsigned long long*>(slot + 96);
+    unsigned long long spins = 0;
+    while (*flag != seq) {
+      if ((++spins & 0x3FFFFF) == 0 && r == h->xch_rank) {
+        const cudaError_t q = cudaStreamQuery(h->stream);
+        if (q != cudaSuccess && q != cudaErrorNotReady) return fail(h, FLIMO_ERR_CUDA, std::string("match kernel: ") + cudaGetErrorString(q));
+      }
+      if (spins > (1ull << 36)) return fail(h, FLIMO_ERR_STATE, "exchange timed out waiting for a peer rank");
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+    for (int i = 0; i < 96; ++i) packed[i] += slot[i];
+  }
+  if (h->ev_pending.size() > 64) {
+    flimo_stats tmp;
+    flimo_get_stats(h, &tmp);
+  }
+  flimo_unpack96(packed, HTH, HTh, n_valid, n_rows, sum_sq_res);
+  return FLIMO_OK;
+}
+
 void flimo_unpack96(const double p[96], double HTH[144], double HTh[12], int64_t* n_valid, int64_t* n_rows,
                     double* sum_sq_res) {
   int e = 0;
@@ -769,6 +854,25 @@ int flimo_update(flimo_handle h, double state26[26], double P529[529], int max_i
     int64_t nv = 0, nr = 0;
     double ss = 0;
     int rc = flimo_match_reduce(h, x, HTH, HTh, &nv, &nr, &ss);
+    if (rc) return rc;
+    u.step(HTH, HTh, nr);
+  }
+  u.end(state26, P529);
+  if (passes_out) *passes_out = u.passes();
+  return FLIMO_OK;
+}
+
+int flimo_update_exchange(flimo_handle h, double state26[26], double P529[529], int max_iter, const double limit23[23],
+                          double R_noise, double D_degeneracy, int* passes_out) {
+  if (!h || !state26 || !P529 || !limit23) return fail(h, FLIMO_ERR_INVALID, "null argument");
+  ekf::IteratedUpdate& u = h->upd;
+  u.begin(state26, P529, max_iter, limit23, R_noise, D_degeneracy);
+  double x[26], HTH[144], HTh[12];
+  while (!u.done()) {
+    u.state(x);
+    int64_t nv = 0, nr = 0;
+    double ss = 0;
+    int rc = flimo_match_reduce_exchange(h, x, HTH, HTh, &nv, &nr, &ss);
     if (rc) return rc;
     u.step(HTH, HTh, nr);
   }

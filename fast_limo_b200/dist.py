@@ -46,3 +46,38 @@ def sharded_update(mapper, x0, P0, max_iter, limits, local_pass, all_reduce, R=0
         passes += 1
     x, P = mapper.ekf_end()
     return x, P, passes
+
+
+EXCHANGE_BYTES_PER_RANK = 2048
+
+
+def attach_exchange(mapper, rank, world, broadcast_object):
+    """Create (rank 0) / open a POSIX shared-memory segment for the fused exchange and attach it.
+
+    broadcast_object(obj_or_None) must return rank 0's object on every rank (e.g. a wrapper around
+    torch.distributed.broadcast_object_list).  Returns the SharedMemory object (keep it alive; rank 0
+    unlinks it at the end)."""
+    from multiprocessing import shared_memory
+    size = max(4096, world * EXCHANGE_BYTES_PER_RANK)
+    size = (size + 4095) // 4096 * 4096
+    if rank == 0:
+        shm = shared_memory.SharedMemory(create=True, size=size)
+        shm.buf[:size] = bytes(size)
+        name = broadcast_object(shm.name)
+    else:
+        name = broadcast_object(None)
+        shm = shared_memory.SharedMemory(name=name)
+    mapper.exchange_attach(shm.buf, rank, world)
+    return shm
+
+
+def sharded_update_exchange(mapper, x0, P0, max_iter, limits, R=0.001, D=5.0):
+    """sharded_update with the measurement pass + exchange done by flimo_match_reduce_exchange."""
+    mapper.ekf_begin(x0, P0, max_iter, limits, R, D)
+    passes, done = 0, max_iter < 0
+    while not done:
+        r = mapper.match_exchange(mapper.ekf_state())
+        done = mapper.ekf_step(r.HTH, r.HTh, r.n_rows)
+        passes += 1
+    x, P = mapper.ekf_end()
+    return x, P, passes

@@ -113,6 +113,23 @@ int flimo_match_reduce(flimo_handle h, const double state14[14], double HTH[144]
  * whole-scan normal equations.  MAX_NUM_MATCHES truncation is NOT applied in this form unless
  * n_valid <= MAX_NUM_MATCHES on every shard (the blocking form handles the general case). */
 int flimo_match_reduce_async(flimo_handle h, const double state14[14], double* d_out96, void* cuda_stream);
+/* Fused exchange for ranks that are processes of ONE node (alternative to the NCCL all-reduce above):
+ * `shared_host_mem` is a host segment mapped by every rank (e.g. POSIX shared memory), at least
+ * world * FLIMO_EXCHANGE_BYTES_PER_RANK bytes, zero-initialised by its creator.  The library pins and
+ * maps it (cudaHostRegister) so that the LAST CTA of the measurement kernel stores this rank's 96 packed
+ * doubles and a sequence word straight into its slot; flimo_match_reduce_exchange then spins until the
+ * slots of all ranks carry the same sequence number and sums them in rank order (deterministic).  No
+ * D2H copy, no stream synchronise, no collective launch: ~2 us after the slowest rank's kernel ends.
+ * Every rank must make the same sequence of flimo_match_reduce_exchange calls. */
+#define FLIMO_EXCHANGE_BYTES_PER_RANK 2048
+int flimo_exchange_attach(flimo_handle h, void* shared_host_mem, size_t bytes, int rank, int world);
+int flimo_match_reduce_exchange(flimo_handle h, const double state14[14], double HTH[144], double HTh[12],
+                                int64_t* n_valid, int64_t* n_rows, double* sum_sq_res);
+
+/* flimo_update with every measurement pass summed over ranks through the exchange segment. */
+int flimo_update_exchange(flimo_handle h, double state26[26], double P529[529], int max_iter,
+                          const double limit23[23], double R_noise, double D_degeneracy, int* passes_out);
+
 /* Expands the 96-double packed form into HTH/HTh/... on the host. */
 void flimo_unpack96(const double packed[96], double HTH[144], double HTh[12], int64_t* n_valid,
                     int64_t* n_rows, double* sum_sq_res);

@@ -298,3 +298,51 @@ def test_insert_tiny_first_scan(oracle, flimo_lib):
         assert m.size() == om.size()
     m.add(np.full((4, 3), np.nan, np.float32))
     assert m.size() == om.size()
+
+
+def _xch_worker(rank, world, name, out):
+    from multiprocessing import shared_memory
+    from fast_limo_b200.dist import shard_bounds
+    case = synth.make_case("tiny")
+    m = mapper()
+    m.add(case.map_pts)
+    shm = shared_memory.SharedMemory(name=name)
+    m.exchange_attach(shm.buf, rank, world)
+    m.set_scan(case.scan)
+    m.shard(*shard_bounds(case.scan.shape[0], rank, world))
+    res = []
+    for rep in range(3):                                   # several updates: sequence numbers keep advancing
+        x, P, passes = m.update_exchange(case.init, synth.default_P0(), 2, 0.0)
+        res.append((x, P, passes))
+    out[rank] = res
+    m.close()
+    shm.close()
+
+
+@pytest.mark.timeout(600)
+def test_fused_exchange_two_processes(oracle, flimo_lib):
+    """Scan sharded over two PROCESSES (sharing cuda:0 here), partial sums exchanged through the mapped
+    host segment written by the kernels' last CTAs: every rank must end in the identical state, equal to
+    the single-process update."""
+    import torch.multiprocessing as mp
+    from multiprocessing import shared_memory
+    world = 2
+    shm = shared_memory.SharedMemory(create=True, size=4096)
+    shm.buf[:4096] = bytes(4096)
+    try:
+        mgr = mp.Manager()
+        out = mgr.dict()
+        mp.spawn(_xch_worker, args=(world, shm.name, out), nprocs=world, join=True)
+    finally:
+        shm.close()
+        shm.unlink()
+    case = synth.make_case("tiny")
+    m = mapper()
+    m.add(case.map_pts)
+    m.set_scan(case.scan)
+    x1, P1, p1 = m.update(case.init, synth.default_P0(), 2, 0.0)
+    for rep in range(3):
+        (xa, Pa, pa), (xb, Pb, pb) = out[0][rep], out[1][rep]
+        assert pa == pb == p1 == 3
+        assert np.array_equal(xa, xb) and np.array_equal(Pa, Pb)
+        assert np.abs(xa - x1).max() <= 1e-10 and np.allclose(Pa, P1, rtol=1e-4, atol=1e-11)
