@@ -34,6 +34,7 @@ class FlimoCfg(C.Structure):
         ("knn_cell", C.c_float),
         ("sort_scan", C.c_int32),
         ("knn_level_ratio", C.c_float),
+        ("knn_tau", C.c_int32),
     ]
 
 

@@ -34,7 +34,8 @@ class MappingConfig:
     octree_downsampling: bool = True
     knn_cell: float = 0.0                # extension: device grid cell (0 = auto)
     sort_scan: bool = False              # extension: Morton-sort the scan on upload (default: in-kernel scatter instead)
-    knn_level_ratio: float = 0.0         # extension: cell growth between index levels (0 = 1.5)
+    knn_level_ratio: float = 0.0         # extension: cell growth between index levels (0 = sqrt 2)
+    knn_tau: int = 0                     # extension: candidates-per-block threshold of the level choice (0 = 24)
 
 
 def _dp(a):
@@ -79,6 +80,7 @@ class Mapper:
         c.knn_cell = float(cfg.knn_cell)
         c.sort_scan = int(bool(cfg.sort_scan))
         c.knn_level_ratio = float(cfg.knn_level_ratio)
+        c.knn_tau = int(cfg.knn_tau)
         if self._h:
             self._L.flimo_destroy(self._h)
             self._h = C.c_void_p()
@@ -180,7 +182,8 @@ class Mapper:
         got = C.c_size_t(0)
         self._ck(self._L.flimo_match_debug(self._h, _dp(st), _fp(out), n, C.byref(got)))
         out = out[:n]
-        return dict(world=out[:, 0:3], plane=out[:, 3:7], dist=out[:, 7], good=out[:, 8] > 0.5, nn_d2=out[:, 9:14])
+        return dict(world=out[:, 0:3], plane=out[:, 3:7], dist=out[:, 7], good=out[:, 8] > 0.5, nn_d2=out[:, 9:14],
+                    levels=out[:, 14].astype(np.int32), first_count=out[:, 15].astype(np.int32))
 
     def scan_to_world(self, state):
         st = np.ascontiguousarray(np.asarray(state, np.float64)[:14])

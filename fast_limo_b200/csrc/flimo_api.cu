@@ -17,6 +17,10 @@
 
 using namespace flimo;
 
+constexpr float kDefaultCell = 0.15f;      // finest grid of the ladder (metres)
+constexpr float kDefaultRatio = 1.41421356f;
+constexpr int kDefaultTau = 24;
+
 struct flimo_ctx {
   flimo_cfg cfg{};
   int device = 0;
@@ -52,7 +56,7 @@ struct flimo_ctx {
   unsigned int* ticket = nullptr;
   size_t ticket_cap = 0;
   double* out96 = nullptr;       // device
-  double* h_out96 = nullptr;     // pinned + mapped host copy: 96 doubles + [96] sequence word
+  double* h_out96 = nullptr;     // pinned + mapped host copy: 96 records {double value, u64 seq} (kernel tail)
   double* d_h_out96 = nullptr;   // device alias of h_out96
   unsigned long long seq = 0;    // sequence number of the last blocking pass
   // multi-process exchange segment (flimo_exchange_attach)
@@ -74,6 +78,9 @@ struct flimo_ctx {
   float* xyz_out = nullptr;
   unsigned long long* timing = nullptr;   // tools/warp_timing.py only
   size_t xyz_cap = 0;
+
+  int knn_tau = 24;              // level choice threshold (MatchParams::tau)
+  int probe_mode = 0, wide_loads = 1;
 
   ekf::IteratedUpdate upd;
   bool upd_active = false;
@@ -220,8 +227,11 @@ int fill_params(flimo_handle h, const double state14[14], MatchParams& P, double
   }
   make_pose(state14, P.pc);
   P.q_begin = (int)h->shard_begin;
-  P.perm_stride = h->cfg.sort_scan ? 0u : coprime_stride((uint32_t)n);   // unsorted scans are scattered instead
+  P.interleave = h->cfg.sort_scan ? 1 : 0;   // unsorted scans are stored scattered instead (scan_prepare)
   P.q_end = (int)h->shard_end;
+  P.tau = h->knn_tau;
+  P.probe_mode = h->probe_mode;
+  P.wide_loads = h->wide_loads;
   P.max_dist_f = ceil_to_float(h->cfg.MAX_DIST_PLANE);
   P.plane_thr = (float)h->cfg.PLANE_THRESHOLD;
   P.estimate_extrinsics = h->cfg.estimate_extrinsics;
@@ -237,9 +247,33 @@ int fill_params(flimo_handle h, const double state14[14], MatchParams& P, double
   return FLIMO_OK;
 }
 
-// Blocking pass.  The last CTA of the kernel also writes the 96 result doubles and then a sequence
-// word into MAPPED pinned host memory; the host spins on that word instead of issuing a D2H copy and
-// a stream synchronise (saves ~10 us of launch/sync latency per pass).  Device time is taken from a
+// Waits until all 96 records {double value, u64 seq} of a result block in mapped host memory carry
+// `seq` and copies the values out.  Each record is written by the kernel with ONE 16-byte store, so
+// value and sequence word become visible together: reading the sequence word first (x86 keeps load
+// order) makes the value that follows current.  Returns 0, 1 (own kernel finished without
+// publishing; only when `own`), or a negative status.
+int wait_records(flimo_handle h, const double* block, unsigned long long seq, double out[96], bool own) {
+  const volatile unsigned long long* rec = reinterpret_cast<const volatile unsigned long long*>(block);
+  unsigned long long spins = 0;
+  for (int i = 95; i >= 0; --i) {
+    while (rec[2 * i + 1] != seq) {
+      if ((++spins & 0xFFFFF) == 0 && own) {              // every ~1M polls: has the kernel died?
+        const cudaError_t q = cudaStreamQuery(h->stream);
+        if (q != cudaSuccess && q != cudaErrorNotReady) return fail(h, FLIMO_ERR_CUDA, std::string("match kernel: ") + cudaGetErrorString(q));
+        if (q == cudaSuccess && rec[2 * i + 1] != seq) return 1;
+      }
+      if (spins > (1ull << 36)) return fail(h, FLIMO_ERR_STATE, "timed out waiting for a measurement result");
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+    unsigned long long bits = rec[2 * i];
+    std::memcpy(&out[i], &bits, sizeof(double));
+  }
+  return 0;
+}
+
+// Blocking pass.  The last CTA of the kernel also writes the 96 result doubles, each tagged with a
+// sequence number, into MAPPED pinned host memory; the host spins on those records instead of issuing a
+// D2H copy and a stream synchronise (saves ~10 us of launch/sync latency per pass).  Device time is taken from a
 // pair of events that is resolved lazily in flimo_get_stats.
 int run_pass_blocking(flimo_handle h, const double state14[14], uint32_t orig_limit, float* dbg, uint8_t* valid,
                       double packed[96]) {
@@ -263,20 +297,12 @@ int run_pass_blocking(flimo_handle h, const double state14[14], uint32_t orig_li
   h->ev_pending.push_back(e1);
   h->stats.kernel_launches++;
   h->stats.match_launches++;
-  volatile unsigned long long* flag = reinterpret_cast<volatile unsigned long long*>(h->h_out96 + 96);
-  unsigned long long spins = 0;
-  while (*flag != P.seq) {
-    if ((++spins & 0xFFFFF) == 0) {                       // every ~1M polls: has the kernel died?
-      const cudaError_t q = cudaStreamQuery(h->stream);
-      if (q != cudaSuccess && q != cudaErrorNotReady) return fail(h, FLIMO_ERR_CUDA, std::string("match kernel: ") + cudaGetErrorString(q));
-      if (q == cudaSuccess && *flag != P.seq) {           // finished without the flag: treat as failure
-        CU(h, cudaMemcpy(h->h_out96, h->out96, 96 * sizeof(double), cudaMemcpyDeviceToHost));
-        break;
-      }
-    }
+  const int wr = wait_records(h, h->h_out96, P.seq, packed, true);
+  if (wr == 1) {                                           // finished without publishing: read the device copy
+    CU(h, cudaMemcpy(packed, h->out96, 96 * sizeof(double), cudaMemcpyDeviceToHost));
+  } else if (wr < 0) {
+    return wr;
   }
-  std::atomic_thread_fence(std::memory_order_acquire);
-  std::memcpy(packed, h->h_out96, 96 * sizeof(double));
   if (h->ev_pending.size() > 64) {                         // keep the lazy list short
     flimo_stats tmp;
     flimo_get_stats(h, &tmp);
@@ -304,6 +330,7 @@ void flimo_cfg_default(flimo_cfg* c) {
   c->knn_cell = 0.f;
   c->sort_scan = 0;
   c->knn_level_ratio = 0.f;
+  c->knn_tau = 0;
 }
 
 const char* flimo_last_error(flimo_handle h) { return h ? h->err.c_str() : g_err.c_str(); }
@@ -335,14 +362,25 @@ int flimo_create(const flimo_cfg* cfg, int device, flimo_handle* out) {
   if (!h) return fail(nullptr, FLIMO_ERR_NOMEM, "host allocation failed");
   h->cfg = *cfg;
   h->device = device;
+  // index ladder: finest cell, growth ratio, candidates-per-block threshold.  The FLIMO_KNN_* environment
+  // variables override the configuration (tuning runs of tools/ only).
+  if (const char* e = std::getenv("FLIMO_KNN_CELL")) h->cfg.knn_cell = (float)std::atof(e);
+  if (const char* e = std::getenv("FLIMO_KNN_RATIO")) h->cfg.knn_level_ratio = (float)std::atof(e);
+  if (const char* e = std::getenv("FLIMO_KNN_TAU")) h->cfg.knn_tau = std::atoi(e);
+  if (!(h->cfg.knn_cell > 0.f)) h->cfg.knn_cell = kDefaultCell;
+  if (!(h->cfg.knn_level_ratio > 1.05f)) h->cfg.knn_level_ratio = kDefaultRatio;
+  if (h->cfg.knn_tau <= 0) h->cfg.knn_tau = kDefaultTau;
+  h->knn_tau = h->cfg.knn_tau;
+  if (const char* e = std::getenv("FLIMO_KNN_PROBE")) h->probe_mode = std::atoi(e);
+  if (const char* e = std::getenv("FLIMO_KNN_WIDE")) h->wide_loads = std::atoi(e);
   CU(h, cudaSetDevice(device));
   CU(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   CU(h, cudaEventCreate(&h->ev0));
   CU(h, cudaEventCreate(&h->ev1));
   CU(h, cudaMalloc(&h->out96, 96 * sizeof(double)));
   CU(h, cudaMemset(h->out96, 0, 96 * sizeof(double)));
-  CU(h, cudaHostAlloc(&h->h_out96, 104 * sizeof(double), cudaHostAllocMapped));
-  std::memset(h->h_out96, 0, 104 * sizeof(double));
+  CU(h, cudaHostAlloc(&h->h_out96, 2 * 96 * sizeof(double), cudaHostAllocMapped));
+  std::memset(h->h_out96, 0, 2 * 96 * sizeof(double));
   CU(h, cudaHostGetDevicePointer(reinterpret_cast<void**>(&h->d_h_out96), h->h_out96, 0));
   CU(h, cudaMalloc(&h->d_count, sizeof(unsigned int)));
   *out = h;
@@ -393,12 +431,12 @@ int flimo_debug_timing(flimo_handle h, int enable, unsigned long long* host_out,
   if (!h || h->device < 0) return FLIMO_ERR_INVALID;
   cudaSetDevice(h->device);
   if (enable && !h->timing) {
-    if (cudaMalloc(&h->timing, n_warps * 6 * sizeof(unsigned long long)) != cudaSuccess) return FLIMO_ERR_NOMEM;
-    cudaMemset(h->timing, 0, n_warps * 6 * sizeof(unsigned long long));
+    if (cudaMalloc(&h->timing, n_warps * 8 * sizeof(unsigned long long)) != cudaSuccess) return FLIMO_ERR_NOMEM;
+    cudaMemset(h->timing, 0, n_warps * 8 * sizeof(unsigned long long));
   }
   if (host_out && h->timing) {
     cudaStreamSynchronize(h->stream);
-    cudaMemcpy(host_out, h->timing, n_warps * 6 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    cudaMemcpy(host_out, h->timing, n_warps * 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
   }
   if (!enable && h->timing) {
     cudaFree(h->timing);
@@ -556,6 +594,7 @@ int flimo_scan_set_device(flimo_handle h, const void* d_xyz, size_t n, size_t st
   h->shard_end = nq;
   if (nq == 0) return FLIMO_OK;
   const int sort = (h->cfg.sort_scan && nq > 1) ? 1 : 0;
+  const unsigned int perm = sort ? 0u : coprime_stride((uint32_t)nq);
   // The upload pipeline (pack + Morton keys, radix sort, gather: 7 launches) is captured once per
   // (source pointer, size) into a CUDA graph and replayed with a single launch afterwards.
   for (auto& g : h->scan_graphs) {
@@ -575,14 +614,14 @@ int flimo_scan_set_device(flimo_handle h, const void* d_xyz, size_t n, size_t st
   cudaGraphExec_t exec = nullptr;
   uint64_t dummy = 0;
   CU(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
-  const cudaError_t ce = scan_prepare(d_xyz, nq, stride_bytes, sort != 0, h->scan, h->scan_tmp, &h->scan_cub, &h->scan_cub_bytes,
+  const cudaError_t ce = scan_prepare(d_xyz, nq, stride_bytes, sort != 0, perm, h->scan, h->scan_tmp, &h->scan_cub, &h->scan_cub_bytes,
                                       &h->scan_keys, &h->scan_keys_cap, h->stream, &dummy);
   const cudaError_t ee = cudaStreamEndCapture(h->stream, &graph);
   if (ce != cudaSuccess || ee != cudaSuccess || graph == nullptr) {
     if (graph) cudaGraphDestroy(graph);
     cudaGetLastError();
     // capture unavailable: run the pipeline directly
-    CU(h, scan_prepare(d_xyz, nq, stride_bytes, sort != 0, h->scan, h->scan_tmp, &h->scan_cub, &h->scan_cub_bytes, &h->scan_keys,
+    CU(h, scan_prepare(d_xyz, nq, stride_bytes, sort != 0, perm, h->scan, h->scan_tmp, &h->scan_cub, &h->scan_cub_bytes, &h->scan_keys,
                        &h->scan_keys_cap, h->stream, &h->stats.kernel_launches));
     return FLIMO_OK;
   }
@@ -643,8 +682,8 @@ int flimo_match_reduce_exchange(flimo_handle h, const double state14[14], double
   const unsigned long long seq = ++h->xch_seq;
   // two buffers per rank, alternating by sequence parity: a rank can be at most one pass ahead of a peer
   // that is still reading (it needs that peer's data of the current pass to advance)
-  const size_t slot_doubles = FLIMO_EXCHANGE_BYTES_PER_RANK / sizeof(double);      // 256
-  const size_t buf_doubles = slot_doubles / 2;                                      // 128 (96 + flag + pad)
+  const size_t slot_doubles = FLIMO_EXCHANGE_BYTES_PER_RANK / sizeof(double);      // 512
+  const size_t buf_doubles = slot_doubles / 2;                                      // 256 (96 records of 16 bytes + pad)
   const size_t my_off = (size_t)h->xch_rank * slot_doubles + (seq & 1) * buf_doubles;
   if (flimo_map_exists(h) && h->shard_end > h->shard_begin) {
     MatchParams P;
@@ -668,26 +707,20 @@ int flimo_match_reduce_exchange(flimo_handle h, const double state14[14], double
     h->stats.kernel_launches++;
     h->stats.match_launches++;
   } else {                                         // nothing to match on this rank: publish zeros
-    double* mine = h->xch_host + my_off;
-    for (int i = 0; i < 96; ++i) mine[i] = 0.0;
+    volatile unsigned long long* mine = reinterpret_cast<volatile unsigned long long*>(h->xch_host + my_off);
+    for (int i = 0; i < 96; ++i) mine[2 * i] = 0ull;
     std::atomic_thread_fence(std::memory_order_release);
-    *reinterpret_cast<volatile unsigned long long*>(mine + 96) = seq;
+    for (int i = 0; i < 96; ++i) mine[2 * i + 1] = seq;
   }
   double packed[96];
   for (int i = 0; i < 96; ++i) packed[i] = 0.0;
   for (int r = 0; r < h->xch_world; ++r) {          // fixed rank order => identical sums on every rank
     const double* slot = h->xch_host + (size_t)r * slot_doubles + (seq & 1) * buf_doubles;
-    volatile const unsigned long long* flag = reinterpret_cast<volatile const unsigned long long*>(slot + 96);
-    unsigned long long spins = 0;
-    while (*flag != seq) {
-      if ((++spins & 0x3FFFFF) == 0 && r == h->xch_rank) {
-        const cudaError_t q = cudaStreamQuery(h->stream);
-        if (q != cudaSuccess && q != cudaErrorNotReady) return fail(h, FLIMO_ERR_CUDA, std::string("match kernel: ") + cudaGetErrorString(q));
-      }
-      if (spins > (1ull << 36)) return fail(h, FLIMO_ERR_STATE, "exchange timed out waiting for a peer rank");
-    }
-    std::atomic_thread_fence(std::memory_order_acquire);
-    for (int i = 0; i < 96; ++i) packed[i] += slot[i];
+    double vals[96];
+    const int wr = wait_records(h, slot, seq, vals, r == h->xch_rank);
+    if (wr < 0) return wr;
+    if (wr == 1) return fail(h, FLIMO_ERR_CUDA, "match kernel finished without publishing its result");
+    for (int i = 0; i < 96; ++i) packed[i] += vals[i];
   }
   if (h->ev_pending.size() > 64) {
     flimo_stats tmp;

@@ -25,7 +25,7 @@ struct GridDesc {
   int nx, ny, nz;
 };
 
-constexpr int kMaxLevels = 8;
+constexpr int kMaxLevels = 12;
 
 struct LevelView {
   const float4* pts;           // super-row storage (9x duplicated), sorted by (row, ix)
@@ -53,7 +53,10 @@ struct MatchParams {
   int n_levels;
   PoseConsts pc;
   int q_begin, q_end;          // slice of the scan handled by this launch
-  unsigned int perm_stride;    // multiplicative scatter of the query order (co-prime with the slice length; 0 = off)
+  int interleave;              // 1 = slot s of tile t takes stored point s*n_tiles+t (Morton-sorted scans); 0 = tiles are contiguous
+  int tau;                     // level choice: finest level whose 3x3x3 block holds >= tau candidates
+  int probe_mode;              // 0 = probe all levels at once, 1 = climb one level at a time
+  int wide_loads;              // 1 = 256-bit candidate loads
   float max_dist_f;            // smallest float >= MAX_DIST_PLANE  (d2_5 < MAX_DIST_PLANE test)
   float plane_thr;             // (float)PLANE_THRESHOLD
   int estimate_extrinsics;
@@ -63,8 +66,8 @@ struct MatchParams {
   double* out96;               // packed result (see flimo.h)
   float* dbg16;                // optional per-point record [n][16], indexed by original index
   uint8_t* valid_by_orig;      // optional accepted flag per original index
-  double* host_out96;          // optional mapped pinned copy of the result (+ [96] = sequence number)
-  unsigned long long seq;      // value written to host_out96[96] when the result is complete
+  double* host_out96;          // optional mapped pinned copy of the result: 96 records {double value, u64 seq}
+  unsigned long long seq;      // sequence number stored with every record
   unsigned long long* timing;  // optional per-warp timestamps (profiling builds of the tools only)
 };
 
@@ -105,7 +108,7 @@ cudaError_t pack_points(const void* d_src, size_t n, size_t stride_bytes, float4
 // Packs a scan: float4 with w = original index bits (no NaN filtering: the reference matches them
 // and they simply fail the kNN gate).
 cudaError_t pack_scan(const void* d_src, size_t n, size_t stride_bytes, float4* dst, cudaStream_t st);
-cudaError_t scan_prepare(const void* d_src, size_t n, size_t stride_bytes, bool sort, float4* scan, float4* tmp, void** cub_tmp,
+cudaError_t scan_prepare(const void* d_src, size_t n, size_t stride_bytes, bool sort, unsigned int perm_stride, float4* scan, float4* tmp, void** cub_tmp,
                          size_t* cub_tmp_bytes, uint32_t** keys, size_t* keys_cap, cudaStream_t st, uint64_t* launches);
 cudaError_t scan_prepare_reserve(size_t n, void** cub_tmp, size_t* cub_tmp_bytes, uint32_t** keys, size_t* keys_cap);
 cudaError_t transform_scan(const float4* scan, size_t n, const PoseConsts& pc, float* d_out_xyz, cudaStream_t st);

@@ -142,12 +142,16 @@ __global__ void __launch_bounds__(256) pack_points_kernel(const unsigned char* _
   if (keep) dst[base + __popc(m & ((1u << lane) - 1))] = make_float4(x, y, z, 0.f);
 }
 
+// Scan upload: float4 with w = original index.  perm_stride != 0 stores point i at position
+// (i * perm_stride) mod n (stride co-prime with n, ~0.618 n): a fixed pseudo-random order, so that
+// the tiles of the match kernel mix points of every region of the scan.
 __global__ void __launch_bounds__(256) pack_scan_kernel(const unsigned char* __restrict__ src, size_t n, size_t stride,
-                                                        float4* __restrict__ dst) {
+                                                        unsigned int perm_stride, float4* __restrict__ dst) {
   const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float* p = reinterpret_cast<const float*>(src + i * stride);
-  dst[i] = make_float4(p[0], p[1], p[2], __uint_as_float((unsigned int)i));
+  const size_t at = perm_stride ? (size_t)(((unsigned long long)i * perm_stride) % (unsigned long long)n) : i;
+  dst[at] = make_float4(p[0], p[1], p[2], __uint_as_float((unsigned int)i));
 }
 
 __device__ __forceinline__ uint32_t spread10(uint32_t v) {
@@ -190,7 +194,7 @@ cudaError_t pack_points(const void* d_src, size_t n, size_t stride_bytes, float4
 
 cudaError_t pack_scan(const void* d_src, size_t n, size_t stride_bytes, float4* dst, cudaStream_t st) {
   if (n == 0) return cudaSuccess;
-  pack_scan_kernel<<<nblk(n), 256, 0, st>>>(static_cast<const unsigned char*>(d_src), n, stride_bytes, dst);
+  pack_scan_kernel<<<nblk(n), 256, 0, st>>>(static_cast<const unsigned char*>(d_src), n, stride_bytes, 0u, dst);
   return cudaGetLastError();
 }
 
@@ -231,11 +235,11 @@ __global__ void __launch_bounds__(256) pack_scan_keys_kernel(const unsigned char
   vals[i] = (uint32_t)i;
 }
 
-cudaError_t scan_prepare(const void* d_src, size_t n, size_t stride_bytes, bool sort, float4* scan, float4* tmp, void** cub_tmp,
+cudaError_t scan_prepare(const void* d_src, size_t n, size_t stride_bytes, bool sort, unsigned int perm_stride, float4* scan, float4* tmp, void** cub_tmp,
                          size_t* cub_tmp_bytes, uint32_t** keys, size_t* keys_cap, cudaStream_t st, uint64_t* launches) {
   if (n == 0) return cudaSuccess;
   if (!sort || n < 2) {
-    pack_scan_kernel<<<nblk(n), 256, 0, st>>>(static_cast<const unsigned char*>(d_src), n, stride_bytes, scan);
+    pack_scan_kernel<<<nblk(n), 256, 0, st>>>(static_cast<const unsigned char*>(d_src), n, stride_bytes, perm_stride, scan);
     if (launches) *launches += 1;
     return cudaGetLastError();
   }
@@ -343,7 +347,7 @@ static cudaError_t build_level(MapIndex& idx, LevelIndex& L, const GridDesc& g, 
     L.pts = nullptr;
     L.cap_entries = 0;
     const size_t cap = 9 * idx.cap_pts;
-    FL_TRY(cudaMalloc(&L.pts, cap * sizeof(float4)));
+    FL_TRY(cudaMalloc(&L.pts, (cap + 8) * sizeof(float4)));     // + slack: the search reads whole 32-byte pairs
     L.cap_entries = cap;
   }
   L.g = g;
@@ -384,8 +388,8 @@ cudaError_t map_index_build(MapIndex& idx, float cell0, float ratio, float coars
     idx.lo[a] = ord2f(hb[a]);
     idx.hi[a] = ord2f(hb[3 + a]);
   }
-  if (!(cell0 > 0.f)) cell0 = 0.25f;
-  if (!(ratio > 1.05f)) ratio = 1.5f;
+  if (!(cell0 > 0.f)) cell0 = 0.15f;
+  if (!(ratio > 1.05f)) ratio = 1.41421356f;
   for (;;) {   // finest level must fit the table budget
     const GridDesc g = make_grid(idx.lo, idx.hi, cell0);
     if ((double)g.nx * g.ny * g.nz <= (double)max_cells) break;

@@ -101,16 +101,40 @@ __device__ __forceinline__ float sqdist(float qx, float qy, float qz, const floa
 
 constexpr uint32_t kPrivateCap = 96;   // longest run a single thread scans by itself
 
-// Thread-private scan of a short run (level 0, <= kPrivateCap candidates).  Returns false when the
-// packed selection cannot be proven exact (or the run is too long): the caller then hands the query
-// to the warp-cooperative exact scan below.  On success t.d[] holds the exact ascending squared
-// distances of the block's five nearest points and t.i[] their positions in L.pts (+inf / 0 if missing).
-__device__ __forceinline__ bool block_scan_private(const LevelView& L, int hx, int hy, int hz, float qx, float qy, float qz,
+// Two consecutive super-row entries with ONE 256-bit load (LDG.E.256, sm_100): each lane streams
+// its own run, so every load instruction costs one L1 wavefront per lane whatever its width —
+// 32 bytes per wavefront instead of 16 halves the wavefront count of the scan.
+struct Pair {
+  float ax, ay, az, aw, bx, by, bz, bw;
+};
+template <bool kWide>
+__device__ __forceinline__ Pair ldg_pair(const float4* p) {
+  Pair r;
+  if (kWide) {
+    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=f"(r.ax), "=f"(r.ay), "=f"(r.az), "=f"(r.aw), "=f"(r.bx), "=f"(r.by), "=f"(r.bz), "=f"(r.bw)
+        : "l"(p));
+  } else {
+    const float4 a = __ldg(p), b = __ldg(p + 1);
+    r.ax = a.x; r.ay = a.y; r.az = a.z; r.aw = a.w;
+    r.bx = b.x; r.by = b.y; r.bz = b.z; r.bw = b.w;
+  }
+  return r;
+}
+__device__ __forceinline__ float sqdist3(float qx, float qy, float qz, float px, float py, float pz) {
+  const float dx = qx - px, dy = qy - py, dz = qz - pz;
+  return dx * dx + (dy * dy + dz * dz);               // Eigen Vector3f::squaredNorm order
+}
+
+// Thread-private scan of a short run [s, e) of level L (<= kPrivateCap candidates).  Returns false
+// when the packed selection cannot be proven exact (or the run is too long): the caller then hands
+// the query to the warp-cooperative exact scan below.  On success t.d[] holds the exact ascending
+// squared distances of the block's five nearest points and t.i[] their positions in L.pts (+inf / 0
+// if missing).  The run is read from its 32-byte aligned start a = s & ~1; ordinals are relative to a,
+// the (at most one) leading entry before s is masked, trailing entries are never ranked.
+template <bool kWide>
+__device__ __forceinline__ bool block_scan_private(const LevelView& L, uint32_t s, uint32_t e, float qx, float qy, float qz,
                                                    Top5& t) {
-  const GridDesc& G = L.g;
-  const int row = (hz * G.ny + hy) * G.nx;
-  const uint32_t s = __ldg(&L.cell_start[row + max(hx - 1, 0)]);
-  const uint32_t e = __ldg(&L.cell_start[row + min(hx + 1, G.nx - 1) + 1]);
   const uint32_t total = e - s;
 #pragma unroll
   for (int j = 0; j < 5; ++j) {
@@ -119,35 +143,38 @@ __device__ __forceinline__ bool block_scan_private(const LevelView& L, int hx, i
   }
   if (total == 0) return true;
   if (total > kPrivateCap) return false;
-  const int B = 32 - __clz(total);               // ordinals 0..total-1 fit in B bits (B <= 7)
-  const float4* __restrict__ pts = L.pts + s;
+  const uint32_t a = s & ~1u;
+  const uint32_t tot = (s - a) + total;          // ordinals [s - a, tot) are candidates
+  const int B = 32 - __clz(tot);                 // ordinals 0..tot-1 fit in B bits (B <= 7)
+  const float4* __restrict__ pts = L.pts + a;
   const uint32_t low = (1u << B) - 1u;
+  const float inf = __int_as_float(0x7f800000);
+  float lead = (s != a) ? inf : 0.f;             // raises the masked leading entry's distance to +inf
   float k[6];
 #pragma unroll
-  for (int j = 0; j < 6; ++j) k[j] = __int_as_float(0x7f800000);
+  for (int j = 0; j < 6; ++j) k[j] = inf;
 
-  // software-pipelined: the next four points are in flight while the current four are ranked
-  const uint32_t last = total - 1;
-  float4 a0 = __ldg(&pts[0]), a1 = __ldg(&pts[min(1u, last)]), a2 = __ldg(&pts[min(2u, last)]), a3 = __ldg(&pts[min(3u, last)]);
+  // software-pipelined: the next two pairs are in flight while the current two are ranked
+  const uint32_t last = (tot - 1) & ~1u;         // first entry of the last pair
+  Pair a0 = ldg_pair<kWide>(pts), a1 = ldg_pair<kWide>(pts + min(2u, last));
   uint32_t n = 0;
 #pragma unroll 1
-  for (; n + 4 <= total; n += 4) {
-    const float4 p0 = a0, p1 = a1, p2 = a2, p3 = a3;
-    a0 = __ldg(&pts[min(n + 4, last)]);
-    a1 = __ldg(&pts[min(n + 5, last)]);
-    a2 = __ldg(&pts[min(n + 6, last)]);
-    a3 = __ldg(&pts[min(n + 7, last)]);
-    const float d0 = sqdist(qx, qy, qz, p0), d1 = sqdist(qx, qy, qz, p1), d2 = sqdist(qx, qy, qz, p2),
-                d3 = sqdist(qx, qy, qz, p3);
+  for (; n + 4 <= tot; n += 4) {
+    const Pair p0 = a0, p1 = a1;
+    a0 = ldg_pair<kWide>(pts + min(n + 4, last));
+    a1 = ldg_pair<kWide>(pts + min(n + 6, last));
+    const float d0 = fmaxf(sqdist3(qx, qy, qz, p0.ax, p0.ay, p0.az), lead), d1 = sqdist3(qx, qy, qz, p0.bx, p0.by, p0.bz),
+                d2 = sqdist3(qx, qy, qz, p1.ax, p1.ay, p1.az), d3 = sqdist3(qx, qy, qz, p1.bx, p1.by, p1.bz);
+    lead = 0.f;
     keys6_insert(k, pack_key(d0, low, n));
     keys6_insert(k, pack_key(d1, low, n + 1));
     keys6_insert(k, pack_key(d2, low, n + 2));
     keys6_insert(k, pack_key(d3, low, n + 3));
   }
-  // tail (< 4 candidates): a0..a2 already hold pts[n], pts[n+1], pts[n+2] (clamped)
-  if (n < total) keys6_insert(k, pack_key(sqdist(qx, qy, qz, a0), low, n));
-  if (n + 1 < total) keys6_insert(k, pack_key(sqdist(qx, qy, qz, a1), low, n + 1));
-  if (n + 2 < total) keys6_insert(k, pack_key(sqdist(qx, qy, qz, a2), low, n + 2));
+  // tail (< 4 candidates): a0 / a1 already hold entries n..n+3 (clamped)
+  if (n < tot) keys6_insert(k, pack_key(fmaxf(sqdist3(qx, qy, qz, a0.ax, a0.ay, a0.az), lead), low, n));
+  if (n + 1 < tot) keys6_insert(k, pack_key(sqdist3(qx, qy, qz, a0.bx, a0.by, a0.bz), low, n + 1));
+  if (n + 2 < tot) keys6_insert(k, pack_key(sqdist3(qx, qy, qz, a1.ax, a1.ay, a1.az), low, n + 2));
 
   // exact re-ranking of the (up to) six kept candidates: sort (exact d2 bits, ordinal) pairs
   unsigned long long ek[6];
@@ -156,7 +183,7 @@ __device__ __forceinline__ bool block_scan_private(const LevelView& L, int hx, i
     const uint32_t kb = __float_as_uint(k[j]);
     const bool have = kb < 0x7f800000u;
     const uint32_t ord = kb & low;
-    float d = __int_as_float(0x7f800000);
+    float d = inf;
     if (have) d = sqdist(qx, qy, qz, __ldg(&pts[ord]));
     ek[j] = ((unsigned long long)__float_as_uint(d) << 32) | (have ? ord : 0xFFFFFFFFu);
   }
@@ -168,7 +195,7 @@ __device__ __forceinline__ bool block_scan_private(const LevelView& L, int hx, i
 #pragma unroll
   for (int j = 0; j < 5; ++j) {
     t.d[j] = __uint_as_float((uint32_t)(ek[j] >> 32));
-    t.i[j] = s + (uint32_t)(ek[j] & 0xFFFFFFFFu);
+    t.i[j] = a + (uint32_t)(ek[j] & 0xFFFFFFFFu);
   }
   const uint32_t k5 = __float_as_uint(k[5]);
   return (k5 >= 0x7f800000u) || ((k5 & ~low) > ((uint32_t)(ek[4] >> 32) & ~low));
@@ -251,32 +278,99 @@ __device__ __forceinline__ bool block_is_final(const GridDesc& G, float max_dist
   return gr2 >= max_dist_f;                                   // outside points fail Plane::close_enough
 }
 
+// One probe of level L: the query's home cell and the run [s, e) of its 3x3x3 block.
+struct Probe {
+  int hx, hy, hz;
+  uint32_t s, e;
+};
+__device__ __forceinline__ void probe_level(const LevelView& L, float qx, float qy, float qz, Probe& p) {
+  const GridDesc& G = L.g;
+  p.hx = cell_coord(qx, G.ox, G.inv_cell, G.nx);
+  p.hy = cell_coord(qy, G.oy, G.inv_cell, G.ny);
+  p.hz = cell_coord(qz, G.oz, G.inv_cell, G.nz);
+  const int row = (p.hz * G.ny + p.hy) * G.nx;
+  p.s = __ldg(&L.cell_start[row + max(p.hx - 1, 0)]);
+  p.e = __ldg(&L.cell_start[row + min(p.hx + 1, G.nx - 1) + 1]);
+}
+
+// Level to rescan after the block of level `lvl` was not final.  d5 is the exact 5th squared
+// distance inside that block, i.e. an upper bound of the true one: the first level whose CELL is at
+// least sqrt(d5) long has a block that provably contains the answer (block_is_final: m >= 1), so one
+// more scan settles the query.  Fewer than five points found (d5 = +inf): climb two levels.
+__device__ __forceinline__ int next_level(const MatchParams& P, int lvl, float d5) {
+  const int top = P.n_levels - 1;
+  if (!(d5 < __int_as_float(0x7f800000))) return min(lvl + 2, top);
+  const float need = sqrtf(d5) * 1.002f + 1.0e-6f;       // covers block_is_final's slack
+  int l = lvl + 1;
+  while (l < top && P.lv[l].g.cell < need) ++l;
+  return min(l, top);
+}
+
 // Exact 5-NN of q, outcome-equivalent to the reference's unbounded octree search
-// (Octree.hpp:526-599) for every query the reference would accept: the finest level whose 3x3x3
-// block provably contains the 5th neighbour answers; the coarsest level's cell is >= sqrt(MAX_DIST_PLANE),
+// (Octree.hpp:526-599) for every query the reference would accept: a level whose 3x3x3 block
+// provably contains the 5th neighbour answers; the coarsest level's cell is >= sqrt(MAX_DIST_PLANE),
 // so its block always covers the radius beyond which Plane::close_enough rejects the match anyway.
-//   level 0  : one thread per query (block_scan_private);
-//   the rest : the queries that are not settled are shared out among TEAMS of lanes
-//              (block_scan_team), one level per round, until every query is settled.
+//   level choice : the grids form a geometric ladder of cell sizes and every query starts on the FINEST
+//                  level whose block holds at least tau candidates (two table reads per probe, the
+//                  next probe is predicted from the count) — the octree's "a leaf holds ~a bucket of
+//                  points" adapted to a flat layout: scan length is ~tau..2 tau whatever the local
+//                  density, lanes of a warp do equal work and few queries need a second scan;
+//   first scan   : one thread per query (block_scan_private);
+//   the rest     : the queries that are not settled are shared out among TEAMS of lanes
+//                  (block_scan_team) at the level next_level() names, until every query is settled.
+// Correctness never depends on the level choice: a block's answer is used only if block_is_final.
 // Must be called by all 32 lanes (inactive lanes pass active = false).  `lvl` returns the level whose
 // storage t.i[] indexes into.
+template <bool kWide>
 __device__ __forceinline__ void knn_search(const MatchParams& P, int lane, bool active, float qx, float qy, float qz, Top5& t,
-                                           int& lvl) {
+                                           int& lvl, int& first_lvl, uint32_t& first_cnt, unsigned long long& t_priv) {
   const unsigned int full = 0xffffffffu;
   lvl = 0;
-  bool exact_here = true;      // does t hold the exact block answer of level `lvl`?
+  first_lvl = 0;
+  first_cnt = 0;
   bool pending = false;
   if (active) {
-    const LevelView& L = P.lv[0];
-    const int hx = cell_coord(qx, L.g.ox, L.g.inv_cell, L.g.nx), hy = cell_coord(qy, L.g.oy, L.g.inv_cell, L.g.ny),
-              hz = cell_coord(qz, L.g.oz, L.g.inv_cell, L.g.nz);
-    exact_here = block_scan_private(L, hx, hy, hz, qx, qy, qz, t);
-    if (!exact_here) {
-      pending = true;                                          // redo level 0 cooperatively
-    } else if (!block_is_final(L.g, P.max_dist_f, qx, qy, qz, hx, hy, hz, t.d[4])) {
-      pending = P.n_levels > 1;
-      lvl = pending ? 1 : 0;
+    const int top = P.n_levels - 1;
+    Probe pr;
+    if (P.probe_mode == 0) {
+      // all levels probed at once (independent table reads, one memory latency): finest level with >= tau
+      uint32_t cs[kMaxLevels], ce[kMaxLevels];
+#pragma unroll
+      for (int l = 0; l < kMaxLevels; ++l) {
+        cs[l] = ce[l] = 0;
+        if (l < P.n_levels) {
+          Probe q;
+          probe_level(P.lv[l], qx, qy, qz, q);
+          cs[l] = q.s;
+          ce[l] = q.e;
+        }
+      }
+      int sel = top;
+#pragma unroll
+      for (int l = kMaxLevels - 1; l >= 0; --l)
+        if (l < P.n_levels && (int)(ce[l] - cs[l]) >= P.tau) sel = l;
+      lvl = sel;
+      probe_level(P.lv[lvl], qx, qy, qz, pr);
+    } else {
+      probe_level(P.lv[0], qx, qy, qz, pr);
+      while (lvl < top && (int)(pr.e - pr.s) < P.tau) {
+        lvl = min(lvl + 1, top);
+        probe_level(P.lv[lvl], qx, qy, qz, pr);
+      }
     }
+    first_lvl = lvl;
+    first_cnt = pr.e - pr.s;
+    const bool exact_here = block_scan_private<kWide>(P.lv[lvl], pr.s, pr.e, qx, qy, qz, t);
+    if (!exact_here) {
+      pending = true;                                          // redo this level cooperatively
+    } else if (!block_is_final(P.lv[lvl].g, P.max_dist_f, qx, qy, qz, pr.hx, pr.hy, pr.hz, t.d[4])) {
+      pending = lvl < top;
+      if (pending) lvl = next_level(P, lvl, t.d[4]);
+    }
+  }
+  if (P.timing) {
+    __syncwarp();
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_priv));
   }
 #pragma unroll 1
   for (;;) {
@@ -313,7 +407,7 @@ __device__ __forceinline__ void knn_search(const MatchParams& P, int lane, bool 
       const int hx = cell_coord(qx, L.g.ox, L.g.inv_cell, L.g.nx), hy = cell_coord(qy, L.g.oy, L.g.inv_cell, L.g.ny),
                 hz = cell_coord(qz, L.g.oz, L.g.inv_cell, L.g.nz);
       if (block_is_final(L.g, P.max_dist_f, qx, qy, qz, hx, hy, hz, t.d[4]) || lvl + 1 >= P.n_levels) pending = false;
-      else ++lvl;
+      else lvl = next_level(P, lvl, t.d[4]);
     }
   }
 }
@@ -502,21 +596,21 @@ __device__ __forceinline__ void tri13(int e, int& i, int& j) {
   j = r + (e - base);
 }
 
+template <bool kWide>
 __global__ void __launch_bounds__(kTileQueries, 7) match_reduce_kernel(const __grid_constant__ MatchParams P) {
   __shared__ double tile[kTileQueries / 32][32][13];
   __shared__ double wsum[kTileQueries / 32][kPartialStride];
   __shared__ int s_last;
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  // Query assignment.  Slot s of tile t takes index i = s*n_tiles + t (consecutive scan points are
-  // spread over all tiles), and i is then scattered by a multiplicative permutation of [0, n)
-  // (stride co-prime with n, ~0.618 n): neighbouring scan points share sparse / dense regions of the map
-  // and therefore search cost, and must not pile up in one warp.  Results do not depend on the assignment.
-  const int n_queries = P.q_end - P.q_begin;
-  const int i_lin = (int)threadIdx.x * (int)gridDim.x + (int)blockIdx.x;
-  const int q = i_lin < n_queries
-                    ? P.q_begin + (P.perm_stride ? (int)(((unsigned long long)i_lin * P.perm_stride) % (unsigned long long)n_queries) : i_lin)
-                    : P.q_end;
+  // Query assignment.  The scan is stored in a pseudo-random order (pack_scan_kernel scatters the points
+  // with a multiplicative permutation on upload): neighbouring scan points share sparse / dense regions
+  // of the map and therefore search cost, and must not pile up in one warp.  A tile simply takes 128
+  // consecutive stored points (coalesced read).  Morton-sorted scans (sort_scan) are interleaved over the
+  // tiles instead.  Results do not depend on the assignment.
+  const int i_lin = P.interleave ? (int)threadIdx.x * (int)gridDim.x + (int)blockIdx.x
+                                 : (int)blockIdx.x * kTileQueries + (int)threadIdx.x;
+  const int q = min(P.q_begin + i_lin, P.q_end);
   const bool in_range = q < P.q_end;
 
   float v13[13];
@@ -540,7 +634,10 @@ __global__ void __launch_bounds__(kTileQueries, 7) match_reduce_kernel(const __g
   int lvl = 0;
   unsigned long long tm0 = 0, tm1 = 0, tm2 = 0;
   if (P.timing) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tm0));
-  knn_search(P, lane, in_range, g[0], g[1], g[2], t, lvl);      // warp-converged call
+  int first_lvl = 0;
+  uint32_t first_cnt = 0;
+  unsigned long long t_priv = 0;
+  knn_search<kWide>(P, lane, in_range, g[0], g[1], g[2], t, lvl, first_lvl, first_cnt, t_priv);      // warp-converged call
   if (P.timing) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tm1));
 
   if (in_range) {
@@ -604,7 +701,7 @@ __global__ void __launch_bounds__(kTileQueries, 7) match_reduce_kernel(const __g
       o[0] = make_float4(g[0], g[1], g[2], n4[0]);
       o[1] = make_float4(n4[1], n4[2], n4[3], dist);
       o[2] = make_float4(accepted ? 1.f : 0.f, t.d[0], t.d[1], t.d[2]);
-      o[3] = make_float4(t.d[3], t.d[4], 0.f, 0.f);
+      o[3] = make_float4(t.d[3], t.d[4], (float)(first_lvl + 16 * lvl), (float)first_cnt);
     }
     if (P.valid_by_orig != nullptr) P.valid_by_orig[orig] = accepted ? 1 : 0;
   }
@@ -654,11 +751,14 @@ __global__ void __launch_bounds__(kTileQueries, 7) match_reduce_kernel(const __g
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tm3));
     unsigned int smid;
     asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-    unsigned long long* o = P.timing + ((size_t)blockIdx.x * (kTileQueries / 32) + warp) * 6;
+    unsigned long long* o = P.timing + ((size_t)blockIdx.x * (kTileQueries / 32) + warp) * 8;
     o[0] = smid; o[1] = tm0; o[2] = tm1; o[3] = tm2; o[4] = tm3;
-    o[5] = (unsigned long long)__popc(__ballot_sync(0xffffffffu, lvl > 0) );
+    o[5] = (unsigned long long)__popc(__ballot_sync(0xffffffffu, lvl != first_lvl));
+    o[6] = t_priv;
+    o[7] = (unsigned long long)__reduce_max_sync(0xffffffffu, first_cnt);
   } else if (P.timing) {
-    (void)__ballot_sync(0xffffffffu, lvl > 0);
+    (void)__ballot_sync(0xffffffffu, lvl != first_lvl);
+    (void)__reduce_max_sync(0xffffffffu, first_cnt);
   }
   // ---- CTA partial, then a deterministic two-level tree over tiles ----------------------------------
   const int n_tiles = gridDim.x;
@@ -687,19 +787,15 @@ __global__ void __launch_bounds__(kTileQueries, 7) match_reduce_kernel(const __g
     const int g_first = group * kGroupTiles;
     const int g_count = min(kGroupTiles, n_tiles - g_first);
     if (threadIdx.x < kPartialStride) {
-      // fixed summation order (tile index ascending); loads are issued eight at a time so the L2
-      // latency is paid once per batch instead of once per tile
+      // fixed summation order (tile index ascending); all loads of the group are in flight at once so
+      // the L2 latency is paid once
       const double* base = tile_part + (size_t)g_first * kPartialStride + threadIdx.x;
+      double v[kGroupTiles];
+#pragma unroll
+      for (int u = 0; u < kGroupTiles; ++u) v[u] = (u < g_count) ? __ldcg(base + (size_t)u * kPartialStride) : 0.0;
       double s = 0.0;
-      int t = 0;
-      for (; t + 8 <= g_count; t += 8) {
-        double v[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) v[u] = __ldcg(base + (size_t)(t + u) * kPartialStride);
-#pragma unroll
-        for (int u = 0; u < 8; ++u) s += v[u];
-      }
-      for (; t < g_count; ++t) s += __ldcg(base + (size_t)t * kPartialStride);
+      for (int u = 0; u < kGroupTiles; ++u) s += v[u];
       __stcg(&group_part[(size_t)group * kPartialStride + threadIdx.x], s);
     }
   }
@@ -715,17 +811,14 @@ __global__ void __launch_bounds__(kTileQueries, 7) match_reduce_kernel(const __g
   __threadfence();
   if (threadIdx.x < kPartialStride) {
     double s = 0.0;
-    {
-      const double* base = group_part + threadIdx.x;
-      int gi = 0;
-      for (; gi + 8 <= n_groups; gi += 8) {
-        double v[8];
+    for (int g0 = 0; g0 < n_groups; g0 += 32) {
+      const double* base = group_part + (size_t)g0 * kPartialStride + threadIdx.x;
+      const int cnt = min(32, n_groups - g0);
+      double v[32];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) v[u] = __ldcg(base + (size_t)(gi + u) * kPartialStride);
+      for (int u = 0; u < 32; ++u) v[u] = (u < cnt) ? __ldcg(base + (size_t)u * kPartialStride) : 0.0;
 #pragma unroll
-        for (int u = 0; u < 8; ++u) s += v[u];
-      }
-      for (; gi < n_groups; ++gi) s += __ldcg(base + (size_t)gi * kPartialStride);
+      for (int u = 0; u < 32; ++u) s += v[u];
     }
     // pack: 13x13 triangle entry e=(i,j) -> [0..77] HTH tri (12x12), [78..89] HTh, [91] sum z^2
     int out_idx;
@@ -740,15 +833,11 @@ __global__ void __launch_bounds__(kTileQueries, 7) match_reduce_kernel(const __g
     else if (e == 92) out_idx = 90;       // n_rows
     else out_idx = e;                     // 93,94,95 reserved (zero)
     P.out96[out_idx] = s;
-    if (P.host_out96 != nullptr) P.host_out96[out_idx] = s;      // mapped pinned host copy
-  }
-  if (P.host_out96 != nullptr) {
-    __threadfence_system();                                      // result words before the sequence word
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      *reinterpret_cast<volatile unsigned long long*>(P.host_out96 + 96) = P.seq;
-      __threadfence_system();
-    }
+    // Mapped pinned host copy: 96 records of {value, sequence number}, each ONE 16-byte store, so a
+    // record is complete as soon as its sequence word is visible — no system-scope fence, no flag.
+    if (P.host_out96 != nullptr)
+      reinterpret_cast<ulonglong2*>(P.host_out96)[out_idx] =
+          make_ulonglong2((unsigned long long)__double_as_longlong(s), P.seq);
   }
   if (threadIdx.x == 0) P.ticket[0] = 0u;
 }
@@ -760,7 +849,8 @@ int match_num_tiles(int n_queries) { return (n_queries + kTileQueries - 1) / kTi
 cudaError_t launch_match(const MatchParams& p, cudaStream_t st) {
   const int n = p.q_end - p.q_begin;
   if (n <= 0) return cudaErrorInvalidValue;
-  match_reduce_kernel<<<match_num_tiles(n), kTileQueries, 0, st>>>(p);
+  if (p.wide_loads) match_reduce_kernel<true><<<match_num_tiles(n), kTileQueries, 0, st>>>(p);
+  else match_reduce_kernel<false><<<match_num_tiles(n), kTileQueries, 0, st>>>(p);
   return cudaGetLastError();
 }
 

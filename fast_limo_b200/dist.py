@@ -48,7 +48,7 @@ def sharded_update(mapper, x0, P0, max_iter, limits, local_pass, all_reduce, R=0
     return x, P, passes
 
 
-EXCHANGE_BYTES_PER_RANK = 2048
+EXCHANGE_BYTES_PER_RANK = 4096
 
 
 def attach_exchange(mapper, rank, world, broadcast_object):

@@ -59,7 +59,8 @@ typedef struct {
   /* Extensions (defaults keep reference behaviour): */
   float knn_cell;               /* side of the device search grid in metres; 0 = choose automatically */
   int32_t sort_scan;            /* 1 = Morton-sort the scan on upload; 0 (default) = the kernel scatters the query order itself */
-  float knn_level_ratio;        /* cell growth between index levels; 0 = default (1.5) */
+  float knn_level_ratio;        /* cell growth between index levels; 0 = default (sqrt 2) */
+  int32_t knn_tau;              /* a query starts on the finest level whose 3x3x3 block holds >= knn_tau points; 0 = default (24) */
 } flimo_cfg;
 
 void flimo_cfg_default(flimo_cfg* cfg);
@@ -117,11 +118,11 @@ int flimo_match_reduce_async(flimo_handle h, const double state14[14], double* d
  * `shared_host_mem` is a host segment mapped by every rank (e.g. POSIX shared memory), at least
  * world * FLIMO_EXCHANGE_BYTES_PER_RANK bytes, zero-initialised by its creator.  The library pins and
  * maps it (cudaHostRegister) so that the LAST CTA of the measurement kernel stores this rank's 96 packed
- * doubles and a sequence word straight into its slot; flimo_match_reduce_exchange then spins until the
+ * doubles, each tagged with a sequence number, straight into its slot; flimo_match_reduce_exchange then spins until the
  * slots of all ranks carry the same sequence number and sums them in rank order (deterministic).  No
  * D2H copy, no stream synchronise, no collective launch: ~2 us after the slowest rank's kernel ends.
  * Every rank must make the same sequence of flimo_match_reduce_exchange calls. */
-#define FLIMO_EXCHANGE_BYTES_PER_RANK 2048
+#define FLIMO_EXCHANGE_BYTES_PER_RANK 4096
 int flimo_exchange_attach(flimo_handle h, void* shared_host_mem, size_t bytes, int rank, int world);
 int flimo_match_reduce_exchange(flimo_handle h, const double state14[14], double HTH[144], double HTh[12],
                                 int64_t* n_valid, int64_t* n_rows, double* sum_sq_res);

@@ -327,8 +327,8 @@ def test_fused_exchange_two_processes(oracle, flimo_lib):
     import torch.multiprocessing as mp
     from multiprocessing import shared_memory
     world = 2
-    shm = shared_memory.SharedMemory(create=True, size=4096)
-    shm.buf[:4096] = bytes(4096)
+    shm = shared_memory.SharedMemory(create=True, size=2 * 4096)
+    shm.buf[:2 * 4096] = bytes(2 * 4096)
     try:
         mgr = mp.Manager()
         out = mgr.dict()

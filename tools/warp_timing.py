@@ -9,20 +9,26 @@ sort = len(sys.argv) > 3 and sys.argv[3] == "sort"
 case = synth.make_case(name)
 m = api.Mapper(api.MappingConfig(MAX_NUM_MATCHES=1 << 20, MAX_NUM_PC2MATCH=1 << 20, knn_cell=cell, sort_scan=sort), device=0)
 m.add(case.map_pts, 0.0); m.set_scan(case.scan)
-for i in range(3): m.match(case.init)
+pose = case.init
+if "conv" in sys.argv:
+    pose, _, _ = m.update(case.init, synth.default_P0(), 2, 0.0)
+for i in range(3): m.match(pose)
 L = _lib.load()
 nw = (case.scan.shape[0] + 127) // 128 * 4
-buf = np.zeros((nw, 6), np.uint64)
+buf = np.zeros((nw, 8), np.uint64)
 L.flimo_debug_timing.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]
 L.flimo_debug_timing(m._h, 1, None, nw)
-m.match(case.init)
+m.match(pose)
 L.flimo_debug_timing(m._h, 1, buf.ctypes.data, nw)
 print("pass ms", m.stats()["last_match_ms"])
 t0 = buf[:, 1].min()
 st, knn, qr, acc = (buf[:, 1] - t0) / 1e3, (buf[:, 2] - buf[:, 1]) / 1e3, (buf[:, 3] - buf[:, 2]) / 1e3, (buf[:, 4] - buf[:, 3]) / 1e3
+priv = (buf[:, 6] - buf[:, 1]) / 1e3
+team = (buf[:, 2] - buf[:, 6]) / 1e3
+maxcnt = buf[:, 7].astype(float)
 end = (buf[:, 4] - t0) / 1e3
 q = lambda a: np.round(np.quantile(a, [0, 0.1, 0.5, 0.9, 0.99, 1.0]), 2)
-print("start us  ", q(st)); print("knn us    ", q(knn)); print("qr us     ", q(qr)); print("acc us    ", q(acc)); print("end us    ", q(end))
+print("start us  ", q(st)); print("knn us    ", q(knn)); print(" private  ", q(priv)); print(" teams    ", q(team)); print(" max cnt  ", q(maxcnt)); print("corr(priv,maxcnt)", np.corrcoef(priv, maxcnt)[0, 1]); print("qr us     ", q(qr)); print("acc us    ", q(acc)); print("end us    ", q(end))
 print("escalated lanes per warp", q(buf[:, 5].astype(float)))
 sm = buf[:, 0].astype(int)
 per_sm_end = np.array([end[sm == s].max() if (sm == s).any() else 0 for s in range(148)])
