@@ -4,6 +4,7 @@
 // entry point fails with a negative status.
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -81,6 +82,11 @@ struct flimo_ctx {
 
   int knn_tau = 24;              // level choice threshold (MatchParams::tau)
   int probe_mode = 0, wide_loads = 1;
+  int interleave = 0, scan_perm = 1;
+  int time_every = 1;            // CUDA-event timing of every n-th blocking pass (0 = never)
+  bool prof = false;             // FLIMO_PROFILE=1: host-side wall-clock breakdown printed by flimo_destroy
+  double prof_launch = 0, prof_wait = 0, prof_step = 0, prof_other = 0;
+  uint64_t prof_passes = 0;
 
   ekf::IteratedUpdate upd;
   bool upd_active = false;
@@ -227,7 +233,7 @@ int fill_params(flimo_handle h, const double state14[14], MatchParams& P, double
   }
   make_pose(state14, P.pc);
   P.q_begin = (int)h->shard_begin;
-  P.interleave = h->cfg.sort_scan ? 1 : 0;   // unsorted scans are stored scattered instead (scan_prepare)
+  P.interleave = h->interleave;
   P.q_end = (int)h->shard_end;
   P.tau = h->knn_tau;
   P.probe_mode = h->probe_mode;
@@ -277,27 +283,41 @@ int wait_records(flimo_handle h, const double* block, unsigned long long seq, do
 // pair of events that is resolved lazily in flimo_get_stats.
 int run_pass_blocking(flimo_handle h, const double state14[14], uint32_t orig_limit, float* dbg, uint8_t* valid,
                       double packed[96]) {
+  const auto tp0 = std::chrono::steady_clock::now();
   MatchParams P;
   int rc = fill_params(h, state14, P, h->out96, orig_limit, dbg, valid);
   if (rc) return rc;
   P.host_out96 = h->d_h_out96;
   P.seq = ++h->seq;
+  // device time of the kernel: a pair of events around every `time_every`-th launch
+  const bool timed = h->time_every > 0 && (h->stats.match_launches % (uint64_t)h->time_every) == 0;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
-  if (h->ev_pool.size() >= 2) {
-    e0 = h->ev_pool.back(); h->ev_pool.pop_back();
-    e1 = h->ev_pool.back(); h->ev_pool.pop_back();
-  } else {
-    CU(h, cudaEventCreate(&e0));
-    CU(h, cudaEventCreate(&e1));
+  if (timed) {
+    if (h->ev_pool.size() >= 2) {
+      e0 = h->ev_pool.back(); h->ev_pool.pop_back();
+      e1 = h->ev_pool.back(); h->ev_pool.pop_back();
+    } else {
+      CU(h, cudaEventCreate(&e0));
+      CU(h, cudaEventCreate(&e1));
+    }
+    CU(h, cudaEventRecord(e0, h->stream));
   }
-  CU(h, cudaEventRecord(e0, h->stream));
   CU(h, launch_match(P, h->stream));
-  CU(h, cudaEventRecord(e1, h->stream));
-  h->ev_pending.push_back(e0);
-  h->ev_pending.push_back(e1);
+  if (timed) {
+    CU(h, cudaEventRecord(e1, h->stream));
+    h->ev_pending.push_back(e0);
+    h->ev_pending.push_back(e1);
+  }
   h->stats.kernel_launches++;
   h->stats.match_launches++;
+  const auto tp1 = std::chrono::steady_clock::now();
   const int wr = wait_records(h, h->h_out96, P.seq, packed, true);
+  if (h->prof) {
+    const auto tp2 = std::chrono::steady_clock::now();
+    h->prof_launch += std::chrono::duration<double, std::micro>(tp1 - tp0).count();
+    h->prof_wait += std::chrono::duration<double, std::micro>(tp2 - tp1).count();
+    h->prof_passes++;
+  }
   if (wr == 1) {                                           // finished without publishing: read the device copy
     CU(h, cudaMemcpy(packed, h->out96, 96 * sizeof(double), cudaMemcpyDeviceToHost));
   } else if (wr < 0) {
@@ -372,7 +392,13 @@ int flimo_create(const flimo_cfg* cfg, int device, flimo_handle* out) {
   if (h->cfg.knn_tau <= 0) h->cfg.knn_tau = kDefaultTau;
   h->knn_tau = h->cfg.knn_tau;
   if (const char* e = std::getenv("FLIMO_KNN_PROBE")) h->probe_mode = std::atoi(e);
+  if (const char* e = std::getenv("FLIMO_PROFILE")) h->prof = std::atoi(e) != 0;
+  if (const char* e = std::getenv("FLIMO_TIME_EVERY")) h->time_every = std::atoi(e);
   if (const char* e = std::getenv("FLIMO_KNN_WIDE")) h->wide_loads = std::atoi(e);
+  if (const char* e = std::getenv("FLIMO_KNN_SORT")) h->cfg.sort_scan = std::atoi(e);
+  h->interleave = h->cfg.sort_scan ? 1 : 0;
+  if (const char* e = std::getenv("FLIMO_KNN_INTERLEAVE")) h->interleave = std::atoi(e);
+  if (const char* e = std::getenv("FLIMO_KNN_PERM")) h->scan_perm = std::atoi(e);
   CU(h, cudaSetDevice(device));
   CU(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   CU(h, cudaEventCreate(&h->ev0));
@@ -389,6 +415,10 @@ int flimo_create(const flimo_cfg* cfg, int device, flimo_handle* out) {
 
 void flimo_destroy(flimo_handle h) {
   if (!h) return;
+  if (h->prof && h->prof_passes)
+    std::fprintf(stderr, "[flimo profile] passes=%llu  per pass: launch %.2f us, wait %.2f us, filter step %.2f us\n",
+                 (unsigned long long)h->prof_passes, h->prof_launch / h->prof_passes, h->prof_wait / h->prof_passes,
+                 h->prof_step / h->prof_passes);
   if (h->device < 0) {
     delete h;
     return;
@@ -431,12 +461,12 @@ int flimo_debug_timing(flimo_handle h, int enable, unsigned long long* host_out,
   if (!h || h->device < 0) return FLIMO_ERR_INVALID;
   cudaSetDevice(h->device);
   if (enable && !h->timing) {
-    if (cudaMalloc(&h->timing, n_warps * 8 * sizeof(unsigned long long)) != cudaSuccess) return FLIMO_ERR_NOMEM;
-    cudaMemset(h->timing, 0, n_warps * 8 * sizeof(unsigned long long));
+    if (cudaMalloc(&h->timing, (n_warps * 8 + 8) * sizeof(unsigned long long)) != cudaSuccess) return FLIMO_ERR_NOMEM;
+    cudaMemset(h->timing, 0, (n_warps * 8 + 8) * sizeof(unsigned long long));
   }
   if (host_out && h->timing) {
     cudaStreamSynchronize(h->stream);
-    cudaMemcpy(host_out, h->timing, n_warps * 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    cudaMemcpy(host_out, h->timing, (n_warps * 8 + 8) * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
   }
   if (!enable && h->timing) {
     cudaFree(h->timing);
@@ -594,7 +624,7 @@ int flimo_scan_set_device(flimo_handle h, const void* d_xyz, size_t n, size_t st
   h->shard_end = nq;
   if (nq == 0) return FLIMO_OK;
   const int sort = (h->cfg.sort_scan && nq > 1) ? 1 : 0;
-  const unsigned int perm = sort ? 0u : coprime_stride((uint32_t)nq);
+  const unsigned int perm = (sort || !h->scan_perm) ? 0u : coprime_stride((uint32_t)nq);
   // The upload pipeline (pack + Morton keys, radix sort, gather: 7 launches) is captured once per
   // (source pointer, size) into a CUDA graph and replayed with a single launch afterwards.
   for (auto& g : h->scan_graphs) {
@@ -888,7 +918,9 @@ int flimo_update(flimo_handle h, double state26[26], double P529[529], int max_i
     double ss = 0;
     int rc = flimo_match_reduce(h, x, HTH, HTh, &nv, &nr, &ss);
     if (rc) return rc;
+    const auto ts0 = std::chrono::steady_clock::now();
     u.step(HTH, HTh, nr);
+    if (h->prof) h->prof_step += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - ts0).count();
   }
   u.end(state26, P529);
   if (passes_out) *passes_out = u.passes();

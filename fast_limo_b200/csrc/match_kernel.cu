@@ -87,6 +87,28 @@ __device__ __forceinline__ float pack_key(float d, uint32_t low, uint32_t ord) {
   return __uint_as_float((__float_as_uint(d) & ~low) | ord);
 }
 
+// Insertion of a SORTED pair x <= y into the ascending 6-list (lowest six survive).  Merging two sorted
+// sequences: c_j = min(a_j, max(a_{j-1}, x), max(a_{j-2}, y)); with 3-input FMNMX3 that is 15 min/max per
+// pair (+2 to sort the pair) instead of 22 for two single insertions.
+__device__ __forceinline__ float fmin3(float a, float b, float c) { return fminf(fminf(a, b), c); }
+__device__ __forceinline__ void keys6_insert2(float (&k)[6], float a, float b) {
+  const float x = fminf(a, b), y = fmaxf(a, b);
+  const float c5 = fmin3(k[5], fmaxf(k[4], x), fmaxf(k[3], y));
+  const float c4 = fmin3(k[4], fmaxf(k[3], x), fmaxf(k[2], y));
+  const float c3 = fmin3(k[3], fmaxf(k[2], x), fmaxf(k[1], y));
+  const float c2 = fmin3(k[2], fmaxf(k[1], x), fmaxf(k[0], y));
+  const float c1 = fmin3(k[1], fmaxf(k[0], x), y);
+  const float c0 = fminf(k[0], x);
+  k[0] = c0; k[1] = c1; k[2] = c2; k[3] = c3; k[4] = c4; k[5] = c5;
+}
+// Ranking distance of the scan loop: fused multiply-adds (2 instructions fewer than the reference's
+// rounding order).  It may differ from the exact value by a few ulp, which block_scan_private's
+// acceptance test allows for; every distance that leaves the scan is recomputed exactly.
+__device__ __forceinline__ float sqdist_rank(float qx, float qy, float qz, float px, float py, float pz) {
+  const float dx = qx - px, dy = qy - py, dz = qz - pz;
+  return __fmaf_rn(dx, dx, __fmaf_rn(dy, dy, dz * dz));
+}
+
 __device__ __forceinline__ void cmpswap64(unsigned long long& a, unsigned long long& b) {
   const bool sw = a > b;
   const unsigned long long ta = sw ? b : a, tb = sw ? a : b;
@@ -121,9 +143,15 @@ __device__ __forceinline__ Pair ldg_pair(const float4* p) {
   }
   return r;
 }
-__device__ __forceinline__ float sqdist3(float qx, float qy, float qz, float px, float py, float pz) {
-  const float dx = qx - px, dy = qy - py, dz = qz - pz;
-  return dx * dx + (dy * dy + dz * dz);               // Eigen Vector3f::squaredNorm order
+constexpr uint32_t kKeyLow = 127u;     // ordinal bits of a packed key (kPrivateCap + 1 < 128)
+
+// Ranks four consecutive run entries (two 32-byte pairs) whose first ordinal is n.
+__device__ __forceinline__ void rank4(float (&k)[6], const Pair& p0, const Pair& p1, float qx, float qy, float qz, uint32_t n,
+                                      float lead) {
+  const float d0 = fmaxf(sqdist_rank(qx, qy, qz, p0.ax, p0.ay, p0.az), lead), d1 = sqdist_rank(qx, qy, qz, p0.bx, p0.by, p0.bz),
+              d2 = sqdist_rank(qx, qy, qz, p1.ax, p1.ay, p1.az), d3 = sqdist_rank(qx, qy, qz, p1.bx, p1.by, p1.bz);
+  keys6_insert2(k, pack_key(d0, kKeyLow, n), pack_key(d1, kKeyLow, n + 1));
+  keys6_insert2(k, pack_key(d2, kKeyLow, n + 2), pack_key(d3, kKeyLow, n + 3));
 }
 
 // Thread-private scan of a short run [s, e) of level L (<= kPrivateCap candidates).  Returns false
@@ -145,36 +173,40 @@ __device__ __forceinline__ bool block_scan_private(const LevelView& L, uint32_t 
   if (total > kPrivateCap) return false;
   const uint32_t a = s & ~1u;
   const uint32_t tot = (s - a) + total;          // ordinals [s - a, tot) are candidates
-  const int B = 32 - __clz(tot);                 // ordinals 0..tot-1 fit in B bits (B <= 7)
   const float4* __restrict__ pts = L.pts + a;
-  const uint32_t low = (1u << B) - 1u;
+  const uint32_t low = kKeyLow;
   const float inf = __int_as_float(0x7f800000);
   float lead = (s != a) ? inf : 0.f;             // raises the masked leading entry's distance to +inf
   float k[6];
 #pragma unroll
   for (int j = 0; j < 6; ++j) k[j] = inf;
 
-  // software-pipelined: the next two pairs are in flight while the current two are ranked
+  // Software-pipelined, two register sets in ping-pong (no register moves): while four entries are
+  // ranked the next four are in flight.
   const uint32_t last = (tot - 1) & ~1u;         // first entry of the last pair
   Pair a0 = ldg_pair<kWide>(pts), a1 = ldg_pair<kWide>(pts + min(2u, last));
   uint32_t n = 0;
 #pragma unroll 1
-  for (; n + 4 <= tot; n += 4) {
-    const Pair p0 = a0, p1 = a1;
-    a0 = ldg_pair<kWide>(pts + min(n + 4, last));
-    a1 = ldg_pair<kWide>(pts + min(n + 6, last));
-    const float d0 = fmaxf(sqdist3(qx, qy, qz, p0.ax, p0.ay, p0.az), lead), d1 = sqdist3(qx, qy, qz, p0.bx, p0.by, p0.bz),
-                d2 = sqdist3(qx, qy, qz, p1.ax, p1.ay, p1.az), d3 = sqdist3(qx, qy, qz, p1.bx, p1.by, p1.bz);
+  for (; n + 8 <= tot; n += 8) {
+    const Pair b0 = ldg_pair<kWide>(pts + min(n + 4, last)), b1 = ldg_pair<kWide>(pts + min(n + 6, last));
+    rank4(k, a0, a1, qx, qy, qz, n, lead);
     lead = 0.f;
-    keys6_insert(k, pack_key(d0, low, n));
-    keys6_insert(k, pack_key(d1, low, n + 1));
-    keys6_insert(k, pack_key(d2, low, n + 2));
-    keys6_insert(k, pack_key(d3, low, n + 3));
+    a0 = ldg_pair<kWide>(pts + min(n + 8, last));
+    a1 = ldg_pair<kWide>(pts + min(n + 10, last));
+    rank4(k, b0, b1, qx, qy, qz, n + 4, 0.f);
   }
-  // tail (< 4 candidates): a0 / a1 already hold entries n..n+3 (clamped)
-  if (n < tot) keys6_insert(k, pack_key(fmaxf(sqdist3(qx, qy, qz, a0.ax, a0.ay, a0.az), lead), low, n));
-  if (n + 1 < tot) keys6_insert(k, pack_key(sqdist3(qx, qy, qz, a0.bx, a0.by, a0.bz), low, n + 1));
-  if (n + 2 < tot) keys6_insert(k, pack_key(sqdist3(qx, qy, qz, a1.ax, a1.ay, a1.az), low, n + 2));
+  if (n + 4 <= tot) {
+    const Pair b0 = ldg_pair<kWide>(pts + min(n + 4, last)), b1 = ldg_pair<kWide>(pts + min(n + 6, last));
+    rank4(k, a0, a1, qx, qy, qz, n, lead);
+    lead = 0.f;
+    a0 = b0;
+    a1 = b1;
+    n += 4;
+  }
+  // tail (< 4 candidates): a0 / a1 hold entries n..n+3 (clamped)
+  if (n < tot) keys6_insert(k, pack_key(fmaxf(sqdist_rank(qx, qy, qz, a0.ax, a0.ay, a0.az), lead), low, n));
+  if (n + 1 < tot) keys6_insert(k, pack_key(sqdist_rank(qx, qy, qz, a0.bx, a0.by, a0.bz), low, n + 1));
+  if (n + 2 < tot) keys6_insert(k, pack_key(sqdist_rank(qx, qy, qz, a1.ax, a1.ay, a1.az), low, n + 2));
 
   // exact re-ranking of the (up to) six kept candidates: sort (exact d2 bits, ordinal) pairs
   unsigned long long ek[6];
@@ -197,8 +229,12 @@ __device__ __forceinline__ bool block_scan_private(const LevelView& L, uint32_t 
     t.d[j] = __uint_as_float((uint32_t)(ek[j] >> 32));
     t.i[j] = a + (uint32_t)(ek[j] & 0xFFFFFFFFu);
   }
+  // Acceptance.  Every candidate that was not kept has a ranking key >= k5 (the sixth smallest), hence a
+  // ranking distance >= bucket_floor(k5) and an exact distance within 4 ulp of that.  If k5's bucket
+  // (128 ulp wide) lies at least TWO buckets above the bucket of the exact fifth distance, all of them
+  // are strictly farther than the fifth neighbour, so the kept set contains the exact answer.
   const uint32_t k5 = __float_as_uint(k[5]);
-  return (k5 >= 0x7f800000u) || ((k5 & ~low) > ((uint32_t)(ek[4] >> 32) & ~low));
+  return (k5 >= 0x7f800000u) || ((k5 & ~low) >= ((uint32_t)(ek[4] >> 32) & ~low) + 2u * (low + 1u));
 }
 
 // TEAM scan: exact top-5 of one query's block at level L by a team of T consecutive lanes
@@ -598,7 +634,7 @@ __device__ __forceinline__ void tri13(int e, int& i, int& j) {
 
 template <bool kWide>
 __global__ void __launch_bounds__(kTileQueries, 7) match_reduce_kernel(const __grid_constant__ MatchParams P) {
-  __shared__ double tile[kTileQueries / 32][32][13];
+  __shared__ __align__(16) float tile[kTileQueries / 32][32][24];   // rows of [row(12), z] as floats; stride 24: conflict-free fragment reads
   __shared__ double wsum[kTileQueries / 32][kPartialStride];
   __shared__ int s_last;
 
@@ -710,34 +746,53 @@ __global__ void __launch_bounds__(kTileQueries, 7) match_reduce_kernel(const __g
     __syncwarp();
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tm2));
   }
-  // ---- warp-cooperative float64 accumulation of [row,z]^T [row,z] -------------------------------
+  // ---- warp-cooperative float64 accumulation of [row,z]^T [row,z] on the FP64 tensor pipe -----------
+  // The warp's 32 rows v (13 floats, zero for lanes that do not contribute) form V[32][16]; the upper
+  // triangle of V^T V is three 8x8 tiles (00, 01, 11), each accumulated over the 32 rows with eight
+  // mma.m8n8k4.f64 (products of two floats are exact in float64).  Fragment of step k: lane l supplies
+  // V[4k + l%4][l/4] (columns 0-7) and V[4k + l%4][8 + l/4] (columns 8-15) — A and B fragments of a
+  // diagonal tile coincide.  H is never written.
   const bool contributes = accepted && (orig < P.orig_limit);
   const unsigned int m_all = __ballot_sync(0xffffffffu, accepted);
-  unsigned int m_rows = __ballot_sync(0xffffffffu, contributes);
-  if (contributes) {
-#pragma unroll
-    for (int c = 0; c < 13; ++c) tile[warp][lane][c] = (double)v13[c];
+  const unsigned int m_rows = __ballot_sync(0xffffffffu, contributes);
+  {
+    float4* rowp = reinterpret_cast<float4*>(&tile[warp][lane][0]);
+    const float zf = contributes ? 1.f : 0.f;     // v13 is already zero unless accepted; orig_limit may veto
+    rowp[0] = make_float4(v13[0] * zf, v13[1] * zf, v13[2] * zf, v13[3] * zf);
+    rowp[1] = make_float4(v13[4] * zf, v13[5] * zf, v13[6] * zf, v13[7] * zf);
+    rowp[2] = make_float4(v13[8] * zf, v13[9] * zf, v13[10] * zf, v13[11] * zf);
+    rowp[3] = make_float4(v13[12] * zf, 0.f, 0.f, 0.f);
   }
   __syncwarp();
-  int ei[3], ej[3];
+  double c00[2] = {0.0, 0.0}, c01[2] = {0.0, 0.0}, c11[2] = {0.0, 0.0};
+  if (m_rows != 0u) {
+    const int fr = lane & 3, fc = lane >> 2;
 #pragma unroll
-  for (int s = 0; s < 3; ++s) {
-    const int e = lane + 32 * s;
-    tri13(e < kTriEntries ? e : 0, ei[s], ej[s]);
+    for (int k = 0; k < 8; ++k) {
+      if ((m_rows >> (4 * k)) & 0xFu) {           // warp-uniform: skip row groups without contributions
+        const double lo = (double)tile[warp][4 * k + fr][fc], hi = (double)tile[warp][4 * k + fr][8 + fc];
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                     : "+d"(c00[0]), "+d"(c00[1]) : "d"(lo), "d"(lo));
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                     : "+d"(c01[0]), "+d"(c01[1]) : "d"(lo), "d"(hi));
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                     : "+d"(c11[0]), "+d"(c11[1]) : "d"(hi), "d"(hi));
+      }
+    }
   }
-  double acc[3] = {0.0, 0.0, 0.0};
-  unsigned int m = m_rows;
-  while (m) {
-    const int r = __ffs(m) - 1;
-    m &= m - 1;
-    const double* rowp = tile[warp][r];
+  // accumulator element u of a tile sits at (i, j) = (lane/4, 2*(lane%4) + u); scatter the upper triangle
+  // of the 13x13 result to its row-major triangle slot e = i*13 - i(i-1)/2 + (j - i)
+  {
+    const int ti = lane >> 2, tj = 2 * (lane & 3);
 #pragma unroll
-    for (int s = 0; s < 3; ++s) acc[s] = fma(rowp[ei[s]], rowp[ej[s]], acc[s]);
-  }
-#pragma unroll
-  for (int s = 0; s < 3; ++s) {
-    const int e = lane + 32 * s;
-    if (e < kPartialStride) wsum[warp][e] = (e < kTriEntries) ? acc[s] : 0.0;
+    for (int u = 0; u < 2; ++u) {
+      const int j = tj + u;
+      if (ti <= j) wsum[warp][ti * 13 - (ti * (ti - 1)) / 2 + (j - ti)] = c00[u];                       // tile 00
+      if (8 + j < 13) wsum[warp][ti * 13 - (ti * (ti - 1)) / 2 + (8 + j - ti)] = c01[u];              // tile 01
+      const int gi = 8 + ti, gj = 8 + j;
+      if (gi <= gj && gj < 13) wsum[warp][gi * 13 - (gi * (gi - 1)) / 2 + (gj - gi)] = c11[u];        // tile 11
+    }
+    if (lane < kPartialStride - kTriEntries) wsum[warp][kTriEntries + lane] = 0.0;
   }
   __syncwarp();
   if (lane == 0) {
@@ -840,6 +895,11 @@ __global__ void __launch_bounds__(kTileQueries, 7) match_reduce_kernel(const __g
           make_ulonglong2((unsigned long long)__double_as_longlong(s), P.seq);
   }
   if (threadIdx.x == 0) P.ticket[0] = 0u;
+  if (P.timing && threadIdx.x == 0) {
+    unsigned long long te;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(te));
+    P.timing[(size_t)gridDim.x * (kTileQueries / 32) * 8] = te;
+  }
 }
 
 }  // namespace

@@ -15,12 +15,15 @@ if "conv" in sys.argv:
 for i in range(3): m.match(pose)
 L = _lib.load()
 nw = (case.scan.shape[0] + 127) // 128 * 4
-buf = np.zeros((nw, 8), np.uint64)
+buf = np.zeros((nw + 1, 8), np.uint64)
 L.flimo_debug_timing.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]
 L.flimo_debug_timing(m._h, 1, None, nw)
 m.match(pose)
 L.flimo_debug_timing(m._h, 1, buf.ctypes.data, nw)
 print("pass ms", m.stats()["last_match_ms"])
+t_final = buf[nw, 0]
+buf = buf[:nw]
+print("final CTA done at us", (t_final - buf[:, 1].min()) / 1e3)
 t0 = buf[:, 1].min()
 st, knn, qr, acc = (buf[:, 1] - t0) / 1e3, (buf[:, 2] - buf[:, 1]) / 1e3, (buf[:, 3] - buf[:, 2]) / 1e3, (buf[:, 4] - buf[:, 3]) / 1e3
 priv = (buf[:, 6] - buf[:, 1]) / 1e3
