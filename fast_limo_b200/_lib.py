@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libflimo_cuda.so")
 SYMBOLS = [
     "flimo_cfg_default", "flimo_create", "flimo_destroy", "flimo_last_error", "flimo_version",
     "flimo_map_add", "flimo_map_add_device", "flimo_map_size", "flimo_map_exists", "flimo_map_last_time",
-    "flimo_map_get_points", "flimo_scan_set", "flimo_scan_set_device", "flimo_scan_shard",
+    "flimo_map_get_points", "flimo_scan_set", "flimo_scan_set_device", "flimo_scan_prefetch", "flimo_scan_shard",
     "flimo_match_reduce", "flimo_match_reduce_async", "flimo_unpack96", "flimo_match_debug",
     "flimo_update", "flimo_ekf_begin", "flimo_ekf_state", "flimo_ekf_step", "flimo_ekf_end",
     "flimo_scan_to_world", "flimo_get_stats", "flimo_stream", "flimo_exchange_attach", "flimo_match_reduce_exchange", "flimo_update_exchange",
@@ -52,6 +52,8 @@ class FlimoStats(C.Structure):
         ("n_levels", C.c_int32),
         ("table_bytes", C.c_uint64),
         ("map_bytes", C.c_uint64),
+        ("persist_ms_total", C.c_double),
+        ("persist_passes", C.c_uint64),
     ]
 
 
@@ -90,6 +92,7 @@ def load():
     L.flimo_map_get_points.argtypes = [vp, pf, sz, C.POINTER(sz)]
     L.flimo_scan_set.argtypes = [vp, vp, sz, sz]
     L.flimo_scan_set_device.argtypes = [vp, vp, sz, sz]
+    L.flimo_scan_prefetch.argtypes = [vp, vp, sz, sz]
     L.flimo_scan_shard.argtypes = [vp, sz, sz]
     L.flimo_match_reduce.argtypes = [vp, pd, pd, pd, C.POINTER(i64), C.POINTER(i64), pd]
     L.flimo_match_reduce_async.argtypes = [vp, pd, vp, vp]

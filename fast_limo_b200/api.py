@@ -34,8 +34,8 @@ class MappingConfig:
     octree_downsampling: bool = True
     knn_cell: float = 0.0                # extension: device grid cell (0 = auto)
     sort_scan: bool = False              # extension: Morton-sort the scan on upload (default: in-kernel scatter instead)
-    knn_level_ratio: float = 0.0         # extension: cell growth between index levels (0 = sqrt 2)
-    knn_tau: int = 0                     # extension: candidates-per-block threshold of the level choice (0 = 24)
+    knn_level_ratio: float = 0.0         # extension: cell growth between index levels (0 = 1.5)
+    knn_tau: int = 0                     # extension: candidates-per-block threshold of the level choice (0 = 8)
 
 
 def _dp(a):
@@ -140,6 +140,15 @@ class Mapper:
     def set_scan_device(self, dptr, n, stride_bytes):
         self._ck(self._L.flimo_scan_set_device(self._h, C.c_void_p(dptr), n, stride_bytes))
         self._scan_n = min(n, self.config.MAX_NUM_PC2MATCH)
+
+    def set_scan_host(self, hptr, n, stride_bytes):
+        """flimo_scan_set on a raw host pointer (e.g. pinned memory); binds a prefetched copy if there is one."""
+        self._ck(self._L.flimo_scan_set(self._h, C.c_void_p(hptr), n, stride_bytes))
+        self._scan_n = min(n, self.config.MAX_NUM_PC2MATCH)
+
+    def prefetch_scan_host(self, hptr, n, stride_bytes):
+        """flimo_scan_prefetch: start the H2D copy of the NEXT scan on the copy stream."""
+        self._ck(self._L.flimo_scan_prefetch(self._h, C.c_void_p(hptr), n, stride_bytes))
 
     def shard(self, begin, end):
         self._ck(self._L.flimo_scan_shard(self._h, begin, end))

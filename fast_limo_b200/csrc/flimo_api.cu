@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <immintrin.h>
 #include <new>
 #include <string>
 #include <vector>
@@ -18,9 +19,11 @@
 
 using namespace flimo;
 
-constexpr float kDefaultCell = 0.15f;      // finest grid of the ladder (metres)
-constexpr float kDefaultRatio = 1.41421356f;
-constexpr int kDefaultTau = 24;
+// Index ladder defaults (tools/tune_knn.py sweeps on the 5 M-point headline map, B200): finest cell 0.25 m,
+// cells grow 1.5x per level, a query starts on the finest level whose block holds >= 8 candidates.
+constexpr float kDefaultCell = 0.25f;
+constexpr float kDefaultRatio = 1.5f;
+constexpr int kDefaultTau = 8;
 
 struct flimo_ctx {
   flimo_cfg cfg{};
@@ -33,7 +36,21 @@ struct flimo_ctx {
   bool map_exists = false;
   double last_time = -1.0;       // Mapper::last_map_time (Mapper.cpp:23)
 
-  float4* scan = nullptr;        // packed scan (w = original index)
+  float4* scan = nullptr;        // packed scan (w = original index); built on demand unless sort_scan
+  const unsigned char* raw_scan = nullptr;   // the bound scan as uploaded (strided xyz, device memory)
+  size_t raw_stride = 0;
+  bool packed_valid = false;     // h->scan holds the bound scan
+  unsigned int raw_inv = 1;      // inverse of the storage permutation's stride (mod scan_n)
+  // host uploads: two staging buffers, so that the next scan can be copied while this one is registered
+  void* scan_stage[2] = {nullptr, nullptr};
+  size_t scan_stage_cap[2] = {0, 0};
+  int scan_stage_bound = 0;
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_prefetch = nullptr;
+  const void* pref_src = nullptr;   // pending prefetch: host pointer, size, stride, staging buffer
+  size_t pref_n = 0, pref_stride = 0;
+  int pref_idx = -1;
+  bool pref_issued = false;
   float4* scan_tmp = nullptr;
   size_t scan_cap = 0, scan_n = 0;
   size_t shard_begin = 0, shard_end = 0;
@@ -81,9 +98,18 @@ struct flimo_ctx {
   size_t xyz_cap = 0;
 
   int knn_tau = 24;              // level choice threshold (MatchParams::tau)
-  int probe_mode = 0, wide_loads = 1;
-  int interleave = 0, scan_perm = 1;
-  int time_every = 1;            // CUDA-event timing of every n-th blocking pass (0 = never)
+  int probe_mode = 1, wide_loads = 1;
+  int interleave = 0, scan_perm = 1, l2_prefetch = 0;
+  int time_every = 8;            // every n-th flimo_update runs one launch per pass, each timed with CUDA events (0 = never)
+  // persistent kernel (one launch per flimo_update)
+  PassCtlWire* h_ctl = nullptr;  // mapped pinned host control block (tagged 16-byte records)
+  PassCtlWire* d_h_ctl = nullptr;   // its device alias
+  PassCtl* dev_ctl = nullptr;    // device copy
+  int persistent = 1;            // 1 = flimo_update keeps one kernel resident over all passes
+  int persist_capacity = 0;      // co-resident CTAs of the persistent kernel
+  double persist_ns_total = 0;   // in-kernel device time of persistent passes
+  uint64_t persist_passes = 0;
+  uint64_t update_calls = 0;
   bool prof = false;             // FLIMO_PROFILE=1: host-side wall-clock breakdown printed by flimo_destroy
   double prof_launch = 0, prof_wait = 0, prof_step = 0, prof_other = 0;
   uint64_t prof_passes = 0;
@@ -224,7 +250,13 @@ int fill_params(flimo_handle h, const double state14[14], MatchParams& P, double
     CU(h, cudaMemsetAsync(h->ticket, 0, h->ticket_cap * sizeof(unsigned int), h->stream));
     CU(h, cudaStreamSynchronize(h->stream));
   }
-  P.scan = h->scan;
+  P.scan = h->packed_valid ? h->scan : nullptr;
+  P.raw_scan = h->raw_scan;
+  P.raw_stride = (uint32_t)h->raw_stride;
+  P.raw_n = (uint32_t)h->scan_n;
+  P.raw_inv = h->raw_inv;
+  P.raw_vec4 = (h->raw_stride % 16 == 0 && (reinterpret_cast<uintptr_t>(h->raw_scan) % 16) == 0) ? 1 : 0;
+  P.raw_magic = h->scan_n ? (~0ull) / (unsigned long long)h->scan_n : 0ull;
   P.n_levels = h->map.n_levels;
   for (int l = 0; l < kMaxLevels; ++l) {
     P.lv[l].pts = h->map.lv[l].pts;
@@ -238,6 +270,7 @@ int fill_params(flimo_handle h, const double state14[14], MatchParams& P, double
   P.tau = h->knn_tau;
   P.probe_mode = h->probe_mode;
   P.wide_loads = h->wide_loads;
+  P.l2_prefetch = h->l2_prefetch;
   P.max_dist_f = ceil_to_float(h->cfg.MAX_DIST_PLANE);
   P.plane_thr = (float)h->cfg.PLANE_THRESHOLD;
   P.estimate_extrinsics = h->cfg.estimate_extrinsics;
@@ -250,6 +283,9 @@ int fill_params(flimo_handle h, const double state14[14], MatchParams& P, double
   P.timing = h->timing;
   P.host_out96 = nullptr;
   P.seq = 0;
+  P.host_ctl = h->d_h_ctl;
+  P.dev_ctl = h->dev_ctl;
+  P.watchdog_ns = 20ull * 1000ull * 1000ull;          // 20 ms of host silence ends the persistent kernel
   return FLIMO_OK;
 }
 
@@ -277,6 +313,17 @@ int wait_records(flimo_handle h, const double* block, unsigned long long seq, do
   return 0;
 }
 
+// Issues a requested prefetch copy now (copy stream).  Called right after the first kernel launch of an
+// update — the API call then overlaps the kernel the host would otherwise only wait for — or, at the
+// latest, by the flimo_scan_set that consumes the prefetch.
+int issue_prefetch(flimo_handle h) {
+  if (h->pref_idx < 0 || h->pref_issued) return FLIMO_OK;
+  CU(h, cudaMemcpyAsync(h->scan_stage[h->pref_idx], h->pref_src, h->pref_n * h->pref_stride, cudaMemcpyHostToDevice, h->copy_stream));
+  CU(h, cudaEventRecord(h->ev_prefetch, h->copy_stream));
+  h->pref_issued = true;
+  return FLIMO_OK;
+}
+
 // Blocking pass.  The last CTA of the kernel also writes the 96 result doubles, each tagged with a
 // sequence number, into MAPPED pinned host memory; the host spins on those records instead of issuing a
 // D2H copy and a stream synchronise (saves ~10 us of launch/sync latency per pass).  Device time is taken from a
@@ -290,7 +337,7 @@ int run_pass_blocking(flimo_handle h, const double state14[14], uint32_t orig_li
   P.host_out96 = h->d_h_out96;
   P.seq = ++h->seq;
   // device time of the kernel: a pair of events around every `time_every`-th launch
-  const bool timed = h->time_every > 0 && (h->stats.match_launches % (uint64_t)h->time_every) == 0;
+  const bool timed = h->time_every > 0 && (h->persistent || (h->stats.match_launches % (uint64_t)h->time_every) == 0);
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (timed) {
     if (h->ev_pool.size() >= 2) {
@@ -310,6 +357,10 @@ int run_pass_blocking(flimo_handle h, const double state14[14], uint32_t orig_li
   }
   h->stats.kernel_launches++;
   h->stats.match_launches++;
+  if (h->pref_idx >= 0 && !h->pref_issued) {               // the requested copy of the next scan overlaps this kernel
+    rc = issue_prefetch(h);
+    if (rc) return rc;
+  }
   const auto tp1 = std::chrono::steady_clock::now();
   const int wr = wait_records(h, h->h_out96, P.seq, packed, true);
   if (h->prof) {
@@ -399,8 +450,11 @@ int flimo_create(const flimo_cfg* cfg, int device, flimo_handle* out) {
   h->interleave = h->cfg.sort_scan ? 1 : 0;
   if (const char* e = std::getenv("FLIMO_KNN_INTERLEAVE")) h->interleave = std::atoi(e);
   if (const char* e = std::getenv("FLIMO_KNN_PERM")) h->scan_perm = std::atoi(e);
+  if (const char* e = std::getenv("FLIMO_KNN_PREFETCH")) h->l2_prefetch = std::atoi(e);
   CU(h, cudaSetDevice(device));
   CU(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  CU(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+  CU(h, cudaEventCreateWithFlags(&h->ev_prefetch, cudaEventDisableTiming));
   CU(h, cudaEventCreate(&h->ev0));
   CU(h, cudaEventCreate(&h->ev1));
   CU(h, cudaMalloc(&h->out96, 96 * sizeof(double)));
@@ -409,6 +463,13 @@ int flimo_create(const flimo_cfg* cfg, int device, flimo_handle* out) {
   std::memset(h->h_out96, 0, 2 * 96 * sizeof(double));
   CU(h, cudaHostGetDevicePointer(reinterpret_cast<void**>(&h->d_h_out96), h->h_out96, 0));
   CU(h, cudaMalloc(&h->d_count, sizeof(unsigned int)));
+  CU(h, cudaHostAlloc(&h->h_ctl, sizeof(PassCtlWire), cudaHostAllocMapped));
+  std::memset(h->h_ctl, 0, sizeof(PassCtlWire));
+  CU(h, cudaHostGetDevicePointer(reinterpret_cast<void**>(&h->d_h_ctl), h->h_ctl, 0));
+  CU(h, cudaMalloc(&h->dev_ctl, sizeof(PassCtl)));
+  CU(h, cudaMemset(h->dev_ctl, 0, sizeof(PassCtl)));
+  h->persist_capacity = match_persistent_capacity();
+  if (const char* e = std::getenv("FLIMO_PERSISTENT")) h->persistent = std::atoi(e);
   *out = h;
   return FLIMO_OK;
 }
@@ -442,6 +503,12 @@ void flimo_destroy(flimo_handle h) {
   for (auto& g : h->scan_graphs) cudaGraphExecDestroy(g.exec);
   if (h->xch_host) cudaHostUnregister(h->xch_host);
   cudaFreeHost(h->h_out96);
+  cudaFreeHost(h->h_ctl);
+  cudaFree(h->scan_stage[0]);
+  cudaFree(h->scan_stage[1]);
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+  if (h->ev_prefetch) cudaEventDestroy(h->ev_prefetch);
+  cudaFree(h->dev_ctl);
   cudaFree(h->dbg16);
   cudaFree(h->valid_flags);
   cudaFree(h->xyz_out);
@@ -500,6 +567,8 @@ int flimo_get_stats(flimo_handle h, flimo_stats* out) {
     h->stats.table_bytes += (h->map.lv[l].n_cells + 2) * sizeof(uint32_t);
     h->stats.map_bytes += h->map.lv[l].n_entries * sizeof(float4);
   }
+  h->stats.persist_ms_total = h->persist_ns_total * 1e-6;
+  h->stats.persist_passes = h->persist_passes;
   *out = h->stats;
   return FLIMO_OK;
 }
@@ -601,12 +670,25 @@ int flimo_map_get_points(flimo_handle h, float* out_xyz, size_t cap_points, size
 }
 
 // ------------------------------------------------------------------------------------------------
-int flimo_scan_set_device(flimo_handle h, const void* d_xyz, size_t n, size_t stride_bytes) {
-  if (!h || (!d_xyz && n)) return fail(h, FLIMO_ERR_INVALID, "null argument");
-  if (stride_bytes < 12 || stride_bytes % 4) return fail(h, FLIMO_ERR_INVALID, "stride must be a multiple of 4 and >= 12");
-  NEED_GPU(h);
-  const size_t cap = h->cfg.MAX_NUM_PC2MATCH > 0 ? (size_t)h->cfg.MAX_NUM_PC2MATCH : 0;
-  const size_t nq = n > cap ? cap : n;                           // first-N rule (Mapper.cpp:63-69)
+// modular inverse of a (mod n), gcd(a, n) = 1
+static uint32_t mod_inverse(uint32_t a, uint32_t n) {
+  long long t = 0, nt = 1, r = n, nr = a % n;
+  while (nr != 0) {
+    const long long q = r / nr;
+    const long long tt = t - q * nt; t = nt; nt = tt;
+    const long long rr = r - q * nr; r = nr; nr = rr;
+  }
+  if (t < 0) t += n;
+  return (uint32_t)t;
+}
+
+// Builds the packed copy h->scan of the bound scan (pack [+ Morton sort]); needed by sort_scan and by the
+// helpers that walk the scan in storage order.  The pipeline is captured once per (source, size) into a
+// CUDA graph and replayed with a single launch afterwards.
+static int pack_bound_scan(flimo_handle h) {
+  const void* d_xyz = h->raw_scan;
+  const size_t nq = h->scan_n, stride_bytes = h->raw_stride;
+  if (nq == 0 || h->packed_valid) return FLIMO_OK;
   if (nq > h->scan_cap) {
     cudaFree(h->scan);
     cudaFree(h->scan_tmp);
@@ -619,14 +701,9 @@ int flimo_scan_set_device(flimo_handle h, const void* d_xyz, size_t n, size_t st
     for (auto& g : h->scan_graphs) cudaGraphExecDestroy(g.exec);   // captured pointers are stale
     h->scan_graphs.clear();
   }
-  h->scan_n = nq;
-  h->shard_begin = 0;
-  h->shard_end = nq;
-  if (nq == 0) return FLIMO_OK;
   const int sort = (h->cfg.sort_scan && nq > 1) ? 1 : 0;
   const unsigned int perm = (sort || !h->scan_perm) ? 0u : coprime_stride((uint32_t)nq);
-  // The upload pipeline (pack + Morton keys, radix sort, gather: 7 launches) is captured once per
-  // (source pointer, size) into a CUDA graph and replayed with a single launch afterwards.
+  h->packed_valid = true;
   for (auto& g : h->scan_graphs) {
     if (g.src == d_xyz && g.n == nq && g.stride == stride_bytes && g.sort == sort) {
       CU(h, cudaGraphLaunch(g.exec, h->stream));
@@ -667,16 +744,79 @@ int flimo_scan_set_device(flimo_handle h, const void* d_xyz, size_t n, size_t st
   return FLIMO_OK;
 }
 
-int flimo_scan_set(flimo_handle h, const float* xyz_body, size_t n, size_t stride_bytes) {
+int flimo_scan_set_device(flimo_handle h, const void* d_xyz, size_t n, size_t stride_bytes) {
+  if (!h || (!d_xyz && n)) return fail(h, FLIMO_ERR_INVALID, "null argument");
+  if (stride_bytes < 12 || stride_bytes % 4) return fail(h, FLIMO_ERR_INVALID, "stride must be a multiple of 4 and >= 12");
+  NEED_GPU(h);
+  const size_t cap = h->cfg.MAX_NUM_PC2MATCH > 0 ? (size_t)h->cfg.MAX_NUM_PC2MATCH : 0;
+  const size_t nq = n > cap ? cap : n;                           // first-N rule (Mapper.cpp:63-69)
+  // The measurement kernel reads the caller's array IN PLACE (no copy, no launch): stored position j of
+  // its pseudo-random query order is original point (j * raw_inv) mod n.  The array must stay valid and
+  // unchanged until the next scan is bound.
+  h->raw_scan = static_cast<const unsigned char*>(d_xyz);
+  h->raw_stride = stride_bytes;
+  h->scan_n = nq;
+  h->shard_begin = 0;
+  h->shard_end = nq;
+  h->packed_valid = false;
+  h->raw_inv = 1;
+  if (nq == 0) return FLIMO_OK;
+  if (h->cfg.sort_scan && nq > 1) return pack_bound_scan(h);     // Morton order needs the packed copy
+  if (h->scan_perm && nq > 2) h->raw_inv = mod_inverse(coprime_stride((uint32_t)nq), (uint32_t)nq);
+  return FLIMO_OK;
+}
+
+static int stage_reserve(flimo_handle h, int idx, size_t bytes) {
+  if (bytes <= h->scan_stage_cap[idx]) return FLIMO_OK;
+  if (h->scan_stage[idx]) cudaFree(h->scan_stage[idx]);
+  h->scan_stage[idx] = nullptr;
+  h->scan_stage_cap[idx] = 0;
+  CU(h, cudaMalloc(&h->scan_stage[idx], bytes + bytes / 4 + 4096));
+  h->scan_stage_cap[idx] = bytes + bytes / 4 + 4096;
+  return FLIMO_OK;
+}
+
+int flimo_scan_prefetch(flimo_handle h, const float* xyz_body, size_t n, size_t stride_bytes) {
   if (!h || (!xyz_body && n)) return fail(h, FLIMO_ERR_INVALID, "null argument");
+  if (stride_bytes < 12 || stride_bytes % 4) return fail(h, FLIMO_ERR_INVALID, "stride must be a multiple of 4 and >= 12");
   NEED_GPU(h);
   const size_t cap = h->cfg.MAX_NUM_PC2MATCH > 0 ? (size_t)h->cfg.MAX_NUM_PC2MATCH : 0;
   const size_t nq = n > cap ? cap : n;
-  if (nq) {
-    int rc = upload(h, xyz_body, nq * stride_bytes);
+  h->pref_idx = -1;
+  h->pref_issued = false;
+  if (nq == 0) return FLIMO_OK;
+  const int idx = h->scan_stage_bound ^ 1;                        // the staging buffer the bound scan does not use
+  int rc = stage_reserve(h, idx, nq * stride_bytes);
+  if (rc) return rc;
+  h->pref_src = xyz_body;
+  h->pref_n = nq;
+  h->pref_stride = stride_bytes;
+  h->pref_idx = idx;
+  return FLIMO_OK;
+}
+
+int flimo_scan_set(flimo_handle h, const float* xyz_body, size_t n, size_t stride_bytes) {
+  if (!h || (!xyz_body && n)) return fail(h, FLIMO_ERR_INVALID, "null argument");
+  if (stride_bytes < 12 || stride_bytes % 4) return fail(h, FLIMO_ERR_INVALID, "stride must be a multiple of 4 and >= 12");
+  NEED_GPU(h);
+  const size_t cap = h->cfg.MAX_NUM_PC2MATCH > 0 ? (size_t)h->cfg.MAX_NUM_PC2MATCH : 0;
+  const size_t nq = n > cap ? cap : n;
+  if (nq == 0) return flimo_scan_set_device(h, h->scan_stage[0], 0, stride_bytes);
+  int idx;
+  if (h->pref_idx >= 0 && h->pref_src == xyz_body && h->pref_n == nq && h->pref_stride == stride_bytes) {
+    idx = h->pref_idx;                                            // already on its way: order the passes after the copy
+    int rc = issue_prefetch(h);
     if (rc) return rc;
+    CU(h, cudaStreamWaitEvent(h->stream, h->ev_prefetch, 0));
+  } else {
+    idx = h->scan_stage_bound ^ 1;
+    int rc = stage_reserve(h, idx, nq * stride_bytes);
+    if (rc) return rc;
+    CU(h, cudaMemcpyAsync(h->scan_stage[idx], xyz_body, nq * stride_bytes, cudaMemcpyHostToDevice, h->stream));
   }
-  return flimo_scan_set_device(h, h->stage, nq, stride_bytes);
+  h->pref_idx = -1;
+  h->scan_stage_bound = idx;
+  return flimo_scan_set_device(h, h->scan_stage[idx], nq, stride_bytes);
 }
 
 int flimo_scan_shard(flimo_handle h, size_t begin, size_t end) {
@@ -872,6 +1012,10 @@ int flimo_scan_to_world(flimo_handle h, const double state14[14], float* out_xyz
   CU(h, grow(&h->xyz_out, &h->xyz_cap, nq * 3));
   PoseConsts pc;
   make_pose(state14, pc);
+  {
+    const int prc = pack_bound_scan(h);
+    if (prc) return prc;
+  }
   CU(h, transform_scan(h->scan, nq, pc, h->xyz_out, h->stream));
   h->stats.kernel_launches++;
   const size_t m = nq < cap_points ? nq : cap_points;
@@ -906,12 +1050,94 @@ int flimo_ekf_end(flimo_handle h, double state26[26], double P529[529]) {
   return FLIMO_OK;
 }
 
+// Hands the persistent kernel its next command through the mapped control block.
+static void post_ctl(flimo_handle h, unsigned long long seq, uint32_t cmd, uint32_t orig_limit, const double* state14) {
+  uint32_t w[3 * kCtlRecords];
+  std::memset(w, 0, sizeof(w));
+  w[0] = cmd;
+  w[1] = orig_limit;
+  if (state14) {
+    PoseConsts pc;
+    make_pose(state14, pc);
+    std::memcpy(&w[2], &pc, sizeof(pc));
+  }
+  for (int r = 0; r < kCtlRecords; ++r) {                // one 16-byte store per record
+    const __m128i v = _mm_set_epi32((int)(uint32_t)seq, (int)w[3 * r + 2], (int)w[3 * r + 1], (int)w[3 * r]);
+    _mm_store_si128(reinterpret_cast<__m128i*>(&h->h_ctl->rec[r][0]), v);
+  }
+}
+
+// flimo_update with ONE kernel launch for all passes (match_persistent_kernel).  Returns 1 when the caller
+// has to finish the update with per-pass launches (kernel ended early, or the MAX_NUM_MATCHES truncation
+// needs the general path); `u` is then positioned at the pass that has to be (re)done.
+static int update_persistent(flimo_handle h, ekf::IteratedUpdate& u) {
+  const size_t n = h->shard_end - h->shard_begin;
+  const int tiles = match_num_tiles((int)n);
+  double x[26], HTH[144], HTh[12], packed[96];
+  u.state(x);
+  MatchParams P;
+  int rc = fill_params(h, x, P, h->out96, 0xFFFFFFFFu, nullptr, nullptr);
+  if (rc) return rc;
+  P.host_out96 = h->d_h_out96;
+  P.seq = h->seq + 1;                                   // sequence number of the first pass
+  const int grid = std::min(tiles, h->persist_capacity);
+  CU(h, launch_match_persistent(P, grid, h->stream));
+  h->stats.kernel_launches++;
+  int fallback = 0;
+  while (!u.done()) {
+    u.state(x);
+    const unsigned long long seq = ++h->seq;
+    const auto tp0 = std::chrono::steady_clock::now();
+    post_ctl(h, seq, 0u, 0xFFFFFFFFu, x);
+    if (h->pref_idx >= 0 && !h->pref_issued) {             // the requested copy of the next scan overlaps this pass
+      rc = issue_prefetch(h);
+      if (rc) return rc;
+    }
+    const int wr = wait_records(h, h->h_out96, seq, packed, true);
+    if (wr < 0) return wr;
+    if (wr == 1) {                                        // watchdog fired / kernel gone: redo this pass classically
+      fallback = 1;
+      break;
+    }
+    h->stats.match_launches++;
+    h->persist_ns_total += packed[93];
+    h->persist_passes++;
+    packed[93] = 0.0;
+    if (h->prof) {
+      h->prof_wait += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - tp0).count();
+      h->prof_passes++;
+    }
+    if ((int64_t)std::llround(packed[92]) > (int64_t)h->cfg.MAX_NUM_MATCHES) {   // first-N truncation: general path
+      fallback = 1;
+      break;
+    }
+    int64_t nv = 0, nr = 0;
+    double ss = 0;
+    flimo_unpack96(packed, HTH, HTh, &nv, &nr, &ss);
+    const auto ts0 = std::chrono::steady_clock::now();
+    u.step(HTH, HTh, nr);
+    if (h->prof) h->prof_step += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - ts0).count();
+  }
+  post_ctl(h, ++h->seq, 1u, 0u, nullptr);                // stop: the kernel exits
+  return fallback;
+}
+
 int flimo_update(flimo_handle h, double state26[26], double P529[529], int max_iter, const double limit23[23],
                  double R_noise, double D_degeneracy, int* passes_out) {
   if (!h || !state26 || !P529 || !limit23) return fail(h, FLIMO_ERR_INVALID, "null argument");
   ekf::IteratedUpdate& u = h->upd;
   u.begin(state26, P529, max_iter, limit23, R_noise, D_degeneracy);
   double x[26], HTH[144], HTh[12];
+  ++h->update_calls;
+  // Every time_every-th update runs with one launch per pass so that the kernel can be timed with CUDA
+  // events (flimo_stats::match_ms_total); the others keep one persistent kernel resident over all passes.
+  const bool classic = !h->persistent || h->device < 0 || h->persist_capacity <= 0 || !flimo_map_exists(h) ||
+                       h->shard_end <= h->shard_begin || h->timing != nullptr ||
+                       (h->time_every > 0 && (h->update_calls % (uint64_t)h->time_every) == 0);
+  if (!classic && !u.done()) {
+    const int rc = update_persistent(h, u);
+    if (rc < 0) return rc;
+  }
   while (!u.done()) {
     u.state(x);
     int64_t nv = 0, nr = 0;

@@ -43,12 +43,43 @@ struct PoseConsts {
   float Rd_LI_inv[9];             // s.offset_R_L_I.conjugate().toRotationMatrix().cast<float>()
 };
 
+// Control block of the persistent kernel (one per handle in mapped pinned host memory, one in device
+// memory).  The host fills everything after `t_begin`, then stores `seq` (release); CTA 0 copies the
+// payload to the device copy, stamps t_begin and publishes seq there.
+struct PassCtl {
+  unsigned long long seq;      // sequence number of the pass this block describes (written last)
+  unsigned long long t_begin;  // device copy only: %globaltimer when the pass was released
+  uint32_t cmd;                // 0 = run the pass, 1 = stop (kernel exits)
+  uint32_t orig_limit;         // first-N cap on contributing rows
+  PoseConsts pc;
+  uint32_t pad[1];
+};
+static_assert(sizeof(PassCtl) % 8 == 0, "PassCtl must be a whole number of 8-byte words");
+// Wire format of the HOST control block: the 56 payload words of a PassCtl (cmd, orig_limit, pose) in 19
+// records of 16 bytes, each {3 payload words, tag = low 32 bits of the pass sequence number}.  The host
+// stores every record with ONE 16-byte store, the device reads every record with ONE 16-byte load and all
+// 19 in parallel: a command is complete when all tags match — a single PCIe read round trip per poll.
+constexpr int kCtlPayloadWords = 2 + (int)(sizeof(PoseConsts) / 4);          // 56
+constexpr int kCtlRecords = (kCtlPayloadWords + 2) / 3;                       // 19
+struct PassCtlWire {
+  uint32_t rec[kCtlRecords][4];
+};
+static_assert(kCtlRecords <= 32, "one warp reads the control block");
+constexpr unsigned long long kPassAbort = ~0ull;
+
 constexpr int kTileQueries = 128;     // queries per CTA tile (== threads per CTA)
 constexpr int kTriEntries = 91;       // upper triangle of the 13x13 outer product of [row(12), z]
 constexpr int kPartialStride = 96;    // doubles per partial record
 
 struct MatchParams {
-  const float4* scan;          // body-frame points; .w carries the original scan index (bit pattern)
+  const float4* scan;          // packed body-frame points; .w carries the original scan index (bit pattern)
+  // Unpacked scan (scan == nullptr): the caller's strided xyz array is read in place.  Stored position j of
+  // the pseudo-random order is original point (j * raw_inv) mod raw_n (raw_inv = inverse of the upload
+  // permutation's stride), evaluated with a 64-bit Barrett reduction (raw_magic = floor(2^64 / raw_n)).
+  const unsigned char* raw_scan;
+  uint32_t raw_stride, raw_n, raw_inv;
+  int raw_vec4;                // stride and base are multiples of 16 bytes: points are read with one 16-byte load
+  unsigned long long raw_magic;
   LevelView lv[kMaxLevels];    // finest first
   int n_levels;
   PoseConsts pc;
@@ -57,6 +88,7 @@ struct MatchParams {
   int tau;                     // level choice: finest level whose 3x3x3 block holds >= tau candidates
   int probe_mode;              // 0 = probe all levels at once, 1 = climb one level at a time
   int wide_loads;              // 1 = 256-bit candidate loads
+  int l2_prefetch;             // 1 = request the whole run with prefetch.global.L2 right after the probe
   float max_dist_f;            // smallest float >= MAX_DIST_PLANE  (d2_5 < MAX_DIST_PLANE test)
   float plane_thr;             // (float)PLANE_THRESHOLD
   int estimate_extrinsics;
@@ -69,6 +101,10 @@ struct MatchParams {
   double* host_out96;          // optional mapped pinned copy of the result: 96 records {double value, u64 seq}
   unsigned long long seq;      // sequence number stored with every record
   unsigned long long* timing;  // optional per-warp timestamps (profiling builds of the tools only)
+  // persistent kernel only
+  const PassCtlWire* host_ctl; // device alias of the host control block
+  PassCtl* dev_ctl;            // device copy
+  unsigned long long watchdog_ns;
 };
 
 // map_index.cu
@@ -156,6 +192,8 @@ cudaError_t points_bbox(const float4* d_pts, size_t n, float* d_scratch8, float 
 
 // match_kernel.cu
 cudaError_t launch_match(const MatchParams& p, cudaStream_t st);
+cudaError_t launch_match_persistent(const MatchParams& p, int grid, cudaStream_t st);
+int match_persistent_capacity();
 int match_num_tiles(int n_queries);
 
 }  // namespace flimo

@@ -388,8 +388,8 @@ cudaError_t map_index_build(MapIndex& idx, float cell0, float ratio, float coars
     idx.lo[a] = ord2f(hb[a]);
     idx.hi[a] = ord2f(hb[3 + a]);
   }
-  if (!(cell0 > 0.f)) cell0 = 0.15f;
-  if (!(ratio > 1.05f)) ratio = 1.41421356f;
+  if (!(cell0 > 0.f)) cell0 = 0.25f;
+  if (!(ratio > 1.05f)) ratio = 1.5f;
   for (;;) {   // finest level must fit the table budget
     const GridDesc g = make_grid(idx.lo, idx.hi, cell0);
     if ((double)g.nx * g.ny * g.nz <= (double)max_cells) break;

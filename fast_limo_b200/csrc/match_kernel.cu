@@ -396,6 +396,15 @@ __device__ __forceinline__ void knn_search(const MatchParams& P, int lane, bool 
     }
     first_lvl = lvl;
     first_cnt = pr.e - pr.s;
+    if (P.l2_prefetch) {
+      // Pull the whole run towards L2 now (fire and forget, no registers): every lane streams a different
+      // run, so a warp-level load waits for the slowest of 32 independent lines — with the run requested
+      // up front the scan's loads find their lines in L2 (or on their way) instead of paying DRAM latency
+      // once per loop iteration.
+      const char* pf = reinterpret_cast<const char*>(P.lv[lvl].pts + (pr.s & ~7u));
+      const char* pe = reinterpret_cast<const char*>(P.lv[lvl].pts + min(pr.e, pr.s + kPrivateCap));
+      for (; pf < pe; pf += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(pf));
+    }
     const bool exact_here = block_scan_private<kWide>(P.lv[lvl], pr.s, pr.e, qx, qy, qz, t);
     if (!exact_here) {
       pending = true;                                          // redo this level cooperatively
@@ -632,20 +641,44 @@ __device__ __forceinline__ void tri13(int e, int& i, int& j) {
   j = r + (e - base);
 }
 
-template <bool kWide>
-__global__ void __launch_bounds__(kTileQueries, 7) match_reduce_kernel(const __grid_constant__ MatchParams P) {
-  __shared__ __align__(16) float tile[kTileQueries / 32][32][24];   // rows of [row(12), z] as floats; stride 24: conflict-free fragment reads
-  __shared__ double wsum[kTileQueries / 32][kPartialStride];
-  __shared__ int s_last;
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 
+__device__ __forceinline__ int match_num_tiles_dev(int n_queries) { return (n_queries + kTileQueries - 1) / kTileQueries; }
+
+// Shared memory of one CTA (one 128-query tile at a time).
+struct TileShared {
+  __align__(16) float tile[kTileQueries / 32][32][24];   // rows of [row(12), z] as floats; stride 24: conflict-free fragment reads
+  double wsum[kTileQueries / 32][kPartialStride];
+  int s_last;
+};
+
+// One tile of one measurement pass: 128 queries -> partial normal equations -> deterministic tree over
+// the tiles; the CTA that completes the tree publishes the pass result.  `pc` is the pose (kernel
+// parameter bank in the one-launch-per-pass kernel, shared memory in the persistent kernel), `seq` the
+// sequence number of the pass, `orig_limit` the first-N cap on contributing rows.
+template <bool kWide>
+__device__ __forceinline__ void match_tile(const MatchParams& P, const PoseConsts& pc, TileShared& sh, const int tile_idx,
+                                           const int n_tiles, const unsigned long long seq, const uint32_t orig_limit,
+                                           const unsigned long long t_begin) {
+  auto& tile = sh.tile;
+  auto& wsum = sh.wsum;
+  int& s_last = sh.s_last;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   // Query assignment.  The scan is stored in a pseudo-random order (pack_scan_kernel scatters the points
   // with a multiplicative permutation on upload): neighbouring scan points share sparse / dense regions
   // of the map and therefore search cost, and must not pile up in one warp.  A tile simply takes 128
   // consecutive stored points (coalesced read).  Morton-sorted scans (sort_scan) are interleaved over the
   // tiles instead.  Results do not depend on the assignment.
-  const int i_lin = P.interleave ? (int)threadIdx.x * (int)gridDim.x + (int)blockIdx.x
-                                 : (int)blockIdx.x * kTileQueries + (int)threadIdx.x;
+  const int i_lin = P.interleave ? (int)threadIdx.x * n_tiles + tile_idx : tile_idx * kTileQueries + (int)threadIdx.x;
   const int q = min(P.q_begin + i_lin, P.q_end);
   const bool in_range = q < P.q_end;
 
@@ -657,9 +690,27 @@ __global__ void __launch_bounds__(kTileQueries, 7) match_reduce_kernel(const __g
 
   float g[3] = {0.f, 0.f, 0.f};
   if (in_range) {
-    const float4 sp = __ldg(&P.scan[q]);
-    orig = __float_as_uint(sp.w);
-    affine_apply(P.pc.R_wb, P.pc.t_wb, sp.x, sp.y, sp.z, g);
+    float sx, sy, sz;
+    if (P.scan != nullptr) {
+      const float4 sp = __ldg(&P.scan[q]);
+      orig = __float_as_uint(sp.w);
+      sx = sp.x; sy = sp.y; sz = sp.z;
+    } else {
+      // in-place read of the caller's array: original index = (q * raw_inv) mod raw_n
+      const unsigned long long prod = (unsigned long long)(uint32_t)q * P.raw_inv;
+      unsigned long long r = prod - __umul64hi(prod, P.raw_magic) * P.raw_n;
+      if (r >= P.raw_n) r -= P.raw_n;
+      orig = (uint32_t)r;
+      const unsigned char* sp = P.raw_scan + (size_t)orig * P.raw_stride;
+      if (P.raw_vec4) {                                    // 16-byte aligned records: one load
+        const float4 v = __ldg(reinterpret_cast<const float4*>(sp));
+        sx = v.x; sy = v.y; sz = v.z;
+      } else {
+        const float* sf = reinterpret_cast<const float*>(sp);
+        sx = __ldg(sf); sy = __ldg(sf + 1); sz = __ldg(sf + 2);
+      }
+    }
+    affine_apply(pc.R_wb, pc.t_wb, sx, sy, sz, g);
   }
   Top5 t;
 #pragma unroll
@@ -710,11 +761,11 @@ __global__ void __launch_bounds__(kTileQueries, 7) match_reduce_kernel(const __g
 
     if (accepted) {
       float p_imu[3], p_lid[3], C[3], RC[3];
-      affine_apply(P.pc.Rinv_wb, P.pc.tinv_wb, g[0], g[1], g[2], p_imu);
-      affine_apply(P.pc.Rinv_LI, P.pc.tinv_LI, p_imu[0], p_imu[1], p_imu[2], p_lid);
+      affine_apply(pc.Rinv_wb, pc.tinv_wb, g[0], g[1], g[2], p_imu);
+      affine_apply(pc.Rinv_LI, pc.tinv_LI, p_imu[0], p_imu[1], p_imu[2], p_lid);
       const float nv[3] = {n4[0], n4[1], n4[2]};
-      mat3_vec(P.pc.Rd_wb_inv, nv, C);
-      mat3_vec(P.pc.Rd_LI_inv, C, RC);
+      mat3_vec(pc.Rd_wb_inv, nv, C);
+      mat3_vec(pc.Rd_LI_inv, C, RC);
       v13[0] = n4[0];
       v13[1] = n4[1];
       v13[2] = n4[2];
@@ -752,7 +803,7 @@ __global__ void __launch_bounds__(kTileQueries, 7) match_reduce_kernel(const __g
   // mma.m8n8k4.f64 (products of two floats are exact in float64).  Fragment of step k: lane l supplies
   // V[4k + l%4][l/4] (columns 0-7) and V[4k + l%4][8 + l/4] (columns 8-15) — A and B fragments of a
   // diagonal tile coincide.  H is never written.
-  const bool contributes = accepted && (orig < P.orig_limit);
+  const bool contributes = accepted && (orig < orig_limit);
   const unsigned int m_all = __ballot_sync(0xffffffffu, accepted);
   const unsigned int m_rows = __ballot_sync(0xffffffffu, contributes);
   {
@@ -806,7 +857,7 @@ __global__ void __launch_bounds__(kTileQueries, 7) match_reduce_kernel(const __g
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tm3));
     unsigned int smid;
     asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-    unsigned long long* o = P.timing + ((size_t)blockIdx.x * (kTileQueries / 32) + warp) * 8;
+    unsigned long long* o = P.timing + ((size_t)tile_idx * (kTileQueries / 32) + warp) * 8;
     o[0] = smid; o[1] = tm0; o[2] = tm1; o[3] = tm2; o[4] = tm3;
     o[5] = (unsigned long long)__popc(__ballot_sync(0xffffffffu, lvl != first_lvl));
     o[6] = t_priv;
@@ -816,16 +867,15 @@ __global__ void __launch_bounds__(kTileQueries, 7) match_reduce_kernel(const __g
     (void)__reduce_max_sync(0xffffffffu, first_cnt);
   }
   // ---- CTA partial, then a deterministic two-level tree over tiles ----------------------------------
-  const int n_tiles = gridDim.x;
   const int n_groups = (n_tiles + kGroupTiles - 1) / kGroupTiles;
-  const int group = blockIdx.x / kGroupTiles;
+  const int group = tile_idx / kGroupTiles;
   double* tile_part = P.partials;                                   // [n_tiles][96]
   double* group_part = P.partials + (size_t)n_tiles * kPartialStride;   // [n_groups][96]
   if (threadIdx.x < kPartialStride) {
     double s = 0.0;
 #pragma unroll
     for (int w = 0; w < kTileQueries / 32; ++w) s += wsum[w][threadIdx.x];
-    __stcg(&tile_part[(size_t)blockIdx.x * kPartialStride + threadIdx.x], s);
+    __stcg(&tile_part[(size_t)tile_idx * kPartialStride + threadIdx.x], s);
   }
   __threadfence();
   __syncthreads();
@@ -887,24 +937,127 @@ __global__ void __launch_bounds__(kTileQueries, 7) match_reduce_kernel(const __g
     } else if (e == 91) out_idx = 92;     // n_valid
     else if (e == 92) out_idx = 90;       // n_rows
     else out_idx = e;                     // 93,94,95 reserved (zero)
-    P.out96[out_idx] = s;
+    if (e == 93 && t_begin != 0ull) s = (double)(globaltimer_ns() - t_begin);   // persistent kernel: device time of the pass (ns)
+    wsum[0][out_idx] = s;                                  // stage in packed order
+  }
+  if (threadIdx.x == 0) P.ticket[0] = 0u;                  // self reset for the next pass / launch
+  __syncthreads();
+  if (threadIdx.x < kPartialStride) {
+    const double v = wsum[0][threadIdx.x];
+    P.out96[threadIdx.x] = v;
     // Mapped pinned host copy: 96 records of {value, sequence number}, each ONE 16-byte store, so a
     // record is complete as soon as its sequence word is visible — no system-scope fence, no flag.
+    // Consecutive threads write consecutive records: the 1.5 KB leave the GPU as twelve full 128-byte
+    // PCIe writes instead of 96 partial ones.
     if (P.host_out96 != nullptr)
-      reinterpret_cast<ulonglong2*>(P.host_out96)[out_idx] =
-          make_ulonglong2((unsigned long long)__double_as_longlong(s), P.seq);
+      reinterpret_cast<ulonglong2*>(P.host_out96)[threadIdx.x] = make_ulonglong2((unsigned long long)__double_as_longlong(v), seq);
   }
-  if (threadIdx.x == 0) P.ticket[0] = 0u;
   if (P.timing && threadIdx.x == 0) {
     unsigned long long te;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(te));
-    P.timing[(size_t)gridDim.x * (kTileQueries / 32) * 8] = te;
+    P.timing[(size_t)n_tiles * (kTileQueries / 32) * 8] = te;
+  }
+}
+
+// One launch = one pass (the pose travels in the kernel parameters).
+template <bool kWide>
+__global__ void __launch_bounds__(kTileQueries, 7) match_reduce_kernel(const __grid_constant__ MatchParams P) {
+  __shared__ TileShared sh;
+  match_tile<kWide>(P, P.pc, sh, (int)blockIdx.x, (int)gridDim.x, P.seq, P.orig_limit, 0ull);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Persistent form: ONE launch per scan registration.  The CTAs stay resident over all passes of
+// esekf::update_iterated_dyn_share_modified (esekfom.hpp:1634-1764); between passes the host runs the
+// 23x23 filter algebra and hands the next pose over through MAPPED PINNED HOST MEMORY instead of a new
+// launch: CTA 0 polls the host control block (one PCIe read per poll), copies the pose to device memory
+// and raises a device flag; every CTA waits for that flag, takes the pose into shared memory and runs
+// its tile(s).  The pass result goes back the same way it does in the per-pass kernel (tagged 16-byte
+// records).  This removes the launch latency (~10 us of host + device time) from every pass.
+// A watchdog ends the kernel if the host stays silent (the host then continues with per-pass launches).
+// ---------------------------------------------------------------------------------------------------
+template <bool kWide>
+__global__ void __launch_bounds__(kTileQueries, 7) match_persistent_kernel(const __grid_constant__ MatchParams P) {
+  __shared__ TileShared sh;
+  __shared__ PassCtl s_ctl;
+  const int n_tiles = match_num_tiles_dev(P.q_end - P.q_begin);
+  PassCtl* dctl = P.dev_ctl;
+  for (unsigned long long want = P.seq;; ++want) {
+    if (blockIdx.x == 0 && threadIdx.x < 32) {
+      // the host's control block: 19 tagged 16-byte records, read by 19 lanes in one PCIe round trip
+      const PassCtlWire* hctl = P.host_ctl;
+      const int lane = (int)threadIdx.x;
+      const uint32_t tag = (uint32_t)want;
+      uint32_t r0 = 0, r1 = 0, r2 = 0, r3 = tag;
+      bool ok = false;
+      const unsigned long long t0 = globaltimer_ns();
+      for (;;) {
+        if (lane < kCtlRecords)
+          asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "l"(&hctl->rec[lane][0]) : "memory");
+        ok = __all_sync(0xffffffffu, r3 == tag);
+        if (ok) break;
+        if (__any_sync(0xffffffffu, globaltimer_ns() - t0 > P.watchdog_ns)) break;
+      }
+      if (ok) {
+        uint32_t* dst = reinterpret_cast<uint32_t*>(&dctl->cmd);          // cmd, orig_limit, pose words follow each other
+        if (lane < kCtlRecords) {
+          if (3 * lane < kCtlPayloadWords) dst[3 * lane] = r0;
+          if (3 * lane + 1 < kCtlPayloadWords) dst[3 * lane + 1] = r1;
+          if (3 * lane + 2 < kCtlPayloadWords) dst[3 * lane + 2] = r2;
+        }
+        if (lane == 0) dctl->t_begin = globaltimer_ns();
+      } else if (lane == 0) {
+        dctl->cmd = 1u;
+      }
+      __threadfence();
+      __syncwarp();
+      if (lane == 0) {
+        const unsigned long long pub = ok ? want : kPassAbort;
+        asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(&dctl->seq), "l"(pub) : "memory");
+      }
+    }
+    if (threadIdx.x == 0) {
+      unsigned long long f;
+      for (;;) {
+        f = ld_acquire_u64(&dctl->seq);
+        if (f == want || f == kPassAbort) break;
+        __nanosleep(64);
+      }
+    }
+    __syncthreads();
+    {
+      const uint32_t* src = reinterpret_cast<const uint32_t*>(dctl);
+      uint32_t* dst = reinterpret_cast<uint32_t*>(&s_ctl);
+      for (int w = (int)threadIdx.x; w < (int)(sizeof(PassCtl) / 4); w += kTileQueries) dst[w] = __ldcg(src + w);
+    }
+    __syncthreads();
+    if (s_ctl.cmd != 0u) return;
+    for (int t = (int)blockIdx.x; t < n_tiles; t += (int)gridDim.x)
+      match_tile<kWide>(P, s_ctl.pc, sh, t, n_tiles, want, s_ctl.orig_limit, s_ctl.t_begin);
+    __syncthreads();
   }
 }
 
 }  // namespace
 
 int match_num_tiles(int n_queries) { return (n_queries + kTileQueries - 1) / kTileQueries; }
+
+cudaError_t launch_match_persistent(const MatchParams& p, int grid, cudaStream_t st) {
+  const int n = p.q_end - p.q_begin;
+  if (n <= 0 || grid <= 0) return cudaErrorInvalidValue;
+  if (p.wide_loads) match_persistent_kernel<true><<<grid, kTileQueries, 0, st>>>(p);
+  else match_persistent_kernel<false><<<grid, kTileQueries, 0, st>>>(p);
+  return cudaGetLastError();
+}
+
+// CTAs of the persistent kernel that can be resident at once on the current device.
+int match_persistent_capacity() {
+  int dev = 0, sms = 0, per_sm = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, match_persistent_kernel<true>, kTileQueries, 0) != cudaSuccess) return 0;
+  return sms * per_sm;
+}
 
 cudaError_t launch_match(const MatchParams& p, cudaStream_t st) {
   const int n = p.q_end - p.q_begin;

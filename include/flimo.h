@@ -59,8 +59,8 @@ typedef struct {
   /* Extensions (defaults keep reference behaviour): */
   float knn_cell;               /* side of the device search grid in metres; 0 = choose automatically */
   int32_t sort_scan;            /* 1 = Morton-sort the scan on upload; 0 (default) = the kernel scatters the query order itself */
-  float knn_level_ratio;        /* cell growth between index levels; 0 = default (sqrt 2) */
-  int32_t knn_tau;              /* a query starts on the finest level whose 3x3x3 block holds >= knn_tau points; 0 = default (24) */
+  float knn_level_ratio;        /* cell growth between index levels; 0 = default (1.5) */
+  int32_t knn_tau;              /* a query starts on the finest level whose 3x3x3 block holds >= knn_tau points; 0 = default (8) */
 } flimo_cfg;
 
 void flimo_cfg_default(flimo_cfg* cfg);
@@ -91,7 +91,15 @@ int flimo_map_get_points(flimo_handle h, float* out_xyz, size_t cap_points, size
 /* Binds Localizer::pc2match (use-ikfom.cpp:18): body-frame points of the current scan.  Only the
  * first min(n, MAX_NUM_PC2MATCH) points are kept (Mapper.cpp:63-69).  One H2D copy per scan. */
 int flimo_scan_set(flimo_handle h, const float* xyz_body, size_t n, size_t stride_bytes);
+/* Same for a scan that already lives in device memory.  The array is read IN PLACE by the measurement
+ * passes (no copy): it must stay valid and unchanged until the next scan is bound. */
 int flimo_scan_set_device(flimo_handle h, const void* d_xyz_body, size_t n, size_t stride_bytes);
+/* Optional: starts the host-to-device copy of the NEXT scan on a separate copy stream and returns at
+ * once, so that the copy overlaps the registration of the current scan (a LiDAR driver delivers scan
+ * k+1 while scan k is being registered).  A later flimo_scan_set with the same (pointer, n, stride)
+ * binds the prefetched copy instead of copying again; any other flimo_scan_set simply ignores it.
+ * The host buffer must stay unchanged until that flimo_scan_set returns. */
+int flimo_scan_prefetch(flimo_handle h, const float* xyz_body, size_t n, size_t stride_bytes);
 /* Multi-GPU: restrict this handle to the contiguous slice [begin, end) of the (capped) scan. */
 int flimo_scan_shard(flimo_handle h, size_t begin, size_t end);
 
@@ -169,7 +177,7 @@ int flimo_scan_to_world(flimo_handle h, const double state14[14], float* out_xyz
 /* ---- introspection (bench / profiles) ------------------------------------------------------- */
 typedef struct {
   uint64_t kernel_launches;     /* CUDA kernels launched by this handle so far */
-  uint64_t match_launches;      /* of which the fused match+reduce kernel */
+  uint64_t match_launches;      /* measurement passes executed (one kernel launch each, or one iteration of the persistent kernel) */
   float last_match_ms;          /* device time of the last timed match launch (CUDA events) */
   double match_ms_total;        /* sum of device times of all match launches (events on the launch stream) */
   uint64_t match_timed;         /* number of launches in that sum */
@@ -177,6 +185,8 @@ typedef struct {
   int32_t grid_nx, grid_ny, grid_nz;
   int32_t n_levels;
   uint64_t table_bytes, map_bytes;
+  double persist_ms_total;      /* in-kernel device time (%globaltimer) of the passes run by the persistent kernel */
+  uint64_t persist_passes;      /* number of such passes */
 } flimo_stats;
 int flimo_get_stats(flimo_handle h, flimo_stats* out);
 void* flimo_stream(flimo_handle h);   /* the handle's cudaStream_t */
