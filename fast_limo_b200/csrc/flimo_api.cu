@@ -106,6 +106,7 @@ struct flimo_ctx {
   PassCtlWire* d_h_ctl = nullptr;   // its device alias
   PassCtl* dev_ctl = nullptr;    // device copy
   int persistent = 1;            // 1 = flimo_update keeps one kernel resident over all passes
+  unsigned long long ctl_seq = 0;   // tag of the last command posted to the persistent kernel
   int persist_capacity = 0;      // co-resident CTAs of the persistent kernel
   double persist_ns_total = 0;   // in-kernel device time of persistent passes
   uint64_t persist_passes = 0;
@@ -282,10 +283,12 @@ int fill_params(flimo_handle h, const double state14[14], MatchParams& P, double
   P.valid_by_orig = valid;
   P.timing = h->timing;
   P.host_out96 = nullptr;
+  P.host_out_alt = 0;
   P.seq = 0;
   P.host_ctl = h->d_h_ctl;
   P.dev_ctl = h->dev_ctl;
   P.watchdog_ns = 20ull * 1000ull * 1000ull;          // 20 ms of host silence ends the persistent kernel
+  P.ctl_seq = 0;
   return FLIMO_OK;
 }
 
@@ -1051,7 +1054,8 @@ int flimo_ekf_end(flimo_handle h, double state26[26], double P529[529]) {
 }
 
 // Hands the persistent kernel its next command through the mapped control block.
-static void post_ctl(flimo_handle h, unsigned long long seq, uint32_t cmd, uint32_t orig_limit, const double* state14) {
+static void post_ctl(flimo_handle h, uint32_t cmd, uint32_t orig_limit, const double* state14) {
+  const unsigned long long seq = ++h->ctl_seq;         // commands carry their own numbering
   uint32_t w[3 * kCtlRecords];
   std::memset(w, 0, sizeof(w));
   w[0] = cmd;
@@ -1070,44 +1074,75 @@ static void post_ctl(flimo_handle h, unsigned long long seq, uint32_t cmd, uint3
 // flimo_update with ONE kernel launch for all passes (match_persistent_kernel).  Returns 1 when the caller
 // has to finish the update with per-pass launches (kernel ended early, or the MAX_NUM_MATCHES truncation
 // needs the general path); `u` is then positioned at the pass that has to be (re)done.
-static int update_persistent(flimo_handle h, ekf::IteratedUpdate& u) {
+static int update_persistent(flimo_handle h, ekf::IteratedUpdate& u, bool exchange) {
   const size_t n = h->shard_end - h->shard_begin;
   const int tiles = match_num_tiles((int)n);
+  const size_t slot_doubles = FLIMO_EXCHANGE_BYTES_PER_RANK / sizeof(double), buf_doubles = slot_doubles / 2;
+  unsigned long long& counter = exchange ? h->xch_seq : h->seq;
   double x[26], HTH[144], HTh[12], packed[96];
   u.state(x);
   MatchParams P;
   int rc = fill_params(h, x, P, h->out96, 0xFFFFFFFFu, nullptr, nullptr);
   if (rc) return rc;
-  P.host_out96 = h->d_h_out96;
-  P.seq = h->seq + 1;                                   // sequence number of the first pass
+  if (exchange) {       // results go straight into this rank's slot of the shared segment, two blocks by sequence parity
+    P.host_out96 = h->xch_dev + (size_t)h->xch_rank * slot_doubles;
+    P.host_out_alt = (unsigned int)buf_doubles;
+  } else {
+    P.host_out96 = h->d_h_out96;
+  }
+  P.seq = counter + 1;                                  // sequence number of the first pass
+  P.ctl_seq = h->ctl_seq + 1;                           // tag of the first command
   const int grid = std::min(tiles, h->persist_capacity);
   CU(h, launch_match_persistent(P, grid, h->stream));
   h->stats.kernel_launches++;
   int fallback = 0;
   while (!u.done()) {
     u.state(x);
-    const unsigned long long seq = ++h->seq;
+    const unsigned long long seq = ++counter;
     const auto tp0 = std::chrono::steady_clock::now();
-    post_ctl(h, seq, 0u, 0xFFFFFFFFu, x);
+    post_ctl(h, 0u, 0xFFFFFFFFu, x);
     if (h->pref_idx >= 0 && !h->pref_issued) {             // the requested copy of the next scan overlaps this pass
       rc = issue_prefetch(h);
       if (rc) return rc;
     }
-    const int wr = wait_records(h, h->h_out96, seq, packed, true);
-    if (wr < 0) return wr;
-    if (wr == 1) {                                        // watchdog fired / kernel gone: redo this pass classically
-      fallback = 1;
-      break;
+    double own_ns = 0.0;
+    if (exchange) {
+      for (int i = 0; i < 96; ++i) packed[i] = 0.0;
+      for (int r = 0; r < h->xch_world && !fallback; ++r) {   // fixed rank order => identical sums on every rank
+        const double* slot = h->xch_host + (size_t)r * slot_doubles + (seq & 1) * buf_doubles;
+        double vals[96];
+        const int wr = wait_records(h, slot, seq, vals, r == h->xch_rank);
+        if (wr < 0) return wr;
+        if (wr == 1) {
+          fallback = 1;
+          break;
+        }
+        if (r == h->xch_rank) own_ns = vals[93];
+        vals[93] = 0.0;
+        for (int i = 0; i < 96; ++i) packed[i] += vals[i];
+      }
+      if (fallback) {
+        --counter;                                          // the classic exchange pass re-publishes under the same number
+        break;
+      }
+    } else {
+      const int wr = wait_records(h, h->h_out96, seq, packed, true);
+      if (wr < 0) return wr;
+      if (wr == 1) {                                        // watchdog fired / kernel gone: redo this pass classically
+        fallback = 1;
+        break;
+      }
+      own_ns = packed[93];
+      packed[93] = 0.0;
     }
     h->stats.match_launches++;
-    h->persist_ns_total += packed[93];
+    h->persist_ns_total += own_ns;
     h->persist_passes++;
-    packed[93] = 0.0;
     if (h->prof) {
       h->prof_wait += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - tp0).count();
       h->prof_passes++;
     }
-    if ((int64_t)std::llround(packed[92]) > (int64_t)h->cfg.MAX_NUM_MATCHES) {   // first-N truncation: general path
+    if (!exchange && (int64_t)std::llround(packed[92]) > (int64_t)h->cfg.MAX_NUM_MATCHES) {   // first-N truncation: general path
       fallback = 1;
       break;
     }
@@ -1118,7 +1153,12 @@ static int update_persistent(flimo_handle h, ekf::IteratedUpdate& u) {
     u.step(HTH, HTh, nr);
     if (h->prof) h->prof_step += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - ts0).count();
   }
-  post_ctl(h, ++h->seq, 1u, 0u, nullptr);                // stop: the kernel exits
+  post_ctl(h, 1u, 0u, nullptr);                          // stop: the kernel exits
+  if (fallback && h->ticket) {
+    // the kernel may have ended in the middle of a pass: clear the last-CTA-done counters before the
+    // per-pass launches reuse them
+    CU(h, cudaMemsetAsync(h->ticket, 0, h->ticket_cap * sizeof(unsigned int), h->stream));
+  }
   return fallback;
 }
 
@@ -1135,7 +1175,7 @@ int flimo_update(flimo_handle h, double state26[26], double P529[529], int max_i
                        h->shard_end <= h->shard_begin || h->timing != nullptr ||
                        (h->time_every > 0 && (h->update_calls % (uint64_t)h->time_every) == 0);
   if (!classic && !u.done()) {
-    const int rc = update_persistent(h, u);
+    const int rc = update_persistent(h, u, false);
     if (rc < 0) return rc;
   }
   while (!u.done()) {
@@ -1156,9 +1196,17 @@ int flimo_update(flimo_handle h, double state26[26], double P529[529], int max_i
 int flimo_update_exchange(flimo_handle h, double state26[26], double P529[529], int max_iter, const double limit23[23],
                           double R_noise, double D_degeneracy, int* passes_out) {
   if (!h || !state26 || !P529 || !limit23) return fail(h, FLIMO_ERR_INVALID, "null argument");
+  if (!h->xch_host) return fail(h, FLIMO_ERR_STATE, "flimo_exchange_attach not called");
   ekf::IteratedUpdate& u = h->upd;
   u.begin(state26, P529, max_iter, limit23, R_noise, D_degeneracy);
   double x[26], HTH[144], HTh[12];
+  ++h->update_calls;
+  const bool classic = !h->persistent || h->persist_capacity <= 0 || !flimo_map_exists(h) || h->shard_end <= h->shard_begin ||
+                       h->timing != nullptr || (h->time_every > 0 && (h->update_calls % (uint64_t)h->time_every) == 0);
+  if (!classic && !u.done()) {
+    const int rc = update_persistent(h, u, true);
+    if (rc < 0) return rc;
+  }
   while (!u.done()) {
     u.state(x);
     int64_t nv = 0, nr = 0;

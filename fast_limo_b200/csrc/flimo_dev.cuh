@@ -65,7 +65,7 @@ struct PassCtlWire {
   uint32_t rec[kCtlRecords][4];
 };
 static_assert(kCtlRecords <= 32, "one warp reads the control block");
-constexpr unsigned long long kPassAbort = ~0ull;
+constexpr unsigned long long kPassAbort = 1ull << 63;   // flag bit: the watchdog ended the kernel at this command
 
 constexpr int kTileQueries = 128;     // queries per CTA tile (== threads per CTA)
 constexpr int kTriEntries = 91;       // upper triangle of the 13x13 outer product of [row(12), z]
@@ -99,12 +99,14 @@ struct MatchParams {
   float* dbg16;                // optional per-point record [n][16], indexed by original index
   uint8_t* valid_by_orig;      // optional accepted flag per original index
   double* host_out96;          // optional mapped pinned copy of the result: 96 records {double value, u64 seq}
+  unsigned int host_out_alt;   // doubles between the two alternating host result blocks (block = seq & 1); 0 = one block
   unsigned long long seq;      // sequence number stored with every record
   unsigned long long* timing;  // optional per-warp timestamps (profiling builds of the tools only)
   // persistent kernel only
   const PassCtlWire* host_ctl; // device alias of the host control block
   PassCtl* dev_ctl;            // device copy
   unsigned long long watchdog_ns;
+  unsigned long long ctl_seq;  // tag of the first command (commands are numbered independently of the results)
 };
 
 // map_index.cu

@@ -950,7 +950,8 @@ __device__ __forceinline__ void match_tile(const MatchParams& P, const PoseConst
     // Consecutive threads write consecutive records: the 1.5 KB leave the GPU as twelve full 128-byte
     // PCIe writes instead of 96 partial ones.
     if (P.host_out96 != nullptr)
-      reinterpret_cast<ulonglong2*>(P.host_out96)[threadIdx.x] = make_ulonglong2((unsigned long long)__double_as_longlong(v), seq);
+      reinterpret_cast<ulonglong2*>(P.host_out96 + (size_t)(seq & 1ull) * P.host_out_alt)[threadIdx.x] =
+          make_ulonglong2((unsigned long long)__double_as_longlong(v), seq);
   }
   if (P.timing && threadIdx.x == 0) {
     unsigned long long te;
@@ -982,12 +983,13 @@ __global__ void __launch_bounds__(kTileQueries, 7) match_persistent_kernel(const
   __shared__ PassCtl s_ctl;
   const int n_tiles = match_num_tiles_dev(P.q_end - P.q_begin);
   PassCtl* dctl = P.dev_ctl;
-  for (unsigned long long want = P.seq;; ++want) {
+  unsigned long long ctl = P.ctl_seq;
+  for (unsigned long long want = P.seq;; ++want, ++ctl) {
     if (blockIdx.x == 0 && threadIdx.x < 32) {
       // the host's control block: 19 tagged 16-byte records, read by 19 lanes in one PCIe round trip
       const PassCtlWire* hctl = P.host_ctl;
       const int lane = (int)threadIdx.x;
-      const uint32_t tag = (uint32_t)want;
+      const uint32_t tag = (uint32_t)ctl;
       uint32_t r0 = 0, r1 = 0, r2 = 0, r3 = tag;
       bool ok = false;
       const unsigned long long t0 = globaltimer_ns();
@@ -1012,7 +1014,7 @@ __global__ void __launch_bounds__(kTileQueries, 7) match_persistent_kernel(const
       __threadfence();
       __syncwarp();
       if (lane == 0) {
-        const unsigned long long pub = ok ? want : kPassAbort;
+        const unsigned long long pub = ok ? ctl : (ctl | kPassAbort);   // the device flag carries the command number (never stale)
         asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(&dctl->seq), "l"(pub) : "memory");
       }
     }
@@ -1020,7 +1022,7 @@ __global__ void __launch_bounds__(kTileQueries, 7) match_persistent_kernel(const
       unsigned long long f;
       for (;;) {
         f = ld_acquire_u64(&dctl->seq);
-        if (f == want || f == kPassAbort) break;
+        if (f == ctl || f == (ctl | kPassAbort)) break;
         __nanosleep(64);
       }
     }
