@@ -8,10 +8,18 @@ import csv, re, subprocess, sys, collections, io
 
 rep, cubin = sys.argv[1], sys.argv[2]
 min_pct = float(sys.argv[3]) if len(sys.argv) > 3 else 0.7
+func = sys.argv[4] if len(sys.argv) > 4 else None      # substring of the (mangled) kernel name when the cubin holds several
 sass = subprocess.run(["nvdisasm", "-g", "-c", cubin], capture_output=True, text=True).stdout
 line_of = {}
 cur = None
+in_func = func is None
 for ln in sass.splitlines():
+    if ln.lstrip().startswith(".section") and ".text." in ln:
+        in_func = func is None or func in ln
+        cur = None
+        continue
+    if not in_func:
+        continue
     m = re.search(r'//## File "([^"]+)", line (\d+)', ln)
     if m:
         cur = (m.group(1).split("/")[-1], int(m.group(2)))
