@@ -16,7 +16,7 @@ SYMBOLS = [
     "flimo_map_get_points", "flimo_scan_set", "flimo_scan_set_device", "flimo_scan_prefetch", "flimo_scan_shard",
     "flimo_match_reduce", "flimo_match_reduce_async", "flimo_unpack96", "flimo_match_debug",
     "flimo_update", "flimo_ekf_begin", "flimo_ekf_state", "flimo_ekf_step", "flimo_ekf_end",
-    "flimo_scan_to_world", "flimo_get_stats", "flimo_stream", "flimo_exchange_attach", "flimo_match_reduce_exchange", "flimo_update_exchange",
+    "flimo_scan_to_world", "flimo_prep_filter_sort", "flimo_prep_deskew", "flimo_prep_get", "flimo_voxel_grid", "flimo_get_stats", "flimo_stream", "flimo_exchange_attach", "flimo_match_reduce_exchange", "flimo_update_exchange",
 ]
 
 
@@ -35,6 +35,21 @@ class FlimoCfg(C.Structure):
         ("sort_scan", C.c_int32),
         ("knn_level_ratio", C.c_float),
         ("knn_tau", C.c_int32),
+    ]
+
+
+class FlimoPrepCfg(C.Structure):
+    """flimo_prep_cfg: Config::filters + the sensor flags of deskewPointCloud."""
+    _fields_ = [
+        ("crop_active", C.c_int32), ("dist_active", C.c_int32), ("rate_active", C.c_int32), ("fov_active", C.c_int32),
+        ("voxel_active", C.c_int32),
+        ("cropBoxMin", C.c_float * 3), ("cropBoxMax", C.c_float * 3),
+        ("min_dist", C.c_double),
+        ("rate_value", C.c_int32),
+        ("fov_angle", C.c_float),
+        ("leafSize", C.c_float),
+        ("sensor_type", C.c_int32),
+        ("end_of_sweep", C.c_int32),
     ]
 
 
@@ -109,6 +124,10 @@ def load():
     L.flimo_ekf_end.argtypes = [vp, pd, pd]
     L.flimo_scan_to_world.argtypes = [vp, pd, pf, sz, C.POINTER(sz)]
     L.flimo_get_stats.argtypes = [vp, C.POINTER(FlimoStats)]
+    L.flimo_prep_filter_sort.argtypes = [vp, vp, sz, dbl, C.POINTER(FlimoPrepCfg), C.POINTER(sz), pd]
+    L.flimo_prep_deskew.argtypes = [vp, vp, C.c_int, pf, pf, pf, dbl, C.POINTER(sz)]
+    L.flimo_prep_get.argtypes = [vp, C.c_int, vp, sz, C.POINTER(sz)]
+    L.flimo_voxel_grid.argtypes = [vp, pf, sz, C.c_float, pf, sz, C.POINTER(sz)]
     L.flimo_stream.argtypes = [vp]
     L.flimo_stream.restype = vp
     _lib = L

@@ -17,7 +17,7 @@ from dataclasses import dataclass
 import numpy as np
 
 from . import _lib
-from ._lib import FlimoCfg, FlimoError, FlimoStats
+from ._lib import FlimoCfg, FlimoError, FlimoPrepCfg, FlimoStats
 
 
 @dataclass
@@ -36,6 +36,45 @@ class MappingConfig:
     sort_scan: bool = False              # extension: Morton-sort the scan on upload (default: in-kernel scatter instead)
     knn_level_ratio: float = 0.0         # extension: cell growth between index levels (0 = 1.5)
     knn_tau: int = 0                     # extension: candidates-per-block threshold of the level choice (0 = 8)
+
+
+# fast_limo::Point (Common.hpp:100-113) and the fast_limo::State members the deskew reads, as numpy records
+RAW_POINT = np.dtype({"names": ["x", "y", "z", "intensity", "t", "time", "timestamp"],
+                      "formats": ["<f4", "<f4", "<f4", "<f4", "<u4", "<f4", "<f8"],
+                      "offsets": [0, 4, 8, 16, 24, 24, 24], "itemsize": 32})
+FRAME = np.dtype([("time", "<f8"), ("q", "<f4", 4), ("p", "<f4", 3), ("v", "<f4", 3), ("w", "<f4", 3), ("a", "<f4", 3),
+                  ("bg", "<f4", 3), ("ba", "<f4", 3), ("g", "<f4", 3)], align=True)
+
+
+@dataclass
+class FilterConfig:
+    """fast_limo::Config::filters + sensor_type / end_of_sweep (Config.hpp:43-55,83-91)."""
+    cropBoxMin: tuple = None             # crop_active when both boxes are given
+    cropBoxMax: tuple = None
+    min_dist: float = None               # dist_active when not None
+    rate_value: int = None               # rate_active when not None
+    fov_angle: float = None              # fov_active when not None (radians)
+    leafSize: float = None               # voxel_active when not None
+    sensor_type: int = 1
+    end_of_sweep: bool = False
+
+    def to_c(self):
+        c = FlimoPrepCfg()
+        if self.cropBoxMin is not None and self.cropBoxMax is not None:
+            c.crop_active = 1
+            c.cropBoxMin[:] = [float(v) for v in self.cropBoxMin]
+            c.cropBoxMax[:] = [float(v) for v in self.cropBoxMax]
+        if self.min_dist is not None:
+            c.dist_active, c.min_dist = 1, float(self.min_dist)
+        c.rate_value = 1
+        if self.rate_value is not None:
+            c.rate_active, c.rate_value = 1, int(self.rate_value)
+        if self.fov_angle is not None:
+            c.fov_active, c.fov_angle = 1, float(self.fov_angle)
+        if self.leafSize is not None:
+            c.voxel_active, c.leafSize = 1, float(self.leafSize)
+        c.sensor_type, c.end_of_sweep = int(self.sensor_type), int(bool(self.end_of_sweep))
+        return c
 
 
 def _dp(a):
@@ -149,6 +188,43 @@ class Mapper:
     def prefetch_scan_host(self, hptr, n, stride_bytes):
         """flimo_scan_prefetch: start the H2D copy of the NEXT scan on the copy stream."""
         self._ck(self._L.flimo_scan_prefetch(self._h, C.c_void_p(hptr), n, stride_bytes))
+
+    # -- scan preparation (Localizer::updatePointCloud before the hot path) -----------------------
+    def prep_filter_sort(self, raw, sweep_ref_time, filters: "FilterConfig"):
+        """Localizer.cpp:262-302 + the time sort of deskewPointCloud.  raw: RAW_POINT records.
+        Returns (n_kept, t_last)."""
+        raw = np.ascontiguousarray(raw, RAW_POINT)
+        c = filters.to_c()
+        n, t = C.c_size_t(0), C.c_double(0)
+        self._ck(self._L.flimo_prep_filter_sort(self._h, raw.ctypes.data, len(raw), float(sweep_ref_time), C.byref(c),
+                                                C.byref(n), C.byref(t)))
+        return int(n.value), float(t.value)
+
+    def prep_deskew(self, frames, last_q, last_p, T_lidar2baselink, offset=0.0):
+        """deskewPointCloud's per-point loop (+ voxel grid if configured); binds pc2match as the scan."""
+        fr = np.ascontiguousarray(frames, FRAME)
+        lq, lp = np.ascontiguousarray(last_q, np.float32), np.ascontiguousarray(last_p, np.float32)
+        T = np.ascontiguousarray(T_lidar2baselink, np.float32).reshape(16)
+        n = C.c_size_t(0)
+        self._ck(self._L.flimo_prep_deskew(self._h, fr.ctypes.data, len(fr), _fp(lq), _fp(lp), _fp(T), float(offset), C.byref(n)))
+        self._scan_n = min(int(n.value), self.config.MAX_NUM_PC2MATCH)
+        return int(n.value)
+
+    def prep_get(self, what):
+        """0: sorted indices into the raw message, 1: deskewed world cloud, 2: deskewed body cloud, 3: pc2match."""
+        n = C.c_size_t(0)
+        self._ck(self._L.flimo_prep_get(self._h, int(what), None, 0, C.byref(n)))
+        out = np.zeros(max(n.value, 1), np.uint32) if what == 0 else np.zeros((max(n.value, 1), 4), np.float32)
+        self._ck(self._L.flimo_prep_get(self._h, int(what), out.ctypes.data, n.value, C.byref(n)))
+        return out[:n.value]
+
+    def voxel_grid(self, pts4, leaf):
+        """pcl::VoxelGrid centroids (leaf, leaf, leaf) of xyz1 points; ascending voxel index."""
+        p = np.ascontiguousarray(pts4, np.float32).reshape(-1, 4)
+        out = np.zeros((max(len(p), 1), 4), np.float32)
+        n = C.c_size_t(0)
+        self._ck(self._L.flimo_voxel_grid(self._h, _fp(p), len(p), float(leaf), _fp(out), len(out), C.byref(n)))
+        return out[:n.value]
 
     def shard(self, begin, end):
         self._ck(self._L.flimo_scan_shard(self._h, begin, end))

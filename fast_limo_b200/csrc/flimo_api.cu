@@ -16,6 +16,7 @@
 #include "../../include/flimo.h"
 #include "ekf_host.hpp"
 #include "flimo_dev.cuh"
+#include "scan_prep.cuh"
 
 using namespace flimo;
 
@@ -114,6 +115,13 @@ struct flimo_ctx {
   bool prof = false;             // FLIMO_PROFILE=1: host-side wall-clock breakdown printed by flimo_destroy
   double prof_launch = 0, prof_wait = 0, prof_step = 0, prof_other = 0;
   uint64_t prof_passes = 0;
+
+  // scan preparation (scan_prep.cu)
+  PrepBuffers prep;
+  flimo_prep_cfg prep_cfg{};
+  const float4* prep_pc2match = nullptr;
+  size_t prep_n_pc2match = 0;
+  bool prep_deskewed = false;
 
   ekf::IteratedUpdate upd;
   bool upd_active = false;
@@ -506,6 +514,7 @@ void flimo_destroy(flimo_handle h) {
   for (auto& g : h->scan_graphs) cudaGraphExecDestroy(g.exec);
   if (h->xch_host) cudaHostUnregister(h->xch_host);
   cudaFreeHost(h->h_out96);
+  prep_free(h->prep);
   cudaFreeHost(h->h_ctl);
   cudaFree(h->scan_stage[0]);
   cudaFree(h->scan_stage[1]);
@@ -1160,6 +1169,124 @@ static int update_persistent(flimo_handle h, ekf::IteratedUpdate& u, bool exchan
     CU(h, cudaMemsetAsync(h->ticket, 0, h->ticket_cap * sizeof(unsigned int), h->stream));
   }
   return fallback;
+}
+
+// ---- scan preparation --------------------------------------------------------------------------------
+int flimo_prep_filter_sort(flimo_handle h, const void* raw_points, size_t n, double sweep_ref_time, const flimo_prep_cfg* cfg,
+                           size_t* n_kept, double* t_last) {
+  if (!h || !cfg || !n_kept || !t_last || (!raw_points && n)) return fail(h, FLIMO_ERR_INVALID, "null argument");
+  if (cfg->sensor_type < 0 || cfg->sensor_type > 3) return fail(h, FLIMO_ERR_INVALID, "unknown LiDAR sensor type");   // Localizer.cpp:778-783
+  if (cfg->rate_active && cfg->rate_value < 1) return fail(h, FLIMO_ERR_INVALID, "rate_value must be >= 1");
+  if (n >= 0x7FFFFFF0ull) return fail(h, FLIMO_ERR_INVALID, "cloud too large");
+  NEED_GPU(h);
+  h->prep_cfg = *cfg;
+  h->prep_deskewed = false;
+  h->prep_pc2match = nullptr;
+  h->prep_n_pc2match = 0;
+  *n_kept = 0;
+  *t_last = 0.0;
+  if (n == 0) return FLIMO_OK;
+  CU(h, prep_reserve(h->prep, n));
+  CU(h, cudaMemcpyAsync(h->prep.raw, raw_points, n * 32, cudaMemcpyHostToDevice, h->stream));
+  PrepDev c{};
+  c.crop_active = cfg->crop_active; c.dist_active = cfg->dist_active; c.rate_active = cfg->rate_active; c.fov_active = cfg->fov_active;
+  for (int i = 0; i < 3; ++i) { c.crop_min[i] = cfg->cropBoxMin[i]; c.crop_max[i] = cfg->cropBoxMax[i]; }
+  c.min_dist = static_cast<float>(cfg->min_dist);
+  c.rate_value = cfg->rate_value > 0 ? cfg->rate_value : 1;
+  c.fov_angle = cfg->fov_angle;
+  c.sensor_type = cfg->sensor_type;
+  c.end_of_sweep = cfg->end_of_sweep;
+  c.sweep_ref_time = sweep_ref_time;
+  uint32_t m = 0;
+  CU(h, prep_filter_sort(h->prep, n, c, h->stream, &m, t_last, &h->stats.kernel_launches));
+  *n_kept = m;
+  return FLIMO_OK;
+}
+
+int flimo_prep_deskew(flimo_handle h, const flimo_frame* frames, int n_frames, const float last_q[4], const float last_p[3],
+                      const float T_lidar2baselink[16], double offset, size_t* n_pc2match) {
+  if (!h || !frames || !last_q || !last_p || !T_lidar2baselink || !n_pc2match) return fail(h, FLIMO_ERR_INVALID, "null argument");
+  NEED_GPU(h);
+  *n_pc2match = 0;
+  if (n_frames < 1) return fail(h, FLIMO_ERR_STATE, "no frames obtained from IMU propagation");   // Localizer.cpp:807-811
+  const size_t m = h->prep.n_sorted;
+  if (m == 0) return flimo_scan_set_device(h, h->prep.xt2, 0, 16);
+  DeskewDev d{};
+  d.offset = offset;
+  d.n_frames = n_frames;
+  std::memcpy(d.T_l2b, T_lidar2baselink, sizeof(d.T_l2b));
+  {   // last_state.get_RT_inv() (State.cpp:145-153), float, Eigen order
+    float R[9];
+    quat_matrix<float>(last_q, R);
+    for (int i = 0; i < 3; ++i) {
+      for (int j = 0; j < 3; ++j) d.Tinv[4 * i + j] = R[3 * j + i];
+      d.Tinv[4 * i + 3] = (-R[i] * last_p[0] + -R[3 + i] * last_p[1]) + -R[6 + i] * last_p[2];
+    }
+    d.Tinv[12] = d.Tinv[13] = d.Tinv[14] = 0.f;
+    d.Tinv[15] = 1.f;
+  }
+  CU(h, prep_deskew(h->prep, d, frames, true, h->stream, &h->stats.kernel_launches));
+  h->prep_deskewed = true;
+  const float4* out = h->prep.xt2;
+  size_t n_out = m;
+  if (h->prep_cfg.voxel_active) {
+    uint32_t nv = 0;
+    bool pass = false;
+    CU(h, prep_voxel(h->prep, h->prep.xt2, (uint32_t)m, reinterpret_cast<const uint32_t*>(h->prep.small), h->prep_cfg.leafSize,
+                     h->stream, &nv, &pass, &h->stats.kernel_launches));
+    if (!pass) {
+      out = h->prep.vox_out;
+      n_out = nv;
+    }
+  }
+  h->prep_pc2match = out;
+  h->prep_n_pc2match = n_out;
+  *n_pc2match = n_out;
+  return flimo_scan_set_device(h, out, n_out, 16);
+}
+
+int flimo_prep_get(flimo_handle h, int what, void* out, size_t cap_items, size_t* n_items) {
+  if (!h || !n_items) return fail(h, FLIMO_ERR_INVALID, "null argument");
+  NEED_GPU(h);
+  const void* src = nullptr;
+  size_t n = 0, item = 16;
+  switch (what) {
+    case 0: src = h->prep.order; n = h->prep.n_sorted; item = 4; break;
+    case 1: src = h->prep.world; n = h->prep_deskewed ? h->prep.n_sorted : 0; break;
+    case 2: src = h->prep.xt2; n = h->prep_deskewed ? h->prep.n_sorted : 0; break;
+    case 3: src = h->prep_pc2match; n = h->prep_n_pc2match; break;
+    default: return fail(h, FLIMO_ERR_INVALID, "unknown cloud selector");
+  }
+  *n_items = n;
+  if (!out || n == 0) return FLIMO_OK;
+  const size_t take = n < cap_items ? n : cap_items;
+  CU(h, cudaMemcpyAsync(out, src, take * item, cudaMemcpyDeviceToHost, h->stream));
+  CU(h, cudaStreamSynchronize(h->stream));
+  return FLIMO_OK;
+}
+
+int flimo_voxel_grid(flimo_handle h, const float* xyz4, size_t n, float leaf, float* out_xyz4, size_t cap_points, size_t* n_out) {
+  if (!h || !n_out || (!xyz4 && n) || !(leaf > 0.f)) return fail(h, FLIMO_ERR_INVALID, "bad argument");
+  NEED_GPU(h);
+  *n_out = 0;
+  if (n == 0) return FLIMO_OK;
+  if (n >= 0x7FFFFFF0ull) return fail(h, FLIMO_ERR_INVALID, "cloud too large");
+  CU(h, prep_reserve(h->prep, n));
+  const uint32_t n32 = (uint32_t)n;
+  CU(h, cudaMemcpyAsync(h->prep.xt2, xyz4, n * sizeof(float4), cudaMemcpyHostToDevice, h->stream));
+  CU(h, cudaMemcpyAsync(h->prep.small, &n32, sizeof(n32), cudaMemcpyHostToDevice, h->stream));
+  uint32_t nv = 0;
+  bool pass = false;
+  CU(h, prep_voxel(h->prep, h->prep.xt2, n32, reinterpret_cast<const uint32_t*>(h->prep.small), leaf, h->stream, &nv, &pass,
+                   &h->stats.kernel_launches));
+  const float4* src = pass ? h->prep.xt2 : h->prep.vox_out;
+  const size_t m = pass ? n : nv;
+  *n_out = m;
+  if (out_xyz4 && m) {
+    CU(h, cudaMemcpyAsync(out_xyz4, src, std::min(m, cap_points) * sizeof(float4), cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+  }
+  return FLIMO_OK;
 }
 
 int flimo_update(flimo_handle h, double state26[26], double P529[529], int max_iter, const double limit23[23],

@@ -234,3 +234,58 @@ def make_case(name, map_points=None):
                    w * d - x * a - y * b - z * c])
     init = make_state(pos + np.array([0.03, -0.03, 0.025]), q2 / np.linalg.norm(q2))
     return Case(name, mp, scan, truth, init, passes)
+
+
+# ---- raw LiDAR messages + IMU-propagated frames for the scan preparation (deskew) tests ---------------
+def make_raw_message(scan_xyz, sensor_type=1, sweep=0.1, stamp=100.0, rings=None, seed=7, n_nan=0):
+    """fast_limo::Point records (32 bytes) for a scan: per-point time grows with the azimuth index
+    (ring-major spinning scans: point i of a ring fires at sweep * i / azimuths).  Returns a numpy
+    record array with the dtype of api.RAW_POINT."""
+    from .api import RAW_POINT
+    n = scan_xyz.shape[0]
+    raw = np.zeros(n, RAW_POINT)
+    raw["x"], raw["y"], raw["z"] = scan_xyz[:, 0], scan_xyz[:, 1], scan_xyz[:, 2]
+    rng = np.random.default_rng(seed)
+    raw["intensity"] = rng.uniform(0, 255, n).astype(np.float32)
+    if rings:
+        az = n // rings
+        frac = (np.arange(n) % az) / az
+    else:
+        frac = np.arange(n) / n
+    frac = frac + rng.uniform(0, 0.2 / n, n)                      # no exact ties in time
+    if sensor_type == 0:
+        raw["t"] = (frac * sweep * 1e9).astype(np.uint32)
+    elif sensor_type == 1:
+        raw["time"] = (frac * sweep).astype(np.float32)
+    elif sensor_type == 2:
+        raw["timestamp"] = stamp + frac * sweep
+    else:
+        raw["timestamp"] = (stamp + frac * sweep) * 1e9
+    if n_nan:
+        bad = rng.choice(n, n_nan, replace=False)
+        raw["x"][bad[: n_nan // 2]] = np.nan
+        raw["z"][bad[n_nan // 2:]] = np.inf
+    return raw
+
+
+def make_frames(t0, t1, rate_hz=200.0, speed=10.0, yaw_rate=0.6, seed=3):
+    """IMU-propagated states (what Localizer::integrateImu returns) covering [t0, t1]: constant
+    forward speed + yaw rate with small accelerations / biases, float32 like fast_limo::State."""
+    from .api import FRAME
+    rng = np.random.default_rng(seed)
+    n = int(np.ceil((t1 - t0) * rate_hz)) + 3
+    fr = np.zeros(n, FRAME)
+    ts = t0 - 1.0 / rate_hz + np.arange(n) / rate_hz
+    fr["time"] = ts
+    yaw = yaw_rate * (ts - t0)
+    fr["q"][:, 2], fr["q"][:, 3] = np.sin(yaw / 2), np.cos(yaw / 2)
+    fr["p"][:, 0] = speed * (ts - t0)
+    fr["p"][:, 1] = 0.5 * speed * yaw_rate * (ts - t0) ** 2
+    fr["p"][:, 2] = 1.8
+    fr["v"][:, 0], fr["v"][:, 1] = speed * np.cos(yaw), speed * np.sin(yaw)
+    fr["w"] = np.array([0.02, -0.03, yaw_rate], np.float32) + rng.normal(0, 0.01, (n, 3)).astype(np.float32)
+    fr["a"] = np.array([0.3, speed * yaw_rate, 9.809], np.float32) + rng.normal(0, 0.05, (n, 3)).astype(np.float32)
+    fr["bg"] = np.array([0.001, -0.002, 0.0015], np.float32)
+    fr["ba"] = np.array([0.01, 0.02, -0.01], np.float32)
+    fr["g"] = np.array([0, 0, -9.809], np.float32)
+    return fr

@@ -150,6 +150,50 @@ void flimo_unpack96(const double packed[96], double HTH[144], double HTh[12], in
 int flimo_match_debug(flimo_handle h, const double state14[14], float* out16, size_t cap_points,
                       size_t* n_points);
 
+/* ---- scan preparation: what Localizer::updatePointCloud does before the hot path ---------------- */
+
+/* Config::filters + the sensor flags deskewPointCloud reads (fast_limo/Utils/Config.hpp:43-55,83-91). */
+typedef struct {
+  int32_t crop_active, dist_active, rate_active, fov_active, voxel_active;
+  float cropBoxMin[3], cropBoxMax[3];   /* negative crop box (Localizer.cpp:57-59,268-271) */
+  double min_dist;                      /* cast to float once, as Localizer.cpp:274 does */
+  int32_t rate_value;
+  float fov_angle;                      /* radians, compared with |atan2(y, x)| (Localizer.cpp:866-869) */
+  float leafSize;                       /* leafSize[0]: the reference passes it for all three axes (Localizer.cpp:61) */
+  int32_t sensor_type;                  /* 0 OUSTER, 1 VELODYNE, 2 HESAI, 3 LIVOX (Localizer.cpp:747-777) */
+  int32_t end_of_sweep;
+} flimo_prep_cfg;
+
+/* fast_limo::State — the members State::update(t) and get_RT() read (fast_limo/Objects/State.hpp). */
+typedef struct {
+  double time;
+  float q[4];                           /* x y z w */
+  float p[3], v[3], w[3], a[3], bg[3], ba[3], g[3];
+} flimo_frame;
+
+/* Localizer.cpp:262-302 + the time sort of deskewPointCloud (:744-789) on a raw LiDAR message of
+ * 32-byte fast_limo::Point records (Common.hpp:100-113: xyz at 0, intensity at 16, time union at 24).
+ * One H2D copy; returns the size of the filtered cloud and the time of its last point
+ * (extract_point_time of the last sorted point, :797,:802) — the host needs it to choose the IMU frames. */
+int flimo_prep_filter_sort(flimo_handle h, const void* raw_points, size_t n, double sweep_ref_time,
+                           const flimo_prep_cfg* cfg, size_t* n_kept, double* t_last);
+/* The per-point loop of deskewPointCloud (Localizer.cpp:822-843) on the cloud left by
+ * flimo_prep_filter_sort: frames = integrateImu(prev_scan_stamp, scan_stamp) (:805), last_q/last_p =
+ * pose of State(_iKFoM.get_x()) (:820), T_lidar2baselink = extr.lidar2baselink_T row-major, offset as
+ * computed at :797-801.  If cfg.voxel_active the voxel grid of :313-321 follows.  The result IS
+ * pc2match: it stays in device memory and is bound as the current scan (as flimo_scan_set_device). */
+int flimo_prep_deskew(flimo_handle h, const flimo_frame* frames, int n_frames, const float last_q[4],
+                      const float last_p[3], const float T_lidar2baselink[16], double offset, size_t* n_pc2match);
+/* Copies an intermediate cloud out (tests, debug clouds of Localizer.cpp:303-305,850-851):
+ * what = 0: indices (uint32) of the filtered + time-sorted points in the raw message,
+ *        1: deskewed points in the world frame (xyz1 float4), 2: in the body frame of the last state
+ *        (deskewed_Xt2), 3: pc2match (after the voxel grid). */
+int flimo_prep_get(flimo_handle h, int what, void* out, size_t cap_items, size_t* n_items);
+/* pcl::VoxelGrid with leaf (leaf, leaf, leaf) on n points given as xyz1 float4 (host); centroids in
+ * ascending voxel index.  Utility / test entry for the voxel stage alone. */
+int flimo_voxel_grid(flimo_handle h, const float* xyz4, size_t n, float leaf, float* out_xyz4, size_t cap_points,
+                     size_t* n_out);
+
 /* ---- iterated update (IKFoM) ---------------------------------------------------------------- */
 
 /* esekf::update_iterated_dyn_share_modified (esekfom.hpp:1620-1823) with the measurement pass

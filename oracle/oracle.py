@@ -37,7 +37,7 @@ class OrcCfg(C.Structure):
 def build(force=False):
     """Compile liboracle.so from the sources in this directory (g++, a few seconds)."""
     so = os.path.join(_HERE, "liboracle.so")
-    srcs = [os.path.join(_HERE, f) for f in ("oracle_capi.cpp", "ioctree.hpp", "plane_match.hpp", "ekf.hpp", "Makefile")]
+    srcs = [os.path.join(_HERE, f) for f in ("oracle_capi.cpp", "ioctree.hpp", "plane_match.hpp", "ekf.hpp", "prep.hpp", "Makefile")]
     stale = (not os.path.exists(so)) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs)
     if force or stale:
         subprocess.run(["make", "-C", _HERE, "-B" if force else "-s"], check=True, stdout=subprocess.DEVNULL)
@@ -220,3 +220,82 @@ def invert(A):
     rc = lib().orc_invert(_p(A, C.c_double), A.shape[0])
     assert rc == 0
     return A
+
+
+# ---- scan preparation (prep.hpp): filters, time sort, deskew, voxel grid ---------------------------
+RAW_POINT = np.dtype({"names": ["x", "y", "z", "intensity", "t", "time", "timestamp"],
+                      "formats": ["<f4", "<f4", "<f4", "<f4", "<u4", "<f4", "<f8"],
+                      "offsets": [0, 4, 8, 16, 24, 24, 24], "itemsize": 32})      # fast_limo::Point (Common.hpp:100-113)
+FRAME = np.dtype([("time", "<f8"), ("q", "<f4", 4), ("p", "<f4", 3), ("v", "<f4", 3), ("w", "<f4", 3), ("a", "<f4", 3),
+                  ("bg", "<f4", 3), ("ba", "<f4", 3), ("g", "<f4", 3)], align=True)  # fast_limo::State members used
+
+
+class PrepCfg(C.Structure):
+    _fields_ = [("crop_active", C.c_int32), ("dist_active", C.c_int32), ("rate_active", C.c_int32), ("fov_active", C.c_int32),
+                ("crop_min", C.c_float * 3), ("crop_max", C.c_float * 3), ("min_dist", C.c_double), ("rate_value", C.c_int32),
+                ("fov_angle", C.c_float), ("sensor_type", C.c_int32), ("end_of_sweep", C.c_int32), ("voxel_active", C.c_int32),
+                ("leaf", C.c_float)]
+
+
+def make_prep_cfg(crop=None, min_dist=None, rate=None, fov=None, sensor_type=1, end_of_sweep=False, leaf=None):
+    c = PrepCfg()
+    if crop is not None:
+        c.crop_active = 1
+        c.crop_min[:] = [float(v) for v in crop[0]]
+        c.crop_max[:] = [float(v) for v in crop[1]]
+    if min_dist is not None:
+        c.dist_active, c.min_dist = 1, float(min_dist)
+    c.rate_value = 1
+    if rate is not None:
+        c.rate_active, c.rate_value = 1, int(rate)
+    if fov is not None:
+        c.fov_active, c.fov_angle = 1, float(fov)
+    c.sensor_type, c.end_of_sweep = int(sensor_type), int(bool(end_of_sweep))
+    if leaf is not None:
+        c.voxel_active, c.leaf = 1, float(leaf)
+    return c
+
+
+def prep_filter_sort(raw, cfg, sort=True):
+    L = lib()
+    L.orc_prep_filter_sort.restype = C.c_size_t
+    L.orc_prep_filter_sort.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(PrepCfg), C.c_int, C.c_void_p]
+    raw = np.ascontiguousarray(raw)
+    out = np.zeros(max(len(raw), 1), np.uint32)
+    m = L.orc_prep_filter_sort(raw.ctypes.data, len(raw), C.byref(cfg), int(sort), out.ctypes.data)
+    return out[:m].copy()
+
+
+def prep_times(raw, order, cfg, sweep_ref_time):
+    L = lib()
+    L.orc_prep_times.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(PrepCfg), C.c_double, C.c_void_p]
+    raw, order = np.ascontiguousarray(raw), np.ascontiguousarray(order, np.uint32)
+    t = np.zeros(len(order), np.float64)
+    L.orc_prep_times(raw.ctypes.data, order.ctypes.data, len(order), C.byref(cfg), float(sweep_ref_time), t.ctypes.data)
+    return t
+
+
+def prep_deskew(raw, order, cfg, sweep_ref_time, offset, frames, last_q, last_p, T_l2b):
+    """Returns (world xyz1, Xt2-frame xyz1), float32 (m, 4) each."""
+    L = lib()
+    L.orc_prep_deskew.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(PrepCfg), C.c_double, C.c_double, C.c_void_p,
+                                  C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    raw, order = np.ascontiguousarray(raw), np.ascontiguousarray(order, np.uint32)
+    frames = np.ascontiguousarray(frames, FRAME)
+    lq, lp = np.ascontiguousarray(last_q, np.float32), np.ascontiguousarray(last_p, np.float32)
+    T = np.ascontiguousarray(T_l2b, np.float32).reshape(16)
+    w = np.zeros((len(order), 4), np.float32)
+    b = np.zeros((len(order), 4), np.float32)
+    L.orc_prep_deskew(raw.ctypes.data, order.ctypes.data, len(order), C.byref(cfg), float(sweep_ref_time), float(offset),
+                      frames.ctypes.data, len(frames), lq.ctypes.data, lp.ctypes.data, T.ctypes.data, w.ctypes.data, b.ctypes.data)
+    return w, b
+
+
+def prep_voxel(pts4, leaf):
+    L = lib()
+    L.orc_prep_voxel.restype = C.c_size_t
+    L.orc_prep_voxel.argtypes = [C.c_void_p, C.c_size_t, C.c_float, C.c_void_p]
+    pts4 = np.ascontiguousarray(pts4, np.float32).reshape(-1, 4)
+    out = np.zeros((max(len(pts4), 1), 4), np.float32)
+    m = L.orc_prep_voxel(pts4.ctypes.data, len(pts4), float(leaf), out.ctypes.data)
+    return out[:m].copy()

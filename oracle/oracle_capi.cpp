@@ -15,6 +15,7 @@
 #include "ekf.hpp"
 #include "ioctree.hpp"
 #include "plane_match.hpp"
+#include "prep.hpp"
 
 using namespace orc;
 
@@ -233,5 +234,31 @@ void orc_boxminus(const double* a26, const double* b26, double* d23) {
   state_boxminus(a, b, d23);
 }
 int orc_invert(double* A, int n) { return invert(A, n) ? 0 : -1; }
+
+// ---- scan preparation (prep.hpp): filters, time sort, deskew, voxel grid ------------------------
+// order_out (capacity n) receives the indices into raw of the filtered cloud [sorted by time if sort != 0].
+size_t orc_prep_filter_sort(const void* raw, size_t n, const PrepCfg* c, int sort, uint32_t* order_out) {
+  const RawPoint* r = static_cast<const RawPoint*>(raw);
+  std::vector<uint32_t> kept = prep_filter(r, n, *c);
+  if (sort) prep_sort(r, kept, *c);
+  std::memcpy(order_out, kept.data(), kept.size() * sizeof(uint32_t));
+  return kept.size();
+}
+void orc_prep_times(const void* raw, const uint32_t* order, size_t m, const PrepCfg* c, double sweep_ref_time, double* t_out) {
+  const RawPoint* r = static_cast<const RawPoint*>(raw);
+  for (size_t k = 0; k < m; ++k) t_out[k] = prep_point_time(r[order[k]], *c, sweep_ref_time);
+}
+void orc_prep_deskew(const void* raw, const uint32_t* order, size_t m, const PrepCfg* c, double sweep_ref_time, double offset,
+                     const Frame* frames, int n_frames, const float* last_q, const float* last_p, const float* T_l2b,
+                     float* out_world4, float* out_xt2_4) {
+  std::vector<uint32_t> ord(order, order + m);
+  prep_deskew(static_cast<const RawPoint*>(raw), ord, *c, sweep_ref_time, offset, frames, n_frames, last_q, last_p, T_l2b,
+              out_world4, out_xt2_4);
+}
+size_t orc_prep_voxel(const float* in4, size_t n, float leaf, float* out4) {
+  const std::vector<float> o = prep_voxel(in4, n, leaf);
+  std::memcpy(out4, o.data(), o.size() * sizeof(float));
+  return o.size() / 4;
+}
 
 }  // extern "C"
