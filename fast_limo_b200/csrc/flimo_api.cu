@@ -114,6 +114,8 @@ struct flimo_ctx {
   uint64_t update_calls = 0;
   bool prof = false;             // FLIMO_PROFILE=1: host-side wall-clock breakdown printed by flimo_destroy
   double prof_launch = 0, prof_wait = 0, prof_step = 0, prof_other = 0;
+  double prof_add_pack = 0, prof_add_insert = 0, prof_add_index = 0;
+  uint64_t prof_adds = 0;
   uint64_t prof_passes = 0;
 
   // scan preparation (scan_prep.cu)
@@ -491,6 +493,10 @@ void flimo_destroy(flimo_handle h) {
     std::fprintf(stderr, "[flimo profile] passes=%llu  per pass: launch %.2f us, wait %.2f us, filter step %.2f us\n",
                  (unsigned long long)h->prof_passes, h->prof_launch / h->prof_passes, h->prof_wait / h->prof_passes,
                  h->prof_step / h->prof_passes);
+  if (h->prof && h->prof_adds)
+    std::fprintf(stderr, "[flimo profile] map adds=%llu  per add: pack+bbox %.1f us, insert rule %.1f us, index build %.1f us\n",
+                 (unsigned long long)h->prof_adds, h->prof_add_pack / h->prof_adds, h->prof_add_insert / h->prof_adds,
+                 h->prof_add_index / h->prof_adds);
   if (h->device < 0) {
     delete h;
     return;
@@ -592,6 +598,7 @@ int flimo_map_add_device(flimo_handle h, const void* d_xyz, size_t n, size_t str
   if (n < 1) return FLIMO_OK;                                   // Mapper::add: size < 1 -> return
   NEED_GPU(h);
   const size_t old_n = h->map_exists ? h->map.n_pts : 0;
+  const auto ta0 = std::chrono::steady_clock::now();
   // 1. pack the batch (drops NaN points, Octree::processPoints :243) and take its bounding box
   if (n > h->batch_cap) {
     cudaFree(h->batch);
@@ -614,9 +621,17 @@ int flimo_map_add_device(flimo_handle h, const void* d_xyz, size_t n, size_t str
   CU(h, cudaStreamSynchronize(h->stream));
   h->stats.kernel_launches += 1;
   if (kept == 0) return FLIMO_OK;                               // Octree::initialize: empty -> no root
+  const auto tb0 = std::chrono::steady_clock::now();
   CU(h, map_index_reserve(h->map, old_n + kept));
+  const auto tb1 = std::chrono::steady_clock::now();
   float lo[3], hi[3];
   CU(h, points_bbox(h->batch, kept, h->map.bbox, lo, hi, h->stream));
+  if (h->prof) {
+    const auto tb2 = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "[add] n=%zu pack %.0f us reserve %.0f us bbox %.0f us\n", n,
+                 std::chrono::duration<double, std::micro>(tb0 - ta0).count(), std::chrono::duration<double, std::micro>(tb1 - tb0).count(),
+                 std::chrono::duration<double, std::micro>(tb2 - tb1).count());
+  }
   h->stats.kernel_launches += 2;
   // 2. the octree lattice: first batch defines it (Octree::initialize), later ones may double the root
   const bool first = !h->map_exists;
@@ -628,6 +643,7 @@ int flimo_map_add_device(flimo_handle h, const void* d_xyz, size_t n, size_t str
     lattice_grow(h->lattice, lo);
   }
   // 3. accept / drop per point, append the accepted ones to the canonical list, update the counts
+  const auto ta1 = std::chrono::steady_clock::now();
   unsigned int accepted = 0;
   CU(h, map_insert_batch(h->lattice, h->counts, h->batch, kept, h->cfg.octree_downsampling, first, h->map.pts + old_n,
                          h->d_count, h->batch_keys, h->batch_accept, &accepted, h->stream, &h->stats.kernel_launches));
@@ -636,6 +652,7 @@ int flimo_map_add_device(flimo_handle h, const void* d_xyz, size_t n, size_t str
   h->last_time = stamp;
   if (accepted == 0) return FLIMO_OK;
   // 4. rebuild the search index over all map points
+  const auto ta2 = std::chrono::steady_clock::now();
   h->map.n_pts = total;
   const size_t max_cells = (size_t)1 << 30;
   // coarsest level: cell >= sqrt(MAX_DIST_PLANE) so its 3x3x3 block covers the close_enough radius
@@ -643,6 +660,13 @@ int flimo_map_add_device(flimo_handle h, const void* d_xyz, size_t n, size_t str
   CU(h, map_index_build(h->map, h->cfg.knn_cell, h->cfg.knn_level_ratio, coarsest, max_cells, h->stream,
                         &h->stats.kernel_launches));
   CU(h, cudaStreamSynchronize(h->stream));
+  if (h->prof) {
+    const auto ta3 = std::chrono::steady_clock::now();
+    h->prof_add_pack += std::chrono::duration<double, std::micro>(ta1 - ta0).count();
+    h->prof_add_insert += std::chrono::duration<double, std::micro>(ta2 - ta1).count();
+    h->prof_add_index += std::chrono::duration<double, std::micro>(ta3 - ta2).count();
+    h->prof_adds++;
+  }
   return FLIMO_OK;
 }
 

@@ -12,6 +12,7 @@
 // the bits needed) -> gather -> boundary scatter + suffix-min scan for the prefix table.
 // All on the device; one small D2H (6 floats) sizes the grids.  Off the per-pass hot path
 // (once per Mapper::add).
+#include <algorithm>
 #include <cfloat>
 #include <cmath>
 #include <cstdio>
@@ -266,8 +267,9 @@ cudaError_t scan_prepare_reserve(size_t n, void** cub_tmp, size_t* cub_tmp_bytes
 
 cudaError_t map_index_reserve(MapIndex& idx, size_t n) {
   if (n > idx.cap_pts) {
-    size_t cap = idx.cap_pts ? idx.cap_pts : 1024;
-    while (cap < n) cap += cap / 2 + 1024;
+    // capacity doubles from 1 M points: every growth re-allocates 54 copies of the map, HBM is plentiful
+    size_t cap = idx.cap_pts ? idx.cap_pts : ((size_t)1 << 20);
+    while (cap < n) cap *= 2;
     float4* np = nullptr;
     FL_TRY(cudaMalloc(&np, cap * sizeof(float4)));
     if (idx.pts) {
@@ -338,7 +340,7 @@ static cudaError_t build_level(MapIndex& idx, LevelIndex& L, const GridDesc& g, 
     if (L.cell_start) cudaFree(L.cell_start);
     L.cell_start = nullptr;
     L.cap_cells = 0;
-    const size_t cap = n_cells + n_cells / 8 + 1024;
+    const size_t cap = std::max(n_cells + n_cells / 2 + 1024, (size_t)1 << 22);   // the grid grows with the map's bounding box
     FL_TRY(cudaMalloc(&L.cell_start, cap * sizeof(uint32_t)));
     L.cap_cells = cap;
   }

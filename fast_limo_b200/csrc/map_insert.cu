@@ -242,7 +242,7 @@ static void lattice_desc(const OctreeLattice& L, LatticeDesc& d) {
 }
 
 static cudaError_t table_reserve(CountTable& T, size_t need_entries, cudaStream_t st) {
-  size_t want = T.cap ? T.cap : (1u << 16);
+  size_t want = T.cap ? T.cap : (1u << 22);      // start large: growing means a rehash and two large (de)allocations
   while (want < 2 * need_entries) want <<= 1;
   if (want == T.cap) return cudaSuccess;
   unsigned long long* nk = nullptr;

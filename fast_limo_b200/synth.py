@@ -289,3 +289,67 @@ def make_frames(t0, t1, rate_hz=200.0, speed=10.0, yaw_rate=0.6, seed=3):
     fr["ba"] = np.array([0.01, 0.02, -0.01], np.float32)
     fr["g"] = np.array([0, 0, -9.809], np.float32)
     return fr
+
+
+# ---- a motion-distorted scan stream (BASELINE config c3: replay with map growth) ------------------------
+class Stream:
+    """Vehicle on a circle (radius r, speed v) inside the canyon world; spinning scans whose points are
+    taken from the pose AT THEIR OWN FIRING TIME (so deskewing is really needed), ideal IMU frames."""
+
+    def __init__(self, seed=1003, rings=64, azimuths=2048, radius=40.0, speed=10.0, scan_dt=0.1, imu_hz=200.0):
+        self.world = make_world(seed, 120.0, 70.0, 25.0, 60)
+        self.rings, self.az, self.r, self.v, self.dt, self.imu_hz, self.seed = rings, azimuths, radius, speed, scan_dt, imu_hz, seed
+        self.omega = speed / radius
+
+    def pose(self, t):
+        """position (…,3), yaw of the trajectory at time(s) t."""
+        t = np.asarray(t, np.float64)
+        th = self.omega * t
+        p = np.stack([self.r * np.sin(th), self.r * (1.0 - np.cos(th)) - self.r, np.full_like(th, 1.8)], -1)
+        return p, th
+
+    def state(self, t):
+        p, yaw = self.pose(t)
+        return make_state(p, quat_from_rpy(0.0, 0.0, float(yaw)), vel=(self.v * np.cos(yaw), self.v * np.sin(yaw), 0.0))
+
+    def scan(self, k):
+        """Raw message k (api.RAW_POINT records, VELODYNE timing: `time` = seconds since the sweep start
+        stamp k*dt) and its start stamp."""
+        from .api import RAW_POINT
+        rng = np.random.default_rng(self.seed + 17 * k)
+        n = self.rings * self.az
+        el = np.deg2rad(np.linspace(2.0, -24.8, self.rings))
+        az = np.linspace(0.0, 2 * np.pi, self.az, endpoint=False)
+        ce, se = np.cos(el)[:, None], np.sin(el)[:, None]
+        d_body = np.stack([ce * np.cos(az)[None, :], ce * np.sin(az)[None, :], np.broadcast_to(se, (self.rings, self.az))], -1).reshape(-1, 3)
+        frac = np.tile(np.arange(self.az) / self.az, self.rings) + rng.uniform(0, 0.2 / n, n)
+        t_rel = (frac * self.dt).astype(np.float32)
+        stamp = k * self.dt
+        p, yaw = self.pose(stamp + t_rel.astype(np.float64))
+        c, s = np.cos(yaw), np.sin(yaw)
+        d_world = np.stack([c * d_body[:, 0] - s * d_body[:, 1], s * d_body[:, 0] + c * d_body[:, 1], d_body[:, 2]], -1)
+        rng_t = _raycast(self.world, (p[:, 0], p[:, 1], p[:, 2]), d_world)
+        bad = ~np.isfinite(rng_t) | (rng_t > 150.0)
+        rng_t = rng_t + rng.normal(0.0, 0.01, n)
+        pts = (d_body * rng_t[:, None]).astype(np.float32)
+        pts[bad] = np.nan                                           # no return: the NaN filter drops them
+        raw = np.zeros(n, RAW_POINT)
+        raw["x"], raw["y"], raw["z"], raw["time"] = pts[:, 0], pts[:, 1], pts[:, 2], t_rel
+        return raw, stamp
+
+    def frames(self, t0, t1):
+        """fast_limo::State records at the IMU rate covering [t0, t1] (ideal IMU, zero biases)."""
+        from .api import FRAME
+        n = int(np.ceil((t1 - t0) * self.imu_hz)) + 3
+        ts = t0 - 1.0 / self.imu_hz + np.arange(n) / self.imu_hz
+        p, yaw = self.pose(ts)
+        fr = np.zeros(n, FRAME)
+        fr["time"] = ts
+        fr["q"][:, 2], fr["q"][:, 3] = np.sin(yaw / 2), np.cos(yaw / 2)
+        fr["p"] = p
+        fr["v"][:, 0], fr["v"][:, 1] = self.v * np.cos(yaw), self.v * np.sin(yaw)
+        fr["w"][:, 2] = self.omega
+        fr["a"][:, 1] = self.v * self.omega                        # centripetal, body frame (y = left)
+        fr["a"][:, 2] = 9.809
+        fr["g"][:, 2] = -9.809
+        return fr

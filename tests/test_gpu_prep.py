@@ -109,3 +109,46 @@ def test_voxel_grid_bit_exact_and_pipeline(oracle, flimo_lib):
     ov = O.prep_voxel(ob, 1.0)
     assert abs(nv - len(ov)) <= max(3, len(ov) // 2000)            # a point within 1e-5 m of a voxel face may change voxel
     assert np.array_equal(m.voxel_grid(m.prep_get(2), 1.0), m.prep_get(3))   # stage consistency on the device cloud
+
+
+def test_stream_replay_parity(oracle, flimo_lib):
+    """BASELINE config c3 in small: a motion-distorted stream through the whole per-scan sequence of
+    Localizer::updatePointCloud (filters -> deskew -> voxel grid -> iterated update -> world cloud ->
+    Mapper::add with the down-sampling rule), device against oracle, scan after scan."""
+    O = oracle
+    S = synth.Stream(azimuths=256, rings=32)
+    m = mapper()
+    om = O.OracleMap()
+    ocfg = O.make_cfg(max_pc2match=BIG, max_matches=BIG, num_threads=2)
+    f = api.FilterConfig(cropBoxMin=(-1, -1, -1), cropBoxMax=(1, 1, 1), min_dist=3.0, leafSize=0.5, sensor_type=1)
+    opc = to_oracle_cfg(O, f)
+    P0, lim = synth.default_P0(), np.full(23, 0.001)
+    T = np.eye(4, dtype=np.float32)
+    rng = np.random.default_rng(2)
+    prev_end = 0.0
+    for k in range(6):
+        raw, stamp = S.scan(k)
+        n, t_last = m.prep_filter_sort(raw, stamp, f)
+        frames = S.frames(prev_end, t_last)
+        pred = S.state(t_last)
+        pred[:3] += rng.normal(0, 0.02, 3)
+        lq, lp = pred[3:7].astype(np.float32), pred[:3].astype(np.float32)
+        npc = m.prep_deskew(frames, lq, lp, T, 0.0)
+        order = O.prep_filter_sort(raw, opc, sort=True)
+        assert np.array_equal(m.prep_get(0), order)
+        # the oracle continues from the DEVICE's pc2match (bit-identical voxel stage, deskew within 2e-5 m)
+        pc = np.ascontiguousarray(m.prep_get(3)[:, :3])
+        _, ob = O.prep_deskew(raw, order, opc, stamp, 0.0, frames, lq, lp, T)
+        assert np.abs(m.prep_get(2) - ob).max() <= 2e-5
+        if k == 0:
+            xg = xo = pred.copy()
+        else:
+            xg, Pg, pg = m.update(pred, P0, 3, lim)
+            xo, Po, tr = om.update(ocfg, pred, P0, 3, lim, pc)
+            assert pg == len(tr)
+            assert np.abs(xg[:3] - xo[:3]).max() <= 1e-9 and np.abs(xg[3:7] - xo[3:7]).max() <= 1e-10
+        world = m.scan_to_world(xg)
+        m.add(world, t_last)
+        om.add(world)
+        assert m.size() == om.size() and npc == len(pc)
+        prev_end = t_last
