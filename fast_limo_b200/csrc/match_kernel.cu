@@ -191,8 +191,10 @@ __device__ __forceinline__ bool block_scan_private(const LevelView& L, uint32_t 
     const Pair b0 = ldg_pair<kWide>(pts + min(n + 4, last)), b1 = ldg_pair<kWide>(pts + min(n + 6, last));
     rank4(k, a0, a1, qx, qy, qz, n, lead);
     lead = 0.f;
-    a0 = ldg_pair<kWide>(pts + min(n + 8, last));
-    a1 = ldg_pair<kWide>(pts + min(n + 10, last));
+    if (n + 8 < tot) {                            // nothing left to rank: do not fetch
+      a0 = ldg_pair<kWide>(pts + min(n + 8, last));
+      a1 = ldg_pair<kWide>(pts + min(n + 10, last));
+    }
     rank4(k, b0, b1, qx, qy, qz, n + 4, 0.f);
   }
   if (n + 4 <= tot) {

@@ -36,7 +36,35 @@ def one(name, max_iter, **cfgkw):
     print(name, cfgkw, "n_valid", r["n_valid"], "rows", r["rows"], "passes", len(tr))
 
 
+def prep_inputs():
+    """Seeded inputs of the scan-preparation fixture (shared with the tests)."""
+    rng = np.random.default_rng(77)
+    xyz = rng.uniform(-50, 50, (6000, 3)).astype(np.float32)
+    xyz[:, 2] = rng.uniform(-2, 7, 6000)
+    ang = np.abs(np.arctan2(xyz[:, 1].astype(np.float64), xyz[:, 0].astype(np.float64)))
+    xyz = xyz[np.abs(ang - 2.6) > 2e-6]                     # clear of the field-of-view decision boundary
+    raw = synth.make_raw_message(xyz, sensor_type=1, sweep=0.1, stamp=100.0, seed=77, n_nan=30)
+    frames = synth.make_frames(100.0, 100.1, rate_hz=200.0, speed=12.0, yaw_rate=1.2)
+    T = np.eye(4, dtype=np.float32)
+    T[:3, 3] = [0.27, -0.03, 0.4]
+    T[:3, :3] = synth.quat_to_R(synth.quat_from_rpy(0.01, -0.02, 0.03)).astype(np.float32)
+    return raw, frames, T
+
+
+def prep():
+    raw, frames, T = prep_inputs()
+    cfg = O.make_prep_cfg(crop=([-1.5, -1.0, -1.0], [1.5, 1.0, 1.0]), min_dist=4.0, rate=2, fov=2.6, sensor_type=1, leaf=1.0)
+    order = O.prep_filter_sort(raw, cfg, sort=True)
+    t = O.prep_times(raw, order, cfg, 100.0)
+    w, b = O.prep_deskew(raw, order, cfg, 100.0, -2.0e-4, frames, frames["q"][-2], frames["p"][-2], T)
+    v = O.prep_voxel(b, 1.0)
+    np.savez_compressed(os.path.join(HERE, "prep_velodyne.npz"), raw_checksum=np.float64(np.nansum(raw["x"].astype(np.float64))),
+                        order=order, t_last=np.float64(t[-1]), world=w, xt2=b, voxel=v)
+    print("prep", len(raw), "->", len(order), "->", len(v))
+
+
 if __name__ == "__main__":
+    prep()
     one("tiny", 2, max_pc2match=1 << 18, max_matches=1 << 18)
     one("tiny", 3, max_pc2match=1500, max_matches=400)       # both first-N caps active (SURVEY H4)
     one("c1", 0, max_pc2match=1 << 18, max_matches=1 << 18)  # BASELINE configs[0]: 16k scan, 100k map, 1 pass

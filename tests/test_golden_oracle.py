@@ -34,3 +34,27 @@ def test_oracle_matches_golden(oracle, name, pc2, mm):
     assert np.allclose(x, g["x_final"], rtol=0, atol=1e-12)
     assert np.allclose(P, g["P_final"], rtol=1e-9, atol=1e-13)
     assert [t["rows"] for t in tr] == g["trace_rows"].tolist()
+
+
+def _prep_inputs():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(G, "make_golden.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod.prep_inputs()
+
+
+def test_oracle_prep_matches_golden(oracle):
+    """Scan preparation (filters, time sort, deskew, voxel grid) against tests/golden/prep_velodyne.npz."""
+    O = oracle
+    g = np.load(os.path.join(G, "prep_velodyne.npz"))
+    raw, frames, T = _prep_inputs()
+    assert np.nansum(raw["x"].astype(np.float64)) == float(g["raw_checksum"])
+    cfg = O.make_prep_cfg(crop=([-1.5, -1.0, -1.0], [1.5, 1.0, 1.0]), min_dist=4.0, rate=2, fov=2.6, sensor_type=1, leaf=1.0)
+    order = O.prep_filter_sort(raw, cfg, sort=True)
+    assert np.array_equal(order, g["order"])
+    assert O.prep_times(raw, order, cfg, 100.0)[-1] == float(g["t_last"])
+    w, b = O.prep_deskew(raw, order, cfg, 100.0, -2.0e-4, frames, frames["q"][-2], frames["p"][-2], T)
+    # sinf / cosf come from libm: allow an ulp-level difference between machines
+    assert np.abs(w - g["world"]).max() <= 2e-5 and np.abs(b - g["xt2"]).max() <= 2e-5
+    assert np.array_equal(O.prep_voxel(g["xt2"], 1.0), g["voxel"])

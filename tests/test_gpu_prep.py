@@ -152,3 +152,24 @@ def test_stream_replay_parity(oracle, flimo_lib):
         om.add(world)
         assert m.size() == om.size() and npc == len(pc)
         prev_end = t_last
+
+
+def test_prep_against_golden_fixture(flimo_lib):
+    """Device scan preparation against the committed fixture tests/golden/prep_velodyne.npz."""
+    import importlib.util
+    import os
+    G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(G, "make_golden.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    raw, frames, T = mod.prep_inputs()
+    g = np.load(os.path.join(G, "prep_velodyne.npz"))
+    m = mapper()
+    f = api.FilterConfig(cropBoxMin=(-1.5, -1.0, -1.0), cropBoxMax=(1.5, 1.0, 1.0), min_dist=4.0, rate_value=2, fov_angle=2.6,
+                         leafSize=1.0, sensor_type=1)
+    n, t_last = m.prep_filter_sort(raw, 100.0, f)
+    assert n == len(g["order"]) and t_last == float(g["t_last"])
+    assert np.array_equal(m.prep_get(0), g["order"])
+    m.prep_deskew(frames, frames["q"][-2], frames["p"][-2], T, -2.0e-4)
+    assert np.abs(m.prep_get(1) - g["world"]).max() <= 2e-5 and np.abs(m.prep_get(2) - g["xt2"]).max() <= 2e-5
+    assert np.array_equal(m.voxel_grid(g["xt2"], 1.0), g["voxel"])

@@ -12,9 +12,12 @@ m.add(case.map_pts, 0.0); m.set_scan(case.scan)
 pose = case.init
 if "conv" in sys.argv:
     pose, _, _ = m.update(case.init, synth.default_P0(), 2, 0.0)
+frac = [int(a.split("=")[1]) for a in sys.argv if a.startswith("shard=")]
+if frac:                      # keep only 1/frac of the scan: the per-warp latency chain at low occupancy
+    m.shard(0, case.scan.shape[0] // frac[0])
 for i in range(3): m.match(pose)
 L = _lib.load()
-nw = (case.scan.shape[0] + 127) // 128 * 4
+nw = ((case.scan.shape[0] // frac[0] if frac else case.scan.shape[0]) + 127) // 128 * 4
 buf = np.zeros((nw + 1, 8), np.uint64)
 L.flimo_debug_timing.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]
 L.flimo_debug_timing(m._h, 1, None, nw)
