@@ -666,6 +666,8 @@ int flimo_map_add_device(flimo_handle h, const void* d_xyz, size_t n, size_t str
     h->prof_add_insert += std::chrono::duration<double, std::micro>(ta2 - ta1).count();
     h->prof_add_index += std::chrono::duration<double, std::micro>(ta3 - ta2).count();
     h->prof_adds++;
+    std::fprintf(stderr, "[add] total %zu: insert %.0f us, index %.0f us\n", total, std::chrono::duration<double, std::micro>(ta2 - ta1).count(),
+                 std::chrono::duration<double, std::micro>(ta3 - ta2).count());
   }
   return FLIMO_OK;
 }
@@ -740,6 +742,11 @@ static int pack_bound_scan(flimo_handle h) {
   const int sort = (h->cfg.sort_scan && nq > 1) ? 1 : 0;
   const unsigned int perm = (sort || !h->scan_perm) ? 0u : coprime_stride((uint32_t)nq);
   h->packed_valid = true;
+  if (!sort) {                                                   // one kernel: launch it directly
+    CU(h, scan_prepare(d_xyz, nq, stride_bytes, false, perm, h->scan, h->scan_tmp, &h->scan_cub, &h->scan_cub_bytes, &h->scan_keys,
+                       &h->scan_keys_cap, h->stream, &h->stats.kernel_launches));
+    return FLIMO_OK;
+  }
   for (auto& g : h->scan_graphs) {
     if (g.src == d_xyz && g.n == nq && g.stride == stride_bytes && g.sort == sort) {
       CU(h, cudaGraphLaunch(g.exec, h->stream));

@@ -14,6 +14,8 @@
 // (once per Mapper::add).
 #include <algorithm>
 #include <cfloat>
+#include <chrono>
+#include <cstdlib>
 #include <cmath>
 #include <cstdio>
 
@@ -210,8 +212,9 @@ static cudaError_t ensure(void** p, size_t* cap, size_t need) {
   if (*p) cudaFree(*p);
   *p = nullptr;
   *cap = 0;
-  FL_TRY(cudaMalloc(p, need));
-  *cap = need;
+  const size_t want = need + need / 2 + (1u << 20);      // head-room: the requirement creeps up with every Mapper::add
+  FL_TRY(cudaMalloc(p, want));
+  *cap = want;
   return cudaSuccess;
 }
 
@@ -399,9 +402,18 @@ cudaError_t map_index_build(MapIndex& idx, float cell0, float ratio, float coars
   }
   int nl = 0;
   float cell = cell0;
+  static const bool prof = std::getenv("FLIMO_PROFILE_INDEX") != nullptr;
   for (;;) {
     if (nl == kMaxLevels - 1 && cell < coarsest_min) cell = coarsest_min;   // force termination
+    const auto t0 = std::chrono::steady_clock::now();
     FL_TRY(build_level(idx, idx.lv[nl], make_grid(idx.lo, idx.hi, cell), st, launches));
+    if (prof) {
+      const auto t1 = std::chrono::steady_clock::now();
+      cudaStreamSynchronize(st);
+      const auto t2 = std::chrono::steady_clock::now();
+      std::fprintf(stderr, "[index] level %d cell %.3f n %zu cells %zu: host %.0f us, +sync %.0f us\n", nl, cell, n, idx.lv[nl].n_cells,
+                   std::chrono::duration<double, std::micro>(t1 - t0).count(), std::chrono::duration<double, std::micro>(t2 - t1).count());
+    }
     ++nl;
     if (cell >= coarsest_min || nl == kMaxLevels) break;
     cell *= ratio;

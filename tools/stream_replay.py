@@ -16,9 +16,14 @@ ap.add_argument("--az", type=int, default=2048)
 ap.add_argument("--leaf", type=float, default=0.5)
 ap.add_argument("--oracle", type=int, default=0)
 ap.add_argument("--max-iter", type=int, default=3)          # kitti.yaml MAX_NUM_ITERS
+ap.add_argument("--rings", type=int, default=64)
+ap.add_argument("--dt", type=float, default=0.1, help="sweep duration = scan period (s)")
+ap.add_argument("--imu-hz", type=float, default=200.0)
+ap.add_argument("--speed", type=float, default=10.0)
+ap.add_argument("--premap", type=int, default=0, help="points of a pre-built map of the world (config c5: 2 000 000)")
 args = ap.parse_args()
 
-S = synth.Stream(azimuths=args.az)
+S = synth.Stream(azimuths=args.az, rings=args.rings, scan_dt=args.dt, imu_hz=args.imu_hz, speed=args.speed)
 BIG = 1 << 20
 m = api.Mapper(api.MappingConfig(MAX_NUM_MATCHES=BIG, MAX_NUM_PC2MATCH=BIG), device=0)
 filt = api.FilterConfig(cropBoxMin=(-1, -1, -1), cropBoxMax=(1, 1, 1), min_dist=3.0, leafSize=args.leaf if args.leaf > 0 else None, sensor_type=1)
@@ -32,6 +37,9 @@ if args.oracle:
     ocfg = O.make_cfg(max_pc2match=BIG, max_matches=BIG, num_threads=O.max_threads())
     opc = O.make_prep_cfg(crop=([-1, -1, -1], [1, 1, 1]), min_dist=3.0, leaf=args.leaf if args.leaf > 0 else None, sensor_type=1)
 
+if args.premap:
+    m.add(synth.sample_map(S.world, args.premap, 1005), 0.0)
+lat_pose = []
 t_gen = t_prep = t_upd = t_add = 0.0
 WARM = 10                                      # scans left out of the averages (allocations, lazy module loading)
 errs, sizes, n_pc = [], [], []
@@ -67,7 +75,7 @@ for k in range(args.n_scans):
     lq, lp = pred[3:7].astype(np.float32), pred[:3].astype(np.float32)
     n_pc2 = m.prep_deskew(frames, lq, lp, T_l2b, 0.0)
     a1 = time.perf_counter()
-    if k == 0:
+    if k == 0 and not args.premap:
         x_est, passes = truth.copy(), 0           # the first mapped scan initialises the map (zero matches); anchored at the truth
     else:
         x_est, Pn, passes = m.update(pred, P0, args.max_iter, lim)
@@ -77,6 +85,7 @@ for k in range(args.n_scans):
     a3 = time.perf_counter()
     if k >= WARM:
         t_prep += a1 - a0; t_upd += a2 - a1; t_add += a3 - a2
+        lat_pose.append(a2 - a0)
     errs.append(float(np.linalg.norm(x_est[:3] - truth[:3]))); sizes.append(m.size()); n_pc.append(n_pc2)
     if om is not None and k < args.oracle:
         c0 = time.perf_counter()
@@ -99,5 +108,8 @@ for k in range(args.n_scans):
               f"per scan after {WARM} warm-up scans: prep {t_prep/max(k+1-WARM,1)*1e3:.2f} ms, update {t_upd/max(k+1-WARM,1)*1e3:.2f} ms, "
               f"to_world+add {t_add/max(k+1-WARM,1)*1e3:.2f} ms => {max(k+1-WARM,1)/max(t_prep+t_upd+t_add,1e-9):.1f} scans/s "
               f"(generation {t_gen/(k+1)*1e3:.0f} ms/scan not counted)", flush=True)
+if lat_pose:
+    lp_ = np.array(lat_pose) * 1e3
+    print(f"latency raw message -> pose on the host (prep + update): p50 {np.percentile(lp_, 50):.2f} ms, p99 {np.percentile(lp_, 99):.2f} ms, max {lp_.max():.2f} ms")
 if args.oracle:
     print(f"CPU oracle: {t_cpu/args.oracle*1e3:.1f} ms per scan over the first {args.oracle} scans ({O.max_threads()} threads)")
