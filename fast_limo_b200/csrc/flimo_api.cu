@@ -112,6 +112,7 @@ struct flimo_ctx {
   double persist_ns_total = 0;   // in-kernel device time of persistent passes
   uint64_t persist_passes = 0;
   uint64_t update_calls = 0;
+  int test_stall_pass = -1;      // FLIMO_TEST_STALL_PASS=k: the host sleeps 60 ms before command k of every update (watchdog test)
   bool prof = false;             // FLIMO_PROFILE=1: host-side wall-clock breakdown printed by flimo_destroy
   double prof_launch = 0, prof_wait = 0, prof_step = 0, prof_other = 0;
   double prof_add_pack = 0, prof_add_insert = 0, prof_add_index = 0;
@@ -483,6 +484,7 @@ int flimo_create(const flimo_cfg* cfg, int device, flimo_handle* out) {
   CU(h, cudaMemset(h->dev_ctl, 0, sizeof(PassCtl)));
   h->persist_capacity = match_persistent_capacity();
   if (const char* e = std::getenv("FLIMO_PERSISTENT")) h->persistent = std::atoi(e);
+  if (const char* e = std::getenv("FLIMO_TEST_STALL_PASS")) h->test_stall_pass = std::atoi(e);
   *out = h;
   return FLIMO_OK;
 }
@@ -1139,6 +1141,10 @@ static int update_persistent(flimo_handle h, ekf::IteratedUpdate& u, bool exchan
   while (!u.done()) {
     u.state(x);
     const unsigned long long seq = ++counter;
+    if (h->test_stall_pass >= 0 && u.passes() == h->test_stall_pass) {      // test hook: outlast the kernel's watchdog
+      const auto until = std::chrono::steady_clock::now() + std::chrono::milliseconds(60);
+      while (std::chrono::steady_clock::now() < until) {}
+    }
     const auto tp0 = std::chrono::steady_clock::now();
     post_ctl(h, 0u, 0xFFFFFFFFu, x);
     if (h->pref_idx >= 0 && !h->pref_issued) {             // the requested copy of the next scan overlaps this pass

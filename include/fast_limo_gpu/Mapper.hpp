@@ -77,6 +77,20 @@ class Mapper {
     check(flimo_scan_set(h_, reinterpret_cast<const float*>(pc->points.data()), pc->points.size(), sizeof(pc->points[0])));
   }
 
+  // Optional: start the host-to-device copy of the NEXT scan; it overlaps the current registration and the
+  // next bind_scan of the same cloud picks it up.
+  template <typename PointCloudPtr>
+  void prefetch_scan(PointCloudPtr& pc) {
+    check(flimo_scan_prefetch(h_, reinterpret_cast<const float*>(pc->points.data()), pc->points.size(), sizeof(pc->points[0])));
+  }
+
+  // pcl::transformPointCloud(*pc2match, *final_scan, state.get_RT()) (Localizer.cpp:361-374) on the device copy.
+  std::size_t scan_to_world(const double state14[14], float* out_xyz, std::size_t cap_points) {
+    std::size_t n = 0;
+    check(flimo_scan_to_world(h_, state14, out_xyz, cap_points, &n));
+    return n;
+  }
+
   // Mapper::match(State, pc) + Localizer::calculate_H + H^T H / H^T h for the bound scan.
   NormalEquations match(const double state14[14]) {
     NormalEquations ne;

@@ -7,6 +7,7 @@
 #include <memory>
 #include <vector>
 
+#include "fast_limo_gpu/Localizer.hpp"
 #include "fast_limo_gpu/Mapper.hpp"
 
 struct Pt {            // fast_limo::Point layout (32 bytes)
@@ -34,6 +35,23 @@ int main() {
   bool threw = false;
   try { M.add(pc, 0.0); } catch (const std::exception& e) { threw = std::strstr(e.what(), "host-only") != nullptr; }
   if (!threw) return 2;
+  // the scan front end (Localizer side) must refuse a host-only handle as loudly
+  struct Filters {
+    std::vector<float> cropBoxMin{-1, -1, -1}, cropBoxMax{1, 1, 1}, leafSize{0.5f, 0.5f, 0.5f};
+    bool crop_active = true, voxel_active = true, dist_active = true, rate_active = false, fov_active = false;
+    double min_dist = 3.0;
+    int rate_value = 1;
+    float fov_angle = 3.0f;
+  } filters;
+  fast_limo_gpu::Localizer L(M.handle());
+  L.set_filters(filters, /*sensor_type=*/1, /*end_of_sweep=*/false);
+  threw = false;
+  double t_last = 0.0;
+  try { L.filter_and_sort(pc, 100.0, t_last); } catch (const std::exception& e) { threw = std::strstr(e.what(), "host-only") != nullptr; }
+  if (!threw) return 8;
+  threw = false;
+  try { M.prefetch_scan(pc); } catch (const std::exception& e) { threw = std::strstr(e.what(), "host-only") != nullptr; }
+  if (!threw) return 9;
   // filter state machine from C++
   double x[26] = {0}, P[529] = {0}, lim[23], HTH[144] = {0}, HTh[12] = {0};
   x[6] = 1.0; x[10] = 1.0; x[25] = -9.809;

@@ -346,3 +346,40 @@ def test_fused_exchange_two_processes(oracle, flimo_lib):
         assert pa == pb == p1 == 3
         assert np.array_equal(xa, xb) and np.array_equal(Pa, Pb)
         assert np.abs(xa - x1).max() <= 1e-10 and np.allclose(Pa, P1, rtol=1e-4, atol=1e-11)
+
+
+def _stall_worker(stall, out):
+    os.environ["FLIMO_TEST_STALL_PASS"] = str(stall)
+    case = synth.make_case("tiny")
+    m = mapper()
+    m.add(case.map_pts)
+    m.set_scan(case.scan)
+    res = []
+    for rep in range(3):
+        x, P, passes = m.update(case.init, synth.default_P0(), 2, 0.0)
+        res.append((x, P, passes))
+    out[stall] = res
+    m.close()
+
+
+@pytest.mark.timeout(600)
+@pytest.mark.parametrize("stall", [0, 1, 2])
+def test_persistent_kernel_watchdog_fallback(flimo_lib, stall):
+    """The host goes silent for 60 ms before a pass (longer than the persistent kernel's 20 ms watchdog):
+    the kernel must end by itself, the update must continue with per-pass launches and give the identical
+    result — also on the following updates (command / ticket state stays consistent)."""
+    import torch.multiprocessing as mp
+    mgr = mp.Manager()
+    out = mgr.dict()
+    p = mp.get_context("spawn").Process(target=_stall_worker, args=(stall, out))
+    p.start()
+    p.join(300)
+    assert p.exitcode == 0
+    case = synth.make_case("tiny")
+    m = mapper()
+    m.add(case.map_pts)
+    m.set_scan(case.scan)
+    x1, P1, p1 = m.update(case.init, synth.default_P0(), 2, 0.0)
+    for (x, P, passes) in out[stall]:
+        assert passes == p1 == 3
+        assert np.array_equal(x, x1) and np.array_equal(P, P1)
