@@ -16,7 +16,7 @@ SYMBOLS = [
     "flimo_map_get_points", "flimo_scan_set", "flimo_scan_set_device", "flimo_scan_prefetch", "flimo_scan_shard",
     "flimo_match_reduce", "flimo_match_reduce_async", "flimo_unpack96", "flimo_match_debug",
     "flimo_update", "flimo_ekf_begin", "flimo_ekf_state", "flimo_ekf_step", "flimo_ekf_end",
-    "flimo_scan_to_world", "flimo_prep_filter_sort", "flimo_prep_deskew", "flimo_prep_get", "flimo_voxel_grid", "flimo_get_stats", "flimo_stream", "flimo_exchange_attach", "flimo_match_reduce_exchange", "flimo_update_exchange",
+    "flimo_scan_to_world", "flimo_prep_filter_sort", "flimo_prep_filter_sort_msg", "flimo_prep_deskew", "flimo_prep_get", "flimo_voxel_grid", "flimo_get_stats", "flimo_stream", "flimo_exchange_attach", "flimo_match_reduce_exchange", "flimo_update_exchange",
 ]
 
 
@@ -51,6 +51,12 @@ class FlimoPrepCfg(C.Structure):
         ("sensor_type", C.c_int32),
         ("end_of_sweep", C.c_int32),
     ]
+
+
+class FlimoMsgLayout(C.Structure):
+    """flimo_msg_layout: byte offsets of the fast_limo::Point fields inside a PointCloud2 point."""
+    _fields_ = [("off_x", C.c_int32), ("off_y", C.c_int32), ("off_z", C.c_int32), ("off_intensity", C.c_int32),
+                ("off_time", C.c_int32), ("time_datatype", C.c_int32)]
 
 
 class FlimoStats(C.Structure):
@@ -125,6 +131,7 @@ def load():
     L.flimo_scan_to_world.argtypes = [vp, pd, pf, sz, C.POINTER(sz)]
     L.flimo_get_stats.argtypes = [vp, C.POINTER(FlimoStats)]
     L.flimo_prep_filter_sort.argtypes = [vp, vp, sz, dbl, C.POINTER(FlimoPrepCfg), C.POINTER(sz), pd]
+    L.flimo_prep_filter_sort_msg.argtypes = [vp, vp, sz, sz, C.POINTER(FlimoMsgLayout), dbl, C.POINTER(FlimoPrepCfg), C.POINTER(sz), pd]
     L.flimo_prep_deskew.argtypes = [vp, vp, C.c_int, pf, pf, pf, dbl, C.POINTER(sz)]
     L.flimo_prep_get.argtypes = [vp, C.c_int, vp, sz, C.POINTER(sz)]
     L.flimo_voxel_grid.argtypes = [vp, pf, sz, C.c_float, pf, sz, C.POINTER(sz)]

@@ -17,7 +17,7 @@ from dataclasses import dataclass
 import numpy as np
 
 from . import _lib
-from ._lib import FlimoCfg, FlimoError, FlimoPrepCfg, FlimoStats
+from ._lib import FlimoCfg, FlimoError, FlimoMsgLayout, FlimoPrepCfg, FlimoStats
 
 
 @dataclass
@@ -198,6 +198,18 @@ class Mapper:
         n, t = C.c_size_t(0), C.c_double(0)
         self._ck(self._L.flimo_prep_filter_sort(self._h, raw.ctypes.data, len(raw), float(sweep_ref_time), C.byref(c),
                                                 C.byref(n), C.byref(t)))
+        return int(n.value), float(t.value)
+
+    def prep_filter_sort_msg(self, data, point_step, sweep_ref_time, filters: "FilterConfig", off_xyz=(0, 4, 8), off_intensity=-1,
+                             off_time=-1, time_datatype=7):
+        """Same on a sensor_msgs/PointCloud2 payload (bytes / uint8 array): decode on the device, then filters + sort."""
+        buf = np.frombuffer(data, np.uint8) if not isinstance(data, np.ndarray) else np.ascontiguousarray(data).view(np.uint8).reshape(-1)
+        n_pts = len(buf) // int(point_step)
+        lay = FlimoMsgLayout(int(off_xyz[0]), int(off_xyz[1]), int(off_xyz[2]), int(off_intensity), int(off_time), int(time_datatype))
+        c = filters.to_c()
+        n, t = C.c_size_t(0), C.c_double(0)
+        self._ck(self._L.flimo_prep_filter_sort_msg(self._h, buf.ctypes.data, n_pts, int(point_step), C.byref(lay), float(sweep_ref_time),
+                                                    C.byref(c), C.byref(n), C.byref(t)))
         return int(n.value), float(t.value)
 
     def prep_deskew(self, frames, last_q, last_p, T_lidar2baselink, offset=0.0):

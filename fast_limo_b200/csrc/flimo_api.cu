@@ -1209,22 +1209,9 @@ static int update_persistent(flimo_handle h, ekf::IteratedUpdate& u, bool exchan
 }
 
 // ---- scan preparation --------------------------------------------------------------------------------
-int flimo_prep_filter_sort(flimo_handle h, const void* raw_points, size_t n, double sweep_ref_time, const flimo_prep_cfg* cfg,
-                           size_t* n_kept, double* t_last) {
-  if (!h || !cfg || !n_kept || !t_last || (!raw_points && n)) return fail(h, FLIMO_ERR_INVALID, "null argument");
-  if (cfg->sensor_type < 0 || cfg->sensor_type > 3) return fail(h, FLIMO_ERR_INVALID, "unknown LiDAR sensor type");   // Localizer.cpp:778-783
-  if (cfg->rate_active && cfg->rate_value < 1) return fail(h, FLIMO_ERR_INVALID, "rate_value must be >= 1");
-  if (n >= 0x7FFFFFF0ull) return fail(h, FLIMO_ERR_INVALID, "cloud too large");
-  NEED_GPU(h);
-  h->prep_cfg = *cfg;
-  h->prep_deskewed = false;
-  h->prep_pc2match = nullptr;
-  h->prep_n_pc2match = 0;
-  *n_kept = 0;
-  *t_last = 0.0;
-  if (n == 0) return FLIMO_OK;
-  CU(h, prep_reserve(h->prep, n));
-  CU(h, cudaMemcpyAsync(h->prep.raw, raw_points, n * 32, cudaMemcpyHostToDevice, h->stream));
+// Stages after the 32-byte records are in h->prep.raw.
+static int prep_filter_sort_common(flimo_handle h, size_t n, double sweep_ref_time, const flimo_prep_cfg* cfg, size_t* n_kept,
+                                   double* t_last) {
   PrepDev c{};
   c.crop_active = cfg->crop_active; c.dist_active = cfg->dist_active; c.rate_active = cfg->rate_active; c.fov_active = cfg->fov_active;
   for (int i = 0; i < 3; ++i) { c.crop_min[i] = cfg->cropBoxMin[i]; c.crop_max[i] = cfg->cropBoxMax[i]; }
@@ -1238,6 +1225,61 @@ int flimo_prep_filter_sort(flimo_handle h, const void* raw_points, size_t n, dou
   CU(h, prep_filter_sort(h->prep, n, c, h->stream, &m, t_last, &h->stats.kernel_launches));
   *n_kept = m;
   return FLIMO_OK;
+}
+
+static int prep_check_args(flimo_handle h, const void* data, size_t n, const flimo_prep_cfg* cfg, size_t* n_kept, double* t_last) {
+  if (!h || !cfg || !n_kept || !t_last || (!data && n)) return fail(h, FLIMO_ERR_INVALID, "null argument");
+  if (cfg->sensor_type < 0 || cfg->sensor_type > 3) return fail(h, FLIMO_ERR_INVALID, "unknown LiDAR sensor type");   // Localizer.cpp:778-783
+  if (cfg->rate_active && cfg->rate_value < 1) return fail(h, FLIMO_ERR_INVALID, "rate_value must be >= 1");
+  if (n >= 0x7FFFFFF0ull) return fail(h, FLIMO_ERR_INVALID, "cloud too large");
+  return FLIMO_OK;
+}
+
+int flimo_prep_filter_sort(flimo_handle h, const void* raw_points, size_t n, double sweep_ref_time, const flimo_prep_cfg* cfg,
+                           size_t* n_kept, double* t_last) {
+  int rc = prep_check_args(h, raw_points, n, cfg, n_kept, t_last);
+  if (rc) return rc;
+  NEED_GPU(h);
+  h->prep_cfg = *cfg;
+  h->prep_deskewed = false;
+  h->prep_pc2match = nullptr;
+  h->prep_n_pc2match = 0;
+  *n_kept = 0;
+  *t_last = 0.0;
+  if (n == 0) return FLIMO_OK;
+  CU(h, prep_reserve(h->prep, n));
+  CU(h, cudaMemcpyAsync(h->prep.raw, raw_points, n * 32, cudaMemcpyHostToDevice, h->stream));
+  return prep_filter_sort_common(h, n, sweep_ref_time, cfg, n_kept, t_last);
+}
+
+int flimo_prep_filter_sort_msg(flimo_handle h, const void* data, size_t n, size_t point_step, const flimo_msg_layout* layout,
+                               double sweep_ref_time, const flimo_prep_cfg* cfg, size_t* n_kept, double* t_last) {
+  int rc = prep_check_args(h, data, n, cfg, n_kept, t_last);
+  if (rc) return rc;
+  if (!layout) return fail(h, FLIMO_ERR_INVALID, "null argument");
+  // debug_limo::checkPointcloudStructure (src/main.cpp:17-20): the message must carry xyz and the sensor's time field
+  const int tsz = layout->time_datatype == 8 ? 8 : 4;
+  if (layout->off_x < 0 || layout->off_y < 0 || layout->off_z < 0) return fail(h, FLIMO_ERR_INVALID, "invalid pointcloud structure: xyz missing");
+  if (layout->off_time >= 0 && layout->time_datatype != 6 && layout->time_datatype != 7 && layout->time_datatype != 8)
+    return fail(h, FLIMO_ERR_INVALID, "invalid pointcloud structure: time field must be UINT32, FLOAT32 or FLOAT64");
+  const long long ends[5] = {layout->off_x + 4LL, layout->off_y + 4LL, layout->off_z + 4LL,
+                             layout->off_intensity >= 0 ? layout->off_intensity + 4LL : 0LL,
+                             layout->off_time >= 0 ? layout->off_time + (long long)tsz : 0LL};
+  for (long long e : ends)
+    if (e > (long long)point_step) return fail(h, FLIMO_ERR_INVALID, "invalid pointcloud structure: field beyond point_step");
+  NEED_GPU(h);
+  h->prep_cfg = *cfg;
+  h->prep_deskewed = false;
+  h->prep_pc2match = nullptr;
+  h->prep_n_pc2match = 0;
+  *n_kept = 0;
+  *t_last = 0.0;
+  if (n == 0) return FLIMO_OK;
+  CU(h, prep_reserve(h->prep, n));
+  rc = upload(h, data, n * point_step);
+  if (rc) return rc;
+  CU(h, prep_decode_msg(h->prep, static_cast<const unsigned char*>(h->stage), n, point_step, *layout, h->stream, &h->stats.kernel_launches));
+  return prep_filter_sort_common(h, n, sweep_ref_time, cfg, n_kept, t_last);
 }
 
 int flimo_prep_deskew(flimo_handle h, const flimo_frame* frames, int n_frames, const float last_q[4], const float last_p[3],

@@ -332,6 +332,33 @@ __global__ void __launch_bounds__(256) vox_centroid_kernel(const float4* __restr
   out[pos[i]] = make_float4(s[0] / cnt, s[1] / cnt, s[2] / cnt, 1.f);
 }
 
+// pcl::fromROSMsg (src/main.cpp:23) for the fields fast_limo::Point registers: byte-wise field reads (any
+// alignment), written as the canonical 32-byte record {x, y, z, 1, intensity, 0, time union}.
+__device__ __forceinline__ uint32_t load_u32_any(const unsigned char* p) {
+  return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
+}
+__global__ void __launch_bounds__(256) decode_msg_kernel(const unsigned char* __restrict__ msg, uint32_t n, uint32_t step,
+                                                         flimo_msg_layout L, unsigned char* __restrict__ raw) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const unsigned char* p = msg + (size_t)i * step;
+  uint4 a, b;
+  a.x = L.off_x >= 0 ? load_u32_any(p + L.off_x) : 0u;
+  a.y = L.off_y >= 0 ? load_u32_any(p + L.off_y) : 0u;
+  a.z = L.off_z >= 0 ? load_u32_any(p + L.off_z) : 0u;
+  a.w = __float_as_uint(1.0f);
+  b.x = L.off_intensity >= 0 ? load_u32_any(p + L.off_intensity) : 0u;
+  b.y = 0u;
+  b.z = b.w = 0u;
+  if (L.off_time >= 0) {
+    b.z = load_u32_any(p + L.off_time);
+    if (L.time_datatype == 8) b.w = load_u32_any(p + L.off_time + 4);
+  }
+  uint4* o = reinterpret_cast<uint4*>(raw + (size_t)i * 32);
+  o[0] = a;
+  o[1] = b;
+}
+
 inline unsigned int nblk(size_t n, int t = 256) { return (unsigned int)((n + t - 1) / t); }
 
 cudaError_t ensure(void** p, size_t* cap, size_t need) {
@@ -388,6 +415,14 @@ cudaError_t prep_reserve(PrepBuffers& b, size_t n) {
   need = t > need ? t : need;
   FP_TRY(ensure(&b.cub_tmp, &b.cub_tmp_bytes, need));
   return cudaSuccess;
+}
+
+cudaError_t prep_decode_msg(PrepBuffers& b, const unsigned char* d_msg, size_t n, size_t point_step, const flimo_msg_layout& L,
+                            cudaStream_t st, uint64_t* launches) {
+  if (n == 0) return cudaSuccess;
+  decode_msg_kernel<<<nblk(n), 256, 0, st>>>(d_msg, (uint32_t)n, (uint32_t)point_step, L, b.raw);
+  if (launches) *launches += 1;
+  return cudaGetLastError();
 }
 
 // u32 scratch layout (10 arrays of cap): 0 flag1/head | 1 idx1/pos | 2 flag2 | 3 pos | 4 order | 5 order_alt | 6 keys32 | 7 keys32_alt | 8 vox vals | 9 vox vals_alt

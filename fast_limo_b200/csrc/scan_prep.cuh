@@ -48,6 +48,9 @@ struct PrepBuffers {
 };
 
 cudaError_t prep_reserve(PrepBuffers& b, size_t n);
+// sensor_msgs/PointCloud2 payload (device copy) -> 32-byte fast_limo::Point records in b.raw
+cudaError_t prep_decode_msg(PrepBuffers& b, const unsigned char* d_msg, size_t n, size_t point_step, const flimo_msg_layout& L,
+                            cudaStream_t st, uint64_t* launches);
 void prep_free(PrepBuffers& b);
 cudaError_t prep_filter_sort(PrepBuffers& b, size_t n, const PrepDev& c, cudaStream_t st, uint32_t* n_kept, double* t_last,
                              uint64_t* launches);

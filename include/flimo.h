@@ -177,6 +177,19 @@ typedef struct {
  * (extract_point_time of the last sorted point, :797,:802) — the host needs it to choose the IMU frames. */
 int flimo_prep_filter_sort(flimo_handle h, const void* raw_points, size_t n, double sweep_ref_time,
                            const flimo_prep_cfg* cfg, size_t* n_kept, double* t_last);
+/* Same for a sensor_msgs/PointCloud2 payload as it arrives on the wire (what src/main.cpp:22-23 feeds to
+ * pcl::fromROSMsg): `data` holds n points of `point_step` bytes, the layout names the byte offsets of the
+ * fields fast_limo::Point registers (Common.hpp:156-163).  The decode to the 32-byte record runs on the
+ * device; offsets < 0 mean "field absent" (left 0, as pcl::fromROSMsg leaves unmatched fields). */
+typedef struct {
+  int32_t off_x, off_y, off_z;          /* FLOAT32 */
+  int32_t off_intensity;                /* FLOAT32, or -1 */
+  int32_t off_time;                     /* the per-point time field of the sensor, or -1 */
+  int32_t time_datatype;                /* sensor_msgs/PointField datatype of that field: 6 UINT32 ("t"), 7 FLOAT32 ("time"), 8 FLOAT64 ("timestamp") */
+} flimo_msg_layout;
+int flimo_prep_filter_sort_msg(flimo_handle h, const void* data, size_t n, size_t point_step,
+                               const flimo_msg_layout* layout, double sweep_ref_time, const flimo_prep_cfg* cfg,
+                               size_t* n_kept, double* t_last);
 /* The per-point loop of deskewPointCloud (Localizer.cpp:822-843) on the cloud left by
  * flimo_prep_filter_sort: frames = integrateImu(prev_scan_stamp, scan_stamp) (:805), last_q/last_p =
  * pose of State(_iKFoM.get_x()) (:820), T_lidar2baselink = extr.lidar2baselink_T row-major, offset as

@@ -173,3 +173,33 @@ def test_prep_against_golden_fixture(flimo_lib):
     m.prep_deskew(frames, frames["q"][-2], frames["p"][-2], T, -2.0e-4)
     assert np.abs(m.prep_get(1) - g["world"]).max() <= 2e-5 and np.abs(m.prep_get(2) - g["xt2"]).max() <= 2e-5
     assert np.array_equal(m.voxel_grid(g["xt2"], 1.0), g["voxel"])
+
+
+@pytest.mark.parametrize("sensor_type,dtype_code,field,np_type", [(0, 6, "t", "<u4"), (1, 7, "time", "<f4"), (2, 8, "timestamp", "<f8")])
+def test_pointcloud2_wire_format_decode(oracle, flimo_lib, sensor_type, dtype_code, field, np_type):
+    """sensor_msgs/PointCloud2 payloads with driver-style layouts (fields at other offsets, unaligned
+    float64, padding, extra fields) decode on the device to the same cloud pcl::fromROSMsg builds on the host:
+    identical filtered order and last-point time as the canonical 32-byte path."""
+    raw = message(30000, sensor_type, seed=13)
+    n = len(raw)
+    # an Ouster / Velodyne / Hesai flavoured point: x y z | intensity | time | ring(u16) | pad
+    step = {6: 26, 7: 22, 8: 30}[dtype_code] + 6           # deliberately odd point_step values
+    wire = np.dtype({"names": ["x", "y", "z", "intensity", "tf", "ring"], "formats": ["<f4", "<f4", "<f4", "<f4", np_type, "<u2"],
+                     "offsets": [0, 4, 8, 14, 18, 18 + np.dtype(np_type).itemsize], "itemsize": step})
+    msg = np.zeros(n, wire)
+    for k in ("x", "y", "z", "intensity"):
+        msg[k] = raw[k]
+    msg["tf"] = raw[field]
+    msg["ring"] = np.arange(n) % 64
+    f = api.FilterConfig(cropBoxMin=(-1.5, -1.0, -1.0), cropBoxMax=(1.5, 1.0, 1.0), min_dist=4.0, rate_value=3,
+                         sensor_type=sensor_type)
+    m = mapper()
+    n1, t1 = m.prep_filter_sort(raw, 100.0, f)
+    o1 = m.prep_get(0).copy()
+    n2, t2 = m.prep_filter_sort_msg(msg.tobytes(), step, 100.0, f, off_xyz=(0, 4, 8), off_intensity=14, off_time=18,
+                                    time_datatype=dtype_code)
+    assert (n1, t1) == (n2, t2) and np.array_equal(m.prep_get(0), o1)
+    order = oracle.prep_filter_sort(raw, to_oracle_cfg(oracle, f), sort=True)
+    assert np.array_equal(o1, order)
+    with pytest.raises(api.FlimoError, match="invalid pointcloud structure"):
+        m.prep_filter_sort_msg(msg.tobytes(), step, 100.0, f, off_xyz=(0, 4, step - 2), off_time=18, time_datatype=dtype_code)
