@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libflimo_cuda.so")
+LIB_PATH = os.path.join(_HERE, os.environ.get("FLIMO_LIB_NAME", "libflimo_cuda.so"))   # FLIMO_LIB_NAME: A/B builds of tools/
 
 # every symbol include/flimo.h declares (tests check that the .so exports all of them)
 SYMBOLS = [

@@ -299,23 +299,29 @@ class Mapper:
         return int(self._L.flimo_stream(self._h) or 0)
 
     # -- iterated update ---------------------------------------------------------------------
+    def _update_buffers(self):
+        """Reusable argument buffers of update(): building ctypes pointers costs more than a whole pass."""
+        b = getattr(self, "_ubuf", None)
+        if b is None:
+            x, Pm, lim = np.zeros(26, np.float64), np.zeros((23, 23), np.float64), np.zeros(23, np.float64)
+            b = self._ubuf = (x, Pm, lim, _dp(x), _dp(Pm), _dp(lim), C.c_int(0))
+        return b
+
+    def _update(self, fn, state26, P, max_iter, limits, R, D):
+        x, Pm, lim, px, pP, pl, passes = self._update_buffers()
+        x[:] = state26
+        Pm[:] = np.asarray(P, np.float64).reshape(23, 23)
+        lim[:] = limits
+        self._ck(fn(self._h, px, pP, int(max_iter), pl, float(R), float(D), C.byref(passes)))
+        return x.copy(), Pm.copy(), int(passes.value)
+
     def update(self, state26, P, max_iter, limits, R=0.001, D=5.0):
         """esekf::update_iterated_dyn_share_modified on the bound scan.  Returns (x, P, passes)."""
-        x = np.array(state26, np.float64).copy()
-        Pm = np.array(P, np.float64).reshape(23, 23).copy()
-        lim = np.ascontiguousarray(np.broadcast_to(np.asarray(limits, np.float64), (23,)))
-        passes = C.c_int(0)
-        self._ck(self._L.flimo_update(self._h, _dp(x), _dp(Pm), int(max_iter), _dp(lim), float(R), float(D), C.byref(passes)))
-        return x, Pm, int(passes.value)
+        return self._update(self._L.flimo_update, state26, P, max_iter, limits, R, D)
 
     def update_exchange(self, state26, P, max_iter, limits, R=0.001, D=5.0):
         """`update` with every pass summed over all ranks through the attached exchange segment."""
-        x = np.array(state26, np.float64).copy()
-        Pm = np.array(P, np.float64).reshape(23, 23).copy()
-        lim = np.ascontiguousarray(np.broadcast_to(np.asarray(limits, np.float64), (23,)))
-        passes = C.c_int(0)
-        self._ck(self._L.flimo_update_exchange(self._h, _dp(x), _dp(Pm), int(max_iter), _dp(lim), float(R), float(D), C.byref(passes)))
-        return x, Pm, int(passes.value)
+        return self._update(self._L.flimo_update_exchange, state26, P, max_iter, limits, R, D)
 
     def ekf_begin(self, state26, P, max_iter, limits, R=0.001, D=5.0):
         x = np.ascontiguousarray(state26, np.float64)
