@@ -433,22 +433,46 @@ class IteratedUpdate {
       cols_by_T<2>(P_, 21, J);
     }
 
-    // gain in information form
-    Mat<N, N> Pi = P_;
-    for (double& v : Pi.a) v /= R_;
-    invert<N>(Pi);
-    for (int r = 0; r < 12; ++r)
-      for (int c = 0; c < 12; ++c) Pi(r, c) += HTH144[r * 12 + c];
-    invert<N>(Pi);   // P_inv
+    // gain in information form (esekfom.hpp:1722-1729).  Only the first 12 columns of
+    //   P_inv = ((P/R)^-1 + U HTH U^T)^-1,  U = [I12; 0],
+    // are ever used.  They satisfy  P_inv U = (P U / R) (I12 + HTH P11 / R)^-1  (multiply the defining
+    // equation by P/R and restrict to the first 12 rows), which needs ONE 12x12 inverse instead of the
+    // reference's two 23x23 ones and is better conditioned.  reference_form_ evaluates it the reference's way.
     double K_h[N];
     Mat<N, N> K_x = Mat<N, N>::zero();
+    Mat<N, 12> X;                                    // P_inv[:, 0:12]
+    if (reference_form_) {
+      Mat<N, N> Pi = P_;
+      for (double& v : Pi.a) v /= R_;
+      invert<N>(Pi);
+      for (int r = 0; r < 12; ++r)
+        for (int c = 0; c < 12; ++c) Pi(r, c) += HTH144[r * 12 + c];
+      invert<N>(Pi);   // P_inv
+      for (int r = 0; r < N; ++r)
+        for (int c = 0; c < 12; ++c) X(r, c) = Pi(r, c);
+    } else {
+      Mat<12, 12> M;
+      for (int r = 0; r < 12; ++r)
+        for (int c = 0; c < 12; ++c) {
+          double s2 = (r == c) ? 1.0 : 0.0;
+          for (int k = 0; k < 12; ++k) s2 += HTH144[r * 12 + k] * (P_(k, c) / R_);
+          M(r, c) = s2;
+        }
+      invert<12>(M);
+      for (int r = 0; r < N; ++r)
+        for (int c = 0; c < 12; ++c) {
+          double s2 = 0;
+          for (int k = 0; k < 12; ++k) s2 += (P_(r, k) / R_) * M(k, c);
+          X(r, c) = s2;
+        }
+    }
     for (int r = 0; r < N; ++r) {
       double s = 0;
-      for (int k = 0; k < 12; ++k) s += Pi(r, k) * HTh12[k];
+      for (int k = 0; k < 12; ++k) s += X(r, k) * HTh12[k];
       K_h[r] = s;
       for (int c = 0; c < 12; ++c) {
         double s2 = 0;
-        for (int k = 0; k < 12; ++k) s2 += Pi(r, k) * HTH144[k * 12 + c];
+        for (int k = 0; k < 12; ++k) s2 += X(r, k) * HTH144[k * 12 + c];
         K_x(r, c) = s2;
       }
     }
@@ -552,6 +576,9 @@ class IteratedUpdate {
   int max_iter_ = 0, iter_ = -1, conv_count_ = 0, passes_ = 0;
   double R_ = 0.001, D_ = 5.0;
   bool done_ = true;
+ public:
+  bool reference_form_ = false;   // true: form the gain with the reference's two 23x23 inversions (FLIMO_EKF_REFERENCE_FORM=1)
+ private:
 };
 
 }  // namespace ekf

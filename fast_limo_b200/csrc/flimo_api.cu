@@ -433,6 +433,7 @@ int flimo_create(const flimo_cfg* cfg, int device, flimo_handle* out) {
     if (!hh) return fail(nullptr, FLIMO_ERR_NOMEM, "host allocation failed");
     hh->cfg = *cfg;
     hh->device = -1;
+    if (const char* e = std::getenv("FLIMO_EKF_REFERENCE_FORM")) hh->upd.reference_form_ = std::atoi(e) != 0;
     *out = hh;
     return FLIMO_OK;
   }
@@ -447,6 +448,7 @@ int flimo_create(const flimo_cfg* cfg, int device, flimo_handle* out) {
   if (!h) return fail(nullptr, FLIMO_ERR_NOMEM, "host allocation failed");
   h->cfg = *cfg;
   h->device = device;
+  if (const char* e = std::getenv("FLIMO_EKF_REFERENCE_FORM")) h->upd.reference_form_ = std::atoi(e) != 0;
   // index ladder: finest cell, growth ratio, candidates-per-block threshold.  The FLIMO_KNN_* environment
   // variables override the configuration (tuning runs of tools/ only).
   if (const char* e = std::getenv("FLIMO_KNN_CELL")) h->cfg.knn_cell = (float)std::atof(e);
