@@ -361,7 +361,7 @@ __device__ __forceinline__ int next_level(const MatchParams& P, int lvl, float d
 // storage t.i[] indexes into.
 template <bool kWide>
 __device__ __forceinline__ void knn_search(const MatchParams& P, int lane, bool active, float qx, float qy, float qz, Top5& t,
-                                           int& lvl, int& first_lvl, uint32_t& first_cnt, unsigned long long& t_priv) {
+                                           int& lvl, int& first_lvl, uint32_t& first_cnt, unsigned long long& t_priv, unsigned long long& t_probe) {
   const unsigned int full = 0xffffffffu;
   lvl = 0;
   first_lvl = 0;
@@ -398,6 +398,10 @@ __device__ __forceinline__ void knn_search(const MatchParams& P, int lane, bool 
     }
     first_lvl = lvl;
     first_cnt = pr.e - pr.s;
+    if (P.timing) {
+      if (pr.e == 0xFFFFFFFFu) first_cnt = 0;   // keep the dependence on the probe
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_probe) :: "memory");
+    }
     if (P.l2_prefetch) {
       // Pull the whole run towards L2 now (fire and forget, no registers): every lane streams a different
       // run, so a warp-level load waits for the slowest of 32 independent lines — with the run requested
@@ -726,7 +730,8 @@ __device__ __forceinline__ void match_tile(const MatchParams& P, const PoseConst
   int first_lvl = 0;
   uint32_t first_cnt = 0;
   unsigned long long t_priv = 0;
-  knn_search<kWide>(P, lane, in_range, g[0], g[1], g[2], t, lvl, first_lvl, first_cnt, t_priv);      // warp-converged call
+  unsigned long long t_probe = 0;
+  knn_search<kWide>(P, lane, in_range, g[0], g[1], g[2], t, lvl, first_lvl, first_cnt, t_priv, t_probe);      // warp-converged call
   if (P.timing) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tm1));
 
   if (in_range) {
@@ -863,7 +868,7 @@ __device__ __forceinline__ void match_tile(const MatchParams& P, const PoseConst
     o[0] = smid; o[1] = tm0; o[2] = tm1; o[3] = tm2; o[4] = tm3;
     o[5] = (unsigned long long)__popc(__ballot_sync(0xffffffffu, lvl != first_lvl));
     o[6] = t_priv;
-    o[7] = (unsigned long long)__reduce_max_sync(0xffffffffu, first_cnt);
+    o[7] = (unsigned long long)__reduce_max_sync(0xffffffffu, first_cnt) | (t_probe << 16);
   } else if (P.timing) {
     (void)__ballot_sync(0xffffffffu, lvl != first_lvl);
     (void)__reduce_max_sync(0xffffffffu, first_cnt);

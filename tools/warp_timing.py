@@ -31,10 +31,11 @@ t0 = buf[:, 1].min()
 st, knn, qr, acc = (buf[:, 1] - t0) / 1e3, (buf[:, 2] - buf[:, 1]) / 1e3, (buf[:, 3] - buf[:, 2]) / 1e3, (buf[:, 4] - buf[:, 3]) / 1e3
 priv = (buf[:, 6] - buf[:, 1]) / 1e3
 team = (buf[:, 2] - buf[:, 6]) / 1e3
-maxcnt = buf[:, 7].astype(float)
+maxcnt = (buf[:, 7] & np.uint64(0xFFFF)).astype(float)
+probe = ((buf[:, 7] >> np.uint64(16)).astype(np.int64) - (buf[:, 1] & np.uint64((1 << 48) - 1)).astype(np.int64)) / 1e3   # lane 0's probe done
 end = (buf[:, 4] - t0) / 1e3
 q = lambda a: np.round(np.quantile(a, [0, 0.1, 0.5, 0.9, 0.99, 1.0]), 2)
-print("start us  ", q(st)); print("knn us    ", q(knn)); print(" private  ", q(priv)); print(" teams    ", q(team)); print(" max cnt  ", q(maxcnt)); print("corr(priv,maxcnt)", np.corrcoef(priv, maxcnt)[0, 1]); print("qr us     ", q(qr)); print("acc us    ", q(acc)); print("end us    ", q(end))
+print("start us  ", q(st)); print("knn us    ", q(knn)); print(" probe    ", q(probe)); print(" private  ", q(priv)); print(" teams    ", q(team)); print(" max cnt  ", q(maxcnt)); print("corr(priv,maxcnt)", np.corrcoef(priv, maxcnt)[0, 1]); print("qr us     ", q(qr)); print("acc us    ", q(acc)); print("end us    ", q(end))
 print("escalated lanes per warp", q(buf[:, 5].astype(float)))
 sm = buf[:, 0].astype(int)
 per_sm_end = np.array([end[sm == s].max() if (sm == s).any() else 0 for s in range(148)])
