@@ -101,6 +101,8 @@ struct flimo_ctx {
   int knn_tau = 24;              // level choice threshold (MatchParams::tau)
   int probe_mode = 1, wide_loads = 1;
   int interleave = 0, scan_perm = 1, l2_prefetch = 0;
+  int index_incremental = 1;     // FLIMO_INDEX_INCREMENTAL=0: every Mapper::add rebuilds the whole index
+  uint64_t stats_index_builds = 0, stats_index_updates = 0;
   int time_every = 8;            // every n-th flimo_update runs one launch per pass, each timed with CUDA events (0 = never)
   // persistent kernel (one launch per flimo_update)
   PassCtlWire* h_ctl = nullptr;  // mapped pinned host control block (tagged 16-byte records)
@@ -467,6 +469,7 @@ int flimo_create(const flimo_cfg* cfg, int device, flimo_handle* out) {
   if (const char* e = std::getenv("FLIMO_KNN_INTERLEAVE")) h->interleave = std::atoi(e);
   if (const char* e = std::getenv("FLIMO_KNN_PERM")) h->scan_perm = std::atoi(e);
   if (const char* e = std::getenv("FLIMO_KNN_PREFETCH")) h->l2_prefetch = std::atoi(e);
+  if (const char* e = std::getenv("FLIMO_INDEX_INCREMENTAL")) h->index_incremental = std::atoi(e);
   CU(h, cudaSetDevice(device));
   CU(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   CU(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
@@ -497,6 +500,9 @@ void flimo_destroy(flimo_handle h) {
     std::fprintf(stderr, "[flimo profile] passes=%llu  per pass: launch %.2f us, wait %.2f us, filter step %.2f us\n",
                  (unsigned long long)h->prof_passes, h->prof_launch / h->prof_passes, h->prof_wait / h->prof_passes,
                  h->prof_step / h->prof_passes);
+  if (h->prof && h->prof_adds)
+    std::fprintf(stderr, "[flimo profile] index: %llu full builds, %llu incremental merges\n", (unsigned long long)h->stats_index_builds,
+                 (unsigned long long)h->stats_index_updates);
   if (h->prof && h->prof_adds)
     std::fprintf(stderr, "[flimo profile] map adds=%llu  per add: pack+bbox %.1f us, insert rule %.1f us, index build %.1f us\n",
                  (unsigned long long)h->prof_adds, h->prof_add_pack / h->prof_adds, h->prof_add_insert / h->prof_adds,
@@ -661,8 +667,19 @@ int flimo_map_add_device(flimo_handle h, const void* d_xyz, size_t n, size_t str
   const size_t max_cells = (size_t)1 << 30;
   // coarsest level: cell >= sqrt(MAX_DIST_PLANE) so its 3x3x3 block covers the close_enough radius
   const float coarsest = (float)(std::sqrt(std::max(h->cfg.MAX_DIST_PLANE, 1e-6)) * 1.0001 + 1e-4);
-  CU(h, map_index_build(h->map, h->cfg.knn_cell, h->cfg.knn_level_ratio, coarsest, max_cells, h->stream,
-                        &h->stats.kernel_launches));
+  if (h->index_incremental && !first && map_index_can_update(h->map, old_n, lo, hi)) {
+    // merge the accepted points into every level (the arrays end up identical to a rebuild)
+    CU(h, map_index_update(h->map, old_n, h->stream, &h->stats.kernel_launches));
+    for (int a = 0; a < 3; ++a) {
+      h->map.lo[a] = std::min(h->map.lo[a], lo[a]);
+      h->map.hi[a] = std::max(h->map.hi[a], hi[a]);
+    }
+    h->stats_index_updates++;
+  } else {
+    CU(h, map_index_build(h->map, h->cfg.knn_cell, h->cfg.knn_level_ratio, coarsest, max_cells, h->stream,
+                          &h->stats.kernel_launches));
+    h->stats_index_builds++;
+  }
   CU(h, cudaStreamSynchronize(h->stream));
   if (h->prof) {
     const auto ta3 = std::chrono::steady_clock::now();

@@ -112,6 +112,9 @@ struct MatchParams {
 // map_index.cu
 struct LevelIndex {
   float4* pts = nullptr;        // duplicated, sorted
+  unsigned long long* keys = nullptr;   // (super-row cell key << 32) | map index of every entry: the total order of pts
+  float4* pts_alt = nullptr;            // ping-pong partners of pts / keys for the incremental merge
+  unsigned long long* keys_alt = nullptr;
   uint32_t* cell_start = nullptr;
   size_t n_entries = 0, cap_entries = 0;
   size_t n_cells = 0, cap_cells = 0;
@@ -124,6 +127,11 @@ struct MapIndex {
   LevelIndex lv[kMaxLevels];
   int n_levels = 0;
   float lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};   // bounding box of the map
+  float glo[3] = {0, 0, 0}, ghi[3] = {0, 0, 0}; // box the grids were laid out for (bounding box + margin)
+  // incremental update scratch (new entries of one level)
+  float4* upd_pts = nullptr;
+  unsigned long long* upd_keys = nullptr;
+  size_t upd_cap = 0;
   // scratch
   uint32_t *keys = nullptr, *keys_alt = nullptr, *vals = nullptr, *vals_alt = nullptr;
   size_t cap_scratch = 0;       // entries (9 per point)
@@ -138,6 +146,11 @@ struct MapIndex {
 cudaError_t map_index_build(MapIndex& idx, float cell0, float ratio, float coarsest_min, size_t max_cells,
                             cudaStream_t st, uint64_t* launches);
 cudaError_t map_index_reserve(MapIndex& idx, size_t n_pts);
+// Incremental form for Mapper::add: the points idx.pts[old_n..idx.n_pts) are merged into every level (sort of
+// the 9*m new entries + one merge pass + table shift) — the arrays end up identical to a full rebuild.
+// Precondition (map_index_can_update): same grids, capacity in place, batch inside the grid box.
+bool map_index_can_update(const MapIndex& idx, size_t old_n, const float batch_lo[3], const float batch_hi[3]);
+cudaError_t map_index_update(MapIndex& idx, size_t old_n, cudaStream_t st, uint64_t* launches);
 void map_index_free(MapIndex& idx);
 
 // Packs strided xyz (device) into float4 with w = 0, dropping NaN points; writes the count.

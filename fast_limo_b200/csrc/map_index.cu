@@ -19,6 +19,7 @@
 #include <cmath>
 #include <cstdio>
 
+#include <cub/device/device_merge.cuh>
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 #include <thrust/iterator/reverse_iterator.h>
@@ -84,7 +85,7 @@ __global__ void __launch_bounds__(256) bbox_kernel(const float4* __restrict__ p,
 // Nine (super-row key, point id) pairs per point: the point's cell column ix in each of the 3x3
 // rows around its own row.  Rows outside the grid get the sentinel key n_cells (sorted to the end).
 __global__ void __launch_bounds__(256) keys9_kernel(const float4* __restrict__ p, size_t n, GridDesc g, uint32_t n_cells,
-                                                    uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+                                                    uint32_t* __restrict__ keys, uint32_t* __restrict__ vals, uint32_t id_base = 0) {
   const size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (e >= 9 * n) return;
   const size_t i = e / 9;
@@ -95,7 +96,7 @@ __global__ void __launch_bounds__(256) keys9_kernel(const float4* __restrict__ p
   const int iz = cell_coord(v.z, g.oz, g.inv_cell, g.nz) + (c / 3 - 1);
   const bool ok = iy >= 0 && iy < g.ny && iz >= 0 && iz < g.nz;
   keys[e] = ok ? (uint32_t)((iz * g.ny + iy) * g.nx + ix) : n_cells;
-  vals[e] = (uint32_t)i;
+  vals[e] = id_base + (uint32_t)i;
 }
 
 __global__ void __launch_bounds__(256) gather_kernel(const float4* __restrict__ src, const uint32_t* __restrict__ order,
@@ -106,12 +107,45 @@ __global__ void __launch_bounds__(256) gather_kernel(const float4* __restrict__ 
 
 // Super-row entry = point coordinates + its canonical map index in .w (bit pattern).
 __global__ void __launch_bounds__(256) gather_tag_kernel(const float4* __restrict__ src, const uint32_t* __restrict__ order,
-                                                         size_t n, float4* __restrict__ dst) {
+                                                         const uint32_t* __restrict__ sorted_keys, size_t n, float4* __restrict__ dst,
+                                                         unsigned long long* __restrict__ keys64) {
   const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (i >= n) return;
   const uint32_t id = order[i];
   const float4 v = src[id];
   dst[i] = make_float4(v.x, v.y, v.z, __uint_as_float(id));
+  keys64[i] = ((unsigned long long)sorted_keys[i] << 32) | id;      // (cell, map index): unique, the order of the array
+}
+
+// Incremental update of the prefix table: every cell start moves up by the number of NEW entries whose
+// cell key is smaller.  new_keys: the sorted 32-bit cell keys of the new entries.  One block shifts 1024
+// consecutive cells; two binary searches bound the window of new keys that fall inside it.
+__global__ void __launch_bounds__(256) table_shift_kernel(uint32_t* __restrict__ cell_start, size_t n_slots,
+                                                          const uint32_t* __restrict__ new_keys, uint32_t m) {
+  __shared__ uint32_t s_lo, s_hi;
+  const size_t first = (size_t)blockIdx.x * 1024;
+  if (threadIdx.x < 2) {
+    const unsigned long long target = threadIdx.x == 0 ? first : first + 1024;   // #keys < target
+    uint32_t lo = 0, hi = m;
+    while (lo < hi) {
+      const uint32_t mid = (lo + hi) >> 1;
+      if ((unsigned long long)new_keys[mid] < target) lo = mid + 1; else hi = mid;
+    }
+    if (threadIdx.x == 0) s_lo = lo; else s_hi = lo;
+  }
+  __syncthreads();
+  const uint32_t wlo = s_lo, whi = s_hi;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const size_t c = first + (size_t)j * 256 + threadIdx.x;
+    if (c >= n_slots) continue;
+    uint32_t lo = wlo, hi = whi;                      // #keys < c lies in [wlo, whi]
+    while (lo < hi) {
+      const uint32_t mid = (lo + hi) >> 1;
+      if ((unsigned long long)new_keys[mid] < (unsigned long long)c) lo = mid + 1; else hi = mid;
+    }
+    if (lo) cell_start[c] += lo;
+  }
 }
 
 // cell_start[c] = first sorted position whose key is >= c.  Occupied cells get their start here,
@@ -301,8 +335,13 @@ void map_index_free(MapIndex& idx) {
   cudaFree(idx.pts);
   for (auto& l : idx.lv) {
     cudaFree(l.pts);
+    cudaFree(l.pts_alt);
+    cudaFree(l.keys);
+    cudaFree(l.keys_alt);
     cudaFree(l.cell_start);
   }
+  cudaFree(idx.upd_pts);
+  cudaFree(idx.upd_keys);
   cudaFree(idx.keys);
   cudaFree(idx.cub_tmp);
   cudaFree(idx.bbox);
@@ -351,8 +390,16 @@ static cudaError_t build_level(MapIndex& idx, LevelIndex& L, const GridDesc& g, 
     if (L.pts) cudaFree(L.pts);
     L.pts = nullptr;
     L.cap_entries = 0;
+    if (L.pts_alt) cudaFree(L.pts_alt);
+    if (L.keys) cudaFree(L.keys);
+    if (L.keys_alt) cudaFree(L.keys_alt);
+    L.pts_alt = nullptr;
+    L.keys = L.keys_alt = nullptr;
     const size_t cap = 9 * idx.cap_pts;
     FL_TRY(cudaMalloc(&L.pts, (cap + 8) * sizeof(float4)));     // + slack: the search reads whole 32-byte pairs
+    FL_TRY(cudaMalloc(&L.pts_alt, (cap + 8) * sizeof(float4)));
+    FL_TRY(cudaMalloc(&L.keys, cap * sizeof(unsigned long long)));
+    FL_TRY(cudaMalloc(&L.keys_alt, cap * sizeof(unsigned long long)));
     L.cap_entries = cap;
   }
   L.g = g;
@@ -368,7 +415,7 @@ static cudaError_t build_level(MapIndex& idx, LevelIndex& L, const GridDesc& g, 
   if (bytes2 > bytes) bytes = bytes2;
   FL_TRY(ensure(&idx.cub_tmp, &idx.cub_tmp_bytes, bytes));
   FL_TRY(cub::DeviceRadixSort::SortPairs(idx.cub_tmp, bytes, dk, dv, (int)n9, 0, bits, st));
-  gather_tag_kernel<<<nblk(n9), 256, 0, st>>>(idx.pts, dv.Current(), n9, L.pts);
+  gather_tag_kernel<<<nblk(n9), 256, 0, st>>>(idx.pts, dv.Current(), dk.Current(), n9, L.pts, L.keys);
   FL_TRY(cudaMemsetAsync(L.cell_start, 0xFF, (n_cells + 2) * sizeof(uint32_t), st));
   boundaries_kernel<<<nblk(n9), 256, 0, st>>>(dk.Current(), n9, n_cells, L.cell_start);
   FL_TRY(cub::DeviceScan::InclusiveScan(idx.cub_tmp, bytes, rb, rb, cub::Min(), (int)(n_cells + 2), st));
@@ -393,10 +440,18 @@ cudaError_t map_index_build(MapIndex& idx, float cell0, float ratio, float coars
     idx.lo[a] = ord2f(hb[a]);
     idx.hi[a] = ord2f(hb[3 + a]);
   }
+  // The grids are laid out for the bounding box plus a margin, so that a map that grows at its rim keeps
+  // its grids (and the incremental update applies) for many scans.
+  for (int a = 0; a < 3; ++a) {
+    const float ext = idx.hi[a] - idx.lo[a];
+    const float margin = std::min(32.0f, std::max(4.0f, 0.10f * ext));
+    idx.glo[a] = idx.lo[a] - margin;
+    idx.ghi[a] = idx.hi[a] + margin;
+  }
   if (!(cell0 > 0.f)) cell0 = 0.25f;
   if (!(ratio > 1.05f)) ratio = 1.5f;
   for (;;) {   // finest level must fit the table budget
-    const GridDesc g = make_grid(idx.lo, idx.hi, cell0);
+    const GridDesc g = make_grid(idx.glo, idx.ghi, cell0);
     if ((double)g.nx * g.ny * g.nz <= (double)max_cells) break;
     cell0 *= 1.25992105f;
   }
@@ -406,7 +461,7 @@ cudaError_t map_index_build(MapIndex& idx, float cell0, float ratio, float coars
   for (;;) {
     if (nl == kMaxLevels - 1 && cell < coarsest_min) cell = coarsest_min;   // force termination
     const auto t0 = std::chrono::steady_clock::now();
-    FL_TRY(build_level(idx, idx.lv[nl], make_grid(idx.lo, idx.hi, cell), st, launches));
+    FL_TRY(build_level(idx, idx.lv[nl], make_grid(idx.glo, idx.ghi, cell), st, launches));
     if (prof) {
       const auto t1 = std::chrono::steady_clock::now();
       cudaStreamSynchronize(st);
@@ -420,6 +475,68 @@ cudaError_t map_index_build(MapIndex& idx, float cell0, float ratio, float coars
   }
   idx.n_levels = nl;
   return cudaSuccess;
+}
+
+
+bool map_index_can_update(const MapIndex& idx, size_t old_n, const float batch_lo[3], const float batch_hi[3]) {
+  if (idx.n_levels <= 0 || old_n == 0 || idx.n_pts <= old_n) return false;
+  const size_t m = idx.n_pts - old_n;
+  if (4 * m > old_n) return false;                                  // a large batch: the full rebuild is as cheap
+  if (idx.n_pts > idx.cap_pts) return false;
+  for (int a = 0; a < 3; ++a)
+    if (!(batch_lo[a] >= idx.glo[a] && batch_hi[a] <= idx.ghi[a])) return false;   // also rejects NaN boxes
+  for (int l = 0; l < idx.n_levels; ++l) {
+    const LevelIndex& L = idx.lv[l];
+    if (!L.keys || !L.pts_alt || !L.keys_alt || 9 * idx.n_pts > L.cap_entries || L.n_entries != 9 * old_n) return false;
+  }
+  return true;
+}
+
+struct Less64 {
+  __host__ __device__ bool operator()(unsigned long long a, unsigned long long b) const { return a < b; }
+};
+
+cudaError_t map_index_update(MapIndex& idx, size_t old_n, cudaStream_t st, uint64_t* launches) {
+  const size_t n = idx.n_pts, m = n - old_n, m9 = 9 * m, n9_old = 9 * old_n;
+  if (m9 > idx.upd_cap) {
+    cudaFree(idx.upd_pts);
+    cudaFree(idx.upd_keys);
+    idx.upd_pts = nullptr;
+    idx.upd_keys = nullptr;
+    idx.upd_cap = 0;
+    const size_t cap = m9 + m9 / 2 + 4096;
+    FL_TRY(cudaMalloc(&idx.upd_pts, cap * sizeof(float4)));
+    FL_TRY(cudaMalloc(&idx.upd_keys, cap * sizeof(unsigned long long)));
+    idx.upd_cap = cap;
+  }
+  for (int l = 0; l < idx.n_levels; ++l) {
+    LevelIndex& L = idx.lv[l];
+    const GridDesc& g = L.g;
+    // 1. the nine (super-row key, id) pairs of every new point, sorted (stable radix sort => (key, id) order)
+    keys9_kernel<<<nblk(m9), 256, 0, st>>>(idx.pts + old_n, m, g, (uint32_t)L.n_cells, idx.keys, idx.vals, (uint32_t)old_n);
+    int bits = 1;
+    while (bits < 32 && ((size_t)1 << bits) <= L.n_cells) ++bits;
+    cub::DoubleBuffer<uint32_t> dk(idx.keys, idx.keys_alt), dv(idx.vals, idx.vals_alt);
+    size_t bytes = 0, bytes2 = 0;
+    FL_TRY(cub::DeviceRadixSort::SortPairs(nullptr, bytes, dk, dv, (int)m9, 0, bits, st));
+    FL_TRY((cub::DeviceMerge::MergePairs(nullptr, bytes2, L.keys, L.pts, (int)n9_old, idx.upd_keys, idx.upd_pts, (int)m9, L.keys_alt,
+                                         L.pts_alt, Less64{}, st)));
+    if (bytes2 > bytes) bytes = bytes2;
+    FL_TRY(ensure(&idx.cub_tmp, &idx.cub_tmp_bytes, bytes));
+    FL_TRY(cub::DeviceRadixSort::SortPairs(idx.cub_tmp, bytes, dk, dv, (int)m9, 0, bits, st));
+    gather_tag_kernel<<<nblk(m9), 256, 0, st>>>(idx.pts, dv.Current(), dk.Current(), m9, idx.upd_pts, idx.upd_keys);
+    // 2. one merge pass: keys are unique, so the result is THE sorted array a full rebuild would produce
+    FL_TRY((cub::DeviceMerge::MergePairs(idx.cub_tmp, bytes, L.keys, L.pts, (int)n9_old, idx.upd_keys, idx.upd_pts, (int)m9, L.keys_alt,
+                                         L.pts_alt, Less64{}, st)));
+    std::swap(L.keys, L.keys_alt);
+    std::swap(L.pts, L.pts_alt);
+    // 3. prefix table: every start moves up by the number of new entries in front of it
+    const size_t n_slots = L.n_cells + 2;
+    table_shift_kernel<<<(unsigned int)((n_slots + 1023) / 1024), 256, 0, st>>>(L.cell_start, n_slots, dk.Current(), (uint32_t)m9);
+    L.n_entries = n9_old + m9;
+    if (launches) *launches += 8;
+  }
+  return cudaGetLastError();
 }
 
 }  // namespace flimo

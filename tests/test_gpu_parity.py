@@ -383,3 +383,40 @@ def test_persistent_kernel_watchdog_fallback(flimo_lib, stall):
     for (x, P, passes) in out[stall]:
         assert passes == p1 == 3
         assert np.array_equal(x, x1) and np.array_equal(P, P1)
+
+
+def test_incremental_index_equals_rebuild(oracle, flimo_lib):
+    """Mapper::add merges the accepted points into the search index (sort of the new entries + one merge pass
+    + table shift).  The result must be indistinguishable from rebuilding the index from scratch: same per-point
+    answers bit for bit, after batches inside the grid box, a batch that enlarges the box (full rebuild) and
+    more batches after it — and equal to the oracle."""
+    case = synth.make_case("c1")
+    rng = np.random.default_rng(5)
+    base = case.map_pts[:60000]
+    batches = [case.map_pts[60000 + 4000 * i: 60000 + 4000 * (i + 1)] for i in range(4)]
+    far = (case.map_pts[:3000] + np.array([400.0, -250.0, 3.0], np.float32)).astype(np.float32)     # outside the padded box
+    batches = batches[:2] + [far] + batches[2:] + [case.map_pts[80000:80050]]
+    os.environ["FLIMO_INDEX_INCREMENTAL"] = "0"
+    try:
+        m_full = mapper()
+    finally:
+        del os.environ["FLIMO_INDEX_INCREMENTAL"]
+    m_inc = mapper()
+    om = oracle.OracleMap()
+    ocfg = oracle.make_cfg(max_pc2match=BIG, max_matches=BIG, num_threads=4)
+    for m in (m_full, m_inc):
+        m.add(base, 0.0)
+        m.set_scan(case.scan)
+    om.add(base)
+    for k, b in enumerate(batches):
+        for m in (m_full, m_inc):
+            m.add(b, float(k + 1))
+        om.add(b)
+        assert m_full.size() == m_inc.size() == om.size()
+        a, c = m_full.match_debug(case.init), m_inc.match_debug(case.init)
+        for key in ("world", "good", "plane", "dist", "nn_d2"):
+            assert np.array_equal(a[key], c[key]), (k, key)
+        ra, rc = m_full.match(case.init), m_inc.match(case.init)
+        assert np.array_equal(ra.HTH, rc.HTH) and ra.n_valid == rc.n_valid
+    ref = om.match(ocfg, case.init[:14], case.scan)
+    check_per_point(m_inc.match_debug(case.init), ref)
