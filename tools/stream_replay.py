@@ -52,6 +52,7 @@ for k in range(args.n_scans):
     t_gen += time.perf_counter() - g0
     a0 = time.perf_counter()
     n_kept, t_last = m.prep_filter_sort(raw, stamp, filt)
+    h0 = time.perf_counter()                      # harness work (synthetic IMU frames, prediction) is not pipeline time
     frames = S.frames(prev_end, t_last)
     truth = S.state(t_last)
     # prediction at the end of the sweep: truth + a small drift (what IMU propagation would hand over)
@@ -73,6 +74,7 @@ for k in range(args.n_scans):
     frames["v"] = (frames["v"].astype(np.float64) @ dR.T).astype(np.float32)
     frames["g"] = (frames["g"].astype(np.float64) @ dR.T).astype(np.float32) * 0 + frames["g"]   # gravity stays world-fixed
     lq, lp = pred[3:7].astype(np.float32), pred[:3].astype(np.float32)
+    a0 += time.perf_counter() - h0
     n_pc2 = m.prep_deskew(frames, lq, lp, T_l2b, 0.0)
     a1 = time.perf_counter()
     if k == 0 and not args.premap:
