@@ -97,6 +97,16 @@ def make_inputs(n_scans):
     return case, scans, inits
 
 
+def host_threads():
+    """Host threads the CPU arm may use: the cores this process is allowed on.  (torchrun exports
+    OMP_NUM_THREADS=1 to its workers; the oracle's loops take their thread count as an argument, like the
+    reference's `num_threads` parameter, so that setting does not bind them.)"""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
 def run_reference(args):
     """CPU arm: the restated reference path (oracle/) on the host cores.  Rank 0 only."""
     if int(os.environ.get("RANK", "0")) != 0:
@@ -105,7 +115,7 @@ def run_reference(args):
     from fast_limo_b200 import synth
     from oracle import oracle as O
     case, scans, inits = make_inputs(min(N_SCANS, 2))
-    threads = O.max_threads()
+    threads = host_threads()
     om = O.OracleMap()
     om.add(case.map_pts)
     cfg = O.make_cfg(max_pc2match=1 << 20, max_matches=1 << 20, num_threads=threads)
@@ -303,7 +313,7 @@ def cpu_baseline(case, scans, inits):
     os.environ.setdefault("OMP_WAIT_POLICY", "passive")     # before libgomp starts
     from fast_limo_b200 import synth
     from oracle import oracle as O
-    threads = O.max_threads()
+    threads = host_threads()
     om = O.OracleMap()
     om.add(case.map_pts)
     cfg = O.make_cfg(max_pc2match=1 << 20, max_matches=1 << 20, num_threads=threads)
