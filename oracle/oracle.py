@@ -299,3 +299,53 @@ def prep_voxel(pts4, leaf):
     out = np.zeros((max(len(pts4), 1), 4), np.float32)
     m = L.orc_prep_voxel(pts4.ctypes.data, len(pts4), float(leaf), out.ctypes.data)
     return out[:m].copy()
+
+
+# ---- oracle/_ref: the REFERENCE's own octree, compiled where it lies (make -C oracle ref) -----------------
+REF_LIB = os.path.join(_HERE, "_ref", "libref_octree.so")
+
+
+def ref_available():
+    return os.path.exists(REF_LIB)
+
+
+class RefOctree:
+    """fast_limo::octree::Octree of the reference (Octree.hpp, unmodified), driven like Mapper drives it."""
+
+    def __init__(self, bucket=2, min_extent=0.2, downsample=True):
+        L = self.L = C.CDLL(REF_LIB)
+        L.ref_octree_new.restype = C.c_void_p
+        L.ref_octree_new.argtypes = [C.c_int, C.c_float, C.c_int]
+        L.ref_octree_free.argtypes = [C.c_void_p]
+        L.ref_octree_update.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+        L.ref_octree_size.restype = C.c_size_t
+        L.ref_octree_size.argtypes = [C.c_void_p]
+        L.ref_octree_dump.restype = C.c_size_t
+        L.ref_octree_dump.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+        L.ref_octree_knn.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        self.h = L.ref_octree_new(int(bucket), float(min_extent), int(bool(downsample)))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.ref_octree_free(self.h)
+            self.h = None
+
+    def add(self, pts):
+        p = np.ascontiguousarray(pts, np.float32).reshape(-1, 3)
+        self.L.ref_octree_update(self.h, p.ctypes.data, len(p))
+
+    def size(self):
+        return int(self.L.ref_octree_size(self.h))
+
+    def points(self):
+        out = np.zeros((max(self.size(), 1), 3), np.float32)
+        n = self.L.ref_octree_dump(self.h, out.ctypes.data, len(out))
+        return out[:n]
+
+    def knn(self, queries, k=5):
+        q = np.ascontiguousarray(queries, np.float32).reshape(-1, 3)
+        xyz = np.zeros((len(q), k, 3), np.float32)
+        d2 = np.zeros((len(q), k), np.float32)
+        cnt = np.zeros(len(q), np.int32)
+        self.L.ref_octree_knn(self.h, q.ctypes.data, len(q), int(k), xyz.ctypes.data, d2.ctypes.data, cnt.ctypes.data)
+        return xyz, d2, cnt

@@ -63,7 +63,61 @@ def prep():
     print("prep", len(raw), "->", len(order), "->", len(v))
 
 
+def ref_octree_inputs():
+    """Seeded batches (dense enough to trigger the drop rule and leaf splits, one batch grows the root) and
+    queries for the reference-octree fixture."""
+    rng = np.random.default_rng(4242)
+    case = synth.make_case("tiny")
+    pts = case.map_pts
+    batches = [pts[:8000]]
+    centres = [pts[rng.integers(len(pts))] for _ in range(3)]
+    for i in range(8):
+        centre = centres[i % 3]                                       # revisited patches: the drop rule fires
+        dense = (centre + rng.normal(0, [1.5, 1.5, 0.02], (2500, 3))).astype(np.float32)          # a dense patch: > 4 points per min-level cell
+        sparse = pts[rng.choice(len(pts), 1500, replace=False)] + rng.normal(0, 0.03, (1500, 3)).astype(np.float32)
+        b = np.concatenate([dense, sparse]).astype(np.float32)
+        if i == 3:
+            b = (b + np.array([70.0, -45.0, 2.0], np.float32)).astype(np.float32)                    # outside the first root
+        batches.append(b)
+    batches.append(np.concatenate([batches[2][:50], np.full((3, 3), np.nan, np.float32)]))        # NaN points are skipped
+    queries = np.concatenate([case.scan[:3000] + np.float32(0.05), batches[4][:500] + np.float32(0.01)]).astype(np.float32)
+    return batches, queries
+
+
+def contents_checksum(pts):
+    """Order-independent fingerprint of a point set: coordinate sums plus the sum of a per-point mix."""
+    p = np.ascontiguousarray(pts, np.float32).reshape(-1, 3)
+    b = p.view(np.uint32).astype(np.uint64)
+    mix = (b[:, 0] * np.uint64(0x9E3779B1) + b[:, 1] * np.uint64(0x85EBCA77) + b[:, 2] * np.uint64(0xC2B2AE3D)) & np.uint64(0xFFFFFFFFFFFF)
+    return np.array([float(len(p)), float(p[:, 0].astype(np.float64).sum()), float(p[:, 1].astype(np.float64).sum()),
+                     float(p[:, 2].astype(np.float64).sum()), float(mix.astype(np.float64).sum())])
+
+
+def ref_octree():
+    """Golden vectors produced by the REFERENCE's own octree (oracle/_ref, Octree.hpp compiled as it lies):
+    map size after every batch, the final contents, exact 5-NN distances / neighbours of the queries."""
+    if not O.ref_available():
+        print("oracle/_ref/libref_octree.so missing (make -C oracle ref; needs /root/reference): fixture not regenerated")
+        return
+    for tag, me, ds in (("a", 0.2, True), ("b", 0.35, True), ("c", 0.2, False)):
+        batches, queries = ref_octree_inputs()
+        ro = O.RefOctree(bucket=2, min_extent=me, downsample=ds)        # bucket_size 2 from the YAML: ignored by the reference (D5)
+        sizes = []
+        for b in batches:
+            ro.add(b)
+            sizes.append(ro.size())
+        pts = ro.points()
+        pts = pts[np.lexsort(pts.T)]
+        xyz, d2, cnt = ro.knn(queries, 5)
+        np.savez_compressed(os.path.join(HERE, f"ref_octree_{tag}.npz"), min_extent=np.float32(me), downsample=np.int32(ds),
+                            sizes=np.array(sizes, np.int64), contents_checksum=contents_checksum(pts), knn_d2=d2,
+                            knn_xyz_checksum=np.float64(xyz.astype(np.float64).sum()), knn_cnt=cnt.astype(np.int8),
+                            in_checksum=np.float64(sum(float(np.nansum(b.astype(np.float64))) for b in batches)))
+        print("ref_octree", tag, sizes)
+
+
 if __name__ == "__main__":
+    ref_octree()
     prep()
     one("tiny", 2, max_pc2match=1 << 18, max_matches=1 << 18)
     one("tiny", 3, max_pc2match=1500, max_matches=400)       # both first-N caps active (SURVEY H4)

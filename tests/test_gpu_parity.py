@@ -420,3 +420,30 @@ def test_incremental_index_equals_rebuild(oracle, flimo_lib):
         assert np.array_equal(ra.HTH, rc.HTH) and ra.n_valid == rc.n_valid
     ref = om.match(ocfg, case.init[:14], case.scan)
     check_per_point(m_inc.match_debug(case.init), ref)
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+def test_against_reference_octree_golden(flimo_lib, tag):
+    """The CUDA path against vectors produced by the REFERENCE's own octree (tests/golden/ref_octree_*.npz,
+    generated from oracle/_ref = Octree.hpp compiled unmodified): map size after every Mapper::add, final
+    contents, and the exact five neighbour distances of 3 500 queries (identity pose: world point = scan point)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(G, "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    g = np.load(os.path.join(G, f"ref_octree_{tag}.npz"))
+    batches, queries = mg.ref_octree_inputs()
+    m = mapper(octree_min_extent=float(g["min_extent"]), octree_downsampling=bool(g["downsample"]))
+    sizes = []
+    for k, b in enumerate(batches):
+        m.add(b, float(k))
+        sizes.append(m.size())
+    assert sizes == g["sizes"].tolist()
+    assert np.array_equal(mg.contents_checksum(m.points()), g["contents_checksum"])
+    m.set_scan(queries)
+    ident = synth.make_state([0.0, 0.0, 0.0], [0.0, 0.0, 0.0, 1.0])
+    dbg = m.match_debug(ident)
+    assert np.array_equal(dbg["world"], queries)
+    close = g["knn_d2"][:, 4] < 2.0                 # beyond MAX_DIST_PLANE the device search may stop early (outcome-equivalent)
+    assert close.sum() > 500
+    assert np.array_equal(dbg["nn_d2"][close], g["knn_d2"][close])
