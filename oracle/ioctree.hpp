@@ -1,10 +1,12 @@
 // ORACLE — TEST INFRASTRUCTURE ONLY (never linked into the product library).
 //
 // CPU restatement of the reference's incremental octree ("i-Octree"), the map
-// container behind fast_limo::Mapper.  Parity status: UNPINNED by the reference
-// (it ships no tests / golden vectors, and cannot be compiled here: Eigen, PCL
-// and Boost are absent) — this file follows the reference line by line in
-// behaviour, not in text.
+// container behind fast_limo::Mapper.  Parity status: PINNED against the reference
+// itself — oracle/_ref/libref_octree.so is the reference's Octree.hpp compiled where
+// it lies, unmodified (make -C oracle ref; Eigen::Vector3f stand-in in ref_shim/), and
+// tests/test_ref_octree.py + tests/golden/ref_octree_*.npz show this restatement
+// bit-identical to it (sizes after every update, contents, 5-NN distances and order).
+// This file follows the reference line by line in behaviour, not in text.
 //
 // Follows /root/reference/include/fast_limo/Objects/Octree.hpp:
 //   Heap              :45-88     -> KnnHeap

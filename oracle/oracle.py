@@ -5,9 +5,11 @@ path: i-Octree kNN, plane fit, Jacobian, HtH, IKFoM iterated update).  Only ``te
 ``__graft_entry__.smoke()`` and the ``cpu_baseline`` / ``--impl reference`` legs of
 ``bench.py`` may import this module; the product package never does.
 
-Parity status: UNPINNED — the reference ships no tests/golden vectors and cannot be compiled
-here (Eigen3/PCL/Boost absent); see the headers of ioctree.hpp / plane_match.hpp / ekf.hpp
-for the reference file:line each function follows.
+Parity status: the octree (kNN, insert) is PINNED against the reference's own Octree.hpp compiled
+unmodified (oracle/_ref, `make -C oracle ref`, tests/test_ref_octree.py); everything that needs real
+Eigen / PCL (plane QR, Jacobian, IKFoM update, deskew algebra, voxel grid) is UNPINNED — the reference
+ships no tests/golden vectors and cannot be compiled here as a whole; see the headers of ioctree.hpp /
+plane_match.hpp / ekf.hpp / prep.hpp for the reference file:line each function follows.
 """
 import ctypes as C
 import os

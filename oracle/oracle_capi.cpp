@@ -3,7 +3,8 @@
 // cpu_baseline / --impl reference legs of bench.py as the CHECKER / CPU BASELINE.
 // The product library (fast_limo_b200/csrc) never links or calls anything in oracle/.
 //
-// Parity status: UNPINNED (see ioctree.hpp / plane_match.hpp / ekf.hpp headers).
+// Parity status: octree PINNED against oracle/_ref (the reference's Octree.hpp compiled unmodified); the rest
+// UNPINNED (see ioctree.hpp / plane_match.hpp / ekf.hpp / prep.hpp headers).
 #include <cstdint>
 #include <cstring>
 #include <vector>
