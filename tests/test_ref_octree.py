@@ -69,3 +69,43 @@ def test_oracle_octree_matches_live_reference(oracle):
     r2.add(pts)
     r32.add(pts)
     assert np.array_equal(r2.knn(pts[:500], 5)[1], r32.knn(pts[:500], 5)[1])
+
+
+def test_property_random_update_sequences_match_reference(oracle):
+    """Property test (hypothesis): random sequences of batches — clustered, duplicated, far away, with NaNs,
+    tiny first scans — give the same tree population and the same exact kNN in the restatement and in the
+    compiled reference octree."""
+    if not oracle.ref_available():
+        pytest.skip("oracle/_ref/libref_octree.so not built (needs /root/reference)")
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=40, deadline=None)
+    @given(seed=st.integers(0, 2**31 - 1), n_batches=st.integers(1, 7), min_extent=st.sampled_from([0.1, 0.2, 0.35, 1.0]),
+           downsample=st.booleans(), spread=st.sampled_from([0.3, 2.0, 15.0]))
+    def run(seed, n_batches, min_extent, downsample, spread):
+        rng = np.random.default_rng(seed)
+        om = oracle.OracleMap(min_extent=min_extent, downsample=downsample)
+        ro = oracle.RefOctree(bucket=2, min_extent=min_extent, downsample=downsample)
+        centres = rng.uniform(-10, 10, (3, 3))
+        allp = []
+        for b in range(n_batches):
+            n = int(rng.integers(1, 1500))
+            p = (centres[rng.integers(3, size=n)] + rng.normal(0, spread, (n, 3))).astype(np.float32)
+            if rng.random() < 0.2:
+                p[rng.integers(n)] = np.nan
+            if rng.random() < 0.15:
+                p = (p + np.float32(rng.uniform(50, 400))).astype(np.float32)
+            if rng.random() < 0.2 and allp:
+                p = np.concatenate([p, allp[-1][: len(allp[-1]) // 2]])            # exact duplicates of earlier points
+            om.add(p)
+            ro.add(p)
+            allp.append(p)
+            assert om.size() == ro.size()
+        a, r = om.points(), ro.points()
+        assert np.array_equal(a[np.lexsort(a.T)], r[np.lexsort(r.T)])
+        q = (centres[rng.integers(3, size=300)] + rng.normal(0, spread * 1.5, (300, 3))).astype(np.float32)
+        d2, nb, cnt = om.knn(q, 5)
+        rx, rd2, rcnt = ro.knn(q, 5)
+        assert np.array_equal(cnt, rcnt) and np.array_equal(d2, rd2) and np.array_equal(nb, rx)
+
+    run()
