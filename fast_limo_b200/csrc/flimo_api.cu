@@ -593,7 +593,8 @@ int flimo_get_stats(flimo_handle h, flimo_stats* out) {
   h->stats.map_bytes = h->map.n_pts * sizeof(float4);
   for (int l = 0; l < h->map.n_levels; ++l) {
     h->stats.table_bytes += (h->map.lv[l].n_cells + 2) * sizeof(uint32_t);
-    h->stats.map_bytes += h->map.lv[l].n_entries * sizeof(float4);
+    // super-row entries: points + 64-bit order keys, each with its ping-pong partner for the incremental merge
+    h->stats.map_bytes += h->map.lv[l].cap_entries * 2 * (sizeof(float4) + sizeof(unsigned long long));
   }
   h->stats.persist_ms_total = h->persist_ns_total * 1e-6;
   h->stats.persist_passes = h->persist_passes;

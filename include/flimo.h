@@ -241,7 +241,7 @@ typedef struct {
   float knn_cell;               /* finest grid cell in use */
   int32_t grid_nx, grid_ny, grid_nz;
   int32_t n_levels;
-  uint64_t table_bytes, map_bytes;
+  uint64_t table_bytes, map_bytes;   /* device memory of the prefix tables / of the point + key arrays (all levels, incl. ping-pong copies) */
   double persist_ms_total;      /* in-kernel device time (%globaltimer) of the passes run by the persistent kernel */
   uint64_t persist_passes;      /* number of such passes */
 } flimo_stats;
