@@ -594,7 +594,7 @@ int flimo_get_stats(flimo_handle h, flimo_stats* out) {
   for (int l = 0; l < h->map.n_levels; ++l) {
     h->stats.table_bytes += (h->map.lv[l].n_cells + 2) * sizeof(uint32_t);
     // super-row entries: points + 64-bit order keys, each with its ping-pong partner for the incremental merge
-    h->stats.map_bytes += h->map.lv[l].cap_entries * 2 * (sizeof(float4) + sizeof(unsigned long long));
+    h->stats.map_bytes += h->map.lv[l].cap_entries * (h->map.lv[l].pts_alt ? 2 : 1) * (sizeof(float4) + sizeof(unsigned long long));
   }
   h->stats.persist_ms_total = h->persist_ns_total * 1e-6;
   h->stats.persist_passes = h->persist_passes;

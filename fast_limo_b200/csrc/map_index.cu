@@ -397,10 +397,8 @@ static cudaError_t build_level(MapIndex& idx, LevelIndex& L, const GridDesc& g, 
     L.keys = L.keys_alt = nullptr;
     const size_t cap = 9 * idx.cap_pts;
     FL_TRY(cudaMalloc(&L.pts, (cap + 8) * sizeof(float4)));     // + slack: the search reads whole 32-byte pairs
-    FL_TRY(cudaMalloc(&L.pts_alt, (cap + 8) * sizeof(float4)));
     FL_TRY(cudaMalloc(&L.keys, cap * sizeof(unsigned long long)));
-    FL_TRY(cudaMalloc(&L.keys_alt, cap * sizeof(unsigned long long)));
-    L.cap_entries = cap;
+    L.cap_entries = cap;                                        // the ping-pong partners are allocated by the first incremental update
   }
   L.g = g;
   L.n_cells = n_cells;
@@ -487,7 +485,7 @@ bool map_index_can_update(const MapIndex& idx, size_t old_n, const float batch_l
     if (!(batch_lo[a] >= idx.glo[a] && batch_hi[a] <= idx.ghi[a])) return false;   // also rejects NaN boxes
   for (int l = 0; l < idx.n_levels; ++l) {
     const LevelIndex& L = idx.lv[l];
-    if (!L.keys || !L.pts_alt || !L.keys_alt || 9 * idx.n_pts > L.cap_entries || L.n_entries != 9 * old_n) return false;
+    if (!L.keys || 9 * idx.n_pts > L.cap_entries || L.n_entries != 9 * old_n) return false;
   }
   return true;
 }
@@ -512,6 +510,8 @@ cudaError_t map_index_update(MapIndex& idx, size_t old_n, cudaStream_t st, uint6
   for (int l = 0; l < idx.n_levels; ++l) {
     LevelIndex& L = idx.lv[l];
     const GridDesc& g = L.g;
+    if (!L.pts_alt) FL_TRY(cudaMalloc(&L.pts_alt, (L.cap_entries + 8) * sizeof(float4)));
+    if (!L.keys_alt) FL_TRY(cudaMalloc(&L.keys_alt, L.cap_entries * sizeof(unsigned long long)));
     // 1. the nine (super-row key, id) pairs of every new point, sorted (stable radix sort => (key, id) order)
     keys9_kernel<<<nblk(m9), 256, 0, st>>>(idx.pts + old_n, m, g, (uint32_t)L.n_cells, idx.keys, idx.vals, (uint32_t)old_n);
     int bits = 1;
