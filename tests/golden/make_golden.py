@@ -85,12 +85,14 @@ def ref_octree_inputs():
 
 
 def contents_checksum(pts):
-    """Order-independent fingerprint of a point set: coordinate sums plus the sum of a per-point mix."""
+    """Order-independent fingerprint of a point set, EXACT in any summation order: the count and wrap-around
+    uint64 sums of the coordinate bit patterns and of a per-point mix."""
     p = np.ascontiguousarray(pts, np.float32).reshape(-1, 3)
     b = p.view(np.uint32).astype(np.uint64)
-    mix = (b[:, 0] * np.uint64(0x9E3779B1) + b[:, 1] * np.uint64(0x85EBCA77) + b[:, 2] * np.uint64(0xC2B2AE3D)) & np.uint64(0xFFFFFFFFFFFF)
-    return np.array([float(len(p)), float(p[:, 0].astype(np.float64).sum()), float(p[:, 1].astype(np.float64).sum()),
-                     float(p[:, 2].astype(np.float64).sum()), float(mix.astype(np.float64).sum())])
+    with np.errstate(over="ignore"):
+        mix = b[:, 0] * np.uint64(0x9E3779B185EBCA87) + b[:, 1] * np.uint64(0xC2B2AE3D27D4EB4F) + b[:, 2] * np.uint64(0x165667B19E3779F9)
+        return np.array([np.uint64(len(p)), b[:, 0].sum(dtype=np.uint64), b[:, 1].sum(dtype=np.uint64), b[:, 2].sum(dtype=np.uint64),
+                         mix.sum(dtype=np.uint64)], np.uint64)
 
 
 def ref_octree():
