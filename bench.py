@@ -207,14 +207,16 @@ def main():
         if from_host:
             # this step's scan: H2D from pinned memory (already under way if the previous step prefetched it);
             # then start the copy of the NEXT step's scan so that it overlaps this registration
-            m.set_scan_host(h_scans[k].data_ptr(), n_pts, 16)
-            m.prefetch_scan_host(h_scans[(k + 1) % N_SCANS].data_ptr(), n_pts, 16)
+            # (N > 1: every rank uploads only ITS slice of the scan and binds it as its whole scan)
+            m.set_scan_host(h_scans[k].data_ptr() + 16 * lo, hi - lo, 16)
+            m.prefetch_scan_host(h_scans[(k + 1) % N_SCANS].data_ptr() + 16 * lo, hi - lo, 16)
         else:
             m.set_scan_device(d_scans[k].data_ptr(), n_pts, 16)
         if world == 1:
             x, P, passes = m.update(inits[k], P0, MAX_ITER, lim)
             return x, passes
-        m.shard(lo, hi)
+        if not from_host:
+            m.shard(lo, hi)
         if shm is not None:
             x, P, passes = m.update_exchange(inits[k], P0, MAX_ITER, lim)
             return x, passes
@@ -284,7 +286,7 @@ def main():
                        % (world, "fused host-segment exchange" if (world > 1 and args.exchange == "shm") else ("NCCL all-reduce" if world > 1 else "no exchange")),
                        "passes_per_scan": passes, "l2_policy": "inputs larger than L2 (multi-level map index %.1f GB, 4 rotating scans)"
                        % (st1["map_bytes"] / 1e9), "pose_err_m": pose_err, "knn_cell": st1["knn_cell"], "levels": st1["n_levels"]},
-            "e2e": {"value": args.steps / (ms_e2e / 1e3), "unit": "scans/s", "h2d_bytes_per_step": n_pts * 16,
+            "e2e": {"value": args.steps / (ms_e2e / 1e3), "unit": "scans/s", "h2d_bytes_per_step": n_pts * 16,   # summed over ranks
                     "d2h_bytes_per_step": passes * 96 * 8 + (26 + 529) * 8},
             "gpu_launches": int(st1["kernel_launches"] - st0["kernel_launches"]),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -875,6 +875,8 @@ int flimo_scan_set(flimo_handle h, const float* xyz_body, size_t n, size_t strid
     CU(h, cudaStreamWaitEvent(h->stream, h->ev_prefetch, 0));
   } else {
     idx = h->scan_stage_bound ^ 1;
+    if (h->pref_idx >= 0 && h->pref_issued)                      // an unrelated prefetch is filling this buffer: let it finish first
+      CU(h, cudaStreamWaitEvent(h->stream, h->ev_prefetch, 0));
     int rc = stage_reserve(h, idx, nq * stride_bytes);
     if (rc) return rc;
     CU(h, cudaMemcpyAsync(h->scan_stage[idx], xyz_body, nq * stride_bytes, cudaMemcpyHostToDevice, h->stream));
