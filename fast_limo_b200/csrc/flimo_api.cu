@@ -99,7 +99,7 @@ struct flimo_ctx {
   size_t xyz_cap = 0;
 
   int knn_tau = 24;              // level choice threshold (MatchParams::tau)
-  int probe_mode = 1, wide_loads = 1;
+  int probe_mode = 1, wide_loads = 1, pair_scan = 0;
   int interleave = 0, scan_perm = 1, l2_prefetch = 0;
   int index_incremental = 1;     // FLIMO_INDEX_INCREMENTAL=0: every Mapper::add rebuilds the whole index
   uint64_t stats_index_builds = 0, stats_index_updates = 0;
@@ -284,6 +284,7 @@ int fill_params(flimo_handle h, const double state14[14], MatchParams& P, double
   P.tau = h->knn_tau;
   P.probe_mode = h->probe_mode;
   P.wide_loads = h->wide_loads;
+  P.pair_scan = h->pair_scan;
   P.l2_prefetch = h->l2_prefetch;
   P.max_dist_f = ceil_to_float(h->cfg.MAX_DIST_PLANE);
   P.plane_thr = (float)h->cfg.PLANE_THRESHOLD;
@@ -464,6 +465,7 @@ int flimo_create(const flimo_cfg* cfg, int device, flimo_handle* out) {
   if (const char* e = std::getenv("FLIMO_PROFILE")) h->prof = std::atoi(e) != 0;
   if (const char* e = std::getenv("FLIMO_TIME_EVERY")) h->time_every = std::atoi(e);
   if (const char* e = std::getenv("FLIMO_KNN_WIDE")) h->wide_loads = std::atoi(e);
+  if (const char* e = std::getenv("FLIMO_KNN_PAIR")) h->pair_scan = std::atoi(e);
   if (const char* e = std::getenv("FLIMO_KNN_SORT")) h->cfg.sort_scan = std::atoi(e);
   h->interleave = h->cfg.sort_scan ? 1 : 0;
   if (const char* e = std::getenv("FLIMO_KNN_INTERLEAVE")) h->interleave = std::atoi(e);

@@ -88,6 +88,7 @@ struct MatchParams {
   int tau;                     // level choice: finest level whose 3x3x3 block holds >= tau candidates
   int probe_mode;              // 0 = probe all levels at once, 1 = climb one level at a time
   int wide_loads;              // 1 = 256-bit candidate loads
+  int pair_scan;               // 1 = two lanes per query in the first scan (adjacent 32-byte loads share a wavefront)
   int l2_prefetch;             // 1 = request the whole run with prefetch.global.L2 right after the probe
   float max_dist_f;            // smallest float >= MAX_DIST_PLANE  (d2_5 < MAX_DIST_PLANE test)
   float plane_thr;             // (float)PLANE_THRESHOLD

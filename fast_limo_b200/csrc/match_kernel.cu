@@ -154,6 +154,41 @@ __device__ __forceinline__ void rank4(float (&k)[6], const Pair& p0, const Pair&
   keys6_insert2(k, pack_key(d2, kKeyLow, n + 2), pack_key(d3, kKeyLow, n + 3));
 }
 
+// Exact re-ranking + acceptance of a packed 6-list (see block_scan_private).  pts = L.pts + a (ordinals are
+// relative to it), a = absolute position of ordinal 0.
+__device__ __forceinline__ bool finish_private(const float (&k)[6], const float4* __restrict__ pts, uint32_t a, float qx, float qy,
+                                               float qz, Top5& t) {
+  const uint32_t low = kKeyLow;
+  const float inf = __int_as_float(0x7f800000);
+  // exact re-ranking of the (up to) six kept candidates: sort (exact d2 bits, ordinal) pairs
+  unsigned long long ek[6];
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    const uint32_t kb = __float_as_uint(k[j]);
+    const bool have = kb < 0x7f800000u;
+    const uint32_t ord = kb & low;
+    float d = inf;
+    if (have) d = sqdist(qx, qy, qz, __ldg(&pts[ord]));
+    ek[j] = ((unsigned long long)__float_as_uint(d) << 32) | (have ? ord : 0xFFFFFFFFu);
+  }
+  cmpswap64(ek[0], ek[5]); cmpswap64(ek[1], ek[3]); cmpswap64(ek[2], ek[4]);
+  cmpswap64(ek[1], ek[2]); cmpswap64(ek[3], ek[4]);
+  cmpswap64(ek[0], ek[3]); cmpswap64(ek[2], ek[5]);
+  cmpswap64(ek[0], ek[1]); cmpswap64(ek[2], ek[3]); cmpswap64(ek[4], ek[5]);
+  cmpswap64(ek[1], ek[2]); cmpswap64(ek[3], ek[4]);
+#pragma unroll
+  for (int j = 0; j < 5; ++j) {
+    t.d[j] = __uint_as_float((uint32_t)(ek[j] >> 32));
+    t.i[j] = a + (uint32_t)(ek[j] & 0xFFFFFFFFu);
+  }
+  // Acceptance.  Every candidate that was not kept has a ranking key >= k5 (the sixth smallest), hence a
+  // ranking distance >= bucket_floor(k5) and an exact distance within 4 ulp of that.  If k5's bucket
+  // (128 ulp wide) lies at least TWO buckets above the bucket of the exact fifth distance, all of them
+  // are strictly farther than the fifth neighbour, so the kept set contains the exact answer.
+  const uint32_t k5 = __float_as_uint(k[5]);
+  return (k5 >= 0x7f800000u) || ((k5 & ~low) >= ((uint32_t)(ek[4] >> 32) & ~low) + 2u * (low + 1u));
+}
+
 // Thread-private scan of a short run [s, e) of level L (<= kPrivateCap candidates).  Returns false
 // when the packed selection cannot be proven exact (or the run is too long): the caller then hands
 // the query to the warp-cooperative exact scan below.  On success t.d[] holds the exact ascending
@@ -210,33 +245,63 @@ __device__ __forceinline__ bool block_scan_private(const LevelView& L, uint32_t 
   if (n + 1 < tot) keys6_insert(k, pack_key(sqdist_rank(qx, qy, qz, a0.bx, a0.by, a0.bz), low, n + 1));
   if (n + 2 < tot) keys6_insert(k, pack_key(sqdist_rank(qx, qy, qz, a1.ax, a1.ay, a1.az), low, n + 2));
 
-  // exact re-ranking of the (up to) six kept candidates: sort (exact d2 bits, ordinal) pairs
-  unsigned long long ek[6];
+  return finish_private(k, pts, a, qx, qy, qz, t);
+}
+
+// ---- two lanes per query (P.pair_scan) ------------------------------------------------------------------
+// The lane pair (2i, 2i+1) scans ONE query's run together, the warp's 32 queries in two rounds: lane parity b
+// ranks every second 32-byte pair of the run, so the pair's two loads are adjacent (one 64-byte segment, one
+// L1 wavefront for both lanes instead of one each), then the two packed 6-lists are merged (6 shuffles +
+// bitonic min + sorting network).  Ordinals are positions in the run counted from its 64-byte aligned start,
+// unique across both lanes, so the merged list is exactly what one lane scanning alone would hold.
+__device__ __forceinline__ void sort6f(float (&m)[6]) {
+#define FL_CS(i, j) { const float lo_ = fminf(m[i], m[j]), hi_ = fmaxf(m[i], m[j]); m[i] = lo_; m[j] = hi_; }
+  FL_CS(0, 5) FL_CS(1, 3) FL_CS(2, 4)
+  FL_CS(1, 2) FL_CS(3, 4)
+  FL_CS(0, 3) FL_CS(2, 5)
+  FL_CS(0, 1) FL_CS(2, 3) FL_CS(4, 5)
+  FL_CS(1, 2) FL_CS(3, 4)
+#undef FL_CS
+}
+template <bool kWide>
+__device__ __forceinline__ void pair_scan_round(const float4* __restrict__ pts, uint32_t lead_n, uint32_t total, int b, bool valid,
+                                                float qx, float qy, float qz, float (&k)[6]) {
+  const float inf = __int_as_float(0x7f800000);
 #pragma unroll
-  for (int j = 0; j < 6; ++j) {
-    const uint32_t kb = __float_as_uint(k[j]);
-    const bool have = kb < 0x7f800000u;
-    const uint32_t ord = kb & low;
-    float d = inf;
-    if (have) d = sqdist(qx, qy, qz, __ldg(&pts[ord]));
-    ek[j] = ((unsigned long long)__float_as_uint(d) << 32) | (have ? ord : 0xFFFFFFFFu);
+  for (int j = 0; j < 6; ++j) k[j] = inf;
+  if (valid) {
+    const uint32_t tot = lead_n + total;
+    const uint32_t lastp = (tot - 1) & ~1u;
+    uint32_t n = 2u * (uint32_t)b;                       // this lane's pairs start at entries 2b, 2b+4, 2b+8, ...
+    Pair c0 = ldg_pair<kWide>(pts + min(n, lastp)), c1 = ldg_pair<kWide>(pts + min(n + 4, lastp));
+#pragma unroll 1
+    for (; n < tot; n += 8) {
+      const Pair p0 = c0, p1 = c1;
+      if (n + 8 < tot) {
+        c0 = ldg_pair<kWide>(pts + min(n + 8, lastp));
+        c1 = ldg_pair<kWide>(pts + min(n + 12, lastp));
+      }
+      const float d0 = sqdist_rank(qx, qy, qz, p0.ax, p0.ay, p0.az), d1 = sqdist_rank(qx, qy, qz, p0.bx, p0.by, p0.bz),
+                  d2 = sqdist_rank(qx, qy, qz, p1.ax, p1.ay, p1.az), d3 = sqdist_rank(qx, qy, qz, p1.bx, p1.by, p1.bz);
+      // entries before the run (ordinal < lead_n) and past its end rank as +inf (exactly: a NaN key would be dropped
+      // by fmin/fmax and duplicate its partner)
+      const float k0 = (n - lead_n < total) ? pack_key(d0, kKeyLow, n) : inf;
+      const float k1 = (n + 1 - lead_n < total) ? pack_key(d1, kKeyLow, n + 1) : inf;
+      const float k2 = (n + 4 - lead_n < total) ? pack_key(d2, kKeyLow, n + 4) : inf;
+      const float k3 = (n + 5 - lead_n < total) ? pack_key(d3, kKeyLow, n + 5) : inf;
+      keys6_insert2(k, k0, k1);
+      keys6_insert2(k, k2, k3);
+    }
   }
-  cmpswap64(ek[0], ek[5]); cmpswap64(ek[1], ek[3]); cmpswap64(ek[2], ek[4]);
-  cmpswap64(ek[1], ek[2]); cmpswap64(ek[3], ek[4]);
-  cmpswap64(ek[0], ek[3]); cmpswap64(ek[2], ek[5]);
-  cmpswap64(ek[0], ek[1]); cmpswap64(ek[2], ek[3]); cmpswap64(ek[4], ek[5]);
-  cmpswap64(ek[1], ek[2]); cmpswap64(ek[3], ek[4]);
+  // merge with the partner lane: min(k[j], partner[5-j]) are the six smallest of the union (bitonic), then sort
+  float m[6];
 #pragma unroll
-  for (int j = 0; j < 5; ++j) {
-    t.d[j] = __uint_as_float((uint32_t)(ek[j] >> 32));
-    t.i[j] = a + (uint32_t)(ek[j] & 0xFFFFFFFFu);
-  }
-  // Acceptance.  Every candidate that was not kept has a ranking key >= k5 (the sixth smallest), hence a
-  // ranking distance >= bucket_floor(k5) and an exact distance within 4 ulp of that.  If k5's bucket
-  // (128 ulp wide) lies at least TWO buckets above the bucket of the exact fifth distance, all of them
-  // are strictly farther than the fifth neighbour, so the kept set contains the exact answer.
-  const uint32_t k5 = __float_as_uint(k[5]);
-  return (k5 >= 0x7f800000u) || ((k5 & ~low) >= ((uint32_t)(ek[4] >> 32) & ~low) + 2u * (low + 1u));
+  for (int j = 0; j < 6; ++j) m[j] = __shfl_xor_sync(0xffffffffu, k[5 - j], 1);
+#pragma unroll
+  for (int j = 0; j < 6; ++j) m[j] = fminf(k[j], m[j]);
+  sort6f(m);
+#pragma unroll
+  for (int j = 0; j < 6; ++j) k[j] = m[j];
 }
 
 // TEAM scan: exact top-5 of one query's block at level L by a team of T consecutive lanes
@@ -359,7 +424,7 @@ __device__ __forceinline__ int next_level(const MatchParams& P, int lvl, float d
 // Correctness never depends on the level choice: a block's answer is used only if block_is_final.
 // Must be called by all 32 lanes (inactive lanes pass active = false).  `lvl` returns the level whose
 // storage t.i[] indexes into.
-template <bool kWide>
+template <bool kWide, bool kPair>
 __device__ __forceinline__ void knn_search(const MatchParams& P, int lane, bool active, float qx, float qy, float qz, Top5& t,
                                            int& lvl, int& first_lvl, uint32_t& first_cnt, unsigned long long& t_priv, unsigned long long& t_probe) {
   const unsigned int full = 0xffffffffu;
@@ -367,6 +432,8 @@ __device__ __forceinline__ void knn_search(const MatchParams& P, int lane, bool 
   first_lvl = 0;
   first_cnt = 0;
   bool pending = false;
+  uint32_t scan_s = 0, scan_e = 0;
+  int hx0 = 0, hy0 = 0, hz0 = 0;
   if (active) {
     const int top = P.n_levels - 1;
     Probe pr;
@@ -411,12 +478,60 @@ __device__ __forceinline__ void knn_search(const MatchParams& P, int lane, bool 
       const char* pe = reinterpret_cast<const char*>(P.lv[lvl].pts + min(pr.e, pr.s + kPrivateCap));
       for (; pf < pe; pf += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(pf));
     }
-    const bool exact_here = block_scan_private<kWide>(P.lv[lvl], pr.s, pr.e, qx, qy, qz, t);
-    if (!exact_here) {
-      pending = true;                                          // redo this level cooperatively
-    } else if (!block_is_final(P.lv[lvl].g, P.max_dist_f, qx, qy, qz, pr.hx, pr.hy, pr.hz, t.d[4])) {
-      pending = lvl < top;
-      if (pending) lvl = next_level(P, lvl, t.d[4]);
+    if (kPair) {
+      scan_s = pr.s;
+      scan_e = pr.e;
+      hx0 = pr.hx; hy0 = pr.hy; hz0 = pr.hz;
+    }
+    if (!kPair) {
+      const bool exact_here = block_scan_private<kWide>(P.lv[lvl], pr.s, pr.e, qx, qy, qz, t);
+      if (!exact_here) {
+        pending = true;                                          // redo this level cooperatively
+      } else if (!block_is_final(P.lv[lvl].g, P.max_dist_f, qx, qy, qz, pr.hx, pr.hy, pr.hz, t.d[4])) {
+        pending = lvl < top;
+        if (pending) lvl = next_level(P, lvl, t.d[4]);
+      }
+    }
+  }
+  if (kPair) {                                                   // warp-converged: two lanes per query, two rounds
+    const uint32_t total_own = scan_e - scan_s;
+    const bool do_scan = active && total_own > 0u && total_own <= kPrivateCap;
+    float kk[6];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) kk[j] = __int_as_float(0x7f800000);
+#pragma unroll 1
+    for (int r = 0; r < 2; ++r) {
+      const int src = (lane & ~1) + r;
+      const float bx = __shfl_sync(full, qx, src), by = __shfl_sync(full, qy, src), bz = __shfl_sync(full, qz, src);
+      const uint32_t bs = __shfl_sync(full, scan_s, src), be = __shfl_sync(full, scan_e, src);
+      const int bl = __shfl_sync(full, lvl, src);
+      const bool bdo = __shfl_sync(full, do_scan ? 1 : 0, src) != 0;
+      const uint32_t ba = bs & ~3u;                              // 64-byte aligned start of the run
+      float k[6];
+      pair_scan_round<kWide>(P.lv[bl].pts + ba, bs - ba, be - bs, lane & 1, bdo, bx, by, bz, k);
+      if (lane == src) {
+#pragma unroll
+        for (int j = 0; j < 6; ++j) kk[j] = k[j];
+      }
+    }
+    if (active) {
+      const int top = P.n_levels - 1;
+#pragma unroll
+      for (int j = 0; j < 5; ++j) {
+        t.d[j] = __int_as_float(0x7f800000);
+        t.i[j] = 0;
+      }
+      bool exact_here = total_own == 0u;                         // empty block: exact (nothing there)
+      if (do_scan) {
+        const uint32_t a = scan_s & ~3u;
+        exact_here = finish_private(kk, P.lv[lvl].pts + a, a, qx, qy, qz, t);
+      }
+      if (!exact_here) {
+        pending = true;
+      } else if (!block_is_final(P.lv[lvl].g, P.max_dist_f, qx, qy, qz, hx0, hy0, hz0, t.d[4])) {
+        pending = lvl < top;
+        if (pending) lvl = next_level(P, lvl, t.d[4]);
+      }
     }
   }
   if (P.timing) {
@@ -671,7 +786,7 @@ struct TileShared {
 // the tiles; the CTA that completes the tree publishes the pass result.  `pc` is the pose (kernel
 // parameter bank in the one-launch-per-pass kernel, shared memory in the persistent kernel), `seq` the
 // sequence number of the pass, `orig_limit` the first-N cap on contributing rows.
-template <bool kWide>
+template <bool kWide, bool kPair>
 __device__ __forceinline__ void match_tile(const MatchParams& P, const PoseConsts& pc, TileShared& sh, const int tile_idx,
                                            const int n_tiles, const unsigned long long seq, const uint32_t orig_limit,
                                            const unsigned long long t_begin) {
@@ -731,7 +846,7 @@ __device__ __forceinline__ void match_tile(const MatchParams& P, const PoseConst
   uint32_t first_cnt = 0;
   unsigned long long t_priv = 0;
   unsigned long long t_probe = 0;
-  knn_search<kWide>(P, lane, in_range, g[0], g[1], g[2], t, lvl, first_lvl, first_cnt, t_priv, t_probe);      // warp-converged call
+  knn_search<kWide, kPair>(P, lane, in_range, g[0], g[1], g[2], t, lvl, first_lvl, first_cnt, t_priv, t_probe);      // warp-converged call
   if (P.timing) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tm1));
 
   if (in_range) {
@@ -968,10 +1083,10 @@ __device__ __forceinline__ void match_tile(const MatchParams& P, const PoseConst
 }
 
 // One launch = one pass (the pose travels in the kernel parameters).
-template <bool kWide>
+template <bool kWide, bool kPair>
 __global__ void __launch_bounds__(kTileQueries, 7) match_reduce_kernel(const __grid_constant__ MatchParams P) {
   __shared__ TileShared sh;
-  match_tile<kWide>(P, P.pc, sh, (int)blockIdx.x, (int)gridDim.x, P.seq, P.orig_limit, 0ull);
+  match_tile<kWide, kPair>(P, P.pc, sh, (int)blockIdx.x, (int)gridDim.x, P.seq, P.orig_limit, 0ull);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -984,7 +1099,7 @@ __global__ void __launch_bounds__(kTileQueries, 7) match_reduce_kernel(const __g
 // records).  This removes the launch latency (~10 us of host + device time) from every pass.
 // A watchdog ends the kernel if the host stays silent (the host then continues with per-pass launches).
 // ---------------------------------------------------------------------------------------------------
-template <bool kWide>
+template <bool kWide, bool kPair>
 __global__ void __launch_bounds__(kTileQueries, 7) match_persistent_kernel(const __grid_constant__ MatchParams P) {
   __shared__ TileShared sh;
   __shared__ PassCtl s_ctl;
@@ -1042,7 +1157,7 @@ __global__ void __launch_bounds__(kTileQueries, 7) match_persistent_kernel(const
     __syncthreads();
     if (s_ctl.cmd != 0u) return;
     for (int t = (int)blockIdx.x; t < n_tiles; t += (int)gridDim.x)
-      match_tile<kWide>(P, s_ctl.pc, sh, t, n_tiles, want, s_ctl.orig_limit, s_ctl.t_begin);
+      match_tile<kWide, kPair>(P, s_ctl.pc, sh, t, n_tiles, want, s_ctl.orig_limit, s_ctl.t_begin);
     __syncthreads();
   }
 }
@@ -1054,8 +1169,9 @@ int match_num_tiles(int n_queries) { return (n_queries + kTileQueries - 1) / kTi
 cudaError_t launch_match_persistent(const MatchParams& p, int grid, cudaStream_t st) {
   const int n = p.q_end - p.q_begin;
   if (n <= 0 || grid <= 0) return cudaErrorInvalidValue;
-  if (p.wide_loads) match_persistent_kernel<true><<<grid, kTileQueries, 0, st>>>(p);
-  else match_persistent_kernel<false><<<grid, kTileQueries, 0, st>>>(p);
+  if (p.pair_scan) match_persistent_kernel<true, true><<<grid, kTileQueries, 0, st>>>(p);
+  else if (p.wide_loads) match_persistent_kernel<true, false><<<grid, kTileQueries, 0, st>>>(p);
+  else match_persistent_kernel<false, false><<<grid, kTileQueries, 0, st>>>(p);
   return cudaGetLastError();
 }
 
@@ -1064,15 +1180,16 @@ int match_persistent_capacity() {
   int dev = 0, sms = 0, per_sm = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return 0;
   if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, match_persistent_kernel<true>, kTileQueries, 0) != cudaSuccess) return 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, match_persistent_kernel<true, false>, kTileQueries, 0) != cudaSuccess) return 0;
   return sms * per_sm;
 }
 
 cudaError_t launch_match(const MatchParams& p, cudaStream_t st) {
   const int n = p.q_end - p.q_begin;
   if (n <= 0) return cudaErrorInvalidValue;
-  if (p.wide_loads) match_reduce_kernel<true><<<match_num_tiles(n), kTileQueries, 0, st>>>(p);
-  else match_reduce_kernel<false><<<match_num_tiles(n), kTileQueries, 0, st>>>(p);
+  if (p.pair_scan) match_reduce_kernel<true, true><<<match_num_tiles(n), kTileQueries, 0, st>>>(p);
+  else if (p.wide_loads) match_reduce_kernel<true, false><<<match_num_tiles(n), kTileQueries, 0, st>>>(p);
+  else match_reduce_kernel<false, false><<<match_num_tiles(n), kTileQueries, 0, st>>>(p);
   return cudaGetLastError();
 }
 
