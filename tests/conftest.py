@@ -10,6 +10,7 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu on the GPU box)")
+    config.addinivalue_line("markers", "gpu_experimental: GPU checks of opt-in code paths (run explicitly with -m gpu_experimental)")
 
 
 def _has_gpu():
@@ -25,7 +26,7 @@ def pytest_collection_modifyitems(config, items):
         return
     skip = pytest.mark.skip(reason="no CUDA device in this container")
     for it in items:
-        if "gpu" in it.keywords:
+        if "gpu" in it.keywords or "gpu_experimental" in it.keywords:
             it.add_marker(skip)
 
 
