@@ -138,7 +138,7 @@ def run_reference(args):
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": "scans/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "strong",
-        "vs_baseline": None, "dtype": "f32 per-point / f64 reduction", "data": "synthetic",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "parallelism": f"openmp x{threads}",
                    "sample": f"every {stride}-th scan point per step ({sub[0].shape[0]} of {scans[0].shape[0]}), value scaled to whole scans"},
         "cpu_baseline": {"value": v, "unit": "scans/s", "cores": threads, "kind": "port",
@@ -281,8 +281,9 @@ def main():
         out = {
             "metric": METRIC, "value": value, "unit": "scans/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f32 per-point / f64 reduction", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "parallelism": "scan-shard x%d (replicated map, 96 doubles summed per pass via %s)"
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "arithmetic": "float32 per point (kNN, plane fit, residual, Jacobian row), float64 normal equations and filter algebra",
+                       "parallelism": "scan-shard x%d (replicated map, 96 doubles summed per pass via %s)"
                        % (world, "fused host-segment exchange" if (world > 1 and args.exchange == "shm") else ("NCCL all-reduce" if world > 1 else "no exchange")),
                        "passes_per_scan": passes, "l2_policy": "inputs larger than L2 (multi-level map index %.1f GB, 4 rotating scans)"
                        % (st1["map_bytes"] / 1e9), "pose_err_m": pose_err, "knn_cell": st1["knn_cell"], "levels": st1["n_levels"]},

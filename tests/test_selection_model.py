@@ -84,3 +84,82 @@ def test_packed_key_acceptance_is_sound():
         else:
             rejected += 1
     assert accepted > 2000 and rejected > 50            # both branches are exercised
+
+
+# ---- 4. block_is_final: the geometric guarantee behind "the block's answer is the global answer" -----------------
+F = np.float32
+
+
+def _cell_units(x, o, inv):
+    return F(F(x - o) * inv)
+
+
+def _cell_coord(x, o, inv, n):
+    u = _cell_units(x, o, inv)
+    c = int(min(np.floor(u), 2.0e9)) if u >= 0 else 0
+    return min(c, n - 1)
+
+
+def _guaranteed_r2(q, h, g):
+    """block_is_final's gr2 (match_kernel.cu): squared radius around q inside which every map point is in the block."""
+    ox, inv, cell, n = g
+    u = [_cell_units(q[a], ox[a], inv) for a in range(3)]
+    f = [F(u[a] - F(h[a])) for a in range(3)]
+    slack = F(F(F(6.0e-7) * max(abs(u[0]), abs(u[1]), abs(u[2]))) + F(1.0e-6))
+    m = None
+    for a in range(3):
+        if h[a] - 1 > 0:
+            v = F(f[a] + F(1.0))
+            m = v if m is None else min(m, v)
+        if h[a] + 1 < n[a] - 1:
+            v = F(F(F(1.0) - f[a]) + F(1.0))
+            m = v if m is None else min(m, v)
+    if m is None:
+        return np.inf
+    me = F(F(F(m - slack) * cell) * F(0.999999))
+    return float(F(me * me)) if me > 0 else 0.0
+
+
+def _sqdist(q, p):
+    dx, dy, dz = F(q[0] - p[0]), F(q[1] - p[1]), F(q[2] - p[2])
+    return float(F(F(dx * dx) + F(F(dy * dy) + F(dz * dz))))
+
+
+def test_block_guarantee_radius_is_sound():
+    """No point binned OUTSIDE the 3x3x3 block of a query can be closer than the radius block_is_final grants —
+    including points a few ulp from a cell face, far from the origin (large cell indices) and at the grid rim."""
+    rng = np.random.default_rng(3)
+    worst = np.inf
+    for trial in range(400):
+        cell = F(rng.choice([0.25, 0.375, 0.5625, 0.84375, 1.265625, 1.8984375, 0.15, 0.6]))
+        inv = F(F(1.0) / cell)
+        n = [int(rng.integers(3, 2000)) for _ in range(3)]
+        ox = [F(rng.uniform(-500, 500)) for _ in range(3)]
+        g = (ox, inv, cell, n)
+        # a query somewhere in the grid (sometimes in the rim cells)
+        hq = [int(rng.integers(0, n[a])) if rng.random() < 0.8 else int(rng.choice([0, 1, n[a] - 2, n[a] - 1])) for a in range(3)]
+        q = [F(F(ox[a]) + F((hq[a] + rng.random()) * float(cell))) for a in range(3)]
+        h = [_cell_coord(q[a], ox[a], inv, n[a]) for a in range(3)]
+        r2 = _guaranteed_r2(q, h, g)
+        for _ in range(60):
+            # candidate point: near a face of the block, just outside it along one axis (adversarial), anywhere else inside
+            p = [F(F(ox[a]) + F((h[a] - 1 + 3 * rng.random()) * float(cell))) for a in range(3)]
+            a = int(rng.integers(3))
+            side = rng.random() < 0.5
+            face = (h[a] + 2) if side else (h[a] - 1)
+            x = F(F(ox[a]) + F(face * float(cell)))
+            steps = int(rng.integers(0, 40))
+            for _s in range(steps):                       # walk a few ulp away from the face, outwards
+                x = np.nextafter(x, F(np.inf) if side else F(-np.inf))
+            if rng.random() < 0.5:
+                x = F(x + F((1 if side else -1) * rng.random() * 0.02 * float(cell)))
+            p[a] = x
+            c = [_cell_coord(p[b], ox[b], inv, n[b]) for b in range(3)]
+            outside = any(c[b] < max(h[b] - 1, 0) or c[b] > min(h[b] + 1, n[b] - 1) for b in range(3))
+            if not outside:
+                continue
+            d2 = _sqdist(q, p)
+            assert d2 >= r2, (trial, q, p, h, c, d2, r2)
+            if r2 > 0:
+                worst = min(worst, d2 / r2)
+    assert worst < 1.5                                      # the adversarial points really probe the margin
