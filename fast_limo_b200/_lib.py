@@ -17,6 +17,7 @@ SYMBOLS = [
     "flimo_match_reduce", "flimo_match_reduce_async", "flimo_unpack96", "flimo_match_debug",
     "flimo_update", "flimo_ekf_begin", "flimo_ekf_state", "flimo_ekf_step", "flimo_ekf_end",
     "flimo_scan_to_world", "flimo_prep_filter_sort", "flimo_prep_filter_sort_msg", "flimo_prep_deskew", "flimo_prep_get", "flimo_voxel_grid", "flimo_get_stats", "flimo_stream", "flimo_exchange_attach", "flimo_match_reduce_exchange", "flimo_update_exchange",
+    "flimo_ekf_predict", "flimo_propagated_frames", "flimo_propagated_clear",
 ]
 
 
@@ -78,6 +79,11 @@ class FlimoStats(C.Structure):
     ]
 
 
+class FlimoImu(C.Structure):
+    """flimo_imu: fast_limo::IMUmeas members propagateImu reads (Common.hpp:126-132)."""
+    _fields_ = [("stamp", C.c_double), ("dt", C.c_double), ("ang_vel", C.c_float * 3), ("lin_accel", C.c_float * 3)]
+
+
 _lib = None
 
 
@@ -135,6 +141,9 @@ def load():
     L.flimo_prep_deskew.argtypes = [vp, vp, C.c_int, pf, pf, pf, dbl, C.POINTER(sz)]
     L.flimo_prep_get.argtypes = [vp, C.c_int, vp, sz, C.POINTER(sz)]
     L.flimo_voxel_grid.argtypes = [vp, pf, sz, C.c_float, pf, sz, C.POINTER(sz)]
+    L.flimo_ekf_predict.argtypes = [vp, pd, pd, C.POINTER(FlimoImu), pd]
+    L.flimo_propagated_frames.argtypes = [vp, dbl, dbl, vp, sz, C.POINTER(sz)]
+    L.flimo_propagated_clear.argtypes = [vp]
     L.flimo_stream.argtypes = [vp]
     L.flimo_stream.restype = vp
     _lib = L

@@ -348,6 +348,32 @@ class Mapper:
         return x, Pm
 
 
+    # ---- IMU rate (host algebra; works on a handle created with device=-1) ----
+    def ekf_predict(self, state26, P, stamp, dt, lin_accel, ang_vel, cov=(6.e-4, 1.e-2, 1.e-5, 3.e-4)):
+        """Localizer::propagateImu(imu): esekf::predict + push of State(x, stamp, a, w) on the propagated ring.
+        cov = Config::iKFoM (cov_gyro, cov_acc, cov_bias_gyro, cov_bias_acc), defaults of src/main.cpp:159-162."""
+        x = np.array(state26, np.float64).reshape(26)
+        Pm = np.array(P, np.float64).reshape(23, 23)
+        imu = _lib.FlimoImu(float(stamp), float(dt))
+        imu.ang_vel[:] = [float(np.float32(v)) for v in ang_vel]
+        imu.lin_accel[:] = [float(np.float32(v)) for v in lin_accel]
+        c4 = np.ascontiguousarray(cov, np.float64).reshape(4)
+        self._ck(self._L.flimo_ekf_predict(self._h, _dp(x), _dp(Pm), C.byref(imu), _dp(c4)))
+        return x, Pm
+
+    def propagated_frames(self, start_time, end_time):
+        """Localizer::integrateImu(start_time, end_time): the frames prep_deskew takes (FRAME records, oldest first)."""
+        n = C.c_size_t(0)
+        self._ck(self._L.flimo_propagated_frames(self._h, float(start_time), float(end_time), None, 0, C.byref(n)))
+        out = np.zeros(n.value, FRAME)
+        if n.value:
+            self._ck(self._L.flimo_propagated_frames(self._h, float(start_time), float(end_time), out.ctypes.data, n.value, C.byref(n)))
+        return out
+
+    def propagated_clear(self):
+        self._ck(self._L.flimo_propagated_clear(self._h))
+
+
 def unpack96(packed):
     L = _lib.load()
     p = np.ascontiguousarray(packed, np.float64)

@@ -15,6 +15,7 @@
 
 #include "../../include/flimo.h"
 #include "ekf_host.hpp"
+#include "imu_host.hpp"
 #include "flimo_dev.cuh"
 #include "scan_prep.cuh"
 
@@ -130,6 +131,8 @@ struct flimo_ctx {
 
   ekf::IteratedUpdate upd;
   bool upd_active = false;
+  ekf::PropagatedRing propagated;                 // Localizer::propagated_buffer
+  std::vector<ekf::PropagatedState> frames_tmp;
 
   flimo_stats stats{};
   std::vector<cudaEvent_t> ev_pending, ev_pool;   // async match launches awaiting timing
@@ -1116,6 +1119,46 @@ int flimo_ekf_end(flimo_handle h, double state26[26], double P529[529]) {
   if (!h || !state26 || !P529 || !h->upd_active) return fail(h, FLIMO_ERR_STATE, "flimo_ekf_begin not called");
   h->upd.end(state26, P529);
   h->upd_active = false;
+  return FLIMO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// IMU rate (imu_host.hpp): host algebra only, usable on a handle without a device.
+static_assert(sizeof(flimo_frame) == sizeof(ekf::PropagatedState), "flimo_frame mirrors ekf::PropagatedState");
+
+int flimo_ekf_predict(flimo_handle h, double state26[26], double P529[529], const flimo_imu* imu,
+                      const double cov4[4]) {
+  if (!h || !state26 || !P529 || !imu || !cov4) return fail(h, FLIMO_ERR_INVALID, "null argument");
+  ekf::State x;
+  x.load(state26);
+  ekf::Mat<ekf::N, ekf::N> P;
+  std::memcpy(P.a, P529, sizeof(P.a));
+  const ekf::V3 acc = {imu->lin_accel[0], imu->lin_accel[1], imu->lin_accel[2]};   // .cast<double>() (Localizer.cpp:585-586)
+  const ekf::V3 gyro = {imu->ang_vel[0], imu->ang_vel[1], imu->ang_vel[2]};
+  ekf::predict(x, P, acc, gyro, imu->dt, ekf::ProcessNoise{cov4[0], cov4[1], cov4[2], cov4[3]});
+  x.store(state26);
+  std::memcpy(P529, P.a, sizeof(P.a));
+  h->propagated.push_front(ekf::make_propagated(x, imu->stamp, imu->lin_accel, imu->ang_vel));
+  return FLIMO_OK;
+}
+
+int flimo_propagated_frames(flimo_handle h, double start_time, double end_time, flimo_frame* out, size_t cap,
+                            size_t* n_frames) {
+  if (!h || !n_frames || (cap && !out)) return fail(h, FLIMO_ERR_INVALID, "null argument");
+  *n_frames = 0;
+  const long n = h->propagated.frames(start_time, end_time, h->frames_tmp);
+  if (n < 0) return fail(h, FLIMO_ERR_STATE, "propagated states end before end_time (IMU behind the scan)");
+  *n_frames = static_cast<size_t>(n);
+  if (cap) {
+    if (cap < static_cast<size_t>(n)) return fail(h, FLIMO_ERR_INVALID, "frame buffer too small");
+    std::memcpy(out, h->frames_tmp.data(), static_cast<size_t>(n) * sizeof(flimo_frame));
+  }
+  return FLIMO_OK;
+}
+
+int flimo_propagated_clear(flimo_handle h) {
+  if (!h) return fail(h, FLIMO_ERR_INVALID, "null handle");
+  h->propagated.clear();
   return FLIMO_OK;
 }
 

@@ -1,12 +1,14 @@
 // Device side of fast_limo::Localizer::updatePointCloud (fast_limo/Modules/Localizer.cpp:245-377) over
 // libflimo_cuda: the stages between the raw LiDAR message and the iterated update, with the reference's
-// names.  The IMU-rate bookkeeping (propagated_buffer, integrateImu, time offset, :797-805) stays in the
-// reference's Localizer; this class is what its scan thread calls instead of the PCL / OpenMP code.
+// names, plus the IMU-rate host algebra (prediction, propagated_buffer, integrateImu).  IMU calibration, the
+// IMU -> base-link transform and the time offset (:401-531, :697-728, :797-801) stay in the reference's
+// Localizer; this class is what its two callbacks call instead of the Eigen / PCL / OpenMP code.
 //
 //   Localizer::updatePointCloud                      here
 //   :262-302  NaN / crop / dist / rate / FoV         filter_and_sort(raw_pc, time_stamp)   -> n kept, time of the last point
 //   :744-789  sort by point time                       (same call)
-//   :805      frames = integrateImu(...)             host (reference code), passed to deskew()
+//   :583-608  propagateImu(imu) (IMU callback)       propagateImu(x, P, imu, cov)  -> predict + push on the ring
+//   :805      frames = integrateImu(...)             integrateImu(prev_scan_stamp, scan_stamp), passed to deskew()
 //   :822-843  per-point deskew                       deskew(frames, last_state pose, lidar2baselink_T, offset) -> pc2match bound
 //   :313-321  voxel grid                               (same call, if voxel_active)
 //   :333      iterated update                        Mapper::update
@@ -65,6 +67,32 @@ class Localizer {
     check(flimo_prep_deskew(h_, frames.data(), static_cast<int>(frames.size()), last_q_xyzw, last_p, lidar2baselink_T_rowmajor,
                             offset, &n));
     return n;
+  }
+
+  // Localizer::propagateImu(const IMUmeas&) (:583-608): x26 / P529 are _iKFoM's x_ and P_ (flat, as in flimo.h),
+  // IKFoMT is fast_limo::Config::iKFoM (cov_gyro, cov_acc, cov_bias_gyro, cov_bias_acc).  ImuT is
+  // fast_limo::IMUmeas (stamp, dt, ang_vel, lin_accel with operator[]).
+  template <typename ImuT, typename IKFoMT>
+  void propagateImu(double x26[26], double P529[529], const ImuT& imu, const IKFoMT& ikfom) {
+    flimo_imu m{};
+    m.stamp = imu.stamp;
+    m.dt = imu.dt;
+    for (int i = 0; i < 3; ++i) {
+      m.ang_vel[i] = imu.ang_vel[i];
+      m.lin_accel[i] = imu.lin_accel[i];
+    }
+    const double cov4[4] = {ikfom.cov_gyro, ikfom.cov_acc, ikfom.cov_bias_gyro, ikfom.cov_bias_acc};
+    check(flimo_ekf_predict(h_, x26, P529, &m, cov4));
+  }
+
+  // Localizer::integrateImu (:855-871).  Empty = "not enough propagated states" (the first scan); throws when
+  // the IMU side has not reached end_time yet (the reference waits on cv_prop_stamp there, :880-887).
+  std::vector<flimo_frame> integrateImu(double start_time, double end_time) {
+    std::size_t n = 0;
+    check(flimo_propagated_frames(h_, start_time, end_time, nullptr, 0, &n));
+    std::vector<flimo_frame> frames(n);
+    if (n) check(flimo_propagated_frames(h_, start_time, end_time, frames.data(), n, &n));
+    return frames;
   }
 
   // get_deskewed_pointcloud / get_pc2match_pointcloud (Localizer.cpp:119-137): xyz1 float4 per point.

@@ -226,6 +226,32 @@ int flimo_ekf_state(flimo_handle h, double state26[26]);
 int flimo_ekf_step(flimo_handle h, const double HTH[144], const double HTh[12], int64_t n_rows, int* done);
 int flimo_ekf_end(flimo_handle h, double state26[26], double P529[529]);
 
+/* ---- IMU rate: prediction and the propagated states the deskew stage reads (host algebra) ------- */
+
+/* fast_limo::IMUmeas (Common.hpp:126-132) — the members Localizer::propagateImu reads: already moved to
+ * the base-link frame and bias-corrected by Localizer::updateIMU (:512-520), which stays with the caller. */
+typedef struct {
+  double stamp, dt;
+  float ang_vel[3], lin_accel[3];
+} flimo_imu;
+
+/* Localizer::propagateImu(const IMUmeas&) (Localizer.cpp:583-608): esekf::predict (esekfom.hpp:279-384)
+ * with the process model of use-ikfom.cpp:46-91 and Q = diag(cov4[0] x3, cov4[1] x3, cov4[2] x3, cov4[3] x3),
+ * cov4 = Config::iKFoM {cov_gyro, cov_acc, cov_bias_gyro, cov_bias_acc} (:588-592); then
+ * State(x, imu.stamp, imu.lin_accel, imu.ang_vel) is pushed on the handle's ring of propagated states
+ * (propagated_buffer, capacity 2000, :54).  state26 / P529: x_ and P_, updated in place. */
+int flimo_ekf_predict(flimo_handle h, double state26[26], double P529[529], const flimo_imu* imu,
+                      const double cov4[4]);
+/* Localizer::integrateImu(start_time, end_time) (Localizer.cpp:855-871) over that ring with the selection
+ * rule of propagatedFromTimeRange (:878-913): frames oldest first, from the last state before start_time up
+ * to the first one at or after end_time — what flimo_prep_deskew takes.  *n_frames = 0 with FLIMO_OK is the
+ * reference's "not enough propagated states" (e.g. the first scan, prev_scan_stamp = 0); FLIMO_ERR_STATE when
+ * the newest state is older than end_time, where the reference blocks until the IMU thread catches up.
+ * out may be NULL with cap = 0 to query the count. */
+int flimo_propagated_frames(flimo_handle h, double start_time, double end_time, flimo_frame* out, size_t cap,
+                            size_t* n_frames);
+int flimo_propagated_clear(flimo_handle h);
+
 /* pcl::transformPointCloud(pc2match -> world) of Localizer.cpp:361-374 on the device copy of the
  * scan, using State::get_RT() of state14; optional convenience so final_scan can come from the GPU. */
 int flimo_scan_to_world(flimo_handle h, const double state14[14], float* out_xyz, size_t cap_points,

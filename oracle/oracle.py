@@ -303,6 +303,61 @@ def prep_voxel(pts4, leaf):
     return out[:m].copy()
 
 
+# ---- IMU rate (predict.hpp) ------------------------------------------------------------------------------
+class Propagator:
+    """Filter state + propagated_buffer: Localizer::propagateImu / integrateImu restated (oracle/predict.hpp)."""
+
+    def __init__(self, state26, P):
+        L = lib()
+        L.orc_prop_new.restype = C.c_void_p
+        L.orc_prop_new.argtypes = [C.c_void_p, C.c_void_p]
+        L.orc_prop_free.argtypes = [C.c_void_p]
+        L.orc_prop_propagate.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_prop_get.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_prop_frames.restype = C.c_long
+        L.orc_prop_frames.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_size_t]
+        x = np.ascontiguousarray(state26, np.float64).reshape(26)
+        Pm = np.ascontiguousarray(np.asarray(P, np.float64).reshape(23, 23))
+        self._L = L
+        self._p = L.orc_prop_new(x.ctypes.data, Pm.ctypes.data)
+
+    def __del__(self):
+        if getattr(self, "_p", None):
+            self._L.orc_prop_free(self._p)
+            self._p = None
+
+    def propagate(self, stamp, dt, lin_accel, ang_vel, cov=(6.e-4, 1.e-2, 1.e-5, 3.e-4)):
+        a, w = np.ascontiguousarray(lin_accel, np.float32), np.ascontiguousarray(ang_vel, np.float32)
+        c4 = np.ascontiguousarray(cov, np.float64)
+        self._L.orc_prop_propagate(self._p, float(stamp), float(dt), a.ctypes.data, w.ctypes.data, c4.ctypes.data)
+
+    def get(self):
+        x, Pm = np.zeros(26, np.float64), np.zeros((23, 23), np.float64)
+        self._L.orc_prop_get(self._p, x.ctypes.data, Pm.ctypes.data)
+        return x, Pm
+
+    def frames(self, start_time, end_time):
+        """None: the reference would block waiting for IMU data; else FRAME records (possibly empty), oldest first."""
+        n = self._L.orc_prop_frames(self._p, float(start_time), float(end_time), None, 0)
+        if n < 0:
+            return None
+        out = np.zeros(n, FRAME)
+        if n:
+            self._L.orc_prop_frames(self._p, float(start_time), float(end_time), out.ctypes.data, n)
+        return out
+
+
+def process_model(state26, acc, gyro):
+    """get_f (24), df_dx (24 x 23), df_dw (24 x 12) of use-ikfom.cpp:46-91."""
+    L = lib()
+    L.orc_process_model.argtypes = [C.c_void_p] * 6
+    x = np.ascontiguousarray(state26, np.float64).reshape(26)
+    a, w = np.ascontiguousarray(acc, np.float64), np.ascontiguousarray(gyro, np.float64)
+    f, fx, fw = np.zeros(24), np.zeros((24, 23)), np.zeros((24, 12))
+    L.orc_process_model(x.ctypes.data, a.ctypes.data, w.ctypes.data, f.ctypes.data, fx.ctypes.data, fw.ctypes.data)
+    return f, fx, fw
+
+
 # ---- oracle/_ref: the REFERENCE's own octree, compiled where it lies (make -C oracle ref) -----------------
 REF_LIB = os.path.join(_HERE, "_ref", "libref_octree.so")
 

@@ -16,6 +16,7 @@
 #include "ekf.hpp"
 #include "ioctree.hpp"
 #include "plane_match.hpp"
+#include "predict.hpp"
 #include "prep.hpp"
 
 using namespace orc;
@@ -260,6 +261,39 @@ size_t orc_prep_voxel(const float* in4, size_t n, float leaf, float* out4) {
   const std::vector<float> o = prep_voxel(in4, n, leaf);
   std::memcpy(out4, o.data(), o.size() * sizeof(float));
   return o.size() / 4;
+}
+
+
+// ---- IMU rate (predict.hpp): prediction + propagated states -------------------------------------
+void* orc_prop_new(const double* state26, const double* P529) {
+  Propagator* p = new Propagator();
+  std::memcpy(&p->x, state26, sizeof(EkfState));
+  std::memcpy(p->P.data(), P529, 529 * sizeof(double));
+  return p;
+}
+void orc_prop_free(void* p) { delete static_cast<Propagator*>(p); }
+void orc_prop_propagate(void* p, double stamp, double dt, const float* lin_accel, const float* ang_vel, const double* cov4) {
+  static_cast<Propagator*>(p)->propagate(stamp, dt, lin_accel, ang_vel, cov4);
+}
+void orc_prop_get(void* p, double* state26, double* P529) {
+  Propagator* q = static_cast<Propagator*>(p);
+  std::memcpy(state26, &q->x, sizeof(EkfState));
+  std::memcpy(P529, q->P.data(), 529 * sizeof(double));
+}
+// out may be NULL to query the count; returns -1 / 0 / n as Propagator::frames_in_range
+long orc_prop_frames(void* p, double start_time, double end_time, Frame* out, size_t cap) {
+  std::vector<Frame> fr;
+  const long n = static_cast<Propagator*>(p)->frames_in_range(start_time, end_time, fr);
+  if (n > 0 && out && cap >= static_cast<size_t>(n)) std::memcpy(out, fr.data(), n * sizeof(Frame));
+  return n;
+}
+// the process model alone, for the finite-difference checks: f (24), df/dx (24 x 23), df/dw (24 x 12)
+void orc_process_model(const double* state26, const double* acc, const double* gyro, double* f, double* fx, double* fw) {
+  EkfState s;
+  std::memcpy(&s, state26, sizeof(EkfState));
+  process_f(s, acc, gyro, f);
+  process_fx(s, acc, fx);
+  process_fw(s, fw);
 }
 
 }  // extern "C"

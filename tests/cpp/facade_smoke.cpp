@@ -68,6 +68,21 @@ int main() {
   }
   if (flimo_ekf_end(h, x, P) != FLIMO_OK) return 6;
   if (passes < 1 || passes > 3 || !(std::fabs(x[0]) > 1e-9) || !(P[0] < 1.0)) return 7;
+  // IMU rate: 40 predictions at 200 Hz, then the frames of a scan interval (host algebra, works without a device)
+  struct Imu { double stamp, dt; float ang_vel[3], lin_accel[3]; } imu{0.0, 0.005, {0.0f, 0.0f, 0.2f}, {0.5f, 0.0f, 9.809f}};
+  struct IKFoM { double cov_gyro = 6e-4, cov_acc = 1e-2, cov_bias_gyro = 1e-5, cov_bias_acc = 3e-4; } ikfom;
+  const double P00_before = P[0];
+  for (int i = 1; i <= 40; ++i) {
+    imu.stamp = 0.005 * i;
+    L.propagateImu(x, P, imu, ikfom);
+  }
+  if (!(P[0] > P00_before) || !(x[14] > 0.09 && x[14] < 0.11)) return 10;       // covariance grows; v_x = 0.5 * 0.2 s
+  const std::vector<flimo_frame> frames = L.integrateImu(0.0512, 0.1512);
+  if (frames.size() != 22 || frames.front().time != 0.05 || frames.back().time != 0.155) return 11;
+  if (!L.integrateImu(0.0, 0.1).empty()) return 12;                              // first scan: nothing before t = 0
+  threw = false;
+  try { L.integrateImu(0.1, 0.5); } catch (const std::exception& e) { threw = std::strstr(e.what(), "IMU behind") != nullptr; }
+  if (!threw) return 13;
   std::printf("facade ok passes=%d x0=%.3e P00=%.3e\n", passes, x[0], P[0]);
   return 0;
 }

@@ -1,0 +1,258 @@
+"""IMU rate: esekf::predict + the propagated-state ring (CPU tests, host algebra of libflimo_cuda).
+
+Reference: IKFoM_toolkit/esekfom/esekfom.hpp:279-384 (predict), IKFoM/use-ikfom.cpp:46-91 (process model),
+fast_limo/Modules/Localizer.cpp:583-608 (propagateImu), :855-913 (integrateImu / propagatedFromTimeRange).
+
+Three independent evaluations are compared: the product (fast_limo_b200/csrc/imu_host.hpp, block-wise closed
+form), the oracle (oracle/predict.hpp, the reference's generic dense shape) and numpy / scipy written here
+(state transition with scipy rotations, Jacobians by finite differences).
+"""
+import numpy as np
+import pytest
+from scipy.spatial.transform import Rotation as Rot
+
+from fast_limo_b200 import api, synth
+
+G = 9.809
+COV = (6.e-4, 1.e-2, 1.e-5, 3.e-4)      # src/main.cpp:159-162
+
+
+def _state(seed):
+    rng = np.random.default_rng(seed)
+    g = rng.normal(size=3)
+    g[0] += 0.3                           # keep away from the chart's singular direction (-L, 0, 0)
+    g *= G / np.linalg.norm(g)
+    return synth.make_state(rng.normal(0, 5, 3), Rot.random(random_state=seed).as_quat(),
+                            Rot.from_rotvec(rng.normal(0, 0.05, 3)).as_quat(), rng.normal(0, 0.1, 3), rng.normal(0, 3, 3),
+                            rng.normal(0, 1e-2, 3), rng.normal(0, 5e-2, 3), g)
+
+
+def _spd(seed, scale=1e-2):
+    rng = np.random.default_rng(seed + 100)
+    A = rng.normal(size=(23, 23))
+    return scale * (A @ A.T / 23 + np.eye(23))
+
+
+def _imu(seed, n, rate=200.0, t0=10.0):
+    rng = np.random.default_rng(seed + 7)
+    stamps = t0 + (1 + np.arange(n)) / rate
+    acc = (rng.normal(0, 1.5, (n, 3)) + [0, 0, G]).astype(np.float32)
+    gyr = rng.normal(0, 0.8, (n, 3)).astype(np.float32)
+    return stamps, np.full(n, 1.0 / rate), acc, gyr
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_predict_matches_oracle(oracle, flimo_lib, seed):
+    x0, P0 = _state(seed), _spd(seed)
+    stamps, dts, acc, gyr = _imu(seed, 60)
+    m = api.Mapper(device=-1)
+    orc = oracle.Propagator(x0, P0)
+    x, P = x0, P0
+    for t, dt, a, w in zip(stamps, dts, acc, gyr):
+        x, P = m.ekf_predict(x, P, t, dt, a, w, COV)
+        orc.propagate(t, dt, a, w, COV)
+    xo, Po = orc.get()
+    assert np.allclose(x, xo, rtol=0, atol=1e-12 * max(1.0, np.abs(xo).max()))
+    assert np.allclose(P, Po, rtol=1e-11, atol=1e-15)
+    assert np.allclose(P, P.T, rtol=1e-12, atol=1e-15)
+    assert np.linalg.eigvalsh(0.5 * (P + P.T)).min() > 0
+    # quaternion stays (numerically) unit: no normalisation in either code, 60 products
+    assert abs(np.linalg.norm(x[3:7]) - 1) < 1e-12
+    # propagated states: the float casts of the SAME doubles => identical records unless the doubles differ in
+    # the last bits; compare field-wise at float32 resolution
+    fo = orc.frames(stamps[9] + 1e-4, stamps[40] + 1e-4)
+    fp = m.propagated_frames(stamps[9] + 1e-4, stamps[40] + 1e-4)
+    assert len(fo) == len(fp) == 33                      # samples 9 .. 41: one before the start, first one past the end
+    assert np.array_equal(fo["time"], fp["time"]) and fo["time"][0] == stamps[9] and fo["time"][-1] == stamps[41]
+    for k in ("w", "a"):
+        assert np.array_equal(fo[k], fp[k])
+    assert np.array_equal(fp["a"], acc[9:42]) and np.array_equal(fp["w"], gyr[9:42])
+    for k in ("q", "p", "v", "bg", "ba", "g"):
+        assert np.allclose(fo[k], fp[k], rtol=3e-7, atol=1e-9)
+
+
+def _transition(x, acc, gyro, dt):
+    """x (+) f(x, u) dt with scipy rotations: pos, rot (xyzw), offR, offT, vel, bg, ba, grav."""
+    y = x.copy()
+    R = Rot.from_quat(x[3:7])
+    y[0:3] = x[0:3] + x[14:17] * dt
+    y[3:7] = (R * Rot.from_rotvec((gyro - x[17:20]) * dt)).as_quat()
+    y[14:17] = x[14:17] + (R.apply(acc - x[20:23]) + x[23:26]) * dt
+    return y
+
+
+def _extract_F(m, x0, acc, gyr, dt):
+    """F of P' = F P F^T + G Q G^T through the C ABI: with Q = 0 and P = e_j e_j^T, P' = F[:, j] F[:, j]^T."""
+    F = np.zeros((23, 23))
+    for j in range(23):
+        P = np.zeros((23, 23))
+        P[j, j] = 1.0
+        _, Pn = m.ekf_predict(x0, P, 0.0, dt, acc, gyr, (0, 0, 0, 0))
+        col = Pn[:, j] / np.sqrt(Pn[j, j])                # F[j, j] > 0 (F = I + O(dt))
+        assert np.allclose(Pn, np.outer(col, col), atol=1e-14)
+        F[:, j] = col
+    return F
+
+
+@pytest.mark.parametrize("seed", [4, 5])
+def test_transition_and_jacobian_against_numpy(oracle, flimo_lib, seed):
+    x0 = _state(seed)
+    rng = np.random.default_rng(seed)
+    acc = (rng.normal(0, 2, 3) + [0, 0, G]).astype(np.float32)
+    gyr = rng.normal(0, 1.0, 3).astype(np.float32)
+    dt = 0.01
+    m = api.Mapper(device=-1)
+    x1, _ = m.ekf_predict(x0, _spd(seed), 0.0, dt, acc, gyr, COV)
+    ref = _transition(x0, acc.astype(np.float64), gyr.astype(np.float64), dt)
+    sgn = np.sign(np.dot(ref[3:7], x1[3:7]))
+    ref[3:7] *= sgn
+    assert np.allclose(x1, ref, atol=1e-12)
+
+    # Jacobian of the transition in (+)/(-) coordinates by central differences, (+)/(-) from the oracle
+    F = _extract_F(m, x0, acc, gyr, dt)
+    eps = 1e-5
+    J = np.zeros((23, 23))
+    a64, w64 = acc.astype(np.float64), gyr.astype(np.float64)
+    mid = _transition(x0, a64, w64, dt)                  # both differences in the chart of the unperturbed result
+    for j in range(23):
+        d = np.zeros(23)
+        d[j] = eps
+        hi = _transition(oracle.boxplus(x0, d), a64, w64, dt)
+        lo = _transition(oracle.boxplus(x0, -d), a64, w64, dt)
+        J[:, j] = (oracle.boxminus(hi, mid) - oracle.boxminus(lo, mid)) / (2 * eps)
+    mask = np.ones((23, 23), bool)
+    mask[3:6, 3:6] = False
+    assert np.allclose(F[mask], J[mask], atol=2e-8)
+    # the rot-rot block: the exact Jacobian is Exp(-(gyro - bg) dt); the reference (and therefore this library)
+    # leaves the identity there because of scalar(1/2) == 0 at esekfom.hpp:312
+    assert np.array_equal(F[3:6, 3:6], np.eye(3))
+    assert np.allclose(J[3:6, 3:6], Rot.from_rotvec(-(w64 - x0[17:20]) * dt).as_matrix(), atol=2e-8)
+
+
+def test_process_model_finite_differences(oracle):
+    x0 = _state(9)
+    acc, gyr = np.array([0.3, -1.0, 9.6]), np.array([0.2, -0.4, 0.7])
+    f, fx, fw = oracle.process_model(x0, acc, gyr)
+    assert np.allclose(f[0:3], x0[14:17]) and np.allclose(f[3:6], gyr - x0[17:20])
+    assert np.allclose(f[12:15], Rot.from_quat(x0[3:7]).apply(acc - x0[20:23]) + x0[23:26])
+    assert not f[6:12].any() and not f[15:].any()
+    eps = 1e-6
+    J = np.zeros((24, 23))
+    for j in range(23):
+        d = np.zeros(23)
+        d[j] = eps
+        J[:, j] = (oracle.process_model(oracle.boxplus(x0, d), acc, gyr)[0] -
+                   oracle.process_model(oracle.boxplus(x0, -d), acc, gyr)[0]) / (2 * eps)
+    assert np.allclose(fx, J, atol=1e-7)
+    # noise enters as gyro - ng, acc - na (use-ikfom.cpp:82-90): df/dw by differences on the inputs
+    Jw = np.zeros((24, 12))
+    for j in range(3):
+        d = np.zeros(3)
+        d[j] = eps
+        Jw[:, j] = (oracle.process_model(x0, acc, gyr - d)[0] - oracle.process_model(x0, acc, gyr + d)[0]) / (2 * eps)
+        Jw[:, 3 + j] = (oracle.process_model(x0, acc - d, gyr)[0] - oracle.process_model(x0, acc + d, gyr)[0]) / (2 * eps)
+    assert np.allclose(fw[:, :6], Jw[:, :6], atol=1e-7)
+    assert np.array_equal(fw[15:18, 6:9], np.eye(3)) and np.array_equal(fw[18:21, 9:12], np.eye(3))
+
+
+def test_noise_term(flimo_lib):
+    """P = 0 isolates G Q G^T: rot <- gyro noise through A, vel <- accel noise through R, biases directly."""
+    x0 = _state(11)
+    acc, gyr = np.float32([0.1, 0.2, 9.7]), np.float32([0.5, -0.3, 0.2])
+    dt = 0.005
+    m = api.Mapper(device=-1)
+    _, Pn = m.ekf_predict(x0, np.zeros((23, 23)), 0.0, dt, acc, gyr, COV)
+    exp = np.zeros((23, 23))
+    w = (gyr.astype(np.float64) - x0[17:20]) * dt
+    th = np.linalg.norm(w)
+    K = np.array([[0, w[2], -w[1]], [-w[2], 0, w[0]], [w[1], -w[0], 0]])      # hat(-w)
+    A = np.eye(3) + (1 - np.cos(th)) / th ** 2 * K + (1 - np.sin(th) / th) / th ** 2 * K @ K
+    exp[3:6, 3:6] = COV[0] * dt * dt * A @ A.T
+    exp[12:15, 12:15] = COV[1] * dt * dt * np.eye(3)
+    exp[15:18, 15:18] = COV[2] * dt * dt * np.eye(3)
+    exp[18:21, 18:21] = COV[3] * dt * dt * np.eye(3)
+    assert np.allclose(Pn, exp, atol=1e-18, rtol=1e-10)
+
+
+def _select(times_newest_first, t0, t1):
+    """propagatedFromTimeRange restated on a plain list (Localizer.cpp:878-913)."""
+    b = times_newest_first
+    if not b or b[0] < t1:
+        return None
+    it, last = 1, 0
+    while it < len(b) and b[it] >= t1:
+        last = it
+        it += 1
+    while it < len(b) and b[it] >= t0:
+        it += 1
+    if it == len(b):
+        return []
+    return list(reversed(b[last:it + 1]))
+
+
+def test_propagated_ring_selection(oracle, flimo_lib):
+    x0, P0 = _state(21), _spd(21)
+    m = api.Mapper(device=-1)
+    orc = oracle.Propagator(x0, P0)
+    n = 2300                                             # > capacity 2000: the oldest 300 fall off
+    stamps, dts, acc, gyr = _imu(21, n, rate=400.0, t0=100.0)
+    gyr *= 0.05
+    acc = (acc - np.float32([0, 0, G])) * np.float32(0.05) + np.float32([0, 0, G])
+    x, P = x0, P0
+    for t, dt, a, w in zip(stamps, dts, acc, gyr):
+        x, P = m.ekf_predict(x, P, t, dt, a, w, COV)
+        orc.propagate(t, dt, a, w, COV)
+    kept = list(stamps[::-1][:2000])
+    windows = [(stamps[500] + 1e-5, stamps[540] + 1e-5),    # ordinary scan
+               (stamps[500], stamps[540]),                  # boundaries exactly on samples (>= in both loops)
+               (stamps[2250], stamps[2299]),                # ends on the newest sample
+               (stamps[2298] + 1e-5, stamps[2299]),         # shortest window
+               (0.0, stamps[700]),                          # first scan: prev_scan_stamp = 0 -> not enough states
+               (stamps[100], stamps[400]),                  # starts before the oldest retained state (index 300)
+               (stamps[300], stamps[400]),                  # starts ON the oldest retained state -> nothing older
+               (stamps[301], stamps[400])]                  # one older state exists
+    for t0, t1 in windows:
+        exp = _select(kept, t0, t1)
+        got = m.propagated_frames(t0, t1)
+        go = orc.frames(t0, t1)
+        assert go is not None and list(go["time"]) == exp
+        assert list(got["time"]) == exp
+    assert len(m.propagated_frames(0.0, stamps[700])) == 0
+    assert len(m.propagated_frames(stamps[301], stamps[400])) == 101
+    # the IMU thread is behind the scan: the reference blocks, the library reports it
+    assert orc.frames(stamps[10], stamps[-1] + 0.01) is None
+    with pytest.raises(api.FlimoError, match="IMU behind"):
+        m.propagated_frames(stamps[10], stamps[-1] + 0.01)
+    m.propagated_clear()
+    with pytest.raises(api.FlimoError, match="IMU behind"):
+        m.propagated_frames(stamps[500], stamps[540])
+
+
+def test_frames_feed_the_deskew_oracle(oracle, flimo_lib):
+    """The records of the ring are what deskewPointCloud consumes: oracle deskew on product frames == on oracle frames."""
+    x0, P0 = _state(31), synth.default_P0()
+    x0[14:17] = [8.0, 0.5, 0.0]
+    m = api.Mapper(device=-1)
+    orc = oracle.Propagator(x0, P0)
+    stamps, dts, acc, gyr = _imu(31, 80, rate=400.0, t0=50.0)
+    gyr *= 0.3
+    x, P = x0, P0
+    for t, dt, a, w in zip(stamps, dts, acc, gyr):
+        x, P = m.ekf_predict(x, P, t, dt, a, w, COV)
+        orc.propagate(t, dt, a, w, COV)
+    t_begin, t_end = stamps[20] + 1e-4, stamps[60] + 1e-4
+    fp, fo = m.propagated_frames(t_begin, t_end), orc.frames(t_begin, t_end)
+    rng = np.random.default_rng(5)
+    n = 4000
+    raw = np.zeros(n, api.RAW_POINT)
+    pts = rng.normal(0, 15, (n, 3)).astype(np.float32)
+    raw["x"], raw["y"], raw["z"] = pts[:, 0], pts[:, 1], pts[:, 2]
+    raw["time"] = np.sort(rng.uniform(0, t_end - t_begin, n)).astype(np.float32)
+    cfg = oracle.make_prep_cfg(sensor_type=1)
+    order = oracle.prep_filter_sort(raw, cfg, sort=True)
+    T = np.eye(4, dtype=np.float32)
+    lq, lp = x[3:7].astype(np.float32), x[0:3].astype(np.float32)
+    wp, bp = oracle.prep_deskew(raw, order, cfg, t_begin, 0.0, fp, lq, lp, T)
+    wo, bo = oracle.prep_deskew(raw, order, cfg, t_begin, 0.0, fo, lq, lp, T)
+    assert np.allclose(wp, wo, atol=2e-5) and np.allclose(bp, bo, atol=2e-5)
+    assert np.isfinite(wp).all()
