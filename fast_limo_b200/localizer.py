@@ -1,0 +1,141 @@
+"""Host mirror of fast_limo::Localizer's two callbacks over libflimo_cuda (ctypes), with the reference's names.
+
+    Localizer::updateIMU         fast_limo/Modules/Localizer.cpp:401-531  (post-calibration branch :512-528)
+    Localizer::propagateImu      :583-608
+    Localizer::updatePointCloud  :245-399
+    Localizer::deskewPointCloud  :733-853 (host part: time offset :797-805, integrateImu :808, last_state :820)
+    Localizer::init_iKFoM_state  :672-694
+
+Only sequencing lives here; every stage is a call into the library (`api.Mapper`): filters / sort / deskew / voxel
+grid and the registration on the GPU, prediction and the propagated-state ring in the library's host algebra.
+What is NOT mirrored: IMU calibration and the IMU -> base-link transform (:409-510, :697-728) — `updateIMU` takes
+the sample as `imu_buffer` stores it — the debug clouds, the CPU statistics and the condition-variable wait of
+`propagatedFromTimeRange` (a scan that arrives before its IMU data raises instead).
+"""
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import api
+
+
+@dataclass
+class LocalizerConfig:
+    """The Config fields the two callbacks read (fast_limo/Utils/Config.hpp)."""
+    filters: api.FilterConfig = field(default_factory=api.FilterConfig)
+    MAX_NUM_ITERS: int = 3                       # iKFoM/MAX_NUM_ITERS
+    LIMITS: float = 0.001                        # iKFoM/LIMITS (one value for all 23, as the YAMLs have it)
+    cov_gyro: float = 6.e-4                      # defaults of src/main.cpp:159-162
+    cov_acc: float = 1.e-2
+    cov_bias_gyro: float = 1.e-5
+    cov_bias_acc: float = 3.e-4
+    time_offset: bool = False
+    gravity: float = 9.81
+    lidar2baselink_R: tuple = ((1, 0, 0), (0, 1, 0), (0, 0, 1))
+    lidar2baselink_t: tuple = (0.0, 0.0, 0.0)
+
+
+def _quat_from_R(R):
+    from scipy.spatial.transform import Rotation
+    return Rotation.from_matrix(np.asarray(R, np.float64)).as_quat()
+
+
+def _RT_f32(q, t):
+    """Eigen::Quaternionf::toRotationMatrix + translation as a row-major 4x4 float32 (State::get_extr_RT)."""
+    x, y, z, w = (np.float32(v) for v in q)
+    two = np.float32(2)
+    tx, ty, tz = two * x, two * y, two * z
+    twx, twy, twz = tx * w, ty * w, tz * w
+    txx, txy, txz = tx * x, ty * x, tz * x
+    tyy, tyz, tzz = ty * y, tz * y, tz * z
+    one = np.float32(1)
+    T = np.eye(4, dtype=np.float32)
+    T[:3, :3] = [[one - (tyy + tzz), txy - twz, txz + twy], [txy + twz, one - (txx + tzz), tyz - twx],
+                 [txz - twy, tyz + twx, one - (txx + tyy)]]
+    T[:3, 3] = np.asarray(t, np.float32)
+    return T
+
+
+class Localizer:
+    def __init__(self, mapper: api.Mapper, config: LocalizerConfig = None, pos=(0, 0, 0), quat=(0, 0, 0, 1), vel=(0, 0, 0),
+                 bias_gyro=(0, 0, 0), bias_accel=(0, 0, 0)):
+        self.map = mapper
+        self.config = config or LocalizerConfig()
+        c = self.config
+        # init_iKFoM_state (:672-694)
+        from .synth import default_P0, make_state
+        self.x = make_state(pos, quat, _quat_from_R(c.lidar2baselink_R), c.lidar2baselink_t, vel, bias_gyro, bias_accel,
+                            (0.0, 0.0, -c.gravity))
+        # S2(Eigen::Vector3d) rescales to length 9.809 whatever `gravity` says (S2.hpp:123-126)
+        self.x[23:26] *= 9.809 / np.linalg.norm(self.x[23:26])
+        self.P = default_P0()
+        self.lidar2baselink_T = _RT_f32(self.x[7:11], self.x[11:14])
+        self.scan_stamp = 0.0
+        self.prev_scan_stamp = 0.0
+        self.imu_stamp = 0.0
+        self.n_imu = 0
+        self.last_imu = None
+        self.last = {}                           # what the last updatePointCloud did (sizes, passes, "null" reason)
+        self.map.propagated_clear()
+
+    def _cov4(self):
+        c = self.config
+        return (c.cov_gyro, c.cov_acc, c.cov_bias_gyro, c.cov_bias_acc)
+
+    # -- IMU callback ---------------------------------------------------------------------------------------------
+    def updateIMU(self, stamp, dt, lin_accel, ang_vel):
+        """:512-528 for a calibrated base-link sample: remember it, propagate the filter, push the propagated state."""
+        self.imu_stamp = float(stamp)
+        self.last_imu = (np.asarray(lin_accel, np.float32), np.asarray(ang_vel, np.float32))
+        self.n_imu += 1
+        self.x, self.P = self.map.ekf_predict(self.x, self.P, stamp, dt, lin_accel, ang_vel, self._cov4())
+
+    # -- LiDAR callback -------------------------------------------------------------------------------------------
+    def updatePointCloud(self, raw, time_stamp):
+        """:245-399.  raw: api.RAW_POINT records of one message.  Returns True when the scan was registered and mapped."""
+        self.last = {}
+        if len(raw) < 1:
+            return self._null("raw pointcloud is empty", stamp=False)
+        if self.n_imu == 0:
+            return self._null("IMU buffer is empty", stamp=False)
+        c = self.config
+        n_kept, t_last = self.map.prep_filter_sort(raw, time_stamp, c.filters)             # :262-302, :744-789
+        self.last["n_filtered"] = n_kept
+        if n_kept < 1:
+            return self._null("no points left after the filters", stamp=False)
+        offset = 0.0
+        if c.time_offset:                                                                   # :797-801
+            offset = min(self.imu_stamp - t_last - 1.e-4, 0.0)
+        self.scan_stamp = t_last + offset                                                   # :805
+        frames = self.map.propagated_frames(self.prev_scan_stamp, self.scan_stamp)          # :808
+        self.last["n_frames"] = len(frames)
+        if len(frames) < 1:
+            return self._null("no frames obtained from IMU propagation")                    # the first scan (prev stamp 0)
+        lq, lp = self.x[3:7].astype(np.float32), self.x[0:3].astype(np.float32)             # last_state (:820)
+        n_pc2match = self.map.prep_deskew(frames, lq, lp, self.lidar2baselink_T, offset)    # :822-843 (+ :313-321)
+        self.last["n_pc2match"] = n_pc2match
+        if n_pc2match <= 1:
+            return self._null("NULL ITERATION")
+        # with an empty map Mapper::match returns no matches (Mapper.cpp:61): every pass has zero rows, the state
+        # stays at the prediction and the map is then initialised with this scan
+        self.x, self.P, passes = self.map.update(self.x, self.P, c.MAX_NUM_ITERS, c.LIMITS)       # :333
+        self.last["passes"] = passes
+        self.lidar2baselink_T = _RT_f32(self.x[7:11], self.x[11:14])                        # :356
+        world = self.map.scan_to_world(self.x)                                              # :361
+        self.map.add(world, self.scan_stamp)                                                # :377
+        self.prev_scan_stamp = self.scan_stamp                                              # :398
+        return True
+
+    def _null(self, why, stamp=True):
+        self.last["null"] = why
+        if stamp:
+            self.prev_scan_stamp = self.scan_stamp                                          # :398 runs on every path past :805
+        return False
+
+    # -- getters ---------------------------------------------------------------------------------------------------
+    def getWorldState(self):
+        """Position, orientation (xyzw) and velocity of the filter state (State(_iKFoM.get_x()), :160-171)."""
+        return self.x[0:3].copy(), self.x[3:7].copy(), self.x[14:17].copy()
+
+    def get_pc2match_pointcloud(self):
+        return self.map.prep_get(3)

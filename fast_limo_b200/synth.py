@@ -337,6 +337,18 @@ class Stream:
         raw["x"], raw["y"], raw["z"], raw["time"] = pts[:, 0], pts[:, 1], pts[:, 2], t_rel
         return raw, stamp
 
+    def imu(self, t0, t1, sigma_acc=0.0, sigma_gyro=0.0, seed=0):
+        """Calibrated base-link IMU samples with t0 < stamp <= t1 on the IMU clock (stamp = i / imu_hz):
+        (stamps, dt, lin_accel (n,3) float32, ang_vel (n,3) float32) — what Localizer::updateIMU pushes on
+        imu_buffer.  Constant speed on the circle: specific force = centripetal (body +y) - gravity."""
+        i0, i1 = int(np.floor(t0 * self.imu_hz + 1e-9)) + 1, int(np.floor(t1 * self.imu_hz + 1e-9))
+        idx = np.arange(i0, i1 + 1)
+        n = len(idx)
+        rng = np.random.default_rng(self.seed + 7919 * i0 + seed)
+        acc = np.tile(np.float64([0.0, self.v * self.omega, 9.809]), (n, 1)) + rng.normal(0, 1, (n, 3)) * sigma_acc
+        gyr = np.tile(np.float64([0.0, 0.0, self.omega]), (n, 1)) + rng.normal(0, 1, (n, 3)) * sigma_gyro
+        return idx / self.imu_hz, np.full(n, 1.0 / self.imu_hz), acc.astype(np.float32), gyr.astype(np.float32)
+
     def frames(self, t0, t1):
         """fast_limo::State records at the IMU rate covering [t0, t1] (ideal IMU, zero biases)."""
         from .api import FRAME

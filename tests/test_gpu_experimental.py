@@ -3,7 +3,11 @@
 FLIMO_KNN_PAIR=1 — two lanes per query in the first scan (csrc/match_kernel.cu, pair_scan_round).  Validated
 bit-identical against the oracle on the headline config c2 (tools/tune_knn.py ... :pair=1 --check) at the end of
 round 1; these cases cover what c2 does not (tiny runs, dense cells, caps, empty blocks) and have to be green
-before the switch becomes the default."""
+before the switch becomes the default.
+
+fast_limo_b200.localizer — the host mirror of Localizer::updateIMU / updatePointCloud in closed loop (IMU samples ->
+prediction -> propagated frames -> device deskew -> update -> map add).  Written after the GPU budget of round 1 was
+spent; its IMU side is covered on the CPU (tests/test_imu_predict.py), the closed loop is checked here."""
 import os
 
 import numpy as np
@@ -71,3 +75,31 @@ def test_pair_scan_dense_sparse_and_update(oracle, flimo_lib):
     xa, Pa, pa = m.update(case.init, synth.default_P0(), 2, 0.0)
     xb, Pb, pb = m0.update(case.init, synth.default_P0(), 2, 0.0)
     assert pa == pb and np.array_equal(xa, xb) and np.array_equal(Pa, Pb)
+
+
+def test_localizer_closed_loop(flimo_lib):
+    """Twelve sweeps of the synthetic stream through the two callbacks: the first scan is dropped (no propagated state
+    before it), the second initialises the map with zero matches, the following ones are registered."""
+    from fast_limo_b200.localizer import Localizer, LocalizerConfig
+    S = synth.Stream(rings=64, azimuths=512, imu_hz=200.0)    # same stream as tests/test_localizer_sequence.py (CPU, oracle stages)
+    m = api.Mapper(api.MappingConfig(MAX_NUM_MATCHES=BIG, MAX_NUM_PC2MATCH=BIG), device=0)
+    filt = api.FilterConfig(cropBoxMin=(-1, -1, -1), cropBoxMax=(1, 1, 1), min_dist=3.0, leafSize=0.5, sensor_type=1)
+    x0 = S.state(0.0)
+    loc = Localizer(m, LocalizerConfig(filters=filt, MAX_NUM_ITERS=3), pos=x0[0:3], quat=x0[3:7], vel=x0[14:17])
+    t_imu, outcome, errs = 0.0, [], []
+    for k in range(12):
+        raw, stamp = S.scan(k)
+        t_need = stamp + S.dt + 1.0 / S.imu_hz               # the newest propagated state must not be older than the last point
+        for smp in zip(*S.imu(t_imu, t_need, sigma_acc=0.05, sigma_gyro=0.002)):
+            loc.updateIMU(smp[0], smp[1], smp[2] + np.float32([0.3, 0.0, 0.0]), smp[3])   # uncalibrated accelerometer bias
+        t_imu = t_need
+        outcome.append(loc.updatePointCloud(raw, stamp))
+        truth = S.state(loc.imu_stamp)
+        errs.append(float(np.linalg.norm(loc.x[0:3] - truth[0:3])))
+        if k == 0:
+            assert loc.last["null"].startswith("no frames") and m.size() == 0
+        if k == 1:
+            assert loc.last["passes"] >= 1 and m.size() > 0   # zero matches against the empty map, then Mapper::add
+    assert outcome == [False] + [True] * 11
+    assert max(errs) < 0.03, errs                             # dead reckoning alone drifts 0.5 * 0.3 * t^2 (22 cm at 1.2 s)
+    assert m.size() > 20000

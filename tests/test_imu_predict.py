@@ -256,3 +256,35 @@ def test_frames_feed_the_deskew_oracle(oracle, flimo_lib):
     wo, bo = oracle.prep_deskew(raw, order, cfg, t_begin, 0.0, fo, lq, lp, T)
     assert np.allclose(wp, wo, atol=2e-5) and np.allclose(bp, bo, atol=2e-5)
     assert np.isfinite(wp).all()
+
+
+def test_localizer_mirror_imu_side(flimo_lib):
+    """Localizer::updateIMU over the synthetic stream's IMU: dead reckoning follows the trajectory, the ring hands out
+    the frames of a scan interval, and the LiDAR callback refuses a host-only handle (no CPU path)."""
+    from fast_limo_b200.localizer import Localizer, LocalizerConfig
+    S = synth.Stream(rings=8, azimuths=64, imu_hz=200.0)
+    x_true = S.state(0.0)
+    m = api.Mapper(device=-1)
+    loc = Localizer(m, LocalizerConfig(), pos=x_true[0:3], quat=x_true[3:7], vel=x_true[14:17])
+    assert abs(np.linalg.norm(loc.x[23:26]) - 9.809) < 1e-12
+    assert loc.updatePointCloud(np.zeros(4, api.RAW_POINT), 0.0) is False and loc.last["null"] == "IMU buffer is empty"
+    stamps, dts, acc, gyr = S.imu(0.0, 1.0)
+    assert len(stamps) == 200 and stamps[0] == 0.005 and stamps[-1] == 1.0
+    for t, dt, a, w in zip(stamps, dts, acc, gyr):
+        loc.updateIMU(t, dt, a, w)
+    p, q, v = loc.getWorldState()
+    truth = S.state(1.0)
+    assert np.linalg.norm(p - truth[0:3]) < 2e-2          # explicit Euler over 200 steps: a few mm
+    assert np.linalg.norm(v - truth[14:17]) < 2e-2
+    assert abs(np.dot(q, truth[3:7])) > 1 - 1e-10         # constant rate: the orientation is exact
+    assert np.all(np.diag(loc.P)[:3] > 1.0)               # position uncertainty grew from the initial 1.0
+    fr = m.propagated_frames(0.5, 0.6)
+    ideal = S.frames(0.5, 0.6)
+    assert len(fr) == 22 and abs(fr["time"][0] - 0.495) < 1e-12 and abs(fr["time"][-1] - 0.6) < 1e-12
+    k = {round(t, 6): i for i, t in enumerate(ideal["time"])}
+    sel = [k[round(t, 6)] for t in fr["time"]]
+    assert np.abs(fr["p"] - ideal["p"][sel]).max() < 1e-2 and np.abs(fr["q"] - ideal["q"][sel]).max() < 1e-6
+    assert np.allclose(fr["w"], ideal["w"][sel]) and np.allclose(fr["a"], ideal["a"][sel], atol=1e-6)
+    raw, stamp = S.scan(3)
+    with pytest.raises(api.FlimoError, match="host-only"):
+        loc.updatePointCloud(raw, stamp)

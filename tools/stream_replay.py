@@ -3,7 +3,11 @@ raw message -> filters / time sort / deskew / voxel grid (device) -> iterated up
 Mapper::add (map growth with the reference's down-sampling rule).  Prints per-stage times, map size and
 pose error; with --oracle K the first K scans are also run through the CPU oracle (pose parity + CPU time).
 
-usage: python tools/stream_replay.py [n_scans] [--az 2048] [--leaf 0.5] [--oracle 0]
+usage: python tools/stream_replay.py [n_scans] [--az 2048] [--leaf 0.5] [--oracle 0] [--imu]
+
+--imu: closed loop through fast_limo_b200.localizer (the mirror of Localizer::updateIMU / updatePointCloud): IMU samples
+-> esekf::predict -> propagated frames -> deskew -> update with the carried covariance -> map add, no ground truth on
+the way in (NOT yet run on a GPU: written after the round-1 GPU budget was spent).
 """
 import argparse, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -20,6 +24,7 @@ ap.add_argument("--rings", type=int, default=64)
 ap.add_argument("--dt", type=float, default=0.1, help="sweep duration = scan period (s)")
 ap.add_argument("--imu-hz", type=float, default=200.0)
 ap.add_argument("--speed", type=float, default=10.0)
+ap.add_argument("--imu", action="store_true", help="closed loop: the filter is driven by synthetic IMU samples")
 ap.add_argument("--premap", type=int, default=0, help="points of a pre-built map of the world (config c5: 2 000 000)")
 args = ap.parse_args()
 
@@ -39,6 +44,34 @@ if args.oracle:
 
 if args.premap:
     m.add(synth.sample_map(S.world, args.premap, 1005), 0.0)
+
+if args.imu:
+    from fast_limo_b200.localizer import Localizer, LocalizerConfig
+    x0 = S.state(0.0)
+    loc = Localizer(m, LocalizerConfig(filters=filt, MAX_NUM_ITERS=args.max_iter), pos=x0[0:3], quat=x0[3:7], vel=x0[14:17])
+    t_imu, t_pred, t_scan, n_timed, errs, lat = 0.0, 0.0, 0.0, 0, [], []
+    for k in range(args.n_scans):
+        raw, stamp = S.scan(k)
+        samples = list(zip(*S.imu(t_imu, stamp + args.dt + 1.0 / args.imu_hz)))
+        t_imu = stamp + args.dt + 1.0 / args.imu_hz
+        a0 = time.perf_counter()
+        for smp in samples:
+            loc.updateIMU(*smp)
+        a1 = time.perf_counter()
+        ok = loc.updatePointCloud(raw, stamp)
+        a2 = time.perf_counter()
+        if k >= 10:
+            t_pred += a1 - a0; t_scan += a2 - a1; n_timed += 1
+            lat.append(a2 - a1)
+        errs.append(float(np.linalg.norm(loc.x[0:3] - S.state(loc.imu_stamp)[0:3])))
+        if (k + 1) % 25 == 0 or k + 1 == args.n_scans:
+            print(f"scan {k+1}: {'registered' if ok else loc.last.get('null')}, map {m.size()} pts, pc2match {loc.last.get('n_pc2match')}, "
+                  f"passes {loc.last.get('passes')}, pose err {errs[-1]*1e3:.1f} mm (max {max(errs)*1e3:.1f}); per scan: IMU side "
+                  f"{t_pred/max(n_timed,1)*1e3:.2f} ms ({len(samples)} predictions), LiDAR callback {t_scan/max(n_timed,1)*1e3:.2f} ms", flush=True)
+    if lat:
+        l_ = np.array(lat) * 1e3
+        print(f"LiDAR callback latency: p50 {np.percentile(l_, 50):.2f} ms, p99 {np.percentile(l_, 99):.2f} ms")
+    sys.exit(0)
 lat_pose = []
 t_gen = t_prep = t_upd = t_add = 0.0
 WARM = 10                                      # scans left out of the averages (allocations, lazy module loading)
