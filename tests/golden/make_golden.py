@@ -63,6 +63,37 @@ def prep():
     print("prep", len(raw), "->", len(order), "->", len(v))
 
 
+def imu_inputs():
+    """Seeded inputs of the IMU-rate fixture (shared with the tests): state, covariance, 120 samples at 400 Hz."""
+    from scipy.spatial.transform import Rotation as Rot
+    rng = np.random.default_rng(4242)
+    g = np.array([0.4, -0.3, -9.7])
+    x0 = synth.make_state(rng.normal(0, 20, 3), Rot.from_rotvec([0.1, -0.2, 1.1]).as_quat(), Rot.from_rotvec([0.01, 0.02, -0.03]).as_quat(),
+                          [0.27, -0.03, 0.4], [9.0, 2.0, -0.3], [0.002, -0.001, 0.003], [0.05, 0.02, -0.04], g * 9.809 / np.linalg.norm(g))
+    A = rng.normal(size=(23, 23))
+    P0 = 1e-3 * (A @ A.T / 23 + np.eye(23))
+    n = 120
+    stamps = 50.0 + (1 + np.arange(n)) / 400.0
+    acc = (rng.normal(0, 2.0, (n, 3)) + [0, 0, 9.8]).astype(np.float32)
+    gyr = rng.normal(0, 0.7, (n, 3)).astype(np.float32)
+    return x0, P0, stamps, np.full(n, 1 / 400.0), acc, gyr
+
+
+IMU_COV = (6.e-4, 1.e-2, 1.e-5, 3.e-4)
+IMU_WINDOW = (50.1001, 50.2001)
+
+
+def imu():
+    x0, P0, stamps, dts, acc, gyr = imu_inputs()
+    pr = O.Propagator(x0, P0)
+    for t, dt, a, w in zip(stamps, dts, acc, gyr):
+        pr.propagate(t, dt, a, w, IMU_COV)
+    x, P = pr.get()
+    fr = pr.frames(*IMU_WINDOW)
+    np.savez_compressed(os.path.join(HERE, "imu_predict.npz"), x=x, P=P, frames=fr.view(np.uint8), n_frames=np.int32(len(fr)))
+    print("imu", len(stamps), "samples ->", len(fr), "frames in the window")
+
+
 def ref_octree_inputs():
     """Seeded batches (dense enough to trigger the drop rule and leaf splits, one batch grows the root) and
     queries for the reference-octree fixture."""
@@ -121,6 +152,7 @@ def ref_octree():
 if __name__ == "__main__":
     ref_octree()
     prep()
+    imu()
     one("tiny", 2, max_pc2match=1 << 18, max_matches=1 << 18)
     one("tiny", 3, max_pc2match=1500, max_matches=400)       # both first-N caps active
     one("c1", 0, max_pc2match=1 << 18, max_matches=1 << 18)  # BASELINE configs[0]: 16k scan, 100k map, 1 pass

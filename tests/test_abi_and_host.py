@@ -89,3 +89,41 @@ def test_unpack96_layout(flimo_lib):
     assert np.array_equal(r.HTH, r.HTH.T)
     assert np.array_equal(r.HTh, np.arange(78, 90))
     assert (r.n_rows, r.sum_sq_res, r.n_valid) == (90, 91.0, 92)
+
+
+def _prototypes():
+    """name -> number of parameters, parsed from include/flimo.h (comments stripped)."""
+    hdr = open(os.path.join(ROOT, "include", "flimo.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", " ", hdr, flags=re.S)
+    out = {}
+    for name, args in re.findall(r"\b(flimo_[a-z0-9_]+)\s*\(([^()]*)\)\s*;", hdr):
+        args = args.strip()
+        out[name] = 0 if args in ("", "void") else len(args.split(","))
+    return out
+
+
+def test_ctypes_declarations_match_header(flimo_lib):
+    """Every prototype of flimo.h has ctypes argtypes of the same arity (an ABI drift between the header and
+    fast_limo_b200/_lib.py would otherwise only show up as stack garbage on the GPU box)."""
+    protos = _prototypes()
+    assert set(protos) == set(_lib.SYMBOLS)
+    for name, n_args in protos.items():
+        fn = getattr(flimo_lib, name)
+        if fn.argtypes is None:
+            assert n_args == 0, f"{name}: {n_args} parameters in flimo.h, no argtypes in _lib.py"
+        else:
+            assert len(fn.argtypes) == n_args, f"{name}: {n_args} parameters in flimo.h, {len(fn.argtypes)} in _lib.py"
+
+
+def test_struct_layouts_match_header(flimo_lib, tmp_path):
+    """sizeof of every struct of flimo.h as gcc lays it out == the ctypes / numpy mirrors."""
+    import subprocess
+    src = tmp_path / "sizes.c"
+    src.write_text('#include <stdio.h>\n#include "flimo.h"\nint main(void) { printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(flimo_cfg), '
+                   'sizeof(flimo_prep_cfg), sizeof(flimo_frame), sizeof(flimo_msg_layout), sizeof(flimo_imu), sizeof(flimo_stats)); return 0; }\n')
+    exe = tmp_path / "sizes"
+    subprocess.run(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    sizes = [int(v) for v in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
+    mirrors = [C.sizeof(_lib.FlimoCfg), C.sizeof(_lib.FlimoPrepCfg), api.FRAME.itemsize, C.sizeof(_lib.FlimoMsgLayout),
+               C.sizeof(_lib.FlimoImu), C.sizeof(_lib.FlimoStats)]
+    assert sizes == mirrors

@@ -58,3 +58,35 @@ def test_oracle_prep_matches_golden(oracle):
     # sinf / cosf come from libm: allow an ulp-level difference between machines
     assert np.abs(w - g["world"]).max() <= 2e-5 and np.abs(b - g["xt2"]).max() <= 2e-5
     assert np.array_equal(O.prep_voxel(g["xt2"], 1.0), g["voxel"])
+
+
+def _golden_module():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(G, "make_golden.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def test_imu_predict_matches_golden(oracle, flimo_lib):
+    """esekf::predict x 120 + the frames of one scan window: oracle AND product (host algebra of libflimo_cuda)
+    against tests/golden/imu_predict.npz."""
+    from fast_limo_b200 import api
+    mod = _golden_module()
+    g = np.load(os.path.join(G, "imu_predict.npz"))
+    x0, P0, stamps, dts, acc, gyr = mod.imu_inputs()
+    pr = oracle.Propagator(x0, P0)
+    m = api.Mapper(device=-1)
+    x, P = x0, P0
+    for t, dt, a, w in zip(stamps, dts, acc, gyr):
+        pr.propagate(t, dt, a, w, mod.IMU_COV)
+        x, P = m.ekf_predict(x, P, t, dt, a, w, mod.IMU_COV)
+    gold_fr = np.frombuffer(g["frames"].tobytes(), oracle.FRAME)
+    assert len(gold_fr) == int(g["n_frames"]) == 42
+    for (xx, PP, fr) in ((*pr.get(), pr.frames(*mod.IMU_WINDOW)), (x, P, m.propagated_frames(*mod.IMU_WINDOW))):
+        # sin / cos / atan come from libm: allow last-bit differences between machines
+        assert np.allclose(xx, g["x"], rtol=0, atol=1e-11)
+        assert np.allclose(PP, g["P"], rtol=1e-10, atol=1e-16)
+        assert np.array_equal(fr["time"], gold_fr["time"]) and np.array_equal(fr["a"], gold_fr["a"]) and np.array_equal(fr["w"], gold_fr["w"])
+        for k in ("q", "p", "v", "bg", "ba", "g"):
+            assert np.allclose(fr[k], gold_fr[k], rtol=3e-7, atol=1e-9)

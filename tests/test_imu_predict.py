@@ -288,3 +288,50 @@ def test_localizer_mirror_imu_side(flimo_lib):
     raw, stamp = S.scan(3)
     with pytest.raises(api.FlimoError, match="host-only"):
         loc.updatePointCloud(raw, stamp)
+
+
+def test_ring_selection_property(flimo_lib):
+    """hypothesis: for arbitrary (irregular, possibly repeated) stamps and windows the ring returns exactly what the
+    reference's iterator walk returns."""
+    from hypothesis import given, settings, strategies as st
+    m = api.Mapper(device=-1)
+    x0, P0 = _state(41), synth.default_P0()
+    a, w = np.float32([0, 0, G]), np.float32([0, 0, 0.1])
+
+    @settings(max_examples=150, deadline=None)
+    @given(st.lists(st.integers(0, 3), min_size=0, max_size=40), st.integers(-5, 130), st.integers(-5, 130))
+    def check(gaps, i0, i1):
+        m.propagated_clear()
+        t, stamps = 0.0, []
+        for gp in gaps:                                   # gaps of 0 repeat a stamp (two IMU messages with one time)
+            t += gp * 0.25
+            stamps.append(t)
+            m.ekf_predict(x0, P0, t, 0.005, a, w, COV)
+        t0, t1 = i0 * 0.125, i1 * 0.125                   # on and between the sample times
+        exp = _select(stamps[::-1], t0, t1)
+        if exp is None:
+            with pytest.raises(api.FlimoError, match="IMU behind"):
+                m.propagated_frames(t0, t1)
+        else:
+            assert list(m.propagated_frames(t0, t1)["time"]) == exp
+
+    check()
+
+
+def test_predict_keeps_covariance_symmetric_positive(flimo_lib):
+    """2000 predictions (10 s at 200 Hz) from the reference's initial covariance: P stays symmetric positive definite
+    and grows monotonically in the unobserved directions."""
+    m = api.Mapper(device=-1)
+    x, P = _state(43), synth.default_P0()
+    rng = np.random.default_rng(43)
+    tr = [np.trace(P)]
+    for i in range(2000):
+        a = (rng.normal(0, 0.5, 3) + [0, 0, G]).astype(np.float32)
+        w = rng.normal(0, 0.3, 3).astype(np.float32)
+        x, P = m.ekf_predict(x, P, 0.005 * (i + 1), 0.005, a, w, COV)
+        if i % 500 == 499:
+            assert np.abs(P - P.T).max() <= 1e-12 * np.abs(P).max()
+            assert np.linalg.eigvalsh(0.5 * (P + P.T)).min() > 0
+            tr.append(np.trace(P))
+    assert all(b > a_ for a_, b in zip(tr, tr[1:]))
+    assert abs(np.linalg.norm(x[3:7]) - 1) < 1e-10 and abs(np.linalg.norm(x[23:26]) - G) < 1e-9
