@@ -133,9 +133,44 @@ class Localizer:
         return False
 
     # -- getters ---------------------------------------------------------------------------------------------------
+    def _state_f32(self):
+        x = self.x
+        return dict(p=x[0:3].astype(np.float32), q=x[3:7].astype(np.float32), qLI=x[7:11].astype(np.float32),
+                    pLI=x[11:14].astype(np.float32), v=x[14:17].astype(np.float32), bg=x[17:20].astype(np.float32),
+                    ba=x[20:23].astype(np.float32), g=x[23:26].astype(np.float32),
+                    w=None if self.last_imu is None else self.last_imu[1], a=None if self.last_imu is None else self.last_imu[0],
+                    time=self.imu_stamp)
+
     def getWorldState(self):
-        """Position, orientation (xyzw) and velocity of the filter state (State(_iKFoM.get_x()), :160-171)."""
-        return self.x[0:3].copy(), self.x[3:7].copy(), self.x[14:17].copy()
+        """:174-188: State(_iKFoM.get_x()) with the last IMU sample and stamp; v is rotated into the body frame."""
+        out = self._state_f32()
+        out["v"] = _RT_f32(out["q"], (0, 0, 0))[:3, :3].T @ out["v"]
+        return out
+
+    def getBodyState(self):
+        """:157-172: the same in the LiDAR frame — p += pLI, q *= qLI (as the reference composes them), local velocity."""
+        out = self._state_f32()
+        out["p"] = out["p"] + out["pLI"]
+        x1, y1, z1, w1 = out["q"]
+        x2, y2, z2, w2 = out["qLI"]
+        out["q"] = np.float32([w1 * x2 + x1 * w2 + y1 * z2 - z1 * y2, w1 * y2 + y1 * w2 + z1 * x2 - x1 * z2,
+                               w1 * z2 + z1 * w2 + x1 * y2 - y1 * x2, w1 * w2 - x1 * x2 - y1 * y2 - z1 * z2])
+        out["v"] = _RT_f32(out["q"], (0, 0, 0))[:3, :3].T @ out["v"]
+        return out
+
+    def getPoseCovariance(self):
+        """:214-229: 6x6 [orientation, position] blocks of P, flattened column-major like Eigen::Map."""
+        P = self.P
+        out = np.zeros((6, 6))
+        out[0:3, 0:3], out[0:3, 3:6], out[3:6, 0:3], out[3:6, 3:6] = P[3:6, 3:6], P[3:6, 0:3], P[0:3, 3:6], P[0:3, 0:3]
+        return out.flatten(order="F")
+
+    def getTwistCovariance(self):
+        """:231-244, as written: the block at (6, 6) — the extrinsic rotation, not the velocity at 12 — and cov_gyro."""
+        out = np.zeros((6, 6))
+        out[0:3, 0:3] = self.P[6:9, 6:9]
+        out[3:6, 3:6] = self.config.cov_gyro * np.eye(3)
+        return out.flatten(order="F")
 
     def get_pc2match_pointcloud(self):
         return self.map.prep_get(3)

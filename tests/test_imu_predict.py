@@ -272,8 +272,16 @@ def test_localizer_mirror_imu_side(flimo_lib):
     assert len(stamps) == 200 and stamps[0] == 0.005 and stamps[-1] == 1.0
     for t, dt, a, w in zip(stamps, dts, acc, gyr):
         loc.updateIMU(t, dt, a, w)
-    p, q, v = loc.getWorldState()
+    p, q, v = loc.x[0:3], loc.x[3:7], loc.x[14:17]
     truth = S.state(1.0)
+    ws, bs = loc.getWorldState(), loc.getBodyState()
+    assert abs(ws["v"][0] - S.v) < 2e-2 and abs(ws["v"][1]) < 2e-2 and ws["time"] == 1.0    # body-frame velocity: forward
+    assert np.allclose(bs["p"], ws["p"]) and np.allclose(bs["v"], ws["v"], atol=1e-6)      # identity extrinsics here
+    assert np.array_equal(ws["w"], gyr[-1]) and np.array_equal(ws["a"], acc[-1])
+    pc = loc.getPoseCovariance().reshape(6, 6, order="F")
+    assert np.array_equal(pc[3:6, 3:6], loc.P[0:3, 0:3]) and np.array_equal(pc[0:3, 3:6], loc.P[3:6, 0:3])
+    tc = loc.getTwistCovariance().reshape(6, 6, order="F")
+    assert np.array_equal(tc[0:3, 0:3], loc.P[6:9, 6:9]) and tc[4, 4] == loc.config.cov_gyro
     assert np.linalg.norm(p - truth[0:3]) < 2e-2          # explicit Euler over 200 steps: a few mm
     assert np.linalg.norm(v - truth[14:17]) < 2e-2
     assert abs(np.dot(q, truth[3:7])) > 1 - 1e-10         # constant rate: the orientation is exact
