@@ -241,6 +241,7 @@ def main():
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(h_stream)
+        x, passes = None, 0
         for s in range(steps):
             x, passes = register(s % N_SCANS, from_host)
         e1.record(h_stream)
@@ -261,6 +262,15 @@ def main():
     st1 = m.stats()
     ms_e2e, x2, _ = timed(args.steps, True)
     clocks = sampler.stop()
+    # Every 8th flimo_update runs with one launch per pass and CUDA events around the kernel.  A run with very few
+    # steps may have none of those inside the timed region: time the kernel over 8 further scans right after it
+    # (all ranks take the same branch: the call count is the same on every rank).
+    st_k0, st_k1, kernel_where = st0, st1, "inside the timed region"
+    if st1["match_timed"] - st0["match_timed"] == 0:
+        st_k0 = m.stats()
+        timed(8, False)
+        st_k1 = m.stats()
+        kernel_where = "over 8 further scans right after the timed region (steps < 8)"
 
     # sanity: the registration really converged onto the true pose of the last scan
     k_last = (args.steps - 1) % N_SCANS
@@ -270,12 +280,12 @@ def main():
     if rank == 0:
         value = args.steps / (ms / 1e3)
         launches = st1["match_launches"] - st0["match_launches"]
-        timed = st1["match_timed"] - st0["match_timed"]
-        if timed == 0:
-            raise SystemExit("no event-timed launch of the fused kernel inside the timed region (steps too small?)")
-        k1_ms = (st1["match_ms_total"] - st0["match_ms_total"]) / timed
-        pp = st1["persist_passes"] - st0["persist_passes"]
-        k1_in_ms = (st1["persist_ms_total"] - st0["persist_ms_total"]) / pp if pp else None
+        n_timed = st_k1["match_timed"] - st_k0["match_timed"]
+        if n_timed == 0:
+            raise SystemExit("no event-timed launch of the fused kernel (FLIMO_TIME_EVERY=0?)")
+        k1_ms = (st_k1["match_ms_total"] - st_k0["match_ms_total"]) / n_timed
+        pp = st_k1["persist_passes"] - st_k0["persist_passes"]
+        k1_in_ms = (st_k1["persist_ms_total"] - st_k0["persist_ms_total"]) / pp if pp else None
         peak, peak_src = _peaks()
         achieved = (hi - lo) * A_PM / (k1_ms * 1e-3) / 1e9
         out = {
@@ -292,7 +302,7 @@ def main():
             "gpu_launches": int(st1["kernel_launches"] - st0["kernel_launches"]),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": _traffic(), "peak_source": peak_src, "kernel": "match_reduce_kernel",
-                         "kernel_ms": k1_ms, "passes": int(launches), "passes_event_timed": int(timed),
+                         "kernel_ms": k1_ms, "passes": int(launches), "passes_event_timed": int(n_timed), "kernel_timed": kernel_where,
                          "kernel_ms_in_persistent_kernel": k1_in_ms, "bytes_per_launch": (hi - lo) * A_PM,
                          "note": "kernel_ms = CUDA-event time of one-launch-per-pass executions (every 8th scan); the other scans run all "
                                  "passes inside one persistent launch, timed in-kernel with %globaltimer"},
