@@ -163,3 +163,59 @@ def test_block_guarantee_radius_is_sound():
             if r2 > 0:
                 worst = min(worst, d2 / r2)
     assert worst < 1.5                                      # the adversarial points really probe the margin
+
+
+# ---- the scan's storage permutation (flimo_api.cu: coprime_stride / mod_inverse; match_kernel.cu: Barrett) ----
+def _coprime_stride(n):
+    from math import gcd
+    if n < 3:
+        return 1
+    s = int(0.6180339887 * n) | 1
+    while gcd(s, n) != 1:
+        s += 2
+    return s % n if s % n else 1
+
+
+def _mod_inverse(a, n):
+    t, nt, r, nr = 0, 1, n, a % n
+    while nr:
+        q = r // nr
+        t, nt = nt, t - q * nt
+        r, nr = nr, r - q * nr
+    return t + n if t < 0 else t
+
+
+def _barrett(prod, n, magic):
+    r = prod - ((prod * magic) >> 64) * n          # __umul64hi(prod, magic) * n
+    return r - n if r >= n else r
+
+
+def test_scan_permutation_model():
+    """Position j of the permuted order holds original point (j * s^-1) mod n, where the upload kernel stores point i
+    at (i * s) mod n; the kernel evaluates the modulus with ONE multiply-high and ONE conditional subtraction."""
+    rng = np.random.default_rng(5)
+    sizes = [3, 4, 5, 6, 7, 8, 9, 10, 12, 15, 16, 17, 255, 256, 257, 1000, 4095, 4096, 16384, 131072, 300000, (1 << 20) - 1, 1 << 20,
+             (1 << 22) + 1] + [int(v) for v in rng.integers(3, 1 << 22, 40)]
+    for n in sizes:
+        s = _coprime_stride(n)
+        inv = _mod_inverse(s, n)
+        assert 0 < s < n and (s * inv) % n == 1
+        magic = ((1 << 64) - 1) // n
+        qs = np.unique(np.concatenate([np.arange(min(n, 64)), np.arange(max(n - 64, 0), n), rng.integers(0, n, 200)]))
+        for q in qs:
+            q = int(q)
+            orig = _barrett(q * inv, n, magic)
+            assert orig == (q * inv) % n                   # the reduction is exact
+            assert (orig * s) % n == q                     # and inverts the upload kernel's placement
+    # a full bijection check on a few sizes
+    for n in (3, 10, 257, 4096, 131072):
+        s, magic = _coprime_stride(n), ((1 << 64) - 1) // n
+        inv = _mod_inverse(s, n)
+        j = np.arange(n, dtype=object)
+        orig = np.array([_barrett(int(v) * inv, n, magic) for v in j[: min(n, 20000)]])
+        assert len(set(orig.tolist())) == len(orig)
+    # worst case for the single conditional subtraction: products up to (n - 1)^2 < 2^63
+    for n in (3, (1 << 20) + 7, (1 << 31) - 1):
+        magic = ((1 << 64) - 1) // n
+        for prod in ((n - 1) * (n - 1), (n - 1) * (n - 2), n * (n - 1) - 1, n - 1, n, 0):
+            assert _barrett(prod, n, magic) == prod % n
