@@ -131,3 +131,38 @@ def test_jacobian_is_derivative_of_residual(oracle):
         same = both & (np.abs(r1["plane"][idx] - r0["plane"][idx]).max(1) < 1e-6)
         assert same.sum() > 20
         assert np.allclose(num[same], H[same, a], atol=5e-3)
+
+
+def test_fixed_radius_search_is_outcome_equivalent(oracle):
+    """SURVEY section 4, property tier: a search that gives up beyond MAX_DIST_PLANE (what the CUDA kernel does — it
+    never widens a block past the gate radius) produces the same matches as the reference's unrestricted exact kNN:
+    every accepted match has all five neighbours strictly inside the gate, and for those queries the five nearest
+    among the points inside the gate ARE the five nearest overall."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=25, deadline=None)
+    @given(st.integers(0, 10 ** 6), st.floats(0.3, 3.0), st.sampled_from([0.5, 2.0, 6.0]))
+    def check(seed, spread, gate):
+        rng = np.random.default_rng(seed)
+        n = int(rng.integers(50, 4000))
+        # planar patches (so that some matches are accepted) + clutter at a density set by `spread`
+        plane = np.c_[rng.uniform(-8, 8, (n, 2)), 1.5 + rng.normal(0, 0.004, n)]
+        clutter = rng.normal(0, 6 * spread, (n // 4, 3))
+        pts = np.r_[plane, clutter].astype(np.float32)
+        q = np.c_[rng.uniform(-9, 9, (200, 2)), 1.5 + rng.uniform(-0.5, 1.0, 200)].astype(np.float32)
+        m = oracle.OracleMap()
+        m.add(pts)
+        cfg = oracle.make_cfg(max_pc2match=10 ** 6, max_matches=10 ** 6, max_dist_plane=gate)
+        r = m.match(cfg, synth.make_state([0, 0, 0], [0, 0, 0, 1])[:14], q)
+        d2 = _bf_d2(q, pts)
+        full5 = np.sort(d2, axis=1)[:, :5]
+        inside = np.where(d2 < np.float32(gate), d2, np.float32(np.inf))     # strict test, Plane.cpp:47
+        near5 = np.sort(inside, axis=1)[:, :5]
+        good = r["good"]
+        assert (full5[good, 4] < gate).all()                                  # accepted => the 5th neighbour passed the gate
+        assert np.array_equal(near5[good], full5[good])                       # => the restricted search saw the same five
+        assert np.array_equal(r["nn_d2"][good], full5[good])
+        # and a query whose restricted search finds fewer than five can never be accepted
+        assert not good[~np.isfinite(near5[:, 4])].any()
+
+    check()
