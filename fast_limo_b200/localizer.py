@@ -8,8 +8,9 @@
 
 Only sequencing lives here; every stage is a call into the library (`api.Mapper`): filters / sort / deskew / voxel
 grid and the registration on the GPU, prediction and the propagated-state ring in the library's host algebra.
-What is NOT mirrored: IMU calibration and the IMU -> base-link transform (:409-510, :697-728) — `updateIMU` takes
-the sample as `imu_buffer` stores it — the debug clouds, the CPU statistics and the condition-variable wait of
+What is NOT mirrored: the standstill IMU calibration (:409-510) — `updateIMU` takes the sample as `imu_buffer` stores
+it, `updateIMU_raw` applies the IMU -> base-link transform and the intrinsic correction first (:697-728, :512-520) —
+the debug clouds, the CPU statistics and the condition-variable wait of
 `propagatedFromTimeRange` (a scan that arrives before its IMU data raises instead).
 """
 from dataclasses import dataclass, field
@@ -89,6 +90,25 @@ class Localizer:
         self.last_imu = (np.asarray(lin_accel, np.float32), np.asarray(ang_vel, np.float32))
         self.n_imu += 1
         self.x, self.P = self.map.ekf_predict(self.x, self.P, stamp, dt, lin_accel, ang_vel, self._cov4())
+
+    def updateIMU_raw(self, stamp, lin_accel, ang_vel, imu2baselink_R=np.eye(3), imu2baselink_t=(0, 0, 0), accel_sm=np.eye(3),
+                      bias_accel=(0, 0, 0), bias_gyro=(0, 0, 0)):
+        """:403-404 + :512-520 for a sample in the IMU frame: imu2baselink (:697-728; float32 like the reference: dt from
+        the stamps with the 1/200 s fallback, rotation into the base-link frame, lever-arm terms) and the intrinsic
+        correction, then `updateIMU`.  The standstill calibration (:409-510) stays with the caller."""
+        f32 = np.float32
+        R, t = np.asarray(imu2baselink_R, f32), np.asarray(imu2baselink_t, f32)
+        dt = float(stamp) - getattr(self, "_prev_imu_stamp", 0.0)
+        if dt == 0.0 or dt > 0.1:
+            dt = 1.0 / 200.0
+        w = R @ np.asarray(ang_vel, f32)
+        w_prev = getattr(self, "_ang_vel_prev", w)            # function-local static, initialised with the first sample
+        a = R @ np.asarray(lin_accel, f32)
+        a = a + np.cross(((w - w_prev) / f32(dt)).astype(f32), -t) + np.cross(w, np.cross(w, -t))
+        self._ang_vel_prev, self._prev_imu_stamp = w, float(stamp)
+        a = (np.asarray(accel_sm, f32) @ a.astype(f32)) - np.asarray(bias_accel, f32)
+        w = w - np.asarray(bias_gyro, f32)
+        self.updateIMU(stamp, dt, a.astype(f32), w.astype(f32))
 
     # -- LiDAR callback -------------------------------------------------------------------------------------------
     def updatePointCloud(self, raw, time_stamp):
