@@ -16,7 +16,7 @@ SYMBOLS = [
     "flimo_map_get_points", "flimo_scan_set", "flimo_scan_set_device", "flimo_scan_prefetch", "flimo_scan_shard",
     "flimo_match_reduce", "flimo_match_reduce_async", "flimo_unpack96", "flimo_match_debug",
     "flimo_update", "flimo_ekf_begin", "flimo_ekf_state", "flimo_ekf_step", "flimo_ekf_end",
-    "flimo_scan_to_world", "flimo_prep_filter_sort", "flimo_prep_filter_sort_msg", "flimo_prep_deskew", "flimo_prep_get", "flimo_voxel_grid", "flimo_get_stats", "flimo_stream", "flimo_exchange_attach", "flimo_match_reduce_exchange", "flimo_update_exchange",
+    "flimo_scan_to_world", "flimo_map_add_scan", "flimo_prep_filter_sort", "flimo_prep_filter_sort_msg", "flimo_prep_deskew", "flimo_prep_get", "flimo_voxel_grid", "flimo_get_stats", "flimo_stream", "flimo_exchange_attach", "flimo_match_reduce_exchange", "flimo_update_exchange",
     "flimo_ekf_predict", "flimo_propagated_frames", "flimo_propagated_clear",
 ]
 
@@ -135,6 +135,7 @@ def load():
     L.flimo_ekf_step.argtypes = [vp, pd, pd, i64, C.POINTER(C.c_int)]
     L.flimo_ekf_end.argtypes = [vp, pd, pd]
     L.flimo_scan_to_world.argtypes = [vp, pd, pf, sz, C.POINTER(sz)]
+    L.flimo_map_add_scan.argtypes = [vp, pd, dbl]
     L.flimo_get_stats.argtypes = [vp, C.POINTER(FlimoStats)]
     L.flimo_prep_filter_sort.argtypes = [vp, vp, sz, dbl, C.POINTER(FlimoPrepCfg), C.POINTER(sz), pd]
     L.flimo_prep_filter_sort_msg.argtypes = [vp, vp, sz, sz, C.POINTER(FlimoMsgLayout), dbl, C.POINTER(FlimoPrepCfg), C.POINTER(sz), pd]

@@ -175,15 +175,18 @@ class Mapper:
         sc = np.ascontiguousarray(scan, dtype=np.float32).reshape(-1, np.shape(scan)[-1] if np.ndim(scan) == 2 else 3)
         self._ck(self._L.flimo_scan_set(self._h, sc.ctypes.data, sc.shape[0], 4 * sc.shape[1]))
         self._scan_n = min(sc.shape[0], self.config.MAX_NUM_PC2MATCH)
+        self._scan_n_full = sc.shape[0]
 
     def set_scan_device(self, dptr, n, stride_bytes):
         self._ck(self._L.flimo_scan_set_device(self._h, C.c_void_p(dptr), n, stride_bytes))
         self._scan_n = min(n, self.config.MAX_NUM_PC2MATCH)
+        self._scan_n_full = n
 
     def set_scan_host(self, hptr, n, stride_bytes):
         """flimo_scan_set on a raw host pointer (e.g. pinned memory); binds a prefetched copy if there is one."""
         self._ck(self._L.flimo_scan_set(self._h, C.c_void_p(hptr), n, stride_bytes))
         self._scan_n = min(n, self.config.MAX_NUM_PC2MATCH)
+        self._scan_n_full = n
 
     def prefetch_scan_host(self, hptr, n, stride_bytes):
         """flimo_scan_prefetch: start the H2D copy of the NEXT scan on the copy stream."""
@@ -220,6 +223,7 @@ class Mapper:
         n = C.c_size_t(0)
         self._ck(self._L.flimo_prep_deskew(self._h, fr.ctypes.data, len(fr), _fp(lq), _fp(lp), _fp(T), float(offset), C.byref(n)))
         self._scan_n = min(int(n.value), self.config.MAX_NUM_PC2MATCH)
+        self._scan_n_full = int(n.value)
         return int(n.value)
 
     def prep_get(self, what):
@@ -283,12 +287,18 @@ class Mapper:
                     levels=out[:, 14].astype(np.int32), first_count=out[:, 15].astype(np.int32))
 
     def scan_to_world(self, state):
+        """pcl::transformPointCloud(pc2match -> world) (Localizer.cpp:361): the WHOLE bound cloud, original order."""
         st = np.ascontiguousarray(np.asarray(state, np.float64)[:14])
-        n = self._scan_n
+        n = self._scan_n_full
         out = np.zeros((max(n, 1), 3), np.float32)
         got = C.c_size_t(0)
         self._ck(self._L.flimo_scan_to_world(self._h, _dp(st), _fp(out), n, C.byref(got)))
         return out[:n]
+
+    def add_scan(self, state, time=0.0):
+        """Localizer.cpp:361 + :377 on the device: transform the bound cloud with `state` and Mapper::add it."""
+        st = np.ascontiguousarray(np.asarray(state, np.float64)[:14])
+        self._ck(self._L.flimo_map_add_scan(self._h, _dp(st), float(time)))
 
     def stats(self):
         s = FlimoStats()

@@ -55,6 +55,7 @@ struct flimo_ctx {
   bool pref_issued = false;
   float4* scan_tmp = nullptr;
   size_t scan_cap = 0, scan_n = 0;
+  size_t scan_n_full = 0;         // points of the bound cloud before the MAX_NUM_PC2MATCH cap (all of them go to the map)
   size_t shard_begin = 0, shard_end = 0;
   uint32_t* scan_keys = nullptr;
   size_t scan_keys_cap = 0;
@@ -826,6 +827,7 @@ int flimo_scan_set_device(flimo_handle h, const void* d_xyz, size_t n, size_t st
   h->raw_scan = static_cast<const unsigned char*>(d_xyz);
   h->raw_stride = stride_bytes;
   h->scan_n = nq;
+  h->scan_n_full = n;
   h->shard_begin = 0;
   h->shard_end = nq;
   h->packed_valid = false;
@@ -850,8 +852,7 @@ int flimo_scan_prefetch(flimo_handle h, const float* xyz_body, size_t n, size_t 
   if (!h || (!xyz_body && n)) return fail(h, FLIMO_ERR_INVALID, "null argument");
   if (stride_bytes < 12 || stride_bytes % 4) return fail(h, FLIMO_ERR_INVALID, "stride must be a multiple of 4 and >= 12");
   NEED_GPU(h);
-  const size_t cap = h->cfg.MAX_NUM_PC2MATCH > 0 ? (size_t)h->cfg.MAX_NUM_PC2MATCH : 0;
-  const size_t nq = n > cap ? cap : n;
+  const size_t nq = n;                                            // the whole cloud travels: Mapper::add takes all of it
   h->pref_idx = -1;
   h->pref_issued = false;
   if (nq == 0) return FLIMO_OK;
@@ -869,8 +870,7 @@ int flimo_scan_set(flimo_handle h, const float* xyz_body, size_t n, size_t strid
   if (!h || (!xyz_body && n)) return fail(h, FLIMO_ERR_INVALID, "null argument");
   if (stride_bytes < 12 || stride_bytes % 4) return fail(h, FLIMO_ERR_INVALID, "stride must be a multiple of 4 and >= 12");
   NEED_GPU(h);
-  const size_t cap = h->cfg.MAX_NUM_PC2MATCH > 0 ? (size_t)h->cfg.MAX_NUM_PC2MATCH : 0;
-  const size_t nq = n > cap ? cap : n;
+  const size_t nq = n;           // the first-N rule (Mapper.cpp:63-69) is applied by flimo_scan_set_device; the map gets all points
   if (nq == 0) return flimo_scan_set_device(h, h->scan_stage[0], 0, stride_bytes);
   int idx;
   if (h->pref_idx >= 0 && h->pref_src == xyz_body && h->pref_n == nq && h->pref_stride == stride_bytes) {
@@ -1078,22 +1078,31 @@ int flimo_match_debug(flimo_handle h, const double state14[14], float* out16, si
 int flimo_scan_to_world(flimo_handle h, const double state14[14], float* out_xyz, size_t cap_points, size_t* n_points) {
   if (!h || !state14 || !n_points) return fail(h, FLIMO_ERR_INVALID, "null argument");
   NEED_GPU(h);
-  const size_t nq = h->scan_n;
+  const size_t nq = h->scan_n_full;                              // the whole pc2match, not only the matched first N (Localizer.cpp:361)
   *n_points = nq;
   if (!out_xyz || nq == 0) return FLIMO_OK;
   CU(h, grow(&h->xyz_out, &h->xyz_cap, nq * 3));
   PoseConsts pc;
   make_pose(state14, pc);
-  {
-    const int prc = pack_bound_scan(h);
-    if (prc) return prc;
-  }
-  CU(h, transform_scan(h->scan, nq, pc, h->xyz_out, h->stream));
+  CU(h, transform_raw(h->raw_scan, nq, h->raw_stride, pc, h->xyz_out, h->stream));
   h->stats.kernel_launches++;
   const size_t m = nq < cap_points ? nq : cap_points;
   CU(h, cudaMemcpyAsync(out_xyz, h->xyz_out, m * 3 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
   CU(h, cudaStreamSynchronize(h->stream));
   return FLIMO_OK;
+}
+
+int flimo_map_add_scan(flimo_handle h, const double state14[14], double stamp) {
+  if (!h || !state14) return fail(h, FLIMO_ERR_INVALID, "null argument");
+  NEED_GPU(h);
+  const size_t nq = h->scan_n_full;
+  if (nq < 1) return FLIMO_OK;
+  CU(h, grow(&h->xyz_out, &h->xyz_cap, nq * 3));
+  PoseConsts pc;
+  make_pose(state14, pc);
+  CU(h, transform_raw(h->raw_scan, nq, h->raw_stride, pc, h->xyz_out, h->stream));
+  h->stats.kernel_launches++;
+  return flimo_map_add_device(h, h->xyz_out, nq, 12, stamp);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -163,6 +163,7 @@ cudaError_t pack_scan(const void* d_src, size_t n, size_t stride_bytes, float4* 
 cudaError_t scan_prepare(const void* d_src, size_t n, size_t stride_bytes, bool sort, unsigned int perm_stride, float4* scan, float4* tmp, void** cub_tmp,
                          size_t* cub_tmp_bytes, uint32_t** keys, size_t* keys_cap, cudaStream_t st, uint64_t* launches);
 cudaError_t scan_prepare_reserve(size_t n, void** cub_tmp, size_t* cub_tmp_bytes, uint32_t** keys, size_t* keys_cap);
+cudaError_t transform_raw(const unsigned char* d_src, size_t n, size_t stride_bytes, const PoseConsts& pc, float* d_out_xyz, cudaStream_t st);
 cudaError_t transform_scan(const float4* scan, size_t n, const PoseConsts& pc, float* d_out_xyz, cudaStream_t st);
 
 // map_insert.cu — the reference's incremental insert rule (Octree::update, Octree.hpp:341-432)

@@ -235,6 +235,28 @@ cudaError_t pack_scan(const void* d_src, size_t n, size_t stride_bytes, float4* 
   return cudaGetLastError();
 }
 
+// pcl::transformPointCloud of a strided xyz cloud, original order (same float operation order as the measurement pass).
+__global__ void __launch_bounds__(256) transform_raw_kernel(const unsigned char* __restrict__ src, size_t n, size_t stride, const PoseConsts pc,
+                                                            float* __restrict__ out) {
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float* p = reinterpret_cast<const float*>(src + i * stride);
+  const float x = p[0], y = p[1], z = p[2];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    float acc = __fmul_rn(pc.R_wb[3 * r], x);
+    acc = __fadd_rn(__fmul_rn(pc.R_wb[3 * r + 1], y), acc);
+    acc = __fadd_rn(__fmul_rn(pc.R_wb[3 * r + 2], z), acc);
+    out[3 * i + r] = __fadd_rn(pc.t_wb[r], acc);
+  }
+}
+
+cudaError_t transform_raw(const unsigned char* d_src, size_t n, size_t stride_bytes, const PoseConsts& pc, float* d_out_xyz, cudaStream_t st) {
+  if (n == 0) return cudaSuccess;
+  transform_raw_kernel<<<(unsigned int)((n + 255) / 256), 256, 0, st>>>(d_src, n, stride_bytes, pc, d_out_xyz);
+  return cudaGetLastError();
+}
+
 cudaError_t transform_scan(const float4* scan, size_t n, const PoseConsts& pc, float* d_out_xyz, cudaStream_t st) {
   if (n == 0) return cudaSuccess;
   transform_kernel<<<nblk(n), 256, 0, st>>>(scan, n, pc, d_out_xyz);

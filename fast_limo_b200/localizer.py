@@ -141,8 +141,7 @@ class Localizer:
         self.x, self.P, passes = self.map.update(self.x, self.P, c.MAX_NUM_ITERS, c.LIMITS)       # :333
         self.last["passes"] = passes
         self.lidar2baselink_T = _RT_f32(self.x[7:11], self.x[11:14])                        # :356
-        world = self.map.scan_to_world(self.x)                                              # :361
-        self.map.add(world, self.scan_stamp)                                                # :377
+        self.map.add_scan(self.x, self.scan_stamp)                                          # :361 + :377, all of pc2match
         self.prev_scan_stamp = self.scan_stamp                                              # :398
         return True
 

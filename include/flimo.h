@@ -252,10 +252,16 @@ int flimo_propagated_frames(flimo_handle h, double start_time, double end_time, 
                             size_t* n_frames);
 int flimo_propagated_clear(flimo_handle h);
 
-/* pcl::transformPointCloud(pc2match -> world) of Localizer.cpp:361-374 on the device copy of the
- * scan, using State::get_RT() of state14; optional convenience so final_scan can come from the GPU. */
+/* pcl::transformPointCloud(pc2match -> world) of Localizer.cpp:361-374 on the device copy of the bound
+ * cloud, using State::get_RT() of state14.  ALL points of the cloud passed to flimo_scan_set* are
+ * transformed, in their original order -- the MAX_NUM_PC2MATCH cap only limits what Mapper::match
+ * queries (Mapper.cpp:63-69), the reference maps the whole pc2match (Localizer.cpp:361,377). */
 int flimo_scan_to_world(flimo_handle h, const double state14[14], float* out_xyz, size_t cap_points,
                         size_t* n_points);
+
+/* Localizer.cpp:361 + :377 without leaving the device: transformPointCloud(pc2match, state.get_RT())
+ * followed by Mapper::add(world cloud, stamp) (Mapper.cpp:88-96). */
+int flimo_map_add_scan(flimo_handle h, const double state14[14], double stamp);
 
 /* ---- introspection (bench / profiles) ------------------------------------------------------- */
 typedef struct {

@@ -1,13 +1,11 @@
-"""GPU checks of OPT-IN code paths (not part of `-m gpu`): run with `pytest tests -m gpu_experimental`.
+"""GPU checks of the two-lanes-per-query scan variant and of the closed loop (promoted into `-m gpu` in round 2 after
+their first run on a B200: 8 / 8 green).
 
-FLIMO_KNN_PAIR=1 — two lanes per query in the first scan (csrc/match_kernel.cu, pair_scan_round).  Validated
-bit-identical against the oracle on the headline config c2 (tools/tune_knn.py ... :pair=1 --check) at the end of
-round 1; these cases cover what c2 does not (tiny runs, dense cells, caps, empty blocks) and have to be green
-before the switch becomes the default.
+FLIMO_KNN_PAIR=1 -- two lanes per query in the first scan (csrc/match_kernel.cu, pair_scan_round): tiny runs, dense cells,
+caps, empty blocks, and the iterated update, all against the oracle.
 
-fast_limo_b200.localizer — the host mirror of Localizer::updateIMU / updatePointCloud in closed loop (IMU samples ->
-prediction -> propagated frames -> device deskew -> update -> map add).  Written after the GPU budget of round 1 was
-spent; its IMU side is covered on the CPU (tests/test_imu_predict.py), the closed loop is checked here."""
+fast_limo_b200.localizer -- the host mirror of Localizer::updateIMU / updatePointCloud in closed loop (IMU samples ->
+prediction -> propagated frames -> device deskew -> update -> map add)."""
 import os
 
 import numpy as np
@@ -15,7 +13,7 @@ import pytest
 
 from fast_limo_b200 import api, synth
 
-pytestmark = pytest.mark.gpu_experimental
+pytestmark = pytest.mark.gpu
 BIG = 1 << 18
 
 
@@ -103,3 +101,27 @@ def test_localizer_closed_loop(flimo_lib):
     assert outcome == [False] + [True] * 11
     assert max(errs) < 0.03, errs                             # dead reckoning alone drifts 0.5 * 0.3 * t^2 (22 cm at 1.2 s)
     assert m.size() > 20000
+
+
+def test_map_receives_whole_cloud_beyond_pc2match_cap(oracle, flimo_lib):
+    """MAX_NUM_PC2MATCH caps what Mapper::match queries (Mapper.cpp:63-69); the reference still transforms and maps the
+    WHOLE pc2match (Localizer.cpp:361,377).  A 6144-point scan with a cap of 1500: the map must grow like the oracle's."""
+    case = synth.make_case("tiny")
+    assert len(case.scan) > 1500
+    m = api.Mapper(api.MappingConfig(MAX_NUM_MATCHES=BIG, MAX_NUM_PC2MATCH=1500), device=0)
+    m.add(case.map_pts, 0.0)
+    m.set_scan(case.scan)
+    r = m.match(case.init)
+    om = oracle.OracleMap()
+    om.add(case.map_pts)
+    ref = om.match(oracle.make_cfg(max_pc2match=1500, max_matches=BIG, num_threads=2), case.init[:14], case.scan)
+    assert r.n_valid == ref["n_valid"]                         # only the first 1500 points were queried
+    world = m.scan_to_world(case.truth)
+    assert world.shape[0] == len(case.scan)                    # ... but all of them are transformed
+    R = synth.quat_to_R(case.truth[3:7].astype(np.float32)).astype(np.float32)
+    assert np.abs(world - (case.scan[:, :3] @ R.T + case.truth[0:3].astype(np.float32))).max() < 1e-4
+    n0 = m.size()
+    m.add_scan(case.truth, 1.0)
+    om.add(world)
+    assert m.size() == om.size() > n0
+    assert np.array_equal(np.sort(m.points().view([("", np.float32)] * 3), axis=0), np.sort(om.points().view([("", np.float32)] * 3), axis=0))

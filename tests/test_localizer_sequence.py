@@ -75,6 +75,9 @@ class OracleStages:
         self.om.add(np.ascontiguousarray(pts))
         self.stamp = stamp
 
+    def add_scan(self, x, stamp):
+        self.add(self.scan_to_world(x), stamp)
+
     def exists(self):
         return self.om.size() > 0
 
