@@ -23,10 +23,18 @@
 //  * Eigen::EigenSolver's eigenvector basis (degenerate geometry only) is replaced by a symmetric
 //    Jacobi decomposition; when all six eigenvalues exceed D the filter is the identity either way.
 #pragma once
-#include <array>
 #include <cmath>
+#include <math.h>
 #include <cstdint>
 #include <cstring>
+
+// The math below is shared with the device-side update (csrc/ekf_step.hpp, run by the last CTA of the
+// registration kernel): every helper is __host__ __device__ when compiled by nvcc.
+#if defined(__CUDACC__)
+#define FLIMO_HD __host__ __device__
+#else
+#define FLIMO_HD
+#endif
 
 namespace flimo {
 namespace ekf {
@@ -38,19 +46,19 @@ constexpr double kS2Len = 98090.0 / 10000.0;
 template <int Rw, int Cl>
 struct Mat {
   double a[Rw * Cl];
-  double& operator()(int r, int c) { return a[r * Cl + c]; }
-  double operator()(int r, int c) const { return a[r * Cl + c]; }
-  static Mat zero() {
+  FLIMO_HD double& operator()(int r, int c) { return a[r * Cl + c]; }
+  FLIMO_HD double operator()(int r, int c) const { return a[r * Cl + c]; }
+  FLIMO_HD static Mat zero() {
     Mat m;
-    for (double& v : m.a) v = 0.0;
+    for (int i = 0; i < Rw * Cl; ++i) m.a[i] = 0.0;
     return m;
   }
-  static Mat identity() {
+  FLIMO_HD static Mat identity() {
     Mat m = zero();
     for (int i = 0; i < (Rw < Cl ? Rw : Cl); ++i) m(i, i) = 1.0;
     return m;
   }
-  Mat<Cl, Rw> T() const {
+  FLIMO_HD Mat<Cl, Rw> T() const {
     Mat<Cl, Rw> t;
     for (int r = 0; r < Rw; ++r)
       for (int c = 0; c < Cl; ++c) t(c, r) = (*this)(r, c);
@@ -58,7 +66,7 @@ struct Mat {
   }
 };
 template <int A, int B, int C>
-inline Mat<A, C> operator*(const Mat<A, B>& x, const Mat<B, C>& y) {
+FLIMO_HD inline Mat<A, C> operator*(const Mat<A, B>& x, const Mat<B, C>& y) {
   Mat<A, C> o;
   for (int r = 0; r < A; ++r)
     for (int c = 0; c < C; ++c) {
@@ -68,43 +76,39 @@ inline Mat<A, C> operator*(const Mat<A, B>& x, const Mat<B, C>& y) {
     }
   return o;
 }
-using V3 = std::array<double, 3>;
-using Q4 = std::array<double, 4>;   // x y z w
+template <int K>
+struct Vec {                         // plain aggregate (std::array is not usable in device code)
+  double v[K];
+  FLIMO_HD double& operator[](int i) { return v[i]; }
+  FLIMO_HD double operator[](int i) const { return v[i]; }
+  FLIMO_HD double* data() { return v; }
+  FLIMO_HD const double* data() const { return v; }
+};
+using V3 = Vec<3>;
+using Q4 = Vec<4>;   // x y z w
 
 struct State {
   V3 pos;
   Q4 rot;
   Q4 offR;
   V3 offT, vel, bg, ba, grav;
-  void load(const double* f) {
-    std::memcpy(pos.data(), f, 24);
-    std::memcpy(rot.data(), f + 3, 32);
-    std::memcpy(offR.data(), f + 7, 32);
-    std::memcpy(offT.data(), f + 11, 24);
-    std::memcpy(vel.data(), f + 14, 24);
-    std::memcpy(bg.data(), f + 17, 24);
-    std::memcpy(ba.data(), f + 20, 24);
-    std::memcpy(grav.data(), f + 23, 24);
+  FLIMO_HD void load(const double* f) {
+    for (int i = 0; i < 3; ++i) { pos[i] = f[i]; offT[i] = f[11 + i]; vel[i] = f[14 + i]; bg[i] = f[17 + i]; ba[i] = f[20 + i]; grav[i] = f[23 + i]; }
+    for (int i = 0; i < 4; ++i) { rot[i] = f[3 + i]; offR[i] = f[7 + i]; }
   }
-  void store(double* f) const {
-    std::memcpy(f, pos.data(), 24);
-    std::memcpy(f + 3, rot.data(), 32);
-    std::memcpy(f + 7, offR.data(), 32);
-    std::memcpy(f + 11, offT.data(), 24);
-    std::memcpy(f + 14, vel.data(), 24);
-    std::memcpy(f + 17, bg.data(), 24);
-    std::memcpy(f + 20, ba.data(), 24);
-    std::memcpy(f + 23, grav.data(), 24);
+  FLIMO_HD void store(double* f) const {
+    for (int i = 0; i < 3; ++i) { f[i] = pos[i]; f[11 + i] = offT[i]; f[14 + i] = vel[i]; f[17 + i] = bg[i]; f[20 + i] = ba[i]; f[23 + i] = grav[i]; }
+    for (int i = 0; i < 4; ++i) { f[3 + i] = rot[i]; f[7 + i] = offR[i]; }
   }
 };
 
-inline V3 cross(const V3& a, const V3& b) {
+FLIMO_HD inline V3 cross(const V3& a, const V3& b) {
   return {a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]};
 }
-inline double dot(const V3& a, const V3& b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
-inline double norm(const V3& a) { return std::sqrt(dot(a, a)); }
+FLIMO_HD inline double dot(const V3& a, const V3& b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+FLIMO_HD inline double norm(const V3& a) { return sqrt(dot(a, a)); }
 
-inline Mat<3, 3> skew(const V3& v) {
+FLIMO_HD inline Mat<3, 3> skew(const V3& v) {
   Mat<3, 3> m = Mat<3, 3>::zero();
   m(0, 1) = -v[2]; m(0, 2) = v[1];
   m(1, 0) = v[2];  m(1, 2) = -v[0];
@@ -112,14 +116,14 @@ inline Mat<3, 3> skew(const V3& v) {
   return m;
 }
 
-inline Q4 qmul(const Q4& a, const Q4& b) {
+FLIMO_HD inline Q4 qmul(const Q4& a, const Q4& b) {
   return {a[3] * b[0] + a[0] * b[3] + a[1] * b[2] - a[2] * b[1],
           a[3] * b[1] + a[1] * b[3] + a[2] * b[0] - a[0] * b[2],
           a[3] * b[2] + a[2] * b[3] + a[0] * b[1] - a[1] * b[0],
           a[3] * b[3] - a[0] * b[0] - a[1] * b[1] - a[2] * b[2]};
 }
 
-inline Mat<3, 3> rotmat(const Q4& q) {
+FLIMO_HD inline Mat<3, 3> rotmat(const Q4& q) {
   const double tx = 2 * q[0], ty = 2 * q[1], tz = 2 * q[2];
   const double twx = tx * q[3], twy = ty * q[3], twz = tz * q[3];
   const double txx = tx * q[0], txy = ty * q[0], txz = tz * q[0];
@@ -132,15 +136,15 @@ inline Mat<3, 3> rotmat(const Q4& q) {
 }
 
 // cos(sqrt(x2)), sin(sqrt(x2))/sqrt(x2) with the Taylor branch of mtkmath.hpp:143-175
-inline void cos_sinc(double x2, double& c, double& sc) {
-  const double bound = std::sqrt(std::sqrt(2.220446049250313e-16));
+FLIMO_HD inline void cos_sinc(double x2, double& c, double& sc) {
+  const double bound = sqrt(sqrt(2.220446049250313e-16));
   if (x2 >= bound) {
-    const double x = std::sqrt(x2);
-    c = std::cos(x);
-    sc = std::sin(x) / x;
+    const double x = sqrt(x2);
+    c = cos(x);
+    sc = sin(x) / x;
     return;
   }
-  static const double inv[7] = {1 / 3., 1 / 4., 1 / 5., 1 / 6., 1 / 7., 1 / 8., 1 / 9.};
+  const double inv[7] = {1 / 3., 1 / 4., 1 / 5., 1 / 6., 1 / 7., 1 / 8., 1 / 9.};
   double ci = 1., si = 1., term = -1 / 2. * x2;
   for (int i = 0; i < 3; ++i) {
     ci += term;
@@ -153,33 +157,33 @@ inline void cos_sinc(double x2, double& c, double& sc) {
 }
 
 // quaternion exp(scale * v) in MTK's convention (mtkmath.hpp:250-257)
-inline Q4 qexp(const V3& v, double scale) {
+FLIMO_HD inline Q4 qexp(const V3& v, double scale) {
   double c, sc;
   cos_sinc(scale * scale * dot(v, v), c, sc);
   const double m = sc * scale;
   return {m * v[0], m * v[1], m * v[2], c};
 }
 
-inline void so3_plus(Q4& q, const V3& d) { q = qmul(q, qexp(d, 0.5)); }
-inline V3 so3_minus(const Q4& a, const Q4& b) {   // log(b^-1 a), SOn.hpp:237-239 + mtkmath.hpp:269-289
+FLIMO_HD inline void so3_plus(Q4& q, const V3& d) { q = qmul(q, qexp(d, 0.5)); }
+FLIMO_HD inline V3 so3_minus(const Q4& a, const Q4& b) {   // log(b^-1 a), SOn.hpp:237-239 + mtkmath.hpp:269-289
   const Q4 r = qmul({-b[0], -b[1], -b[2], b[3]}, a);
-  double nv = std::sqrt(r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
+  double nv = sqrt(r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
   if (nv < kTol) nv = kTol;
-  const double s = 2.0 / nv * std::atan(nv / r[3]);
+  const double s = 2.0 / nv * atan(nv / r[3]);
   return {s * r[0], s * r[1], s * r[2]};
 }
 
-inline Mat<3, 3> A_matrix(const V3& v) {
-  const double sq = dot(v, v), n = std::sqrt(sq);
+FLIMO_HD inline Mat<3, 3> A_matrix(const V3& v) {
+  const double sq = dot(v, v), n = sqrt(sq);
   Mat<3, 3> A = Mat<3, 3>::identity();
   if (n < kTol) return A;
   const Mat<3, 3> K = skew(v), K2 = K * K;
-  const double a = (1 - std::cos(n)) / sq, b = (1 - std::sin(n) / n) / sq;
+  const double a = (1 - cos(n)) / sq, b = (1 - sin(n) / n) / sq;
   for (int i = 0; i < 9; ++i) A.a[i] += a * K.a[i] + b * K2.a[i];
   return A;
 }
 
-inline Mat<3, 2> s2_Bx(const V3& v) {   // chart type 1 (S2.hpp:216-231)
+FLIMO_HD inline Mat<3, 2> s2_Bx(const V3& v) {   // chart type 1 (S2.hpp:216-231)
   Mat<3, 2> B = Mat<3, 2>::zero();
   const double L = kS2Len;
   if (v[0] + L > kTol) {
@@ -187,7 +191,7 @@ inline Mat<3, 2> s2_Bx(const V3& v) {   // chart type 1 (S2.hpp:216-231)
     B(0, 0) = -v[1];               B(0, 1) = -v[2];
     B(1, 0) = L - v[1] * v[1] / d; B(1, 1) = -v[2] * v[1] / d;
     B(2, 0) = -v[2] * v[1] / d;    B(2, 1) = L - v[2] * v[2] / d;
-    for (double& x : B.a) x /= L;
+    for (int i = 0; i < 6; ++i) B.a[i] /= L;
   } else {
     B(1, 1) = -1;
     B(2, 0) = 1;
@@ -195,7 +199,7 @@ inline Mat<3, 2> s2_Bx(const V3& v) {   // chart type 1 (S2.hpp:216-231)
   return B;
 }
 
-inline void s2_plus(V3& v, double d0, double d1) {
+FLIMO_HD inline void s2_plus(V3& v, double d0, double d1) {
   const Mat<3, 2> B = s2_Bx(v);
   const V3 Bu = {B(0, 0) * d0 + B(0, 1) * d1, B(1, 0) * d0 + B(1, 1) * d1, B(2, 0) * d0 + B(2, 1) * d1};
   const Mat<3, 3> R = rotmat(qexp(Bu, 0.5));
@@ -203,11 +207,11 @@ inline void s2_plus(V3& v, double d0, double d1) {
        R(2, 0) * v[0] + R(2, 1) * v[1] + R(2, 2) * v[2]};
 }
 
-inline void s2_minus(const V3& a, const V3& b, double& r0, double& r1) {
+FLIMO_HD inline void s2_minus(const V3& a, const V3& b, double& r0, double& r1) {
   const double v_sin = norm(cross(a, b)), v_cos = dot(a, b);
-  const double theta = std::atan2(v_sin, v_cos);
+  const double theta = atan2(v_sin, v_cos);
   if (v_sin < kTol) {
-    r0 = (std::fabs(theta) > kTol) ? 3.1415926 : 0.0;
+    r0 = (fabs(theta) > kTol) ? 3.1415926 : 0.0;
     r1 = 0.0;
     return;
   }
@@ -218,24 +222,24 @@ inline void s2_minus(const V3& a, const V3& b, double& r0, double& r1) {
   r1 = f * (B(0, 1) * w[0] + B(1, 1) * w[1] + B(2, 1) * w[2]);
 }
 
-inline Mat<2, 3> s2_Nx_yy(const V3& v) {
+FLIMO_HD inline Mat<2, 3> s2_Nx_yy(const V3& v) {
   Mat<2, 3> Nx = s2_Bx(v).T() * skew(v);
-  for (double& x : Nx.a) x *= 1 / kS2Len / kS2Len;
+  for (int i = 0; i < 6; ++i) Nx.a[i] *= 1 / kS2Len / kS2Len;
   return Nx;
 }
 
-inline Mat<3, 2> s2_Mx(const V3& v, double d0, double d1) {
+FLIMO_HD inline Mat<3, 2> s2_Mx(const V3& v, double d0, double d1) {
   const Mat<3, 2> B = s2_Bx(v);
   Mat<3, 3> negH = skew(v);
-  for (double& x : negH.a) x = -x;
-  if (std::sqrt(d0 * d0 + d1 * d1) < kTol) return negH * B;
+  for (int i = 0; i < 9; ++i) negH.a[i] = -negH.a[i];
+  if (sqrt(d0 * d0 + d1 * d1) < kTol) return negH * B;
   const V3 Bu = {B(0, 0) * d0 + B(0, 1) * d1, B(1, 0) * d0 + B(1, 1) * d1, B(2, 0) * d0 + B(2, 1) * d1};
   // the reference builds this rotation with scale scalar(1/2) == 0 (integer division, S2.hpp:277):
   const Mat<3, 3> E = rotmat(qexp(Bu, 0.0));
   return (E * negH) * (A_matrix(Bu).T() * B);
 }
 
-inline void boxplus(State& x, const double* d) {
+FLIMO_HD inline void boxplus(State& x, const double* d) {
   for (int i = 0; i < 3; ++i) x.pos[i] += d[i];
   so3_plus(x.rot, {d[3], d[4], d[5]});
   so3_plus(x.offR, {d[6], d[7], d[8]});
@@ -248,7 +252,7 @@ inline void boxplus(State& x, const double* d) {
   s2_plus(x.grav, d[21], d[22]);
 }
 
-inline void boxminus(const State& x, const State& y, double* d) {
+FLIMO_HD inline void boxminus(const State& x, const State& y, double* d) {
   for (int i = 0; i < 3; ++i) d[i] = x.pos[i] - y.pos[i];
   const V3 r = so3_minus(x.rot, y.rot), r2 = so3_minus(x.offR, y.offR);
   for (int i = 0; i < 3; ++i) {
@@ -264,10 +268,10 @@ inline void boxminus(const State& x, const State& y, double* d) {
 
 // Inverse of an n x n row-major matrix by Gauss-Jordan elimination with partial (row) pivoting on the
 // augmented system [A | I]; every inner loop runs over a contiguous row, so the host compiler
-// vectorises it (the 23x23 case takes a few microseconds).  Returns false on an exactly singular pivot.
+// vectorises it (the 23x23 case takes a few microseconds).  Returns false on a zero / non-finite pivot.
 template <int n>
-inline bool invert(Mat<n, n>& M) {
-  alignas(32) double w[n][2 * n];
+FLIMO_HD inline bool invert(Mat<n, n>& M) {
+  double w[n][2 * n];
   for (int r = 0; r < n; ++r) {
     for (int c = 0; c < n; ++c) {
       w[r][c] = M(r, c);
@@ -276,17 +280,21 @@ inline bool invert(Mat<n, n>& M) {
   }
   for (int c = 0; c < n; ++c) {
     int p = c;
-    double best = std::fabs(w[c][c]);
+    double best = fabs(w[c][c]);
     for (int r = c + 1; r < n; ++r) {
-      const double v = std::fabs(w[r][c]);
+      const double v = fabs(w[r][c]);
       if (v > best) {
         best = v;
         p = r;
       }
     }
-    if (best == 0.0) return false;
+    if (!(best > 0.0) || best > 1.7e308) return false;   // zero, NaN or Inf pivot
     if (p != c)
-      for (int k = 0; k < 2 * n; ++k) std::swap(w[c][k], w[p][k]);
+      for (int k = 0; k < 2 * n; ++k) {
+        const double t = w[c][k];
+        w[c][k] = w[p][k];
+        w[p][k] = t;
+      }
     const double inv = 1.0 / w[c][c];
     for (int k = 0; k < 2 * n; ++k) w[c][k] *= inv;
     for (int r = 0; r < n; ++r) {
@@ -303,16 +311,16 @@ inline bool invert(Mat<n, n>& M) {
 
 // true when every eigenvalue of the symmetric 6x6 S exceeds `floor` by a safe margin: S - floor*I has
 // a Cholesky factorisation whose pivots are all comfortably positive.
-inline bool all_eigs_above(const Mat<6, 6>& S, double floor) {
+FLIMO_HD inline bool all_eigs_above(const Mat<6, 6>& S, double floor) {
   double L[6][6];
   double scale = 0.0;
-  for (int i = 0; i < 6; ++i) scale = std::fmax(scale, std::fabs(S(i, i)));
-  const double tiny = 1e-9 * (scale + std::fabs(floor)) + 1e-300;
+  for (int i = 0; i < 6; ++i) scale = fmax(scale, fabs(S(i, i)));
+  const double tiny = 1e-9 * (scale + fabs(floor)) + 1e-300;
   for (int j = 0; j < 6; ++j) {
     double d = S(j, j) - floor;
     for (int k = 0; k < j; ++k) d -= L[j][k] * L[j][k];
     if (!(d > tiny)) return false;
-    const double dj = std::sqrt(d);
+    const double dj = sqrt(d);
     L[j][j] = dj;
     for (int i = j + 1; i < 6; ++i) {
       double v = S(i, j);
@@ -324,7 +332,7 @@ inline bool all_eigs_above(const Mat<6, 6>& S, double floor) {
 }
 
 // Symmetric Jacobi eigen-decomposition (6x6), columns of V are eigenvectors.
-inline void sym_eig6(const Mat<6, 6>& S, double w[6], Mat<6, 6>& V) {
+FLIMO_HD inline void sym_eig6(const Mat<6, 6>& S, double w[6], Mat<6, 6>& V) {
   Mat<6, 6> A = S;
   V = Mat<6, 6>::identity();
   for (int sweep = 0; sweep < 64; ++sweep) {
@@ -336,8 +344,8 @@ inline void sym_eig6(const Mat<6, 6>& S, double w[6], Mat<6, 6>& V) {
       for (int q = p + 1; q < 6; ++q) {
         if (A(p, q) == 0.0) continue;
         const double th = (A(q, q) - A(p, p)) / (2 * A(p, q));
-        const double t = (th >= 0 ? 1.0 : -1.0) / (std::fabs(th) + std::sqrt(th * th + 1));
-        const double c = 1 / std::sqrt(t * t + 1), s = t * c;
+        const double t = (th >= 0 ? 1.0 : -1.0) / (fabs(th) + sqrt(th * th + 1));
+        const double c = 1 / sqrt(t * t + 1), s = t * c;
         for (int k = 0; k < 6; ++k) {
           const double x = A(k, p), y = A(k, q);
           A(k, p) = c * x - s * y;
@@ -358,9 +366,48 @@ inline void sym_eig6(const Mat<6, 6>& S, double w[6], Mat<6, 6>& V) {
   for (int i = 0; i < 6; ++i) w[i] = A(i, i);
 }
 
+// Fast exit of the degeneracy filter: every eigenvalue of the pose block HTH[0:6, 0:6] is safely above both
+// thresholds of the filter (D and, for the product test, 1e-20^(1/6)); the reference then computes
+// V^-1 * V * dx = dx, so the decomposition can be skipped.
+FLIMO_HD inline bool all_eigs_above6(const double* HTH144, double floor) {
+  Mat<6, 6> S6;
+  for (int r = 0; r < 6; ++r)
+    for (int c = 0; c < 6; ++c) S6(r, c) = HTH144[r * 12 + c];
+  return all_eigs_above(S6, floor);
+}
+
+// The filter itself (esekfom.hpp:1736-1744): dxn[0:6] = V^-1 * (V with the rows of small eigenvalues zeroed) * dxk[0:6].
+// have_hth = false reproduces the N < 23 branch (HTH := 0, see the header comment).  Returns false if V is singular
+// (dxn[0:6] is then left equal to dxk[0:6]).
+FLIMO_HD inline bool degeneracy_filter(const double* HTH144, bool have_hth, double D, const double* dxk, double* dxn) {
+  Mat<6, 6> S6 = Mat<6, 6>::zero();
+  if (have_hth)
+    for (int r = 0; r < 6; ++r)
+      for (int c = 0; c < 6; ++c) S6(r, c) = HTH144[r * 12 + c];
+  double w[6];
+  Mat<6, 6> V;
+  sym_eig6(S6, w, V);
+  double prod = 1;
+  for (int i = 0; i < 6; ++i) prod *= w[i];
+  if (prod < 1e-20) V = Mat<6, 6>::identity();
+  Mat<6, 6> Sel = V;
+  for (int k = 0; k < 6; ++k)
+    if (w[k] < D)
+      for (int c = 0; c < 6; ++c) Sel(k, c) = 0.0;    // row k, as in the reference
+  Mat<6, 6> Vi = V;
+  if (!invert<6>(Vi)) return false;
+  const Mat<6, 6> T = Vi * Sel;
+  for (int r = 0; r < 6; ++r) {
+    double s = 0;
+    for (int c = 0; c < 6; ++c) s += T(r, c) * dxk[c];
+    dxn[r] = s;
+  }
+  return true;
+}
+
 // Left/right congruence of a square matrix by a small block Jacobian J at [idx, idx+B).
 template <int B>
-inline void rows_by(Mat<N, N>& P, int idx, const Mat<B, B>& J, const Mat<N, N>& src) {
+FLIMO_HD inline void rows_by(Mat<N, N>& P, int idx, const Mat<B, B>& J, const Mat<N, N>& src) {
   for (int c = 0; c < N; ++c) {
     double t[B];
     for (int i = 0; i < B; ++i) {
@@ -372,7 +419,7 @@ inline void rows_by(Mat<N, N>& P, int idx, const Mat<B, B>& J, const Mat<N, N>& 
   }
 }
 template <int B>
-inline void cols_by_T(Mat<N, N>& P, int idx, const Mat<B, B>& J) {
+FLIMO_HD inline void cols_by_T(Mat<N, N>& P, int idx, const Mat<B, B>& J) {
   for (int r = 0; r < N; ++r) {
     double t[B];
     for (int i = 0; i < B; ++i) {
@@ -398,6 +445,7 @@ class IteratedUpdate {
     iter_ = -1;
     conv_count_ = 0;
     done_ = (iter_ >= max_iter_);   // max_iter < 0: the reference's loop body never runs
+    failed_ = false;
     passes_ = 0;
   }
   bool done() const { return done_; }
@@ -444,10 +492,11 @@ class IteratedUpdate {
     if (reference_form_) {
       Mat<N, N> Pi = P_;
       for (double& v : Pi.a) v /= R_;
-      invert<N>(Pi);
+      bool ok = invert<N>(Pi);
       for (int r = 0; r < 12; ++r)
         for (int c = 0; c < 12; ++c) Pi(r, c) += HTH144[r * 12 + c];
-      invert<N>(Pi);   // P_inv
+      ok = ok && invert<N>(Pi);   // P_inv
+      if (!ok) return fail_singular();
       for (int r = 0; r < N; ++r)
         for (int c = 0; c < 12; ++c) X(r, c) = Pi(r, c);
     } else {
@@ -458,7 +507,7 @@ class IteratedUpdate {
           for (int k = 0; k < 12; ++k) s2 += HTH144[r * 12 + k] * (P_(k, c) / R_);
           M(r, c) = s2;
         }
-      invert<12>(M);
+      if (!invert<12>(M)) return fail_singular();
       for (int r = 0; r < N; ++r)
         for (int c = 0; c < 12; ++c) {
           double s2 = 0;
@@ -486,35 +535,7 @@ class IteratedUpdate {
     // degeneracy filter on the pose block (esekfom.hpp:1736-1744)
     double dxn[N];
     std::memcpy(dxn, dxk, sizeof(dxk));
-    {
-      Mat<6, 6> S6 = Mat<6, 6>::zero();
-      if (n_rows >= N)
-        for (int r = 0; r < 6; ++r)
-          for (int c = 0; c < 6; ++c) S6(r, c) = HTH144[r * 12 + c];
-      double w[6];
-      Mat<6, 6> V;
-      // Fast exit: if every eigenvalue is safely above both thresholds of the filter (D and, for the
-      // product test, 1e-20^(1/6)), the reference computes V^-1 * V * dx = dx; skip the decomposition.
-      const bool clear = n_rows >= N && all_eigs_above(S6, std::fmax(D_, 1e-3));
-      if (clear) goto filter_done;
-      sym_eig6(S6, w, V);
-      double prod = 1;
-      for (double v : w) prod *= v;
-      if (prod < 1e-20) V = Mat<6, 6>::identity();
-      Mat<6, 6> Sel = V;
-      for (int k = 0; k < 6; ++k)
-        if (w[k] < D_)
-          for (int c = 0; c < 6; ++c) Sel(k, c) = 0.0;    // row k, as in the reference
-      Mat<6, 6> Vi = V;
-      invert<6>(Vi);
-      const Mat<6, 6> T = Vi * Sel;
-      for (int r = 0; r < 6; ++r) {
-        double s = 0;
-        for (int c = 0; c < 6; ++c) s += T(r, c) * dxk[c];
-        dxn[r] = s;
-      }
-    }
-  filter_done:
+    if (!(n_rows >= N && all_eigs_above6(HTH144, std::fmax(D_, 1e-3)))) degeneracy_filter(HTH144, n_rows >= N, D_, dxk, dxn);
 
     boxplus(x_, dxn);
     bool converge = true;
@@ -567,6 +588,18 @@ class IteratedUpdate {
   }
 
   const double* last_dx() const { return last_dx_; }
+  bool failed() const { return failed_; }   // a singular / non-finite system was met: x and P are the propagated ones
+
+ private:
+  // A singular pivot (NaN/Inf in HTH or P, degenerate covariance): the update is abandoned, state and covariance stay
+  // at the propagated values and the caller reports FLIMO_ERR_STATE.
+  bool fail_singular() {
+    x_ = x_prop_;
+    P_ = P_prop_;
+    failed_ = true;
+    done_ = true;
+    return true;
+  }
 
  private:
   State x_, x_prop_;
@@ -575,7 +608,7 @@ class IteratedUpdate {
   double last_dx_[N];
   int max_iter_ = 0, iter_ = -1, conv_count_ = 0, passes_ = 0;
   double R_ = 0.001, D_ = 5.0;
-  bool done_ = true;
+  bool done_ = true, failed_ = false;
  public:
   bool reference_form_ = false;   // true: form the gain with the reference's two 23x23 inversions (FLIMO_EKF_REFERENCE_FORM=1)
  private:

@@ -15,6 +15,7 @@
 
 #include "../../include/flimo.h"
 #include "ekf_host.hpp"
+#include "ekf_step.hpp"
 #include "imu_host.hpp"
 #include "flimo_dev.cuh"
 #include "scan_prep.cuh"
@@ -131,6 +132,8 @@ struct flimo_ctx {
   bool prep_deskewed = false;
 
   ekf::IteratedUpdate upd;
+  ekf::CoopUpdate coop;            // FLIMO_EKF_COOP=1: flimo_ekf_* run the device code path's algebra (ekf_step.hpp) on the host
+  bool use_coop = false;
   bool upd_active = false;
   ekf::PropagatedRing propagated;                 // Localizer::propagated_buffer
   std::vector<ekf::PropagatedState> frames_tmp;
@@ -441,6 +444,7 @@ int flimo_create(const flimo_cfg* cfg, int device, flimo_handle* out) {
     hh->cfg = *cfg;
     hh->device = -1;
     if (const char* e = std::getenv("FLIMO_EKF_REFERENCE_FORM")) hh->upd.reference_form_ = std::atoi(e) != 0;
+    if (const char* e = std::getenv("FLIMO_EKF_COOP")) hh->use_coop = std::atoi(e) != 0;
     *out = hh;
     return FLIMO_OK;
   }
@@ -456,6 +460,7 @@ int flimo_create(const flimo_cfg* cfg, int device, flimo_handle* out) {
   h->cfg = *cfg;
   h->device = device;
   if (const char* e = std::getenv("FLIMO_EKF_REFERENCE_FORM")) h->upd.reference_form_ = std::atoi(e) != 0;
+  if (const char* e = std::getenv("FLIMO_EKF_COOP")) h->use_coop = std::atoi(e) != 0;
   // index ladder: finest cell, growth ratio, candidates-per-block threshold.  The FLIMO_KNN_* environment
   // variables override the configuration (tuning runs of tools/ only).
   if (const char* e = std::getenv("FLIMO_KNN_CELL")) h->cfg.knn_cell = (float)std::atof(e);
@@ -1109,24 +1114,29 @@ int flimo_map_add_scan(flimo_handle h, const double state14[14], double stamp) {
 int flimo_ekf_begin(flimo_handle h, const double state26[26], const double P529[529], int max_iter,
                     const double limit23[23], double R_noise, double D_degeneracy) {
   if (!h || !state26 || !P529 || !limit23) return fail(h, FLIMO_ERR_INVALID, "null argument");
-  h->upd.begin(state26, P529, max_iter, limit23, R_noise, D_degeneracy);
+  if (h->use_coop) h->coop.begin(state26, P529, max_iter, limit23, R_noise, D_degeneracy);
+  else h->upd.begin(state26, P529, max_iter, limit23, R_noise, D_degeneracy);
   h->upd_active = true;
   return FLIMO_OK;
 }
 int flimo_ekf_state(flimo_handle h, double state26[26]) {
   if (!h || !state26 || !h->upd_active) return fail(h, FLIMO_ERR_STATE, "flimo_ekf_begin not called");
-  h->upd.state(state26);
+  if (h->use_coop) h->coop.state(state26);
+  else h->upd.state(state26);
   return FLIMO_OK;
 }
 int flimo_ekf_step(flimo_handle h, const double HTH[144], const double HTh[12], int64_t n_rows, int* done) {
   if (!h || !HTH || !HTh || !h->upd_active) return fail(h, FLIMO_ERR_STATE, "flimo_ekf_begin not called");
-  const bool d = h->upd.step(HTH, HTh, n_rows);
+  const bool d = h->use_coop ? h->coop.step(HTH, HTh, n_rows) : h->upd.step(HTH, HTh, n_rows);
   if (done) *done = d ? 1 : 0;
+  if (h->use_coop ? h->coop.failed() : h->upd.failed())
+    return fail(h, FLIMO_ERR_STATE, "singular or non-finite normal equations: state left at the prediction");
   return FLIMO_OK;
 }
 int flimo_ekf_end(flimo_handle h, double state26[26], double P529[529]) {
   if (!h || !state26 || !P529 || !h->upd_active) return fail(h, FLIMO_ERR_STATE, "flimo_ekf_begin not called");
-  h->upd.end(state26, P529);
+  if (h->use_coop) h->coop.end(state26, P529);
+  else h->upd.end(state26, P529);
   h->upd_active = false;
   return FLIMO_OK;
 }
@@ -1472,6 +1482,7 @@ int flimo_update(flimo_handle h, double state26[26], double P529[529], int max_i
   }
   u.end(state26, P529);
   if (passes_out) *passes_out = u.passes();
+  if (u.failed()) return fail(h, FLIMO_ERR_STATE, "singular or non-finite normal equations: state left at the prediction");
   return FLIMO_OK;
 }
 
@@ -1499,6 +1510,7 @@ int flimo_update_exchange(flimo_handle h, double state26[26], double P529[529], 
   }
   u.end(state26, P529);
   if (passes_out) *passes_out = u.passes();
+  if (u.failed()) return fail(h, FLIMO_ERR_STATE, "singular or non-finite normal equations: state left at the prediction");
   return FLIMO_OK;
 }
 

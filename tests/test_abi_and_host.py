@@ -46,15 +46,20 @@ def test_unsupported_k_rejected(flimo_lib):
         api.Mapper(api.MappingConfig(NUM_MATCH_POINTS=7), device=-1)
 
 
-@pytest.mark.parametrize("reference_form", [False, True])
-@pytest.mark.parametrize("n_rows,max_iter,limit", [(800, 3, 0.001), (800, 0, 0.001), (800, 4, 1e9), (10, 2, 0.001), (0, 2, 0.001)])
-def test_host_ekf_matches_oracle(oracle, flimo_lib, n_rows, max_iter, limit, reference_form, monkeypatch):
+@pytest.mark.parametrize("form", ["12x12", "reference", "cooperative"])
+@pytest.mark.parametrize("n_rows,max_iter,limit", [(800, 3, 0.001), (800, 0, 0.001), (800, 4, 1e9), (10, 2, 0.001), (0, 2, 0.001),
+                                                   (800, 6, 1e-3), (40, 3, 1e-7)])
+def test_host_ekf_matches_oracle(oracle, flimo_lib, n_rows, max_iter, limit, form, monkeypatch):
     # the gain is formed with one 12x12 inverse by default; FLIMO_EKF_REFERENCE_FORM=1 (read when the handle is
-    # created) evaluates it with the reference's two 23x23 inversions — both must agree with the oracle
-    if reference_form:
+    # created) evaluates it with the reference's two 23x23 inversions; FLIMO_EKF_COOP=1 runs the DEVICE code path's
+    # phase-structured step (csrc/ekf_step.hpp, one 12x25 elimination per pass) item by item on the host — all three
+    # must agree with the oracle
+    monkeypatch.delenv("FLIMO_EKF_REFERENCE_FORM", raising=False)
+    monkeypatch.delenv("FLIMO_EKF_COOP", raising=False)
+    if form == "reference":
         monkeypatch.setenv("FLIMO_EKF_REFERENCE_FORM", "1")
-    else:
-        monkeypatch.delenv("FLIMO_EKF_REFERENCE_FORM", raising=False)
+    if form == "cooperative":
+        monkeypatch.setenv("FLIMO_EKF_COOP", "1")
     rng = np.random.default_rng(n_rows + max_iter)
     from scipy.spatial.transform import Rotation as Rot
     x0 = synth.make_state(rng.normal(0, 3, 3), Rot.random(random_state=1).as_quat(),
