@@ -155,8 +155,9 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--cell", type=float, default=0.0)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--exchange", choices=["shm", "nccl"], default="shm",
-                    help="N>1: how the 96 doubles per pass are summed over ranks (fused host-segment exchange | NCCL all-reduce)")
+    ap.add_argument("--exchange", choices=["peer", "shm", "nccl"], default="peer",
+                    help="N>1: how the 96 doubles per pass are summed over ranks (peer: NVLink peer stores from inside the "
+                         "registration kernel, filter step on the device | shm: fused host-segment exchange | nccl: NCCL all-reduce)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -199,6 +200,11 @@ def main():
             return box[0]
         shm = attach_exchange(m, rank, world, bcast)
         dist.barrier()
+    if world > 1 and args.exchange == "peer":
+        handles = [None] * world
+        dist.all_gather_object(handles, m.peer_export())
+        m.peer_attach(rank, world, handles)
+        dist.barrier()
     h_stream = torch.cuda.ExternalStream(m.stream())
     cur = torch.cuda.current_stream()
 
@@ -217,6 +223,9 @@ def main():
             return x, passes
         if not from_host:
             m.shard(lo, hi)
+        if args.exchange == "peer":
+            x, P, passes = m.update_peer(inits[k], P0, MAX_ITER, lim)
+            return x, passes
         if shm is not None:
             x, P, passes = m.update_exchange(inits[k], P0, MAX_ITER, lim)
             return x, passes
@@ -294,7 +303,8 @@ def main():
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "arithmetic": "float32 per point (kNN, plane fit, residual, Jacobian row), float64 normal equations and filter algebra",
                        "parallelism": "scan-shard x%d (replicated map, 96 doubles summed per pass via %s)"
-                       % (world, "fused host-segment exchange" if (world > 1 and args.exchange == "shm") else ("NCCL all-reduce" if world > 1 else "no exchange")),
+                       % (world, {"peer": "NVLink peer stores inside the registration kernel", "shm": "fused host-segment exchange",
+                                   "nccl": "NCCL all-reduce"}[args.exchange] if world > 1 else "no exchange"),
                        "passes_per_scan": passes, "l2_policy": "inputs larger than L2 (multi-level map index %.1f GB, 4 rotating scans)"
                        % (st1["map_bytes"] / 1e9), "pose_err_m": pose_err, "knn_cell": st1["knn_cell"], "levels": st1["n_levels"]},
             "e2e": {"value": args.steps / (ms_e2e / 1e3), "unit": "scans/s", "h2d_bytes_per_step": n_pts * 16,   # summed over ranks

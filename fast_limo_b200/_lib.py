@@ -18,6 +18,7 @@ SYMBOLS = [
     "flimo_update", "flimo_ekf_begin", "flimo_ekf_state", "flimo_ekf_step", "flimo_ekf_end",
     "flimo_scan_to_world", "flimo_map_add_scan", "flimo_prep_filter_sort", "flimo_prep_filter_sort_msg", "flimo_prep_deskew", "flimo_prep_get", "flimo_voxel_grid", "flimo_get_stats", "flimo_stream", "flimo_exchange_attach", "flimo_match_reduce_exchange", "flimo_update_exchange",
     "flimo_ekf_predict", "flimo_propagated_frames", "flimo_propagated_clear",
+    "flimo_peer_export", "flimo_peer_attach", "flimo_update_peer", "flimo_update_trace",
 ]
 
 
@@ -130,6 +131,10 @@ def load():
     L.flimo_match_debug.argtypes = [vp, pd, pf, sz, C.POINTER(sz)]
     L.flimo_update.argtypes = [vp, pd, pd, C.c_int, pd, dbl, dbl, C.POINTER(C.c_int)]
     L.flimo_update_exchange.argtypes = [vp, pd, pd, C.c_int, pd, dbl, dbl, C.POINTER(C.c_int)]
+    L.flimo_update_peer.argtypes = [vp, pd, pd, C.c_int, pd, dbl, dbl, C.POINTER(C.c_int)]
+    L.flimo_peer_export.argtypes = [vp, vp]
+    L.flimo_peer_attach.argtypes = [vp, C.c_int, C.c_int, vp]
+    L.flimo_update_trace.argtypes = [vp, pd, sz, C.POINTER(sz)]
     L.flimo_ekf_begin.argtypes = [vp, pd, pd, C.c_int, pd, dbl, dbl]
     L.flimo_ekf_state.argtypes = [vp, pd]
     L.flimo_ekf_step.argtypes = [vp, pd, pd, i64, C.POINTER(C.c_int)]

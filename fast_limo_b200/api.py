@@ -333,6 +333,31 @@ class Mapper:
         """`update` with every pass summed over all ranks through the attached exchange segment."""
         return self._update(self._L.flimo_update_exchange, state26, P, max_iter, limits, R, D)
 
+    def update_peer(self, state26, P, max_iter, limits, R=0.001, D=5.0):
+        """`update` of a scan sharded over the ranks attached with peer_attach: the whole update runs on the device,
+        pass sums travel over NVLink peer memory (flimo_update_peer)."""
+        return self._update(self._L.flimo_update_peer, state26, P, max_iter, limits, R, D)
+
+    def peer_export(self):
+        """This rank's inbox as a CUDA IPC handle (64 bytes) for the other ranks."""
+        buf = (C.c_ubyte * 64)()
+        self._ck(self._L.flimo_peer_export(self._h, C.cast(buf, C.c_void_p)))
+        return bytes(buf)
+
+    def peer_attach(self, rank, world, handles):
+        """handles: the 64-byte IPC handles of all ranks, in rank order."""
+        blob = b"".join(handles)
+        assert len(blob) == 64 * world
+        buf = (C.c_ubyte * len(blob)).from_buffer_copy(blob)
+        self._ck(self._L.flimo_peer_attach(self._h, int(rank), int(world), C.cast(buf, C.c_void_p)))
+
+    def update_trace(self):
+        """Per-pass records of the last device-resident update: (passes, 32) = state26, n_valid, n_rows, ns, row limit."""
+        out = np.zeros((16, 32), np.float64)
+        n = C.c_size_t(0)
+        self._ck(self._L.flimo_update_trace(self._h, _dp(out), 16, C.byref(n)))
+        return out[:n.value]
+
     def ekf_begin(self, state26, P, max_iter, limits, R=0.001, D=5.0):
         x = np.ascontiguousarray(state26, np.float64)
         Pm = np.ascontiguousarray(np.asarray(P, np.float64).reshape(23, 23))

@@ -101,12 +101,19 @@ FLIMO_HD inline void store9T(const Mat<3, 3>& A, double* out) {   // out = A^T, 
     for (int j = 0; j < 3; ++j) out[i * 3 + j] = A(j, i);
 }
 
+// The carried state is written by a different CTA every pass: read it past the (non-coherent) L1.
+#if defined(__CUDA_ARCH__)
+#define FLIMO_LD_CG(p) __ldcg(p)
+#else
+#define FLIMO_LD_CG(p) (*(p))
+#endif
+
 // One pass.  packed96 = the summed measurement (flimo.h layout).  On return st holds the new state and counters;
 // st.done says whether this was the last pass (st.P is then the updated covariance).
 template <class Ex>
 FLIMO_HD inline void iterated_step(Ex& ex, StepShared& s, const UpdInit& in, UpdState& st, const double* packed96) {
   const long long n_rows = (long long)(packed96[90] + 0.5);
-  const int iter = st.iter, conv_count = st.conv_count;
+  const int iter = FLIMO_LD_CG(&st.iter), conv_count = FLIMO_LD_CG(&st.conv_count), passes = FLIMO_LD_CG(&st.passes);
 
   // A. unpack the measurement, fetch the states
   ex.par(144, [&](int e) {
@@ -115,7 +122,7 @@ FLIMO_HD inline void iterated_step(Ex& ex, StepShared& s, const UpdInit& in, Upd
   });
   ex.par(12, [&](int i) { s.HTh[i] = packed96[78 + i]; });
   ex.par(26, [&](int i) {
-    s.x[i] = st.x[i];
+    s.x[i] = FLIMO_LD_CG(&st.x[i]);
     s.xp[i] = in.x[i];
   });
   ex.par(1, [&](int) { s.singular = 0; });
@@ -248,7 +255,7 @@ FLIMO_HD inline void iterated_step(Ex& ex, StepShared& s, const UpdInit& in, Upd
     ex.par(1, [&](int) {
       st.failed = 1;
       st.done = 1;
-      st.passes = st.passes + 1;
+      st.passes = passes + 1;
     });
     ex.sync();
     return;
@@ -336,7 +343,7 @@ FLIMO_HD inline void iterated_step(Ex& ex, StepShared& s, const UpdInit& in, Upd
   ex.par(N, [&](int i) { st.last_dx[i] = s.dxk[i]; });
   ex.par(1, [&](int) {
     st.conv_count = conv_count + s.converge;
-    st.passes = st.passes + 1;
+    st.passes = passes + 1;
     if (final_pass) {
       st.done = 1;
     } else {

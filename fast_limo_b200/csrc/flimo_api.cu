@@ -18,6 +18,7 @@
 #include "ekf_step.hpp"
 #include "imu_host.hpp"
 #include "flimo_dev.cuh"
+#include "pose_consts.hpp"
 #include "scan_prep.cuh"
 
 using namespace flimo;
@@ -114,6 +115,21 @@ struct flimo_ctx {
   int persistent = 1;            // 1 = flimo_update keeps one kernel resident over all passes
   unsigned long long ctl_seq = 0;   // tag of the last command posted to the persistent kernel
   int persist_capacity = 0;      // co-resident CTAs of the persistent kernel
+  // registration kernel (whole update on the device, filter step included)
+  int device_ekf = 1;            // FLIMO_DEVICE_EKF=0: keep the filter step on the host (persistent kernel + handshake)
+  int reg_capacity = 0;
+  ekf::UpdState* upd_state = nullptr;   // device
+  double* h_res = nullptr;       // mapped pinned result block: kResRecords records {value, seq}
+  double* d_h_res = nullptr;
+  unsigned long long res_seq = 0;
+  uint32_t* flag_words = nullptr;
+  size_t flag_words_cap = 0;
+  uint64_t device_updates = 0, device_redone = 0;
+  // peer exchange over NVLink (flimo_peer_*): every rank's inbox mapped through CUDA IPC
+  double* inbox = nullptr;
+  double* peer_inbox[kMaxPeers] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  int peer_rank = 0, peer_world = 0;
+  unsigned long long peer_xseq = 0;
   double persist_ns_total = 0;   // in-kernel device time of persistent passes
   uint64_t persist_passes = 0;
   uint64_t update_calls = 0;
@@ -177,51 +193,6 @@ cudaError_t grow(T** p, size_t* cap, size_t need) {
   if (e != cudaSuccess) return e;
   *cap = want;
   return cudaSuccess;
-}
-
-// --- pose constants, float32 exactly as the reference builds them -----------------------------
-template <typename T>
-void quat_matrix(const T q[4], T R[9]) {   // Eigen QuaternionBase::toRotationMatrix
-  const T tx = T(2) * q[0], ty = T(2) * q[1], tz = T(2) * q[2];
-  const T twx = tx * q[3], twy = ty * q[3], twz = tz * q[3];
-  const T txx = tx * q[0], txy = ty * q[0], txz = tz * q[0];
-  const T tyy = ty * q[1], tyz = tz * q[1], tzz = tz * q[2];
-  R[0] = T(1) - (tyy + tzz); R[1] = txy - twz;          R[2] = txz + twy;
-  R[3] = txy + twz;          R[4] = T(1) - (txx + tzz); R[5] = tyz - twx;
-  R[6] = txz - twy;          R[7] = tyz + twx;          R[8] = T(1) - (txx + tyy);
-}
-
-// [R|t]^-1 = [R^T | -R^T t] with Eigen's fixed-size evaluation order (State.cpp:145-153)
-void rigid_inverse(const float R[9], const float t[3], float Ri[9], float ti[3]) {
-  for (int r = 0; r < 3; ++r)
-    for (int c = 0; c < 3; ++c) Ri[3 * r + c] = R[3 * c + r];
-  for (int r = 0; r < 3; ++r) {
-    const volatile float a = (-Ri[3 * r]) * t[0], b = (-Ri[3 * r + 1]) * t[1], c = (-Ri[3 * r + 2]) * t[2];
-    const volatile float bc = b + c;
-    ti[r] = a + bc;
-  }
-}
-
-void make_pose(const double s[14], PoseConsts& pc) {
-  // State::State(const state_ikfom&) casts (State.cpp:38-55)
-  float q[4], qLI[4], p[3], pLI[3];
-  for (int i = 0; i < 3; ++i) p[i] = (float)s[i];
-  for (int i = 0; i < 4; ++i) q[i] = (float)s[3 + i];
-  for (int i = 0; i < 4; ++i) qLI[i] = (float)s[7 + i];
-  for (int i = 0; i < 3; ++i) pLI[i] = (float)s[11 + i];
-  quat_matrix<float>(q, pc.R_wb);
-  for (int i = 0; i < 3; ++i) pc.t_wb[i] = p[i];
-  rigid_inverse(pc.R_wb, p, pc.Rinv_wb, pc.tinv_wb);
-  float R_LI[9];
-  quat_matrix<float>(qLI, R_LI);
-  rigid_inverse(R_LI, pLI, pc.Rinv_LI, pc.tinv_LI);
-  // Localizer.cpp:554-555: conjugate of the DOUBLE quaternion -> matrix -> cast<float>
-  double qc[4] = {-s[3], -s[4], -s[5], s[6]}, Rd[9];
-  quat_matrix<double>(qc, Rd);
-  for (int i = 0; i < 9; ++i) pc.Rd_wb_inv[i] = (float)Rd[i];
-  double qc2[4] = {-s[7], -s[8], -s[9], s[10]};
-  quat_matrix<double>(qc2, Rd);
-  for (int i = 0; i < 9; ++i) pc.Rd_LI_inv[i] = (float)Rd[i];
 }
 
 // stride ~ 0.618 n that is co-prime with n: i -> (i * stride) mod n is a permutation of [0, n)
@@ -318,10 +289,14 @@ int fill_params(flimo_handle h, const double state14[14], MatchParams& P, double
 // value and sequence word become visible together: reading the sequence word first (x86 keeps load
 // order) makes the value that follows current.  Returns 0, 1 (own kernel finished without
 // publishing; only when `own`), or a negative status.
+int wait_records_n(flimo_handle h, const double* block, unsigned long long seq, double* out, int n, bool own);
 int wait_records(flimo_handle h, const double* block, unsigned long long seq, double out[96], bool own) {
+  return wait_records_n(h, block, seq, out, 96, own);
+}
+int wait_records_n(flimo_handle h, const double* block, unsigned long long seq, double* out, int n, bool own) {
   const volatile unsigned long long* rec = reinterpret_cast<const volatile unsigned long long*>(block);
   unsigned long long spins = 0;
-  for (int i = 95; i >= 0; --i) {
+  for (int i = n - 1; i >= 0; --i) {
     while (rec[2 * i + 1] != seq) {
       if ((++spins & 0xFFFFF) == 0 && own) {              // every ~1M polls: has the kernel died?
         const cudaError_t q = cudaStreamQuery(h->stream);
@@ -499,6 +474,13 @@ int flimo_create(const flimo_cfg* cfg, int device, flimo_handle* out) {
   CU(h, cudaMalloc(&h->dev_ctl, sizeof(PassCtl)));
   CU(h, cudaMemset(h->dev_ctl, 0, sizeof(PassCtl)));
   h->persist_capacity = match_persistent_capacity();
+  h->reg_capacity = registration_capacity();
+  CU(h, cudaMalloc(&h->upd_state, sizeof(ekf::UpdState)));
+  CU(h, cudaMemset(h->upd_state, 0, sizeof(ekf::UpdState)));
+  CU(h, cudaHostAlloc(&h->h_res, (size_t)kResRecords * 16, cudaHostAllocMapped));
+  std::memset(h->h_res, 0, (size_t)kResRecords * 16);
+  CU(h, cudaHostGetDevicePointer(reinterpret_cast<void**>(&h->d_h_res), h->h_res, 0));
+  if (const char* e = std::getenv("FLIMO_DEVICE_EKF")) h->device_ekf = std::atoi(e);
   if (const char* e = std::getenv("FLIMO_PERSISTENT")) h->persistent = std::atoi(e);
   if (const char* e = std::getenv("FLIMO_TEST_STALL_PASS")) h->test_stall_pass = std::atoi(e);
   *out = h;
@@ -548,6 +530,12 @@ void flimo_destroy(flimo_handle h) {
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   if (h->ev_prefetch) cudaEventDestroy(h->ev_prefetch);
   cudaFree(h->dev_ctl);
+  cudaFree(h->upd_state);
+  cudaFreeHost(h->h_res);
+  cudaFree(h->flag_words);
+  for (int r = 0; r < h->peer_world; ++r)
+    if (h->peer_inbox[r] && r != h->peer_rank) cudaIpcCloseMemHandle(h->peer_inbox[r]);
+  cudaFree(h->inbox);
   cudaFree(h->dbg16);
   cudaFree(h->valid_flags);
   cudaFree(h->xyz_out);
@@ -973,6 +961,8 @@ int flimo_match_reduce_exchange(flimo_handle h, const double state14[14], double
     flimo_stats tmp;
     flimo_get_stats(h, &tmp);
   }
+  if ((int64_t)std::llround(packed[92]) > (int64_t)h->cfg.MAX_NUM_MATCHES)
+    return fail(h, FLIMO_ERR_STATE, "more accepted matches than MAX_NUM_MATCHES: the host-segment exchange cannot apply the first-N rule across shards (use flimo_update_peer)");
   flimo_unpack96(packed, HTH, HTh, n_valid, n_rows, sum_sq_res);
   return FLIMO_OK;
 }
@@ -1274,7 +1264,11 @@ static int update_persistent(flimo_handle h, ekf::IteratedUpdate& u, bool exchan
       h->prof_wait += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - tp0).count();
       h->prof_passes++;
     }
-    if (!exchange && (int64_t)std::llround(packed[92]) > (int64_t)h->cfg.MAX_NUM_MATCHES) {   // first-N truncation: general path
+    if ((int64_t)std::llround(packed[92]) > (int64_t)h->cfg.MAX_NUM_MATCHES) {   // first-N truncation: general path
+      if (exchange) {
+        post_ctl(h, 1u, 0u, nullptr);
+        return fail(h, FLIMO_ERR_STATE, "more accepted matches than MAX_NUM_MATCHES: the host-segment exchange cannot apply the first-N rule across shards (use flimo_update_peer)");
+      }
       fallback = 1;
       break;
     }
@@ -1292,6 +1286,75 @@ static int update_persistent(flimo_handle h, ekf::IteratedUpdate& u, bool exchan
     CU(h, cudaMemsetAsync(h->ticket, 0, h->ticket_cap * sizeof(unsigned int), h->stream));
   }
   return fallback;
+}
+
+// flimo_update entirely on the device (registration_kernel): one launch, the filter step runs in the CTA that completes a
+// pass, the host only waits for the final state + covariance in the mapped result block.  With `exchange` the scan is
+// sharded over the ranks attached with flimo_peer_attach and the pass sums travel over NVLink peer memory.
+// Returns 0, or 1 when the caller has to run the update the classic way (nothing was changed), or a negative status.
+static int update_device(flimo_handle h, double state26[26], double P529[529], int max_iter, const double limit23[23], double R_noise,
+                         double D_degeneracy, int* passes_out, bool exchange) {
+  const size_t n = h->shard_end - h->shard_begin;
+  if (n == 0 || max_iter < 0 || h->reg_capacity <= 0) return 1;
+  if (exchange && h->peer_world < 1) return fail(h, FLIMO_ERR_STATE, "flimo_peer_attach not called");
+  RegParams RP;
+  std::memset(&RP, 0, sizeof(RP));
+  int rc = fill_params(h, state26, RP.m, h->out96, 0xFFFFFFFFu, nullptr, nullptr);
+  if (rc) return rc;
+  std::memcpy(RP.u.x, state26, sizeof(RP.u.x));
+  std::memcpy(RP.u.P, P529, sizeof(RP.u.P));
+  std::memcpy(RP.u.limit, limit23, sizeof(RP.u.limit));
+  RP.u.R = R_noise;
+  RP.u.D = D_degeneracy;
+  RP.u.max_iter = max_iter;
+  RP.u.max_matches = h->cfg.MAX_NUM_MATCHES;
+  RP.st = h->upd_state;
+  RP.host_res = h->d_h_res;
+  RP.res_seq = ++h->res_seq;
+  RP.world = exchange ? h->peer_world : 1;
+  RP.rank = exchange ? h->peer_rank : 0;
+  for (int r = 0; r < kMaxPeers; ++r) RP.inbox[r] = exchange ? h->peer_inbox[r] : nullptr;
+  RP.peer_timeout_ns = 2000ull * 1000ull * 1000ull;
+  const int max_cmds = 2 * (max_iter + 2) + 2;          // every pass may be repeated once (first-N rule) + stop
+  RP.xseq = h->peer_xseq + 1;
+  h->peer_xseq += (unsigned long long)max_cmds;
+  RP.m.ctl_seq = h->ctl_seq + 1;
+  h->ctl_seq += (unsigned long long)max_cmds;
+  // first-N rule: only possible when the scan holds more points than the cap (summed over all shards)
+  if ((long long)h->scan_n > (long long)h->cfg.MAX_NUM_MATCHES) {
+    const size_t nq = h->scan_n, nw = (nq + 31) / 32;
+    if (nw > (size_t)kFlagWordsCap && exchange) return 1;
+    CU(h, grow(&h->valid_flags, &h->valid_cap, nq + 64));
+    CU(h, grow(&h->flag_words, &h->flag_words_cap, nw + 64));
+    CU(h, cudaMemsetAsync(h->valid_flags, 0, nq, h->stream));
+    RP.m.valid_by_orig = h->valid_flags;
+    RP.flag_words = h->flag_words;
+  }
+  const int tiles = match_num_tiles((int)n);
+  const int grid = std::min(tiles, h->reg_capacity);
+  CU(h, launch_registration(RP, grid, h->stream));
+  h->stats.kernel_launches++;
+  if (h->pref_idx >= 0 && !h->pref_issued) {               // the requested copy of the next scan overlaps the update
+    rc = issue_prefetch(h);
+    if (rc) return rc;
+  }
+  double res[kResRecords];
+  const int wr = wait_records_n(h, h->h_res, RP.res_seq, res, kResRecords, true);
+  if (wr < 0) return wr;
+  if (wr == 1) return fail(h, FLIMO_ERR_CUDA, "registration kernel finished without publishing its result");
+  const int passes = (int)std::llround(res[kResPasses]);
+  const int failed = (int)std::llround(res[kResFailed]);
+  std::memcpy(state26, &res[kResX], 26 * sizeof(double));
+  std::memcpy(P529, &res[kResP], 529 * sizeof(double));
+  if (passes_out) *passes_out = passes;
+  h->stats.match_launches += (uint64_t)passes + (uint64_t)std::llround(res[kResRedone]);
+  h->persist_ns_total += res[kResDevNs];
+  h->persist_passes += (uint64_t)passes + (uint64_t)std::llround(res[kResRedone]);
+  h->device_updates++;
+  h->device_redone += (uint64_t)std::llround(res[kResRedone]);
+  if (failed == 2) return fail(h, FLIMO_ERR_STATE, "a peer rank did not deliver its pass sums in time");
+  if (failed) return fail(h, FLIMO_ERR_STATE, "singular or non-finite normal equations: state left at the prediction");
+  return FLIMO_OK;
 }
 
 // ---- scan preparation --------------------------------------------------------------------------------
@@ -1458,14 +1521,19 @@ int flimo_update(flimo_handle h, double state26[26], double P529[529], int max_i
                  double R_noise, double D_degeneracy, int* passes_out) {
   if (!h || !state26 || !P529 || !limit23) return fail(h, FLIMO_ERR_INVALID, "null argument");
   ekf::IteratedUpdate& u = h->upd;
-  u.begin(state26, P529, max_iter, limit23, R_noise, D_degeneracy);
-  double x[26], HTH[144], HTh[12];
   ++h->update_calls;
   // Every time_every-th update runs with one launch per pass so that the kernel can be timed with CUDA
   // events (flimo_stats::match_ms_total); the others keep one persistent kernel resident over all passes.
   const bool classic = !h->persistent || h->device < 0 || h->persist_capacity <= 0 || !flimo_map_exists(h) ||
                        h->shard_end <= h->shard_begin || h->timing != nullptr ||
                        (h->time_every > 0 && (h->update_calls % (uint64_t)h->time_every) == 0);
+  if (!classic && h->device_ekf) {                        // the whole update on the device
+    NEED_GPU(h);
+    const int rc = update_device(h, state26, P529, max_iter, limit23, R_noise, D_degeneracy, passes_out, false);
+    if (rc <= 0) return rc;
+  }
+  u.begin(state26, P529, max_iter, limit23, R_noise, D_degeneracy);
+  double x[26], HTH[144], HTh[12];
   if (!classic && !u.done()) {
     const int rc = update_persistent(h, u, false);
     if (rc < 0) return rc;
@@ -1484,6 +1552,78 @@ int flimo_update(flimo_handle h, double state26[26], double P529[529], int max_i
   if (passes_out) *passes_out = u.passes();
   if (u.failed()) return fail(h, FLIMO_ERR_STATE, "singular or non-finite normal equations: state left at the prediction");
   return FLIMO_OK;
+}
+
+int flimo_update_trace(flimo_handle h, double* out32, size_t cap_passes, size_t* n_passes) {
+  if (!h || !n_passes) return fail(h, FLIMO_ERR_INVALID, "null argument");
+  NEED_GPU(h);
+  *n_passes = 0;
+  static ekf::UpdState tmp;                                // 10 KB: not on the stack of a callback thread
+  CU(h, cudaStreamSynchronize(h->stream));
+  CU(h, cudaMemcpy(&tmp, h->upd_state, sizeof(tmp), cudaMemcpyDeviceToHost));
+  const size_t n = (size_t)std::min(std::max(tmp.passes, 0), ekf::kMaxTrace);
+  *n_passes = n;
+  if (out32)
+    for (size_t i = 0; i < n && i < cap_passes; ++i) std::memcpy(out32 + 32 * i, tmp.trace[i], 32 * sizeof(double));
+  return FLIMO_OK;
+}
+
+// ---- peer exchange over NVLink -------------------------------------------------------------------------
+int flimo_peer_export(flimo_handle h, void* ipc_handle_64) {
+  if (!h || !ipc_handle_64) return fail(h, FLIMO_ERR_INVALID, "null argument");
+  NEED_GPU(h);
+  static_assert(sizeof(cudaIpcMemHandle_t) == FLIMO_PEER_HANDLE_BYTES, "cudaIpcMemHandle_t is 64 bytes");
+  if (!h->inbox) {
+    CU(h, cudaMalloc(&h->inbox, kInboxBytes));
+    CU(h, cudaMemset(h->inbox, 0, kInboxBytes));
+    CU(h, cudaDeviceSynchronize());
+  }
+  cudaIpcMemHandle_t hd;
+  CU(h, cudaIpcGetMemHandle(&hd, h->inbox));
+  std::memcpy(ipc_handle_64, &hd, sizeof(hd));
+  return FLIMO_OK;
+}
+
+int flimo_peer_attach(flimo_handle h, int rank, int world, const void* ipc_handles) {
+  if (!h || !ipc_handles || world < 1 || world > kMaxPeers || rank < 0 || rank >= world)
+    return fail(h, FLIMO_ERR_INVALID, "bad peer arguments (at most 8 ranks)");
+  NEED_GPU(h);
+  if (!h->inbox) return fail(h, FLIMO_ERR_STATE, "flimo_peer_export not called");
+  for (int r = 0; r < h->peer_world; ++r)
+    if (h->peer_inbox[r] && r != h->peer_rank) cudaIpcCloseMemHandle(h->peer_inbox[r]);
+  for (int r = 0; r < kMaxPeers; ++r) h->peer_inbox[r] = nullptr;
+  h->peer_world = 0;
+  for (int r = 0; r < world; ++r) {
+    if (r == rank) {
+      h->peer_inbox[r] = h->inbox;
+      continue;
+    }
+    cudaIpcMemHandle_t hd;
+    std::memcpy(&hd, static_cast<const unsigned char*>(ipc_handles) + (size_t)r * sizeof(hd), sizeof(hd));
+    void* p = nullptr;
+    CU(h, cudaIpcOpenMemHandle(&p, hd, cudaIpcMemLazyEnablePeerAccess));
+    h->peer_inbox[r] = static_cast<double*>(p);
+  }
+  h->peer_rank = rank;
+  h->peer_world = world;
+  h->peer_xseq = 0;
+  return FLIMO_OK;
+}
+
+int flimo_update_peer(flimo_handle h, double state26[26], double P529[529], int max_iter, const double limit23[23],
+                      double R_noise, double D_degeneracy, int* passes_out) {
+  if (!h || !state26 || !P529 || !limit23) return fail(h, FLIMO_ERR_INVALID, "null argument");
+  NEED_GPU(h);
+  if (h->peer_world < 1) return fail(h, FLIMO_ERR_STATE, "flimo_peer_attach not called");
+  if (!flimo_map_exists(h)) return fail(h, FLIMO_ERR_STATE, "flimo_update_peer needs a map on every rank");
+  if (max_iter < 0) {
+    if (passes_out) *passes_out = 0;
+    return FLIMO_OK;
+  }
+  ++h->update_calls;
+  const int rc = update_device(h, state26, P529, max_iter, limit23, R_noise, D_degeneracy, passes_out, true);
+  if (rc == 1) return fail(h, FLIMO_ERR_STATE, "this rank has no scan points to match (every rank needs a non-empty shard)");
+  return rc;
 }
 
 int flimo_update_exchange(flimo_handle h, double state26[26], double P529[529], int max_iter, const double limit23[23],

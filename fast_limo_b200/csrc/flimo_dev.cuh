@@ -5,6 +5,8 @@
 
 #include <vector>
 
+#include "ekf_step.hpp"
+
 namespace flimo {
 
 // One level of the device map index.
@@ -110,6 +112,33 @@ struct MatchParams {
   unsigned long long ctl_seq;  // tag of the first command (commands are numbered independently of the results)
 };
 
+// Parameter block of the registration kernel (one launch = one whole iterated update, no host between passes).
+constexpr int kResRecords = 576;      // host result block: records {double value, u64 seq}
+constexpr int kResX = 0, kResP = 26, kResPasses = 555, kResFailed = 556, kResDevNs = 557, kResNValid = 558, kResNRows = 559,
+              kResRedone = 560;
+constexpr int kMaxPeers = 8;
+// Peer inbox (device memory of every rank, mapped by all ranks of the node through CUDA IPC):
+//   records : [parity 2][source rank 8][128] x {double value, u64 seq}   (0..95 pass sums, 96 = "flag words stored")
+//   flagbits: [parity 2][source rank 8][kFlagWordsCap] u32               accepted-match bits by original scan index
+constexpr int kInboxSlot = 128;                         // records per (parity, source)
+constexpr int kFlagWordsCap = 1 << 15;                  // 2^20 scan points
+constexpr size_t kInboxRecordBytes = (size_t)2 * kMaxPeers * kInboxSlot * 16;
+constexpr size_t kInboxBytes = kInboxRecordBytes + (size_t)2 * kMaxPeers * kFlagWordsCap * 4;
+struct RegParams {
+  MatchParams m;
+  ekf::UpdInit u;
+  ekf::UpdState* st;             // carried state (device memory)
+  double* host_res;              // device alias of the mapped pinned result block
+  unsigned long long res_seq;    // tag of this update's result records
+  // scan sharded over several GPUs: every rank stores its 96 partial sums into every rank's inbox (peer memory
+  // over NVLink), sums the inbox in rank order and runs the identical step
+  int world, rank;
+  double* inbox[kMaxPeers];      // inbox[r] = rank r's inbox as mapped in this process; layout [parity][source rank][96] records of 16 bytes
+  unsigned long long xseq;       // sequence number of the first exchange of this update
+  unsigned long long peer_timeout_ns;
+  uint32_t* flag_words;          // scratch: this rank's accepted-match bits (ceil(raw_n / 32) words)
+};
+
 // map_index.cu
 struct LevelIndex {
   float4* pts = nullptr;        // duplicated, sorted
@@ -210,7 +239,9 @@ cudaError_t points_bbox(const float4* d_pts, size_t n, float* d_scratch8, float 
 // match_kernel.cu
 cudaError_t launch_match(const MatchParams& p, cudaStream_t st);
 cudaError_t launch_match_persistent(const MatchParams& p, int grid, cudaStream_t st);
+cudaError_t launch_registration(const RegParams& p, int grid, cudaStream_t st);
 int match_persistent_capacity();
+int registration_capacity();
 int match_num_tiles(int n_queries);
 
 }  // namespace flimo

@@ -135,9 +135,33 @@ int flimo_exchange_attach(flimo_handle h, void* shared_host_mem, size_t bytes, i
 int flimo_match_reduce_exchange(flimo_handle h, const double state14[14], double HTH[144], double HTh[12],
                                 int64_t* n_valid, int64_t* n_rows, double* sum_sq_res);
 
-/* flimo_update with every measurement pass summed over ranks through the exchange segment. */
+/* flimo_update with every measurement pass summed over ranks through the exchange segment.  The host-segment
+ * exchange cannot order accepted matches across shards: when the summed n_valid exceeds MAX_NUM_MATCHES
+ * (Localizer.cpp:539) both exchange calls FAIL with FLIMO_ERR_STATE instead of returning normal equations that
+ * differ from the single-GPU ones -- flimo_update_peer below applies the first-N rule across shards. */
 int flimo_update_exchange(flimo_handle h, double state26[26], double P529[529], int max_iter,
                           const double limit23[23], double R_noise, double D_degeneracy, int* passes_out);
+
+/* ---- multi-GPU over NVLink peer memory (one process per GPU, one node) ------------------------
+ * The scan is sharded over the ranks (flimo_scan_shard), the map is replicated.  Every rank owns an INBOX in
+ * device memory; flimo_peer_export returns its CUDA IPC handle (64 bytes), the ranks exchange the handles by
+ * any means (torch.distributed.all_gather in fast_limo_b200/dist.py) and flimo_peer_attach maps all of them.
+ * flimo_update_peer then runs the WHOLE iterated update (esekfom.hpp:1620-1823) inside one kernel per rank:
+ * the CTA that completes a pass stores its 96 partial sums into every rank's inbox with peer stores over
+ * NVLink, sums the records of all ranks in rank order and runs the filter step on the device -- identical on
+ * every rank, no host, no collective launch, no pose exchange.  The MAX_NUM_MATCHES first-N rule
+ * (Localizer.cpp:539,547-548) is applied across shards (the accepted-match bits travel the same way), so the
+ * result equals the single-GPU one up to the float64 summation order. */
+#define FLIMO_PEER_HANDLE_BYTES 64
+int flimo_peer_export(flimo_handle h, void* ipc_handle_64);
+int flimo_peer_attach(flimo_handle h, int rank, int world, const void* ipc_handles /* world x 64 bytes, rank order */);
+int flimo_update_peer(flimo_handle h, double state26[26], double P529[529], int max_iter,
+                      const double limit23[23], double R_noise, double D_degeneracy, int* passes_out);
+
+/* Per-pass records of the last update that ran on the device (flimo_update, flimo_update_peer): for each pass
+ * 32 doubles = state26 after the pass, n_valid, n_rows, device time of the pass in ns, row limit, 0, 0.
+ * Returns the number of passes recorded (at most 16). */
+int flimo_update_trace(flimo_handle h, double* out32, size_t cap_passes, size_t* n_passes);
 
 /* Expands the 96-double packed form into HTH/HTh/... on the host. */
 void flimo_unpack96(const double packed[96], double HTH[144], double HTh[12], int64_t* n_valid,

@@ -350,6 +350,7 @@ def test_fused_exchange_two_processes(oracle, flimo_lib):
 
 def _stall_worker(stall, out):
     os.environ["FLIMO_TEST_STALL_PASS"] = str(stall)
+    os.environ["FLIMO_DEVICE_EKF"] = "0"                   # the host-driven form: persistent kernel + handshake
     case = synth.make_case("tiny")
     m = mapper()
     m.add(case.map_pts)
@@ -376,7 +377,11 @@ def test_persistent_kernel_watchdog_fallback(flimo_lib, stall):
     p.join(300)
     assert p.exitcode == 0
     case = synth.make_case("tiny")
-    m = mapper()
+    os.environ["FLIMO_DEVICE_EKF"] = "0"
+    try:
+        m = mapper()
+    finally:
+        del os.environ["FLIMO_DEVICE_EKF"]
     m.add(case.map_pts)
     m.set_scan(case.scan)
     x1, P1, p1 = m.update(case.init, synth.default_P0(), 2, 0.0)
