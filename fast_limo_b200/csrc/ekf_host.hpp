@@ -35,6 +35,11 @@
 #else
 #define FLIMO_HD
 #endif
+#if defined(__CUDA_ARCH__)
+#define FLIMO_UNROLL _Pragma("unroll")
+#else
+#define FLIMO_UNROLL
+#endif
 
 namespace flimo {
 namespace ekf {
@@ -137,7 +142,7 @@ FLIMO_HD inline Mat<3, 3> rotmat(const Q4& q) {
 
 // cos(sqrt(x2)), sin(sqrt(x2))/sqrt(x2) with the Taylor branch of mtkmath.hpp:143-175
 FLIMO_HD inline void cos_sinc(double x2, double& c, double& sc) {
-  const double bound = sqrt(sqrt(2.220446049250313e-16));
+  const double bound = 1.220703125e-4;   // sqrt(sqrt(epsilon)) = 2^-13 exactly (mtkmath.hpp:146)
   if (x2 >= bound) {
     const double x = sqrt(x2);
     c = cos(x);
@@ -314,21 +319,28 @@ FLIMO_HD inline bool invert(Mat<n, n>& M) {
 FLIMO_HD inline bool all_eigs_above(const Mat<6, 6>& S, double floor) {
   double L[6][6];
   double scale = 0.0;
+FLIMO_UNROLL
   for (int i = 0; i < 6; ++i) scale = fmax(scale, fabs(S(i, i)));
   const double tiny = 1e-9 * (scale + fabs(floor)) + 1e-300;
+  bool ok = true;
+FLIMO_UNROLL
   for (int j = 0; j < 6; ++j) {
     double d = S(j, j) - floor;
+FLIMO_UNROLL
     for (int k = 0; k < j; ++k) d -= L[j][k] * L[j][k];
-    if (!(d > tiny)) return false;
-    const double dj = sqrt(d);
+    if (!(d > tiny)) ok = false;
+    const double dj = sqrt(ok ? d : 1.0);
     L[j][j] = dj;
+    const double inv = 1.0 / dj;
+FLIMO_UNROLL
     for (int i = j + 1; i < 6; ++i) {
       double v = S(i, j);
+FLIMO_UNROLL
       for (int k = 0; k < j; ++k) v -= L[i][k] * L[j][k];
-      L[i][j] = v / dj;
+      L[i][j] = v * inv;
     }
   }
-  return true;
+  return ok;
 }
 
 // Symmetric Jacobi eigen-decomposition (6x6), columns of V are eigenvectors.
@@ -547,7 +559,7 @@ class IteratedUpdate {
     if (converge) ++conv_count_;
     std::memcpy(last_dx_, dxk, sizeof(dxk));
 
-    if (conv_count_ > 1 || iter_ == max_iter_ - 1) {
+    if (conv_count_ > 1 || iter_ == max_iter_ - 1 || force_final_) {
       Mat<N, N> L = P_;
       for (int idx : {3, 6}) {
         const Mat<3, 3> J = A_matrix({dxk[idx], dxk[idx + 1], dxk[idx + 2]}).T();
@@ -587,6 +599,18 @@ class IteratedUpdate {
     return done_;
   }
 
+  // The last pass of an update whose earlier passes ran elsewhere (device-resident registration): continue from the
+  // state the last pass was evaluated at and take the final branch (esekfom.hpp:1764-1819) whatever the local
+  // convergence test says — the caller has already decided that this pass ends the loop.
+  bool finish(const double* x_eval26, const double* HTH144, const double* HTh12, int64_t n_rows) {
+    x_.load(x_eval26);
+    done_ = false;
+    force_final_ = true;
+    const bool d = step(HTH144, HTh12, n_rows);
+    force_final_ = false;
+    return d;
+  }
+
   const double* last_dx() const { return last_dx_; }
   bool failed() const { return failed_; }   // a singular / non-finite system was met: x and P are the propagated ones
 
@@ -608,7 +632,7 @@ class IteratedUpdate {
   double last_dx_[N];
   int max_iter_ = 0, iter_ = -1, conv_count_ = 0, passes_ = 0;
   double R_ = 0.001, D_ = 5.0;
-  bool done_ = true, failed_ = false;
+  bool done_ = true, failed_ = false, force_final_ = false;
  public:
   bool reference_form_ = false;   // true: form the gain with the reference's two 23x23 inversions (FLIMO_EKF_REFERENCE_FORM=1)
  private:

@@ -119,12 +119,17 @@ struct flimo_ctx {
   int device_ekf = 1;            // FLIMO_DEVICE_EKF=0: keep the filter step on the host (persistent kernel + handshake)
   int reg_capacity = 0;
   ekf::UpdState* upd_state = nullptr;   // device
+  ekf::UpdInit* h_in = nullptr;         // mapped pinned input block of the filter kernel
+  ekf::UpdInit* d_h_in = nullptr;       // its device alias
+  ekf::UpdInit* dev_in = nullptr;       // device copy (made by the filter kernel)
+  cudaStream_t filter_stream = nullptr;
   double* h_res = nullptr;       // mapped pinned result block: kResRecords records {value, seq}
   double* d_h_res = nullptr;
   unsigned long long res_seq = 0;
   uint32_t* flag_words = nullptr;
   size_t flag_words_cap = 0;
   uint64_t device_updates = 0, device_redone = 0;
+  double last_x_dev[26] = {0};   // the device's own state after the last pass of the last update (tests)
   // peer exchange over NVLink (flimo_peer_*): every rank's inbox mapped through CUDA IPC
   double* inbox = nullptr;
   double* peer_inbox[kMaxPeers] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -474,9 +479,15 @@ int flimo_create(const flimo_cfg* cfg, int device, flimo_handle* out) {
   CU(h, cudaMalloc(&h->dev_ctl, sizeof(PassCtl)));
   CU(h, cudaMemset(h->dev_ctl, 0, sizeof(PassCtl)));
   h->persist_capacity = match_persistent_capacity();
+  CU(h, preload_match_kernels());
+  CU(h, preload_filter_kernel());
   h->reg_capacity = registration_capacity();
   CU(h, cudaMalloc(&h->upd_state, sizeof(ekf::UpdState)));
   CU(h, cudaMemset(h->upd_state, 0, sizeof(ekf::UpdState)));
+  CU(h, cudaHostAlloc(&h->h_in, sizeof(ekf::UpdInit), cudaHostAllocMapped));
+  CU(h, cudaHostGetDevicePointer(reinterpret_cast<void**>(&h->d_h_in), h->h_in, 0));
+  CU(h, cudaMalloc(&h->dev_in, sizeof(ekf::UpdInit)));
+  CU(h, cudaStreamCreateWithFlags(&h->filter_stream, cudaStreamNonBlocking));
   CU(h, cudaHostAlloc(&h->h_res, (size_t)kResRecords * 16, cudaHostAllocMapped));
   std::memset(h->h_res, 0, (size_t)kResRecords * 16);
   CU(h, cudaHostGetDevicePointer(reinterpret_cast<void**>(&h->d_h_res), h->h_res, 0));
@@ -531,6 +542,12 @@ void flimo_destroy(flimo_handle h) {
   if (h->ev_prefetch) cudaEventDestroy(h->ev_prefetch);
   cudaFree(h->dev_ctl);
   cudaFree(h->upd_state);
+  cudaFreeHost(h->h_in);
+  cudaFree(h->dev_in);
+  if (h->filter_stream) {
+    cudaStreamSynchronize(h->filter_stream);
+    cudaStreamDestroy(h->filter_stream);
+  }
   cudaFreeHost(h->h_res);
   cudaFree(h->flag_words);
   for (int r = 0; r < h->peer_world; ++r)
@@ -1301,13 +1318,16 @@ static int update_device(flimo_handle h, double state26[26], double P529[529], i
   std::memset(&RP, 0, sizeof(RP));
   int rc = fill_params(h, state26, RP.m, h->out96, 0xFFFFFFFFu, nullptr, nullptr);
   if (rc) return rc;
-  std::memcpy(RP.u.x, state26, sizeof(RP.u.x));
-  std::memcpy(RP.u.P, P529, sizeof(RP.u.P));
-  std::memcpy(RP.u.limit, limit23, sizeof(RP.u.limit));
-  RP.u.R = R_noise;
-  RP.u.D = D_degeneracy;
-  RP.u.max_iter = max_iter;
-  RP.u.max_matches = h->cfg.MAX_NUM_MATCHES;
+  ekf::UpdInit& in = *h->h_in;                           // read by the filter kernel over PCIe at its start
+  std::memcpy(in.x, state26, sizeof(in.x));
+  std::memcpy(in.P, P529, sizeof(in.P));
+  std::memcpy(in.limit, limit23, sizeof(in.limit));
+  in.R = R_noise;
+  in.D = D_degeneracy;
+  in.max_iter = max_iter;
+  in.max_matches = h->cfg.MAX_NUM_MATCHES;
+  RP.host_in = h->d_h_in;
+  RP.dev_in = h->dev_in;
   RP.st = h->upd_state;
   RP.host_res = h->d_h_res;
   RP.res_seq = ++h->res_seq;
@@ -1315,6 +1335,7 @@ static int update_device(flimo_handle h, double state26[26], double P529[529], i
   RP.rank = exchange ? h->peer_rank : 0;
   for (int r = 0; r < kMaxPeers; ++r) RP.inbox[r] = exchange ? h->peer_inbox[r] : nullptr;
   RP.peer_timeout_ns = 2000ull * 1000ull * 1000ull;
+  RP.m.watchdog_ns = 4000ull * 1000ull * 1000ull;       // hang protection only: tiles without a filter kernel (or vice versa) give up
   const int max_cmds = 2 * (max_iter + 2) + 2;          // every pass may be repeated once (first-N rule) + stop
   RP.xseq = h->peer_xseq + 1;
   h->peer_xseq += (unsigned long long)max_cmds;
@@ -1332,8 +1353,10 @@ static int update_device(flimo_handle h, double state26[26], double P529[529], i
   }
   const int tiles = match_num_tiles((int)n);
   const int grid = std::min(tiles, h->reg_capacity);
-  CU(h, launch_registration(RP, grid, h->stream));
-  h->stats.kernel_launches++;
+  // the filter CTA first (its own stream: it has to run beside the tiles), then the tiles
+  CU(h, launch_filter(RP, h->filter_stream));
+  CU(h, launch_registration_tiles(RP.m, grid, h->stream));
+  h->stats.kernel_launches += 2;
   if (h->pref_idx >= 0 && !h->pref_issued) {               // the requested copy of the next scan overlaps the update
     rc = issue_prefetch(h);
     if (rc) return rc;
@@ -1343,16 +1366,36 @@ static int update_device(flimo_handle h, double state26[26], double P529[529], i
   if (wr < 0) return wr;
   if (wr == 1) return fail(h, FLIMO_ERR_CUDA, "registration kernel finished without publishing its result");
   const int passes = (int)std::llround(res[kResPasses]);
-  const int failed = (int)std::llround(res[kResFailed]);
-  std::memcpy(state26, &res[kResX], 26 * sizeof(double));
-  std::memcpy(P529, &res[kResP], 529 * sizeof(double));
+  int failed = (int)std::llround(res[kResFailed]);
   if (passes_out) *passes_out = passes;
-  h->stats.match_launches += (uint64_t)passes + (uint64_t)std::llround(res[kResRedone]);
+  const uint64_t redone = (uint64_t)std::llround(res[kResRedone]);
+  h->stats.match_launches += (uint64_t)passes + redone;
   h->persist_ns_total += res[kResDevNs];
-  h->persist_passes += (uint64_t)passes + (uint64_t)std::llround(res[kResRedone]);
+  h->persist_passes += (uint64_t)passes + redone;
   h->device_updates++;
-  h->device_redone += (uint64_t)std::llround(res[kResRedone]);
-  if (failed == 2) return fail(h, FLIMO_ERR_STATE, "a peer rank did not deliver its pass sums in time");
+  h->device_redone += redone;
+  if (!failed) {
+    // the last pass: final state and covariance (esekfom.hpp:1764-1819) from the state it was evaluated at and its sums
+    double HTH[144], HTh[12];
+    int64_t nv = 0, nr = 0;
+    double ss = 0;
+    flimo_unpack96(&res[kResSums], HTH, HTh, &nv, &nr, &ss);
+    ekf::IteratedUpdate& u = h->upd;
+    u.begin(state26, P529, max_iter, limit23, R_noise, D_degeneracy);
+    const auto ts0 = std::chrono::steady_clock::now();
+    u.finish(&res[kResXEval], HTH, HTh, nr);
+    if (h->prof) h->prof_step += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - ts0).count();
+    u.end(state26, P529);
+    std::memcpy(h->last_x_dev, &res[kResXDev], sizeof(h->last_x_dev));
+    if (u.failed()) failed = 1;
+  }
+  if (failed) {
+    // the kernels may have stopped in the middle of a pass: drain them and clear the last-CTA-done counters
+    cudaStreamSynchronize(h->filter_stream);
+    cudaStreamSynchronize(h->stream);
+    if (h->ticket) cudaMemset(h->ticket, 0, h->ticket_cap * sizeof(unsigned int));
+  }
+  if (failed == 2) return fail(h, FLIMO_ERR_STATE, "a peer rank (or this rank's tile kernel) did not deliver its pass sums in time");
   if (failed) return fail(h, FLIMO_ERR_STATE, "singular or non-finite normal equations: state left at the prediction");
   return FLIMO_OK;
 }
@@ -1565,6 +1608,12 @@ int flimo_update_trace(flimo_handle h, double* out32, size_t cap_passes, size_t*
   *n_passes = n;
   if (out32)
     for (size_t i = 0; i < n && i < cap_passes; ++i) std::memcpy(out32 + 32 * i, tmp.trace[i], 32 * sizeof(double));
+  if (h->prof)
+    for (size_t i = 0; i < n; ++i) {
+      std::fprintf(stderr, "[step %zu] ns after tree:", i);
+      for (int k = 0; k < 10; ++k) std::fprintf(stderr, " %c=%.0f", "ABCDEFGHIJ"[k], tmp.phase_ns[i][k]);
+      std::fprintf(stderr, "  pass total %.0f\n", tmp.trace[i][28]);
+    }
   return FLIMO_OK;
 }
 

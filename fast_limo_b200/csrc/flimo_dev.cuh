@@ -112,10 +112,12 @@ struct MatchParams {
   unsigned long long ctl_seq;  // tag of the first command (commands are numbered independently of the results)
 };
 
-// Parameter block of the registration kernel (one launch = one whole iterated update, no host between passes).
-constexpr int kResRecords = 576;      // host result block: records {double value, u64 seq}
-constexpr int kResX = 0, kResP = 26, kResPasses = 555, kResFailed = 556, kResDevNs = 557, kResNValid = 558, kResNRows = 559,
-              kResRedone = 560;
+// Parameter block of the filter kernel (filter_kernel.cu; with registration_tiles_kernel: one whole iterated update,
+// no host between passes).
+constexpr int kResRecords = 160;      // host result block: records {double value, u64 seq}
+// x_eval = state the LAST pass was evaluated at, sums = its 96 packed sums (the host forms the final state and
+// covariance from them, IteratedUpdate::finish), x_dev = the device's own state after the last pass (tests)
+constexpr int kResXEval = 0, kResSums = 26, kResPasses = 122, kResFailed = 123, kResDevNs = 124, kResRedone = 125, kResXDev = 128;
 constexpr int kMaxPeers = 8;
 // Peer inbox (device memory of every rank, mapped by all ranks of the node through CUDA IPC):
 //   records : [parity 2][source rank 8][128] x {double value, u64 seq}   (0..95 pass sums, 96 = "flag words stored")
@@ -126,8 +128,9 @@ constexpr size_t kInboxRecordBytes = (size_t)2 * kMaxPeers * kInboxSlot * 16;
 constexpr size_t kInboxBytes = kInboxRecordBytes + (size_t)2 * kMaxPeers * kFlagWordsCap * 4;
 struct RegParams {
   MatchParams m;
-  ekf::UpdInit u;
-  ekf::UpdState* st;             // carried state (device memory)
+  const ekf::UpdInit* host_in;   // device alias of the mapped pinned input block (read once, over PCIe, at kernel start)
+  ekf::UpdInit* dev_in;          // its copy in device memory
+  ekf::UpdState* st;             // results / trace (device memory)
   double* host_res;              // device alias of the mapped pinned result block
   unsigned long long res_seq;    // tag of this update's result records
   // scan sharded over several GPUs: every rank stores its 96 partial sums into every rank's inbox (peer memory
@@ -239,9 +242,12 @@ cudaError_t points_bbox(const float4* d_pts, size_t n, float* d_scratch8, float 
 // match_kernel.cu
 cudaError_t launch_match(const MatchParams& p, cudaStream_t st);
 cudaError_t launch_match_persistent(const MatchParams& p, int grid, cudaStream_t st);
-cudaError_t launch_registration(const RegParams& p, int grid, cudaStream_t st);
+cudaError_t launch_registration_tiles(const MatchParams& p, int grid, cudaStream_t st);
+cudaError_t launch_filter(const RegParams& p, cudaStream_t st);
 int match_persistent_capacity();
 int registration_capacity();
+cudaError_t preload_match_kernels();
+cudaError_t preload_filter_kernel();
 int match_num_tiles(int n_queries);
 
 }  // namespace flimo

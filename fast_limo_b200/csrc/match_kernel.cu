@@ -27,7 +27,6 @@
 
 #include "flimo_dev.cuh"
 #include "grid_math.cuh"
-#include "pose_consts.hpp"
 
 namespace flimo {
 
@@ -790,7 +789,7 @@ struct TileShared {
 // Returns true (in every thread of the CTA) when this CTA completed the tree: the packed result of the pass
 // (flimo.h layout, 96 doubles) is then staged in sh.wsum[0] and the caller decides what happens with it
 // (publish_result for the host-driven kernels, the filter step in the registration kernel).
-template <bool kWide, bool kPair>
+template <bool kWide, bool kPair, bool kExternalFinal = false>
 __device__ __forceinline__ bool match_tile(const MatchParams& P, const PoseConsts& pc, TileShared& sh, const int tile_idx,
                                            const int n_tiles, const uint32_t orig_limit) {
   auto& tile = sh.tile;
@@ -1036,6 +1035,7 @@ __device__ __forceinline__ bool match_tile(const MatchParams& P, const PoseConst
     const unsigned int prev = atomicAdd(&P.ticket[0], 1u);
     s_last = (prev == (unsigned int)(n_groups - 1)) ? 1 : 0;
   }
+  if (kExternalFinal) return false;   // the filter kernel waits for ticket[0] == n_groups and sums the group partials itself
   __syncthreads();
   if (!s_last) return false;
   __threadfence();
@@ -1173,184 +1173,19 @@ __global__ void __launch_bounds__(kTileQueries, 7) match_persistent_kernel(const
 }
 
 // ---------------------------------------------------------------------------------------------------
-// Registration kernel: ONE launch = one whole esekf::update_iterated_dyn_share_modified (esekfom.hpp:1620-1823)
-// with NO host between the passes.  The CTAs stay resident; the CTA that completes the reduction tree of a
-// pass
-//   1. (scan sharded over several GPUs) stores its 96 partial sums into every rank's inbox — peer memory over
-//      NVLink, one tagged 16-byte record per value — waits for the records of all ranks in its own inbox and
-//      sums them in rank order, so that every rank holds bit-identical normal equations;
-//   2. applies the MAX_NUM_MATCHES first-N rule (Localizer.cpp:539,547-548) when more matches were accepted than
-//      the cap: the accepted-match bits are ordered by original scan index, the index after which rows stop
-//      counting is found by a prefix count, and the pass is repeated with that limit;
-//   3. runs the filter step (ekf_step.hpp) with its 128 threads, derives the pose constants of the next pass
-//      and releases the other CTAs through a device flag — or stores state + covariance into the mapped host
-//      result block when the update is complete.
-// Every rank runs the identical step on identical sums: no pose exchange, no host, no collective launch.
+// Registration, tile side: ONE launch = all measurement passes of one iterated update, with NO host between the
+// passes.  The CTAs stay resident; the pose of the first pass travels in the parameter block, the poses of the
+// following passes are posted to `dev_ctl` by the FILTER kernel (filter_kernel.cu: one CTA on a second stream that
+// sums the group partials of a pass as soon as the last group is complete, runs the filter step and derives the
+// next pose — or ends the update).  A CTA leaves when it reads the stop command, or after 0.5 s of silence.
 // ---------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void st_record(double* slot, double v, unsigned long long seq) {
-  *reinterpret_cast<ulonglong2*>(slot) = make_ulonglong2((unsigned long long)__double_as_longlong(v), seq);
-}
-__device__ __forceinline__ ulonglong2 ld_record(const double* slot) {
-  ulonglong2 r;
-  asm volatile("ld.volatile.global.v2.u64 {%0,%1}, [%2];" : "=l"(r.x), "=l"(r.y) : "l"(slot) : "memory");
-  return r;
-}
-__device__ __forceinline__ double* inbox_slot(double* inbox, unsigned long long xs, int src, int i) {
-  return inbox + ((((size_t)(xs & 1ull) * kMaxPeers + (size_t)src) * kInboxSlot + (size_t)i) * 2);
-}
-__device__ __forceinline__ uint32_t* inbox_flags(double* inbox, unsigned long long xs, int src) {
-  return reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(inbox) + kInboxRecordBytes) +
-         ((size_t)(xs & 1ull) * kMaxPeers + (size_t)src) * kFlagWordsCap;
-}
-
-// Exchange of the staged pass sums (sh.wsum[0]) over all ranks.  Returns false on a peer time-out.
-__device__ __forceinline__ bool peer_exchange_sums(const RegParams& RP, TileShared& sh, const unsigned long long xs, int* s_flag) {
-  const int t = (int)threadIdx.x;
-  if (t == 0) *s_flag = 1;
-  __syncthreads();
-  if (t < kPartialStride) {
-    const double mine = sh.wsum[0][t];
-    for (int r = 0; r < RP.world; ++r) st_record(inbox_slot(RP.inbox[r], xs, RP.rank, t), mine, xs);
-    const unsigned long long t0 = globaltimer_ns();
-    double sum = 0.0;
-    for (int r = 0; r < RP.world; ++r) {                 // fixed rank order: identical sums on every rank
-      const double* slot = inbox_slot(RP.inbox[RP.rank], xs, r, t);
-      ulonglong2 rec = ld_record(slot);
-      while (rec.y != xs) {
-        if (globaltimer_ns() - t0 > RP.peer_timeout_ns) {
-          *s_flag = 0;
-          break;
-        }
-        rec = ld_record(slot);
-      }
-      double v = __longlong_as_double((long long)rec.x);
-      if (t == 93) v = 0.0;                              // slot 93 is per-rank bookkeeping
-      sum += v;
-    }
-    sh.wsum[1][t] = sum;
-  }
-  __syncthreads();
-  if (t < kPartialStride) sh.wsum[0][t] = sh.wsum[1][t];
-  __syncthreads();
-  return *s_flag != 0;
-}
-
-// First-N rule: returns the original index after which accepted rows stop counting (cap-th accepted match in scan
-// order, over all ranks), or 0xFFFFFFFF on a peer time-out.  Called by all threads of the step CTA.
-__device__ __forceinline__ uint32_t first_n_limit(const RegParams& RP, TileShared& sh, const unsigned long long xs, const long long cap) {
-  const MatchParams& P = RP.m;
-  const int t = (int)threadIdx.x;
-  const uint32_t n = P.raw_n, n_words = (n + 31u) >> 5;
-  uint32_t* words = RP.flag_words;
-  int* s_i = reinterpret_cast<int*>(&sh.wsum[2][0]);       // [0..127] counts, [128] chunk, [129] before, [130] limit, [131] ok
-  if (cap <= 0) return 0u;
-  // 1. pack this rank's byte flags into bits (flags of points outside the shard are zero)
-  for (uint32_t w = (uint32_t)t; w < n_words; w += kTileQueries) {
-    uint32_t bits = 0;
-    const uint32_t base = w << 5;
-    if (base + 32u <= n) {
-      const uint4 a = __ldcg(reinterpret_cast<const uint4*>(P.valid_by_orig + base)), b = __ldcg(reinterpret_cast<const uint4*>(P.valid_by_orig + base + 16));
-      const uint32_t v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-#pragma unroll
-      for (int k = 0; k < 8; ++k)
-        bits |= (((v[k] & 1u) | ((v[k] >> 7) & 2u) | ((v[k] >> 14) & 4u) | ((v[k] >> 21) & 8u)) << (4 * k));
-    } else {
-      for (uint32_t i = base; i < n; ++i) bits |= (uint32_t)(__ldcg(P.valid_by_orig + i) & 1u) << (i - base);
-    }
-    words[w] = bits;
-    if (RP.world > 1)
-      for (int r = 0; r < RP.world; ++r) inbox_flags(RP.inbox[r], xs, RP.rank)[w] = bits;
-  }
-  if (t == 0) s_i[131] = 1;
-  __syncthreads();
-  if (RP.world > 1) {
-    __threadfence_system();                               // the bit words are visible before the "stored" record
-    __syncthreads();
-    if (t < RP.world) st_record(inbox_slot(RP.inbox[t], xs, RP.rank, 96), (double)n_words, xs);
-    if (t < RP.world) {
-      const unsigned long long t0 = globaltimer_ns();
-      const double* slot = inbox_slot(RP.inbox[RP.rank], xs, t, 96);
-      while (ld_record(slot).y != xs)
-        if (globaltimer_ns() - t0 > RP.peer_timeout_ns) {
-          s_i[131] = 0;
-          break;
-        }
-    }
-    __syncthreads();
-    if (!s_i[131]) return 0xFFFFFFFFu;
-    for (uint32_t w = (uint32_t)t; w < n_words; w += kTileQueries) {   // shards are disjoint: OR = union
-      uint32_t bits = 0;
-      for (int r = 0; r < RP.world; ++r) {
-        uint32_t v;
-        asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(inbox_flags(RP.inbox[RP.rank], xs, r) + w) : "memory");
-        bits |= v;
-      }
-      words[w] = bits;
-    }
-    __syncthreads();
-  }
-  // 2. prefix count over contiguous chunks of words
-  const uint32_t chunk = (n_words + kTileQueries - 1) / kTileQueries;
-  const uint32_t w0 = min((uint32_t)t * chunk, n_words), w1 = min(w0 + chunk, n_words);
-  int cnt = 0;
-  for (uint32_t w = w0; w < w1; ++w) cnt += __popc(words[w]);
-  s_i[t] = cnt;
-  __syncthreads();
-  if (t == 0) {
-    long long before = 0;
-    int sel = -1;
-    for (int k = 0; k < kTileQueries; ++k) {
-      if (before + s_i[k] >= cap) {
-        sel = k;
-        break;
-      }
-      before += s_i[k];
-    }
-    s_i[128] = sel;
-    s_i[129] = (int)before;
-    s_i[130] = (int)n;                                    // fewer than cap accepted: everything counts
-  }
-  __syncthreads();
-  if (s_i[128] == t) {
-    long long need = cap - (long long)s_i[129];           // the need-th set bit of this chunk
-    for (uint32_t w = w0; w < w1; ++w) {
-      const uint32_t bits = words[w];
-      const int c = __popc(bits);
-      if (need <= c) {
-        const uint32_t pos = __fns(bits, 0, (int)need);   // position of the need-th set bit
-        s_i[130] = (int)((w << 5) + pos + 1u);
-        break;
-      }
-      need -= c;
-    }
-  }
-  __syncthreads();
-  return (uint32_t)s_i[130];
-}
-
 template <bool kWide, bool kPair>
-__global__ void __launch_bounds__(kTileQueries, 7) registration_kernel(const __grid_constant__ RegParams RP) {
+__global__ void __launch_bounds__(kTileQueries, 7) registration_tiles_kernel(const __grid_constant__ MatchParams P) {
   __shared__ TileShared sh;
   __shared__ PassCtl s_ctl;
-  __shared__ int s_flag;
-  static_assert(sizeof(ekf::StepShared) <= sizeof(sh.tile), "the step scratch overlays the tile buffer");
-  const MatchParams& P = RP.m;
   const int n_tiles = match_num_tiles_dev(P.q_end - P.q_begin);
   PassCtl* dctl = P.dev_ctl;
-  ekf::UpdState& st = *RP.st;
   const int tid = (int)threadIdx.x;
-  const unsigned long long t_kernel = globaltimer_ns();
-  if (blockIdx.x == 0) {                                   // carried state of a fresh update (IteratedUpdate::begin)
-    for (int i = tid; i < 26; i += kTileQueries) st.x[i] = RP.u.x[i];
-    if (tid == 0) {
-      st.iter = -1;
-      st.conv_count = 0;
-      st.passes = 0;
-      st.done = 0;
-      st.failed = 0;
-      st.pad_ = 0;                                         // passes that were repeated for the first-N rule
-    }
-  }
   for (unsigned long long cmd_no = 0;; ++cmd_no) {
     if (cmd_no == 0) {                                     // first pass: the pose travels in the parameter block
       const uint32_t* src = reinterpret_cast<const uint32_t*>(&P.pc);
@@ -1358,100 +1193,31 @@ __global__ void __launch_bounds__(kTileQueries, 7) registration_kernel(const __g
       for (int w = tid; w < (int)(sizeof(PoseConsts) / 4); w += kTileQueries) dst[w] = src[w];
       if (tid == 0) {
         s_ctl.cmd = 0u;
-        s_ctl.orig_limit = 0xFFFFFFFFu;
-        s_ctl.t_begin = t_kernel;
+        s_ctl.orig_limit = P.orig_limit;
       }
     } else {
       const unsigned long long want = P.ctl_seq + cmd_no - 1ull;
       if (tid == 0) {
-        while (ld_acquire_u64(&dctl->seq) != want) __nanosleep(64);
+        const unsigned long long t0 = globaltimer_ns();
+        unsigned int naps = 0;
+        while (ld_acquire_u64(&dctl->seq) != want) {
+          __nanosleep(32);
+          if ((++naps & 1023u) == 0u && globaltimer_ns() - t0 > P.watchdog_ns) {   // the filter kernel is gone
+            s_ctl.cmd = 2u;
+            break;
+          }
+        }
+        if (s_ctl.cmd != 2u) s_ctl.cmd = 0u;
       }
       __syncthreads();
+      if (s_ctl.cmd == 2u) return;
       const uint32_t* src = reinterpret_cast<const uint32_t*>(dctl);
       uint32_t* dst = reinterpret_cast<uint32_t*>(&s_ctl);
       for (int w = tid; w < (int)(sizeof(PassCtl) / 4); w += kTileQueries) dst[w] = __ldcg(src + w);
     }
     __syncthreads();
     if (s_ctl.cmd != 0u) return;
-    bool last = false;
-    for (int t = (int)blockIdx.x; t < n_tiles; t += (int)gridDim.x)
-      last = match_tile<kWide, kPair>(P, s_ctl.pc, sh, t, n_tiles, s_ctl.orig_limit);
-    if (last) {
-      // ---- this CTA completed the tree: sh.wsum[0] holds the packed sums of this rank ------------------
-      const unsigned long long xs = RP.xseq + cmd_no;
-      bool ok = true;
-      if (RP.world > 1) ok = peer_exchange_sums(RP, sh, xs, &s_flag);
-      uint32_t next_cmd = 0u, next_limit = 0xFFFFFFFFu;
-      bool new_pose = false;
-      const long long n_valid = (long long)(sh.wsum[0][92] + 0.5), cap = (long long)RP.u.max_matches;
-      if (!ok) {
-        if (tid == 0) st.failed = 2;                       // a peer did not answer
-        next_cmd = 1u;
-      } else if (P.valid_by_orig != nullptr && s_ctl.orig_limit == 0xFFFFFFFFu && n_valid > cap) {
-        next_limit = first_n_limit(RP, sh, xs, cap);       // repeat the pass: same pose, rows limited to the first `cap` matches
-        if (next_limit == 0xFFFFFFFFu) {
-          if (tid == 0) st.failed = 2;
-          next_cmd = 1u;
-        } else if (tid == 0) {
-          st.pad_ = st.pad_ + 1;
-        }
-      } else {
-        ekf::StepShared& ss = *reinterpret_cast<ekf::StepShared*>(&sh.tile[0][0][0]);
-        ekf::CtaExec ex{tid, kTileQueries};
-        const int pass_idx = FLIMO_LD_CG(&st.passes);
-        ekf::iterated_step(ex, ss, RP.u, st, &sh.wsum[0][0]);
-        __syncthreads();
-        if (pass_idx < ekf::kMaxTrace) {                   // per-pass record (tests, profiling)
-          double* tr = st.trace[pass_idx];
-          if (tid < 26) tr[tid] = ss.x[tid];
-          if (tid == 26) tr[26] = sh.wsum[0][92];
-          if (tid == 27) tr[27] = sh.wsum[0][90];
-          if (tid == 28) tr[28] = (double)(globaltimer_ns() - s_ctl.t_begin);
-          if (tid == 29) tr[29] = (double)s_ctl.orig_limit;
-        }
-        new_pose = true;
-        if (FLIMO_LD_CG(&st.done) != 0) next_cmd = 1u;
-      }
-      __syncthreads();
-      if (next_cmd != 0u && RP.host_res != nullptr) {
-        // the update is complete: state, covariance and counters go to the mapped host block as tagged records
-        const ekf::StepShared& ss = *reinterpret_cast<const ekf::StepShared*>(&sh.tile[0][0][0]);
-        const bool failed = FLIMO_LD_CG(&st.failed) != 0;
-        for (int i = tid; i < kResRecords; i += kTileQueries) {
-          double v = 0.0;
-          if (i < kResP) v = failed ? RP.u.x[i] : (new_pose ? ss.x[i] : FLIMO_LD_CG(&st.x[i]));
-          else if (i < kResP + ekf::N * ekf::N) v = failed ? RP.u.P[i - kResP] : FLIMO_LD_CG(&st.P[i - kResP]);
-          else if (i == kResPasses) v = (double)FLIMO_LD_CG(&st.passes);
-          else if (i == kResFailed) v = (double)FLIMO_LD_CG(&st.failed);
-          else if (i == kResDevNs) v = (double)(globaltimer_ns() - t_kernel);
-          else if (i == kResNValid) v = sh.wsum[0][92];
-          else if (i == kResNRows) v = sh.wsum[0][90];
-          else if (i == kResRedone) v = (double)FLIMO_LD_CG(&st.pad_);
-          st_record(RP.host_res + 2 * (size_t)i, v, RP.res_seq);
-        }
-      }
-      // post the next command for all CTAs of this rank
-      if (next_cmd == 0u && new_pose && tid == 0) {
-        double x14[14];
-        for (int i = 0; i < 14; ++i) x14[i] = FLIMO_LD_CG(&st.x[i]);
-        make_pose(x14, dctl->pc);
-      } else if (next_cmd == 0u && !new_pose) {           // repeated pass: same pose
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(&s_ctl.pc);
-        uint32_t* dst = reinterpret_cast<uint32_t*>(&dctl->pc);
-        for (int w = tid; w < (int)(sizeof(PoseConsts) / 4); w += kTileQueries) dst[w] = src[w];
-      }
-      if (tid == 0) {
-        dctl->cmd = next_cmd;
-        dctl->orig_limit = next_limit;
-        dctl->t_begin = globaltimer_ns();
-      }
-      __threadfence();
-      __syncthreads();
-      if (tid == 0) {
-        const unsigned long long pub = P.ctl_seq + cmd_no;
-        asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(&dctl->seq), "l"(pub) : "memory");
-      }
-    }
+    for (int t = (int)blockIdx.x; t < n_tiles; t += (int)gridDim.x) match_tile<kWide, kPair, true>(P, s_ctl.pc, sh, t, n_tiles, s_ctl.orig_limit);
     __syncthreads();
   }
 }
@@ -1478,21 +1244,40 @@ int match_persistent_capacity() {
   return sms * per_sm;
 }
 
-cudaError_t launch_registration(const RegParams& p, int grid, cudaStream_t st) {
-  const int n = p.m.q_end - p.m.q_begin;
+cudaError_t launch_registration_tiles(const MatchParams& p, int grid, cudaStream_t st) {
+  const int n = p.q_end - p.q_begin;
   if (n <= 0 || grid <= 0) return cudaErrorInvalidValue;
-  if (p.m.pair_scan) registration_kernel<true, true><<<grid, kTileQueries, 0, st>>>(p);
-  else if (p.m.wide_loads) registration_kernel<true, false><<<grid, kTileQueries, 0, st>>>(p);
-  else registration_kernel<false, false><<<grid, kTileQueries, 0, st>>>(p);
+  if (p.pair_scan) registration_tiles_kernel<true, true><<<grid, kTileQueries, 0, st>>>(p);
+  else if (p.wide_loads) registration_tiles_kernel<true, false><<<grid, kTileQueries, 0, st>>>(p);
+  else registration_tiles_kernel<false, false><<<grid, kTileQueries, 0, st>>>(p);
   return cudaGetLastError();
+}
+
+// CUDA loads kernels lazily at their first launch, and that load can wait for the device to drain — which never
+// happens while the resident filter CTA spins for the tiles of the very kernel being loaded.  Load every variant up front.
+cudaError_t preload_match_kernels() {
+  cudaFuncAttributes fa;
+  cudaError_t e;
+#define FL_LOAD(k) if ((e = cudaFuncGetAttributes(&fa, k)) != cudaSuccess) return e;
+  FL_LOAD((registration_tiles_kernel<true, true>))
+  FL_LOAD((registration_tiles_kernel<true, false>))
+  FL_LOAD((registration_tiles_kernel<false, false>))
+  FL_LOAD((match_persistent_kernel<true, true>))
+  FL_LOAD((match_persistent_kernel<true, false>))
+  FL_LOAD((match_persistent_kernel<false, false>))
+  FL_LOAD((match_reduce_kernel<true, true>))
+  FL_LOAD((match_reduce_kernel<true, false>))
+  FL_LOAD((match_reduce_kernel<false, false>))
+#undef FL_LOAD
+  return cudaSuccess;
 }
 
 int registration_capacity() {
   int dev = 0, sms = 0, per_sm = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return 0;
   if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, registration_kernel<true, false>, kTileQueries, 0) != cudaSuccess) return 0;
-  return sms * per_sm;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, registration_tiles_kernel<true, false>, kTileQueries, 0) != cudaSuccess) return 0;
+  return sms * per_sm - per_sm;        // one SM's worth of slots is left to the filter kernel's CTA (it needs many registers)
 }
 
 cudaError_t launch_match(const MatchParams& p, cudaStream_t st) {
