@@ -34,6 +34,8 @@ class LocalizerConfig:
     gravity: float = 9.81
     lidar2baselink_R: tuple = ((1, 0, 0), (0, 1, 0), (0, 0, 1))
     lidar2baselink_t: tuple = (0.0, 0.0, 0.0)
+    calibrate_gyro: bool = False                 # True: the stand-still gyro bias stays constant (Localizer.cpp:344-345)
+    calibrate_accel: bool = False
 
 
 def _quat_from_R(R):
@@ -77,6 +79,10 @@ class Localizer:
         self.n_imu = 0
         self.last_imu = None
         self.last = {}                           # what the last updatePointCloud did (sizes, passes, "null" reason)
+        # this->state.b: the biases subtracted from raw IMU samples (:514-515).  They follow the filter's estimate after
+        # every LiDAR update unless the calibrate_* flags pin them to the calibrated values (:344-351).
+        self.state_b_gyro = np.asarray(bias_gyro, np.float32).copy()
+        self.state_b_accel = np.asarray(bias_accel, np.float32).copy()
         self.map.propagated_clear()
 
     def _cov4(self):
@@ -91,8 +97,7 @@ class Localizer:
         self.n_imu += 1
         self.x, self.P = self.map.ekf_predict(self.x, self.P, stamp, dt, lin_accel, ang_vel, self._cov4())
 
-    def updateIMU_raw(self, stamp, lin_accel, ang_vel, imu2baselink_R=np.eye(3), imu2baselink_t=(0, 0, 0), accel_sm=np.eye(3),
-                      bias_accel=(0, 0, 0), bias_gyro=(0, 0, 0)):
+    def updateIMU_raw(self, stamp, lin_accel, ang_vel, imu2baselink_R=np.eye(3), imu2baselink_t=(0, 0, 0), accel_sm=np.eye(3)):
         """:403-404 + :512-520 for a sample in the IMU frame: imu2baselink (:697-728; float32 like the reference: dt from
         the stamps with the 1/200 s fallback, rotation into the base-link frame, lever-arm terms) and the intrinsic
         correction, then `updateIMU`.  The standstill calibration (:409-510) stays with the caller."""
@@ -106,8 +111,8 @@ class Localizer:
         a = R @ np.asarray(lin_accel, f32)
         a = a + np.cross(((w - w_prev) / f32(dt)).astype(f32), -t) + np.cross(w, np.cross(w, -t))
         self._ang_vel_prev, self._prev_imu_stamp = w, float(stamp)
-        a = (np.asarray(accel_sm, f32) @ a.astype(f32)) - np.asarray(bias_accel, f32)
-        w = w - np.asarray(bias_gyro, f32)
+        a = (np.asarray(accel_sm, f32) @ a.astype(f32)) - self.state_b_accel
+        w = w - self.state_b_gyro
         self.updateIMU(stamp, dt, a.astype(f32), w.astype(f32))
 
     # -- LiDAR callback -------------------------------------------------------------------------------------------
@@ -140,6 +145,10 @@ class Localizer:
         # stays at the prediction and the map is then initialised with this scan
         self.x, self.P, passes = self.map.update(self.x, self.P, c.MAX_NUM_ITERS, c.LIMITS)       # :333
         self.last["passes"] = passes
+        if not c.calibrate_gyro:                                                            # state = corrected_state (:344-351)
+            self.state_b_gyro = self.x[17:20].astype(np.float32)
+        if not c.calibrate_accel:
+            self.state_b_accel = self.x[20:23].astype(np.float32)
         self.lidar2baselink_T = _RT_f32(self.x[7:11], self.x[11:14])                        # :356
         self.map.add_scan(self.x, self.scan_stamp)                                          # :361 + :377, all of pc2match
         self.prev_scan_stamp = self.scan_stamp                                              # :398

@@ -349,11 +349,11 @@ def test_raw_imu_to_baselink(flimo_lib):
     """imu2baselink (Localizer.cpp:697-728): rotation into the base-link frame, lever arm, dt fallback, intrinsic correction."""
     from fast_limo_b200.localizer import Localizer
     m = api.Mapper(device=-1)
-    loc = Localizer(m)
+    loc = Localizer(m, bias_accel=(0.1, 0, 0), bias_gyro=(0, 0, 0.5))    # this->state.b (Localizer.cpp:67-68)
     Rz = Rot.from_euler("z", 90, degrees=True).as_matrix()
     lever = np.array([0.5, 0.0, 0.0])
     # first sample: dt = stamp - 0 > 0.1 -> 1/200; no angular acceleration term (previous rate := current)
-    loc.updateIMU_raw(10.0, [1.0, 0.0, 9.809], [0.0, 0.0, 2.0], Rz, lever, bias_accel=(0.1, 0, 0), bias_gyro=(0, 0, 0.5))
+    loc.updateIMU_raw(10.0, [1.0, 0.0, 9.809], [0.0, 0.0, 2.0], Rz, lever)
     a, w = loc.last_imu
     # R a = (0, 1, 9.809); centripetal w x (w x -t) with w = (0,0,2), t = (0.5,0,0): +4 * 0.5 along x
     assert np.allclose(a, [0.0 + 2.0 - 0.1, 1.0, 9.809], atol=1e-5) and np.allclose(w, [0, 0, 1.5], atol=1e-6)
@@ -363,6 +363,6 @@ def test_raw_imu_to_baselink(flimo_lib):
     loc.updateIMU_raw(10.01, [1.0, 0.0, 9.809], [0.0, 0.0, 3.0], Rz, lever)
     a2, w2 = loc.last_imu
     alpha = (3.0 - 2.0) / np.float32(0.01)
-    assert np.allclose(w2, [0, 0, 3.0], atol=1e-6)
-    assert np.allclose(a2, [0.0 + 9.0 * 0.5, 1.0 - alpha * 0.5, 9.809], rtol=2e-4, atol=1e-3)
+    assert np.allclose(w2, [0, 0, 3.0 - 0.5], atol=1e-6)
+    assert np.allclose(a2, [0.0 + 9.0 * 0.5 - 0.1, 1.0 - alpha * 0.5, 9.809], rtol=2e-4, atol=1e-3)
     assert abs(loc.imu_stamp - 10.01) < 1e-12 and loc.n_imu == 2

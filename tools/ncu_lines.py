@@ -29,10 +29,12 @@ for ln in sass.splitlines():
         line_of[int(m.group(1), 16)] = cur
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
-hi = [i for i, r in enumerate(rows) if len(r) > 5 and r[0] == "Address"][0]
+his = [i for i, r in enumerate(rows) if len(r) > 5 and r[0] == "Address"]
+hi = his[0]                                             # first captured launch of the report
 hdr = rows[hi]
 ix = {n: i for i, n in enumerate(hdr)}
-data = [r for r in rows[hi + 1:] if len(r) == len(hdr)]
+end = his[1] if len(his) > 1 else len(rows)
+data = [r for r in rows[hi + 1:end] if len(r) == len(hdr) and r[0] != "Address"]
 base = int(data[0][0], 16)
 stall_cols = [n for n in hdr if n.startswith("stall_") and "Not Issued" not in n]
 agg = collections.defaultdict(lambda: dict(inst=0, thr=0, samp=0, st=collections.Counter()))
