@@ -424,6 +424,38 @@ __device__ __forceinline__ int next_level(const MatchParams& P, int lvl, float d
 // Correctness never depends on the level choice: a block's answer is used only if block_is_final.
 // Must be called by all 32 lanes (inactive lanes pass active = false).  `lvl` returns the level whose
 // storage t.i[] indexes into.
+// Level choice of a query (see knn_search): finest level whose 3x3x3 block holds at least tau candidates.
+__device__ __forceinline__ void knn_probe(const MatchParams& P, float qx, float qy, float qz, int& lvl, Probe& pr) {
+  const int top = P.n_levels - 1;
+  lvl = 0;
+  if (P.probe_mode == 0) {
+    // all levels probed at once (independent table reads, one memory latency): finest level with >= tau
+    uint32_t cs[kMaxLevels], ce[kMaxLevels];
+#pragma unroll
+    for (int l = 0; l < kMaxLevels; ++l) {
+      cs[l] = ce[l] = 0;
+      if (l < P.n_levels) {
+        Probe q;
+        probe_level(P.lv[l], qx, qy, qz, q);
+        cs[l] = q.s;
+        ce[l] = q.e;
+      }
+    }
+    int sel = top;
+#pragma unroll
+    for (int l = kMaxLevels - 1; l >= 0; --l)
+      if (l < P.n_levels && (int)(ce[l] - cs[l]) >= P.tau) sel = l;
+    lvl = sel;
+    probe_level(P.lv[lvl], qx, qy, qz, pr);
+  } else {
+    probe_level(P.lv[0], qx, qy, qz, pr);
+    while (lvl < top && (int)(pr.e - pr.s) < P.tau) {
+      lvl = min(lvl + 1, top);
+      probe_level(P.lv[lvl], qx, qy, qz, pr);
+    }
+  }
+}
+
 template <bool kWide, bool kPair>
 __device__ __forceinline__ void knn_search(const MatchParams& P, int lane, bool active, float qx, float qy, float qz, Top5& t,
                                            int& lvl, int& first_lvl, uint32_t& first_cnt, unsigned long long& t_priv, unsigned long long& t_probe) {
@@ -437,32 +469,7 @@ __device__ __forceinline__ void knn_search(const MatchParams& P, int lane, bool 
   if (active) {
     const int top = P.n_levels - 1;
     Probe pr;
-    if (P.probe_mode == 0) {
-      // all levels probed at once (independent table reads, one memory latency): finest level with >= tau
-      uint32_t cs[kMaxLevels], ce[kMaxLevels];
-#pragma unroll
-      for (int l = 0; l < kMaxLevels; ++l) {
-        cs[l] = ce[l] = 0;
-        if (l < P.n_levels) {
-          Probe q;
-          probe_level(P.lv[l], qx, qy, qz, q);
-          cs[l] = q.s;
-          ce[l] = q.e;
-        }
-      }
-      int sel = top;
-#pragma unroll
-      for (int l = kMaxLevels - 1; l >= 0; --l)
-        if (l < P.n_levels && (int)(ce[l] - cs[l]) >= P.tau) sel = l;
-      lvl = sel;
-      probe_level(P.lv[lvl], qx, qy, qz, pr);
-    } else {
-      probe_level(P.lv[0], qx, qy, qz, pr);
-      while (lvl < top && (int)(pr.e - pr.s) < P.tau) {
-        lvl = min(lvl + 1, top);
-        probe_level(P.lv[lvl], qx, qy, qz, pr);
-      }
-    }
+    knn_probe(P, qx, qy, qz, lvl, pr);
     first_lvl = lvl;
     first_cnt = pr.e - pr.s;
     if (P.timing) {
