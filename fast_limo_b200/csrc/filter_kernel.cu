@@ -246,7 +246,15 @@ __global__ void __launch_bounds__(kFilterThreads, 1) filter_kernel(const __grid_
   int redone = 0;
   if (tid == 0) fs.stamps[14] = t_kernel;                   // when the current command was posted
   for (unsigned long long cmd_no = 0;; ++cmd_no) {
-    if (need_pre) ekf::pre_step(ex, ss, in);               // overlaps the tiles' work on this pass
+    // The pass that exhausts MAX_NUM_ITERS is known to be the last one before it starts: its sums go straight to the host,
+    // which forms the final state and covariance (IteratedUpdate::finish) — nothing to prepare or to solve here.
+    const bool known_last = ss.iter == in.max_iter - 1;
+    if (need_pre && !known_last) ekf::pre_step(ex, ss, in);   // overlaps the tiles' work on this pass
+    if (need_pre && known_last) {
+      if (tid < 26) ss.x_eval[tid] = ss.x[tid];
+      if (tid == 0) ss.singular = 0;
+      __syncthreads();
+    }
     need_pre = false;
     // ---- wait for the last group of this pass, sum the group partials in a fixed order -------------------
     if (tid == 0) {
@@ -300,6 +308,17 @@ __global__ void __launch_bounds__(kFilterThreads, 1) filter_kernel(const __grid_
       } else {
         ++redone;
       }
+    } else if (known_last) {
+      next_cmd = 1u;
+      if (pass_idx < ekf::kMaxTrace && tid < 32) {         // trace: sums of the pass; the state after it is the host's
+        double* tr = st.trace[pass_idx];
+        tr[tid] = tid < 26 ? ss.x_eval[tid] : (tid == 26 ? fs.sums[0][92] : (tid == 27 ? fs.sums[0][90] : (tid == 28 ? pass_ns : (tid == 29 ? (double)cur_limit : 0.0))));
+      }
+      __syncthreads();
+      if (tid == 0) {
+        ss.passes = ss.passes + 1;
+        ss.done = 1;
+      }
     } else {
       ekf::unpack_measurement(ex, ss, fs.sums[0]);
       ekf::post_step_pose(ex, ss, in, (long long)(fs.sums[0][90] + 0.5));
@@ -317,7 +336,7 @@ __global__ void __launch_bounds__(kFilterThreads, 1) filter_kernel(const __grid_
         for (int w = tid; w < (int)(sizeof(PoseConsts) / 4); w += kFilterThreads) dst[w] = src[w];
       }                                                    // (a repeated later pass finds its pose still in dev_ctl)
       if (tid == 0) {
-        dctl->cmd = 0u;
+        dctl->cmd = stepped ? 0u : 3u;                       // 3 = same pose again, rows limited (the tiles may reuse their rows)
         dctl->orig_limit = next_limit;
         const unsigned long long now = gtime_ns();
         dctl->t_begin = now;

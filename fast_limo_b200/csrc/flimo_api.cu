@@ -1386,7 +1386,7 @@ static int update_device(flimo_handle h, double state26[26], double P529[529], i
     u.finish(&res[kResXEval], HTH, HTh, nr);
     if (h->prof) h->prof_step += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - ts0).count();
     u.end(state26, P529);
-    std::memcpy(h->last_x_dev, &res[kResXDev], sizeof(h->last_x_dev));
+    std::memcpy(h->last_x_dev, state26, sizeof(h->last_x_dev));   // the state after the last pass (formed here)
     if (u.failed()) failed = 1;
   }
   if (failed) {
@@ -1607,7 +1607,10 @@ int flimo_update_trace(flimo_handle h, double* out32, size_t cap_passes, size_t*
   const size_t n = (size_t)std::min(std::max(tmp.passes, 0), ekf::kMaxTrace);
   *n_passes = n;
   if (out32)
-    for (size_t i = 0; i < n && i < cap_passes; ++i) std::memcpy(out32 + 32 * i, tmp.trace[i], 32 * sizeof(double));
+    for (size_t i = 0; i < n && i < cap_passes; ++i) {
+      std::memcpy(out32 + 32 * i, tmp.trace[i], 32 * sizeof(double));
+      if (i + 1 == n) std::memcpy(out32 + 32 * i, h->last_x_dev, 26 * sizeof(double));   // the last pass is completed on the host
+    }
   if (h->prof)
     for (size_t i = 0; i < n; ++i) {
       std::fprintf(stderr, "[step %zu] ns after tree:", i);

@@ -51,7 +51,7 @@ struct PoseConsts {
 struct PassCtl {
   unsigned long long seq;      // sequence number of the pass this block describes (written last)
   unsigned long long t_begin;  // device copy only: %globaltimer when the pass was released
-  uint32_t cmd;                // 0 = run the pass, 1 = stop (kernel exits)
+  uint32_t cmd;                // 0 = run the pass, 1 = stop (kernel exits), 3 = run it again with the same pose and a row limit
   uint32_t orig_limit;         // first-N cap on contributing rows
   PoseConsts pc;
   uint32_t pad[1];

@@ -798,7 +798,7 @@ struct TileShared {
 // (publish_result for the host-driven kernels, the filter step in the registration kernel).
 template <bool kWide, bool kPair, bool kExternalFinal = false>
 __device__ __forceinline__ bool match_tile(const MatchParams& P, const PoseConsts& pc, TileShared& sh, const int tile_idx,
-                                           const int n_tiles, const uint32_t orig_limit) {
+                                           const int n_tiles, const uint32_t orig_limit, const bool reuse_rows = false) {
   auto& tile = sh.tile;
   auto& wsum = sh.wsum;
   int& s_last = sh.s_last;
@@ -818,112 +818,119 @@ __device__ __forceinline__ bool match_tile(const MatchParams& P, const PoseConst
   bool accepted = false;   // Match::lisanAlGaib()
   uint32_t orig = 0;
 
-  float g[3] = {0.f, 0.f, 0.f};
-  if (in_range) {
-    float sx, sy, sz;
-    if (P.scan != nullptr) {
-      const float4 sp = __ldg(&P.scan[q]);
-      orig = __float_as_uint(sp.w);
-      sx = sp.x; sy = sp.y; sz = sp.z;
-    } else {
-      // in-place read of the caller's array: original index = (q * raw_inv) mod raw_n
-      const unsigned long long prod = (unsigned long long)(uint32_t)q * P.raw_inv;
-      unsigned long long r = prod - __umul64hi(prod, P.raw_magic) * P.raw_n;
-      if (r >= P.raw_n) r -= P.raw_n;
-      orig = (uint32_t)r;
-      const unsigned char* sp = P.raw_scan + (size_t)orig * P.raw_stride;
-      if (P.raw_vec4) {                                    // 16-byte aligned records: one load
-        const float4 v = __ldg(reinterpret_cast<const float4*>(sp));
-        sx = v.x; sy = v.y; sz = v.z;
-      } else {
-        const float* sf = reinterpret_cast<const float*>(sp);
-        sx = __ldg(sf); sy = __ldg(sf + 1); sz = __ldg(sf + 2);
-      }
-    }
-    affine_apply(pc.R_wb, pc.t_wb, sx, sy, sz, g);
-  }
-  Top5 t;
-#pragma unroll
-  for (int j = 0; j < 5; ++j) {
-    t.d[j] = __int_as_float(0x7f800000);
-    t.i[j] = 0;
-  }
-  int lvl = 0;
   unsigned long long tm0 = 0, tm1 = 0, tm2 = 0;
-  if (P.timing) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tm0));
+  int lvl = 0;
   int first_lvl = 0;
-  uint32_t first_cnt = 0;
   unsigned long long t_priv = 0;
   unsigned long long t_probe = 0;
-  knn_search<kWide, kPair>(P, lane, in_range, g[0], g[1], g[2], t, lvl, first_lvl, first_cnt, t_priv, t_probe);      // warp-converged call
-  if (P.timing) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tm1));
+  uint32_t first_cnt = 0;
+  if (reuse_rows) {
+    // Repeated pass with the SAME pose and a row limit (first-N rule): the rows of this tile are still in shared memory
+    // from the first evaluation (this CTA owns exactly one tile); only their selection changes.
+    orig = __float_as_uint(tile[warp][lane][16]);
+    accepted = tile[warp][lane][17] != 0.f;
+  } else {
+    float g[3] = {0.f, 0.f, 0.f};
+    if (in_range) {
+      float sx, sy, sz;
+      if (P.scan != nullptr) {
+        const float4 sp = __ldg(&P.scan[q]);
+        orig = __float_as_uint(sp.w);
+        sx = sp.x; sy = sp.y; sz = sp.z;
+      } else {
+        // in-place read of the caller's array: original index = (q * raw_inv) mod raw_n
+        const unsigned long long prod = (unsigned long long)(uint32_t)q * P.raw_inv;
+        unsigned long long r = prod - __umul64hi(prod, P.raw_magic) * P.raw_n;
+        if (r >= P.raw_n) r -= P.raw_n;
+        orig = (uint32_t)r;
+        const unsigned char* sp = P.raw_scan + (size_t)orig * P.raw_stride;
+        if (P.raw_vec4) {                                    // 16-byte aligned records: one load
+          const float4 v = __ldg(reinterpret_cast<const float4*>(sp));
+          sx = v.x; sy = v.y; sz = v.z;
+        } else {
+          const float* sf = reinterpret_cast<const float*>(sp);
+          sx = __ldg(sf); sy = __ldg(sf + 1); sz = __ldg(sf + 2);
+        }
+      }
+      affine_apply(pc.R_wb, pc.t_wb, sx, sy, sz, g);
+    }
+    Top5 t;
+  #pragma unroll
+    for (int j = 0; j < 5; ++j) {
+      t.d[j] = __int_as_float(0x7f800000);
+      t.i[j] = 0;
+    }
+    if (P.timing) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tm0));
+    knn_search<kWide, kPair>(P, lane, in_range, g[0], g[1], g[2], t, lvl, first_lvl, first_cnt, t_priv, t_probe);      // warp-converged call
+    if (P.timing) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tm1));
 
-  if (in_range) {
-    const float4* __restrict__ src = P.lv[lvl].pts;             // storage t.i[] indexes into
-    float n4[4] = {0.f, 0.f, 0.f, 0.f};
-    float dist = 0.f;
-    // Plane::enough_points + close_enough: an empty slot is +inf and fails the strict '<'.
-    if (t.d[4] < P.max_dist_f) {
-      float A[5][3];
-      float4 nb[5];
-#pragma unroll
-      for (int j = 0; j < 5; ++j) {
-        nb[j] = __ldg(&src[t.i[j]]);
-        A[j][0] = nb[j].x;
-        A[j][1] = nb[j].y;
-        A[j][2] = nb[j].z;
+    if (in_range) {
+      const float4* __restrict__ src = P.lv[lvl].pts;             // storage t.i[] indexes into
+      float n4[4] = {0.f, 0.f, 0.f, 0.f};
+      float dist = 0.f;
+      // Plane::enough_points + close_enough: an empty slot is +inf and fails the strict '<'.
+      if (t.d[4] < P.max_dist_f) {
+        float A[5][3];
+        float4 nb[5];
+  #pragma unroll
+        for (int j = 0; j < 5; ++j) {
+          nb[j] = __ldg(&src[t.i[j]]);
+          A[j][0] = nb[j].x;
+          A[j][1] = nb[j].y;
+          A[j][2] = nb[j].z;
+        }
+        float x[3];
+        plane_qr_solve(A, x);
+        const float nrm = sqrtf(x[0] * x[0] + (x[1] * x[1] + x[2] * x[2]));
+        n4[0] = x[0] / nrm;
+        n4[1] = x[1] / nrm;
+        n4[2] = x[2] / nrm;
+        n4[3] = 1.0f / nrm;   // == float(1.0 / double(nrm)): double rounding is innocuous for division
+        bool ok = true;
+  #pragma unroll
+        for (int j = 0; j < 5; ++j) {
+          const float res = ((n4[0] * nb[j].x + n4[1] * nb[j].y) + n4[2] * nb[j].z) + n4[3];
+          if (fabsf(res) > P.plane_thr) ok = false;
+        }
+        accepted = ok;
+        dist = ((n4[0] * g[0] + n4[1] * g[1]) + n4[2] * g[2]) + n4[3];
       }
-      float x[3];
-      plane_qr_solve(A, x);
-      const float nrm = sqrtf(x[0] * x[0] + (x[1] * x[1] + x[2] * x[2]));
-      n4[0] = x[0] / nrm;
-      n4[1] = x[1] / nrm;
-      n4[2] = x[2] / nrm;
-      n4[3] = 1.0f / nrm;   // == float(1.0 / double(nrm)): double rounding is innocuous for division
-      bool ok = true;
-#pragma unroll
-      for (int j = 0; j < 5; ++j) {
-        const float res = ((n4[0] * nb[j].x + n4[1] * nb[j].y) + n4[2] * nb[j].z) + n4[3];
-        if (fabsf(res) > P.plane_thr) ok = false;
+
+      if (accepted) {
+        float p_imu[3], p_lid[3], C[3], RC[3];
+        affine_apply(pc.Rinv_wb, pc.tinv_wb, g[0], g[1], g[2], p_imu);
+        affine_apply(pc.Rinv_LI, pc.tinv_LI, p_imu[0], p_imu[1], p_imu[2], p_lid);
+        const float nv[3] = {n4[0], n4[1], n4[2]};
+        mat3_vec(pc.Rd_wb_inv, nv, C);
+        mat3_vec(pc.Rd_LI_inv, C, RC);
+        v13[0] = n4[0];
+        v13[1] = n4[1];
+        v13[2] = n4[2];
+        v13[3] = p_imu[1] * C[2] - p_imu[2] * C[1];
+        v13[4] = p_imu[2] * C[0] - p_imu[0] * C[2];
+        v13[5] = p_imu[0] * C[1] - p_imu[1] * C[0];
+        if (P.estimate_extrinsics) {
+          v13[6] = p_lid[1] * RC[2] - p_lid[2] * RC[1];
+          v13[7] = p_lid[2] * RC[0] - p_lid[0] * RC[2];
+          v13[8] = p_lid[0] * RC[1] - p_lid[1] * RC[0];
+          v13[9] = C[0];
+          v13[10] = C[1];
+          v13[11] = C[2];
+        }
+        v13[12] = -dist;
       }
-      accepted = ok;
-      dist = ((n4[0] * g[0] + n4[1] * g[1]) + n4[2] * g[2]) + n4[3];
+
+      if (P.dbg16 != nullptr) {
+        float4* o = reinterpret_cast<float4*>(P.dbg16 + (size_t)orig * 16);
+        o[0] = make_float4(g[0], g[1], g[2], n4[0]);
+        o[1] = make_float4(n4[1], n4[2], n4[3], dist);
+        o[2] = make_float4(accepted ? 1.f : 0.f, t.d[0], t.d[1], t.d[2]);
+        o[3] = make_float4(t.d[3], t.d[4], (float)(first_lvl + 16 * lvl), (float)first_cnt);
+      }
+      if (P.valid_by_orig != nullptr) P.valid_by_orig[orig] = accepted ? 1 : 0;
     }
 
-    if (accepted) {
-      float p_imu[3], p_lid[3], C[3], RC[3];
-      affine_apply(pc.Rinv_wb, pc.tinv_wb, g[0], g[1], g[2], p_imu);
-      affine_apply(pc.Rinv_LI, pc.tinv_LI, p_imu[0], p_imu[1], p_imu[2], p_lid);
-      const float nv[3] = {n4[0], n4[1], n4[2]};
-      mat3_vec(pc.Rd_wb_inv, nv, C);
-      mat3_vec(pc.Rd_LI_inv, C, RC);
-      v13[0] = n4[0];
-      v13[1] = n4[1];
-      v13[2] = n4[2];
-      v13[3] = p_imu[1] * C[2] - p_imu[2] * C[1];
-      v13[4] = p_imu[2] * C[0] - p_imu[0] * C[2];
-      v13[5] = p_imu[0] * C[1] - p_imu[1] * C[0];
-      if (P.estimate_extrinsics) {
-        v13[6] = p_lid[1] * RC[2] - p_lid[2] * RC[1];
-        v13[7] = p_lid[2] * RC[0] - p_lid[0] * RC[2];
-        v13[8] = p_lid[0] * RC[1] - p_lid[1] * RC[0];
-        v13[9] = C[0];
-        v13[10] = C[1];
-        v13[11] = C[2];
-      }
-      v13[12] = -dist;
-    }
-
-    if (P.dbg16 != nullptr) {
-      float4* o = reinterpret_cast<float4*>(P.dbg16 + (size_t)orig * 16);
-      o[0] = make_float4(g[0], g[1], g[2], n4[0]);
-      o[1] = make_float4(n4[1], n4[2], n4[3], dist);
-      o[2] = make_float4(accepted ? 1.f : 0.f, t.d[0], t.d[1], t.d[2]);
-      o[3] = make_float4(t.d[3], t.d[4], (float)(first_lvl + 16 * lvl), (float)first_cnt);
-    }
-    if (P.valid_by_orig != nullptr) P.valid_by_orig[orig] = accepted ? 1 : 0;
   }
-
   if (P.timing) {
     __syncwarp();
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tm2));
@@ -939,11 +946,16 @@ __device__ __forceinline__ bool match_tile(const MatchParams& P, const PoseConst
   const unsigned int m_rows = __ballot_sync(0xffffffffu, contributes);
   {
     float4* rowp = reinterpret_cast<float4*>(&tile[warp][lane][0]);
-    const float zf = contributes ? 1.f : 0.f;     // v13 is already zero unless accepted; orig_limit may veto
-    rowp[0] = make_float4(v13[0] * zf, v13[1] * zf, v13[2] * zf, v13[3] * zf);
-    rowp[1] = make_float4(v13[4] * zf, v13[5] * zf, v13[6] * zf, v13[7] * zf);
-    rowp[2] = make_float4(v13[8] * zf, v13[9] * zf, v13[10] * zf, v13[11] * zf);
-    rowp[3] = make_float4(v13[12] * zf, 0.f, 0.f, 0.f);
+    if (reuse_rows) {
+      if (!contributes) rowp[0] = rowp[1] = rowp[2] = rowp[3] = make_float4(0.f, 0.f, 0.f, 0.f);
+    } else {
+      const float zf = contributes ? 1.f : 0.f;     // v13 is already zero unless accepted; orig_limit may veto
+      rowp[0] = make_float4(v13[0] * zf, v13[1] * zf, v13[2] * zf, v13[3] * zf);
+      rowp[1] = make_float4(v13[4] * zf, v13[5] * zf, v13[6] * zf, v13[7] * zf);
+      rowp[2] = make_float4(v13[8] * zf, v13[9] * zf, v13[10] * zf, v13[11] * zf);
+      rowp[3] = make_float4(v13[12] * zf, 0.f, 0.f, 0.f);
+      rowp[4] = make_float4(__uint_as_float(orig), accepted ? 1.f : 0.f, 0.f, 0.f);   // columns 16.. are padding of the fragment layout: kept for a repeated pass
+    }
   }
   __syncwarp();
   double c00[2] = {0.0, 0.0}, c01[2] = {0.0, 0.0}, c11[2] = {0.0, 0.0};
@@ -1223,8 +1235,11 @@ __global__ void __launch_bounds__(kTileQueries, 7) registration_tiles_kernel(con
       for (int w = tid; w < (int)(sizeof(PassCtl) / 4); w += kTileQueries) dst[w] = __ldcg(src + w);
     }
     __syncthreads();
-    if (s_ctl.cmd != 0u) return;
-    for (int t = (int)blockIdx.x; t < n_tiles; t += (int)gridDim.x) match_tile<kWide, kPair, true>(P, s_ctl.pc, sh, t, n_tiles, s_ctl.orig_limit);
+    if (s_ctl.cmd != 0u && s_ctl.cmd != 3u) return;
+    // cmd 3 = the pass is repeated with the same pose and a row limit: a CTA that owns exactly one tile re-selects the rows
+    // it still holds in shared memory instead of matching the tile again
+    const bool reuse = s_ctl.cmd == 3u && (int)gridDim.x >= n_tiles;
+    for (int t = (int)blockIdx.x; t < n_tiles; t += (int)gridDim.x) match_tile<kWide, kPair, true>(P, s_ctl.pc, sh, t, n_tiles, s_ctl.orig_limit, reuse);
     __syncthreads();
   }
 }
