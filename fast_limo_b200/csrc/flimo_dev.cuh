@@ -92,6 +92,7 @@ struct MatchParams {
   int wide_loads;              // 1 = 256-bit candidate loads
   int pair_scan;               // 1 = two lanes per query in the first scan (adjacent 32-byte loads share a wavefront)
   int l2_prefetch;             // 1 = request the whole run with prefetch.global.L2 right after the probe
+  int stage_runs;              // 1 = one-launch-per-pass kernel stages the runs in shared memory with cp.async.bulk (TMA) + mbarrier
   float max_dist_f;            // smallest float >= MAX_DIST_PLANE  (d2_5 < MAX_DIST_PLANE test)
   float plane_thr;             // (float)PLANE_THRESHOLD
   int estimate_extrinsics;

@@ -129,10 +129,15 @@ constexpr uint32_t kPrivateCap = 96;   // longest run a single thread scans by i
 struct Pair {
   float ax, ay, az, aw, bx, by, bz, bw;
 };
-template <bool kWide>
+// kSrc: 0 = two 128-bit global loads, 1 = one 256-bit global load, 2 = the run has been staged in shared memory
+template <int kSrc>
 __device__ __forceinline__ Pair ldg_pair(const float4* p) {
   Pair r;
-  if (kWide) {
+  if (kSrc == 2) {
+    const float4 a = p[0], b = p[1];
+    r.ax = a.x; r.ay = a.y; r.az = a.z; r.aw = a.w;
+    r.bx = b.x; r.by = b.y; r.bz = b.z; r.bw = b.w;
+  } else if (kSrc == 1) {
     asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
         : "=f"(r.ax), "=f"(r.ay), "=f"(r.az), "=f"(r.aw), "=f"(r.bx), "=f"(r.by), "=f"(r.bz), "=f"(r.bw)
         : "l"(p));
@@ -156,6 +161,7 @@ __device__ __forceinline__ void rank4(float (&k)[6], const Pair& p0, const Pair&
 
 // Exact re-ranking + acceptance of a packed 6-list (see block_scan_private).  pts = L.pts + a (ordinals are
 // relative to it), a = absolute position of ordinal 0.
+template <int kSrc = 1>
 __device__ __forceinline__ bool finish_private(const float (&k)[6], const float4* __restrict__ pts, uint32_t a, float qx, float qy,
                                                float qz, Top5& t) {
   const uint32_t low = kKeyLow;
@@ -168,7 +174,7 @@ __device__ __forceinline__ bool finish_private(const float (&k)[6], const float4
     const bool have = kb < 0x7f800000u;
     const uint32_t ord = kb & low;
     float d = inf;
-    if (have) d = sqdist(qx, qy, qz, __ldg(&pts[ord]));
+    if (have) d = sqdist(qx, qy, qz, kSrc == 2 ? pts[ord] : __ldg(&pts[ord]));
     ek[j] = ((unsigned long long)__float_as_uint(d) << 32) | (have ? ord : 0xFFFFFFFFu);
   }
   cmpswap64(ek[0], ek[5]); cmpswap64(ek[1], ek[3]); cmpswap64(ek[2], ek[4]);
@@ -195,9 +201,9 @@ __device__ __forceinline__ bool finish_private(const float (&k)[6], const float4
 // squared distances of the block's five nearest points and t.i[] their positions in L.pts (+inf / 0
 // if missing).  The run is read from its 32-byte aligned start a = s & ~1; ordinals are relative to a,
 // the (at most one) leading entry before s is masked, trailing entries are never ranked.
-template <bool kWide>
+template <int kWide>
 __device__ __forceinline__ bool block_scan_private(const LevelView& L, uint32_t s, uint32_t e, float qx, float qy, float qz,
-                                                   Top5& t) {
+                                                   Top5& t, const float4* staged = nullptr) {
   const uint32_t total = e - s;
 #pragma unroll
   for (int j = 0; j < 5; ++j) {
@@ -208,7 +214,7 @@ __device__ __forceinline__ bool block_scan_private(const LevelView& L, uint32_t 
   if (total > kPrivateCap) return false;
   const uint32_t a = s & ~1u;
   const uint32_t tot = (s - a) + total;          // ordinals [s - a, tot) are candidates
-  const float4* __restrict__ pts = L.pts + a;
+  const float4* __restrict__ pts = (kWide == 2) ? staged : L.pts + a;   // staged: the copy of [a, a + tot) in shared memory
   const uint32_t low = kKeyLow;
   const float inf = __int_as_float(0x7f800000);
   float lead = (s != a) ? inf : 0.f;             // raises the masked leading entry's distance to +inf
@@ -245,7 +251,7 @@ __device__ __forceinline__ bool block_scan_private(const LevelView& L, uint32_t 
   if (n + 1 < tot) keys6_insert(k, pack_key(sqdist_rank(qx, qy, qz, a0.bx, a0.by, a0.bz), low, n + 1));
   if (n + 2 < tot) keys6_insert(k, pack_key(sqdist_rank(qx, qy, qz, a1.ax, a1.ay, a1.az), low, n + 2));
 
-  return finish_private(k, pts, a, qx, qy, qz, t);
+  return finish_private<kWide>(k, pts, a, qx, qy, qz, t);
 }
 
 // ---- two lanes per query (P.pair_scan) ------------------------------------------------------------------
@@ -456,9 +462,41 @@ __device__ __forceinline__ void knn_probe(const MatchParams& P, float qx, float 
   }
 }
 
-template <bool kWide, bool kPair>
+// ---- staging of the runs with bulk asynchronous copies (TMA, 1-D) -----------------------------------------------
+// Variant kStage (FLIMO_KNN_STAGE=1, one-launch-per-pass kernel only): after the probe every lane asks the TMA unit for ITS
+// run with one cp.async.bulk (global -> its slice of the warp's shared-memory stage, completion on the warp's mbarrier);
+// the 32 copies of a warp are in flight together, the scan and the exact re-ranking then read shared memory.  Runs longer
+// than kStageCap entries keep the streaming path.  Measured slower than streaming on c2 (profiles/README.md, round 2): the
+// stage costs 24.5 KB per warp, i.e. 2 CTAs per SM instead of 7, and the run loads were not the critical path.
+constexpr uint32_t kStageCap = 48;      // entries per lane
+constexpr uint32_t kStageStride = 49;   // entries between lane slices (784 bytes: conflict-free 128-bit reads across a quarter warp)
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+               : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void bulk_copy_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+struct StageCtx {
+  float4* lane_slice;           // this lane's slice of the warp's stage (nullptr: no staging)
+  unsigned long long* bar;      // the warp's mbarrier
+  uint32_t* phase;              // its phase parity (per thread copy, all lanes of the warp agree)
+};
+
+template <bool kWide, bool kPair, bool kStage = false>
 __device__ __forceinline__ void knn_search(const MatchParams& P, int lane, bool active, float qx, float qy, float qz, Top5& t,
-                                           int& lvl, int& first_lvl, uint32_t& first_cnt, unsigned long long& t_priv, unsigned long long& t_probe) {
+                                           int& lvl, int& first_lvl, uint32_t& first_cnt, unsigned long long& t_priv, unsigned long long& t_probe,
+                                           const StageCtx stage = StageCtx{nullptr, nullptr, nullptr}) {
   const unsigned int full = 0xffffffffu;
   lvl = 0;
   first_lvl = 0;
@@ -490,8 +528,8 @@ __device__ __forceinline__ void knn_search(const MatchParams& P, int lane, bool 
       scan_e = pr.e;
       hx0 = pr.hx; hy0 = pr.hy; hz0 = pr.hz;
     }
-    if (!kPair) {
-      const bool exact_here = block_scan_private<kWide>(P.lv[lvl], pr.s, pr.e, qx, qy, qz, t);
+    if (!kPair && !kStage) {
+      const bool exact_here = block_scan_private<kWide ? 1 : 0>(P.lv[lvl], pr.s, pr.e, qx, qy, qz, t);
       if (!exact_here) {
         pending = true;                                          // redo this level cooperatively
       } else if (!block_is_final(P.lv[lvl].g, P.max_dist_f, qx, qy, qz, pr.hx, pr.hy, pr.hz, t.d[4])) {
@@ -499,6 +537,39 @@ __device__ __forceinline__ void knn_search(const MatchParams& P, int lane, bool 
         if (pending) lvl = next_level(P, lvl, t.d[4]);
       }
     }
+    if (kStage) {
+      scan_s = pr.s;
+      scan_e = pr.e;
+      hx0 = pr.hx; hy0 = pr.hy; hz0 = pr.hz;
+    }
+  }
+  if (kStage) {                                                  // warp-converged: stage the runs, then scan them
+    const uint32_t total = scan_e - scan_s, a = scan_s & ~1u, tot = (scan_s - a) + total;
+    const bool staged = active && total > 0u && tot <= kStageCap;
+    const uint32_t bytes = staged ? ((tot + 1u) & ~1u) * (uint32_t)sizeof(float4) : 0u;   // whole 32-byte pairs (the arrays carry slack)
+    const uint32_t warp_bytes = __reduce_add_sync(full, bytes);
+    if (warp_bytes != 0u) {
+      if (lane == 0) mbar_expect_tx(stage.bar, warp_bytes);
+      __syncwarp();
+      if (staged) bulk_copy_g2s(stage.lane_slice, P.lv[lvl].pts + a, bytes, stage.bar);
+      unsigned int spins = 0;
+      while (!mbar_try_wait(stage.bar, *stage.phase)) {
+        if (++spins > (1u << 22)) break;                         // never observed; a lost copy must not hang the GPU
+      }
+      *stage.phase ^= 1u;
+    }
+    if (active) {
+      const int top = P.n_levels - 1;
+      const bool exact_here = staged ? block_scan_private<2>(P.lv[lvl], scan_s, scan_e, qx, qy, qz, t, stage.lane_slice)
+                                     : block_scan_private<kWide ? 1 : 0>(P.lv[lvl], scan_s, scan_e, qx, qy, qz, t);
+      if (!exact_here) {
+        pending = true;
+      } else if (!block_is_final(P.lv[lvl].g, P.max_dist_f, qx, qy, qz, hx0, hy0, hz0, t.d[4])) {
+        pending = lvl < top;
+        if (pending) lvl = next_level(P, lvl, t.d[4]);
+      }
+    }
+    __syncwarp();                                                // the slices are free again (next tile of a resident kernel)
   }
   if (kPair) {                                                   // warp-converged: two lanes per query, two rounds
     const uint32_t total_own = scan_e - scan_s;
@@ -796,9 +867,10 @@ struct TileShared {
 // Returns true (in every thread of the CTA) when this CTA completed the tree: the packed result of the pass
 // (flimo.h layout, 96 doubles) is then staged in sh.wsum[0] and the caller decides what happens with it
 // (publish_result for the host-driven kernels, the filter step in the registration kernel).
-template <bool kWide, bool kPair, bool kExternalFinal = false>
+template <bool kWide, bool kPair, bool kExternalFinal = false, bool kStage = false>
 __device__ __forceinline__ bool match_tile(const MatchParams& P, const PoseConsts& pc, TileShared& sh, const int tile_idx,
-                                           const int n_tiles, const uint32_t orig_limit, const bool reuse_rows = false) {
+                                           const int n_tiles, const uint32_t orig_limit, const bool reuse_rows = false,
+                                           const StageCtx stage = StageCtx{nullptr, nullptr, nullptr}) {
   auto& tile = sh.tile;
   auto& wsum = sh.wsum;
   int& s_last = sh.s_last;
@@ -861,7 +933,7 @@ __device__ __forceinline__ bool match_tile(const MatchParams& P, const PoseConst
       t.i[j] = 0;
     }
     if (P.timing) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tm0));
-    knn_search<kWide, kPair>(P, lane, in_range, g[0], g[1], g[2], t, lvl, first_lvl, first_cnt, t_priv, t_probe);      // warp-converged call
+    knn_search<kWide, kPair, kStage>(P, lane, in_range, g[0], g[1], g[2], t, lvl, first_lvl, first_cnt, t_priv, t_probe, stage);      // warp-converged call
     if (P.timing) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tm1));
 
     if (in_range) {
@@ -1118,6 +1190,20 @@ __global__ void __launch_bounds__(kTileQueries, 7) match_reduce_kernel(const __g
   if (match_tile<kWide, kPair>(P, P.pc, sh, (int)blockIdx.x, (int)gridDim.x, P.orig_limit)) publish_result(P, sh, P.seq, 0ull);
 }
 
+// One launch = one pass, runs staged in shared memory by bulk asynchronous copies (see StageCtx above).
+__global__ void __launch_bounds__(kTileQueries, 2) match_reduce_staged_kernel(const __grid_constant__ MatchParams P) {
+  __shared__ TileShared sh;
+  __shared__ __align__(8) unsigned long long s_bar[kTileQueries / 32];
+  extern __shared__ __align__(16) float4 s_stage[];          // [warps][32 lanes][kStageStride]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) mbar_init(&s_bar[warp], 1u);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncthreads();
+  uint32_t phase = 0u;
+  const StageCtx stage{s_stage + ((size_t)warp * 32 + lane) * kStageStride, &s_bar[warp], &phase};
+  if (match_tile<true, false, false, true>(P, P.pc, sh, (int)blockIdx.x, (int)gridDim.x, P.orig_limit, false, stage)) publish_result(P, sh, P.seq, 0ull);
+}
+
 // ---------------------------------------------------------------------------------------------------
 // Persistent form: ONE launch per scan registration.  The CTAs stay resident over all passes of
 // esekf::update_iterated_dyn_share_modified (esekfom.hpp:1634-1764); between passes the host runs the
@@ -1290,6 +1376,7 @@ cudaError_t preload_match_kernels() {
   FL_LOAD((match_reduce_kernel<true, true>))
   FL_LOAD((match_reduce_kernel<true, false>))
   FL_LOAD((match_reduce_kernel<false, false>))
+  FL_LOAD(match_reduce_staged_kernel)
 #undef FL_LOAD
   return cudaSuccess;
 }
@@ -1305,6 +1392,19 @@ int registration_capacity() {
 cudaError_t launch_match(const MatchParams& p, cudaStream_t st) {
   const int n = p.q_end - p.q_begin;
   if (n <= 0) return cudaErrorInvalidValue;
+  if (p.stage_runs && !p.pair_scan) {
+    const size_t dyn = (size_t)(kTileQueries / 32) * 32 * kStageStride * sizeof(float4);
+    static bool attr_set[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+      const cudaError_t e = cudaFuncSetAttribute(match_reduce_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+      if (e != cudaSuccess) return e;
+      attr_set[dev] = true;
+    }
+    match_reduce_staged_kernel<<<match_num_tiles(n), kTileQueries, dyn, st>>>(p);
+    return cudaGetLastError();
+  }
   if (p.pair_scan) match_reduce_kernel<true, true><<<match_num_tiles(n), kTileQueries, 0, st>>>(p);
   else if (p.wide_loads) match_reduce_kernel<true, false><<<match_num_tiles(n), kTileQueries, 0, st>>>(p);
   else match_reduce_kernel<false, false><<<match_num_tiles(n), kTileQueries, 0, st>>>(p);

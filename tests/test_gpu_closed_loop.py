@@ -125,3 +125,29 @@ def test_map_receives_whole_cloud_beyond_pc2match_cap(oracle, flimo_lib):
     om.add(world)
     assert m.size() == om.size() > n0
     assert np.array_equal(np.sort(m.points().view([("", np.float32)] * 3), axis=0), np.sort(om.points().view([("", np.float32)] * 3), axis=0))
+
+
+@pytest.mark.parametrize("name", ["tiny", "c1"])
+def test_tma_staged_scan_variant_parity(oracle, flimo_lib, name):
+    """FLIMO_KNN_STAGE=1: the runs are staged in shared memory with cp.async.bulk + mbarrier (1-D TMA, UBLKCP in SASS) before
+    they are scanned.  Slower than streaming on c2 (96.6 vs 35.5 us, profiles/README.md) and therefore off by default, but it
+    has to stay exact: same accepted set, planes, distances and sums as the oracle."""
+    case = synth.make_case(name)
+    os.environ["FLIMO_KNN_STAGE"] = "1"
+    try:
+        m = api.Mapper(api.MappingConfig(MAX_NUM_MATCHES=BIG, MAX_NUM_PC2MATCH=BIG), device=0)
+    finally:
+        del os.environ["FLIMO_KNN_STAGE"]
+    m.add(case.map_pts, 0.0)
+    m.set_scan(case.scan)
+    om = oracle.OracleMap()
+    om.add(case.map_pts)
+    ref = om.match(oracle.make_cfg(max_pc2match=BIG, max_matches=BIG, num_threads=4), case.init[:14], case.scan)
+    dbg = m.match_debug(case.init)
+    assert np.array_equal(dbg["good"], ref["good"])
+    g = ref["good"]
+    assert np.array_equal(dbg["plane"][g], ref["plane"][g]) and np.array_equal(dbg["dist"][g], ref["dist"][g])
+    close = ref["nn_d2"][:, -1] < 2.0
+    assert np.array_equal(dbg["nn_d2"][close], ref["nn_d2"][close])
+    r = m.match(case.init)
+    assert r.n_valid == ref["n_valid"] and np.allclose(r.HTH, ref["HTH"], rtol=1e-12, atol=1e-9)
