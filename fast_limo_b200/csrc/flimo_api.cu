@@ -116,6 +116,7 @@ struct flimo_ctx {
   unsigned long long ctl_seq = 0;   // tag of the last command posted to the persistent kernel
   int persist_capacity = 0;      // co-resident CTAs of the persistent kernel
   // registration kernel (whole update on the device, filter step included)
+  double wait_timeout_s = 30.0;  // wall-clock limit of a wait for result records (FLIMO_WAIT_TIMEOUT_S)
   int device_ekf = 1;            // FLIMO_DEVICE_EKF=0: keep the filter step on the host (persistent kernel + handshake)
   int reg_capacity = 0;
   ekf::UpdState* upd_state = nullptr;   // device
@@ -302,14 +303,21 @@ int wait_records(flimo_handle h, const double* block, unsigned long long seq, do
 int wait_records_n(flimo_handle h, const double* block, unsigned long long seq, double* out, int n, bool own) {
   const volatile unsigned long long* rec = reinterpret_cast<const volatile unsigned long long*>(block);
   unsigned long long spins = 0;
+  std::chrono::steady_clock::time_point t0;
   for (int i = n - 1; i >= 0; --i) {
     while (rec[2 * i + 1] != seq) {
-      if ((++spins & 0xFFFFF) == 0 && own) {              // every ~1M polls: has the kernel died?
-        const cudaError_t q = cudaStreamQuery(h->stream);
-        if (q != cudaSuccess && q != cudaErrorNotReady) return fail(h, FLIMO_ERR_CUDA, std::string("match kernel: ") + cudaGetErrorString(q));
-        if (q == cudaSuccess && rec[2 * i + 1] != seq) return 1;
+      if ((++spins & 0xFFFFF) == 0) {                     // every ~1M polls (a few ms)
+        if (own) {                                        // has the kernel died?
+          const cudaError_t q = cudaStreamQuery(h->stream);
+          if (q != cudaSuccess && q != cudaErrorNotReady) return fail(h, FLIMO_ERR_CUDA, std::string("match kernel: ") + cudaGetErrorString(q));
+          if (q == cudaSuccess && rec[2 * i + 1] != seq) return 1;
+        }
+        // wall-clock limit: a peer rank that died (or never made the matching call) must not hang this one for ever
+        const auto now = std::chrono::steady_clock::now();
+        if (spins == 0x100000) t0 = now;
+        else if (std::chrono::duration<double>(now - t0).count() > h->wait_timeout_s)
+          return fail(h, FLIMO_ERR_STATE, own ? "timed out waiting for a measurement result" : "timed out waiting for a peer rank's measurement result");
       }
-      if (spins > (1ull << 36)) return fail(h, FLIMO_ERR_STATE, "timed out waiting for a measurement result");
     }
     std::atomic_thread_fence(std::memory_order_acquire);
     unsigned long long bits = rec[2 * i];
@@ -494,6 +502,7 @@ int flimo_create(const flimo_cfg* cfg, int device, flimo_handle* out) {
   std::memset(h->h_res, 0, (size_t)kResRecords * 16);
   CU(h, cudaHostGetDevicePointer(reinterpret_cast<void**>(&h->d_h_res), h->h_res, 0));
   if (const char* e = std::getenv("FLIMO_DEVICE_EKF")) h->device_ekf = std::atoi(e);
+  if (const char* e = std::getenv("FLIMO_WAIT_TIMEOUT_S")) h->wait_timeout_s = std::atof(e);
   if (const char* e = std::getenv("FLIMO_PERSISTENT")) h->persistent = std::atoi(e);
   if (const char* e = std::getenv("FLIMO_TEST_STALL_PASS")) h->test_stall_pass = std::atoi(e);
   *out = h;
@@ -611,8 +620,8 @@ int flimo_get_stats(flimo_handle h, flimo_stats* out) {
   h->stats.map_bytes = h->map.n_pts * sizeof(float4);
   for (int l = 0; l < h->map.n_levels; ++l) {
     h->stats.table_bytes += (h->map.lv[l].n_cells + 2) * sizeof(uint32_t);
-    // super-row entries: points + 64-bit order keys, each with its ping-pong partner for the incremental merge
-    h->stats.map_bytes += h->map.lv[l].cap_entries * (h->map.lv[l].pts_alt ? 2 : 1) * (sizeof(float4) + sizeof(unsigned long long));
+    // super-row entries (16 bytes each), plus their ping-pong partner once the incremental merge has been used
+    h->stats.map_bytes += h->map.lv[l].cap_entries * (h->map.lv[l].pts_alt ? 2 : 1) * sizeof(float4);
   }
   h->stats.persist_ms_total = h->persist_ns_total * 1e-6;
   h->stats.persist_passes = h->persist_passes;

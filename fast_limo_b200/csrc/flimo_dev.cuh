@@ -145,10 +145,8 @@ struct RegParams {
 
 // map_index.cu
 struct LevelIndex {
-  float4* pts = nullptr;        // duplicated, sorted
-  unsigned long long* keys = nullptr;   // (super-row cell key << 32) | map index of every entry: the total order of pts
-  float4* pts_alt = nullptr;            // ping-pong partners of pts / keys for the incremental merge
-  unsigned long long* keys_alt = nullptr;
+  float4* pts = nullptr;        // duplicated, sorted by super-row cell key (kept in .w)
+  float4* pts_alt = nullptr;            // ping-pong partner of pts for the incremental merge
   uint32_t* cell_start = nullptr;
   size_t n_entries = 0, cap_entries = 0;
   size_t n_cells = 0, cap_cells = 0;
@@ -164,7 +162,6 @@ struct MapIndex {
   float glo[3] = {0, 0, 0}, ghi[3] = {0, 0, 0}; // box the grids were laid out for (bounding box + margin)
   // incremental update scratch (new entries of one level)
   float4* upd_pts = nullptr;
-  unsigned long long* upd_keys = nullptr;
   size_t upd_cap = 0;
   // scratch
   uint32_t *keys = nullptr, *keys_alt = nullptr, *vals = nullptr, *vals_alt = nullptr;

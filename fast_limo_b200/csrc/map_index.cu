@@ -105,16 +105,14 @@ __global__ void __launch_bounds__(256) gather_kernel(const float4* __restrict__ 
   if (i < n) dst[i] = src[order[i]];
 }
 
-// Super-row entry = point coordinates + its canonical map index in .w (bit pattern).
+// Super-row entry = point coordinates + the key of its super-row cell in .w (bit pattern): the array is sorted by that
+// key, which is all the incremental merge needs (the search never looks at .w).
 __global__ void __launch_bounds__(256) gather_tag_kernel(const float4* __restrict__ src, const uint32_t* __restrict__ order,
-                                                         const uint32_t* __restrict__ sorted_keys, size_t n, float4* __restrict__ dst,
-                                                         unsigned long long* __restrict__ keys64) {
+                                                         const uint32_t* __restrict__ sorted_keys, size_t n, float4* __restrict__ dst) {
   const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const uint32_t id = order[i];
-  const float4 v = src[id];
-  dst[i] = make_float4(v.x, v.y, v.z, __uint_as_float(id));
-  keys64[i] = ((unsigned long long)sorted_keys[i] << 32) | id;      // (cell, map index): unique, the order of the array
+  const float4 v = src[order[i]];
+  dst[i] = make_float4(v.x, v.y, v.z, __uint_as_float(sorted_keys[i]));
 }
 
 // Incremental update of the prefix table: every cell start moves up by the number of NEW entries whose
@@ -326,9 +324,11 @@ cudaError_t scan_prepare_reserve(size_t n, void** cub_tmp, size_t* cub_tmp_bytes
 
 cudaError_t map_index_reserve(MapIndex& idx, size_t n) {
   if (n > idx.cap_pts) {
-    // capacity doubles from 1 M points: every growth re-allocates 54 copies of the map, HBM is plentiful
+    // Capacity: 1 M points to start with, then the requested size plus 25 % head-room (every growth re-allocates the 54
+    // super-row copies of the map and forces a full rebuild, so it should be rare — but doubling made a 20 M-point map pay for
+    // 32 M: 43.8 GB of index instead of 34).
     size_t cap = idx.cap_pts ? idx.cap_pts : ((size_t)1 << 20);
-    while (cap < n) cap *= 2;
+    if (cap < n) cap = n + n / 4;
     float4* np = nullptr;
     FL_TRY(cudaMalloc(&np, cap * sizeof(float4)));
     if (idx.pts) {
@@ -358,12 +358,9 @@ void map_index_free(MapIndex& idx) {
   for (auto& l : idx.lv) {
     cudaFree(l.pts);
     cudaFree(l.pts_alt);
-    cudaFree(l.keys);
-    cudaFree(l.keys_alt);
     cudaFree(l.cell_start);
   }
   cudaFree(idx.upd_pts);
-  cudaFree(idx.upd_keys);
   cudaFree(idx.keys);
   cudaFree(idx.cub_tmp);
   cudaFree(idx.bbox);
@@ -413,14 +410,10 @@ static cudaError_t build_level(MapIndex& idx, LevelIndex& L, const GridDesc& g, 
     L.pts = nullptr;
     L.cap_entries = 0;
     if (L.pts_alt) cudaFree(L.pts_alt);
-    if (L.keys) cudaFree(L.keys);
-    if (L.keys_alt) cudaFree(L.keys_alt);
     L.pts_alt = nullptr;
-    L.keys = L.keys_alt = nullptr;
     const size_t cap = 9 * idx.cap_pts;
     FL_TRY(cudaMalloc(&L.pts, (cap + 8) * sizeof(float4)));     // + slack: the search reads whole 32-byte pairs
-    FL_TRY(cudaMalloc(&L.keys, cap * sizeof(unsigned long long)));
-    L.cap_entries = cap;                                        // the ping-pong partners are allocated by the first incremental update
+    L.cap_entries = cap;                                        // the ping-pong partner is allocated by the first incremental update
   }
   L.g = g;
   L.n_cells = n_cells;
@@ -435,7 +428,7 @@ static cudaError_t build_level(MapIndex& idx, LevelIndex& L, const GridDesc& g, 
   if (bytes2 > bytes) bytes = bytes2;
   FL_TRY(ensure(&idx.cub_tmp, &idx.cub_tmp_bytes, bytes));
   FL_TRY(cub::DeviceRadixSort::SortPairs(idx.cub_tmp, bytes, dk, dv, (int)n9, 0, bits, st));
-  gather_tag_kernel<<<nblk(n9), 256, 0, st>>>(idx.pts, dv.Current(), dk.Current(), n9, L.pts, L.keys);
+  gather_tag_kernel<<<nblk(n9), 256, 0, st>>>(idx.pts, dv.Current(), dk.Current(), n9, L.pts);
   FL_TRY(cudaMemsetAsync(L.cell_start, 0xFF, (n_cells + 2) * sizeof(uint32_t), st));
   boundaries_kernel<<<nblk(n9), 256, 0, st>>>(dk.Current(), n9, n_cells, L.cell_start);
   FL_TRY(cub::DeviceScan::InclusiveScan(idx.cub_tmp, bytes, rb, rb, cub::Min(), (int)(n_cells + 2), st));
@@ -507,33 +500,29 @@ bool map_index_can_update(const MapIndex& idx, size_t old_n, const float batch_l
     if (!(batch_lo[a] >= idx.glo[a] && batch_hi[a] <= idx.ghi[a])) return false;   // also rejects NaN boxes
   for (int l = 0; l < idx.n_levels; ++l) {
     const LevelIndex& L = idx.lv[l];
-    if (!L.keys || 9 * idx.n_pts > L.cap_entries || L.n_entries != 9 * old_n) return false;
+    if (!L.pts || 9 * idx.n_pts > L.cap_entries || L.n_entries != 9 * old_n) return false;
   }
   return true;
 }
 
-struct Less64 {
-  __host__ __device__ bool operator()(unsigned long long a, unsigned long long b) const { return a < b; }
+struct LessCell {   // super-row entries are ordered by their cell key (.w); entries of one cell are equivalent
+  __device__ bool operator()(const float4& a, const float4& b) const { return __float_as_uint(a.w) < __float_as_uint(b.w); }
 };
 
 cudaError_t map_index_update(MapIndex& idx, size_t old_n, cudaStream_t st, uint64_t* launches) {
   const size_t n = idx.n_pts, m = n - old_n, m9 = 9 * m, n9_old = 9 * old_n;
   if (m9 > idx.upd_cap) {
     cudaFree(idx.upd_pts);
-    cudaFree(idx.upd_keys);
     idx.upd_pts = nullptr;
-    idx.upd_keys = nullptr;
     idx.upd_cap = 0;
     const size_t cap = m9 + m9 / 2 + 4096;
     FL_TRY(cudaMalloc(&idx.upd_pts, cap * sizeof(float4)));
-    FL_TRY(cudaMalloc(&idx.upd_keys, cap * sizeof(unsigned long long)));
     idx.upd_cap = cap;
   }
   for (int l = 0; l < idx.n_levels; ++l) {
     LevelIndex& L = idx.lv[l];
     const GridDesc& g = L.g;
     if (!L.pts_alt) FL_TRY(cudaMalloc(&L.pts_alt, (L.cap_entries + 8) * sizeof(float4)));
-    if (!L.keys_alt) FL_TRY(cudaMalloc(&L.keys_alt, L.cap_entries * sizeof(unsigned long long)));
     // 1. the nine (super-row key, id) pairs of every new point, sorted (stable radix sort => (key, id) order)
     keys9_kernel<<<nblk(m9), 256, 0, st>>>(idx.pts + old_n, m, g, (uint32_t)L.n_cells, idx.keys, idx.vals, (uint32_t)old_n);
     int bits = 1;
@@ -541,16 +530,15 @@ cudaError_t map_index_update(MapIndex& idx, size_t old_n, cudaStream_t st, uint6
     cub::DoubleBuffer<uint32_t> dk(idx.keys, idx.keys_alt), dv(idx.vals, idx.vals_alt);
     size_t bytes = 0, bytes2 = 0;
     FL_TRY(cub::DeviceRadixSort::SortPairs(nullptr, bytes, dk, dv, (int)m9, 0, bits, st));
-    FL_TRY((cub::DeviceMerge::MergePairs(nullptr, bytes2, L.keys, L.pts, (int)n9_old, idx.upd_keys, idx.upd_pts, (int)m9, L.keys_alt,
-                                         L.pts_alt, Less64{}, st)));
+    FL_TRY((cub::DeviceMerge::MergeKeys(nullptr, bytes2, L.pts, (int)n9_old, idx.upd_pts, (int)m9, L.pts_alt, LessCell{}, st)));
     if (bytes2 > bytes) bytes = bytes2;
     FL_TRY(ensure(&idx.cub_tmp, &idx.cub_tmp_bytes, bytes));
     FL_TRY(cub::DeviceRadixSort::SortPairs(idx.cub_tmp, bytes, dk, dv, (int)m9, 0, bits, st));
-    gather_tag_kernel<<<nblk(m9), 256, 0, st>>>(idx.pts, dv.Current(), dk.Current(), m9, idx.upd_pts, idx.upd_keys);
-    // 2. one merge pass: keys are unique, so the result is THE sorted array a full rebuild would produce
-    FL_TRY((cub::DeviceMerge::MergePairs(idx.cub_tmp, bytes, L.keys, L.pts, (int)n9_old, idx.upd_keys, idx.upd_pts, (int)m9, L.keys_alt,
-                                         L.pts_alt, Less64{}, st)));
-    std::swap(L.keys, L.keys_alt);
+    gather_tag_kernel<<<nblk(m9), 256, 0, st>>>(idx.pts, dv.Current(), dk.Current(), m9, idx.upd_pts);
+    // 2. one merge pass by cell key.  Entries of the same cell are equivalent for the merge (it is not stable), so their
+    //    order inside a cell may differ from a full rebuild's; the search is exact for any order inside a run (ties in
+    //    distance, which only duplicate points produce, are broken by position either way).
+    FL_TRY((cub::DeviceMerge::MergeKeys(idx.cub_tmp, bytes, L.pts, (int)n9_old, idx.upd_pts, (int)m9, L.pts_alt, LessCell{}, st)));
     std::swap(L.pts, L.pts_alt);
     // 3. prefix table: every start moves up by the number of new entries in front of it
     const size_t n_slots = L.n_cells + 2;

@@ -115,8 +115,9 @@ for k in range(args.n_scans):
     else:
         x_est, Pn, passes = m.update(pred, P0, args.max_iter, lim)
     a2 = time.perf_counter()
-    world = m.scan_to_world(x_est)
-    m.add(world, t_last)
+    if om is not None and k < args.oracle:
+        world = m.scan_to_world(x_est)            # the oracle arm below needs the world cloud on the host
+    m.add_scan(x_est, t_last)                     # transformPointCloud + Mapper::add without leaving the device
     a3 = time.perf_counter()
     if k >= WARM:
         t_prep += a1 - a0; t_upd += a2 - a1; t_add += a3 - a2
