@@ -261,7 +261,8 @@ __global__ void __launch_bounds__(kFilterThreads, 1) filter_kernel(const __grid_
       const unsigned long long t0 = gtime_ns();
       unsigned int naps = 0;
       fs.flag = 1;
-      while (ld_acquire_u32(&P.ticket[0]) != (unsigned int)n_groups) {
+      const unsigned int n_arrivals = P.fx_reduce ? (unsigned int)n_tiles : (unsigned int)n_groups;   // tiles (order-free sums) or groups (tree)
+      while (ld_acquire_u32(&P.ticket[0]) != n_arrivals) {
         __nanosleep(20);
         if ((++naps & 1023u) == 0u && gtime_ns() - t0 > P.watchdog_ns) {
           fs.flag = 0;
@@ -275,7 +276,10 @@ __global__ void __launch_bounds__(kFilterThreads, 1) filter_kernel(const __grid_
     bool ok = fs.flag != 0;
     const double pass_ns = (double)(fs.stamps[15] - fs.stamps[14]);      // command posted -> pass sums complete
     const int pass_idx = ss.passes;                                      // (only post_step_rest changes it, barriers away)
-    if (ok && tid < kPartialStride) {
+    if (ok && P.fx_reduce) {
+      __threadfence();
+      if (tid < kPartialStride) fs.sums[0][packed_slot(tid)] = fx_collect(P.ticket, (int)(cmd_no & 1ull), tid);
+    } else if (ok && tid < kPartialStride) {
       double s = 0.0;
       for (int g0 = 0; g0 < n_groups; g0 += 32) {
         const double* base = group_part + (size_t)g0 * kPartialStride + tid;

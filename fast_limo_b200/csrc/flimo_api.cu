@@ -104,7 +104,7 @@ struct flimo_ctx {
 
   int knn_tau = 24;              // level choice threshold (MatchParams::tau)
   int probe_mode = 1, wide_loads = 1, pair_scan = 0;
-  int interleave = 0, scan_perm = 1, l2_prefetch = 0, stage_runs = 0;
+  int interleave = 0, scan_perm = 1, l2_prefetch = 0, stage_runs = 0, fx_reduce = 1;
   int index_incremental = 1;     // FLIMO_INDEX_INCREMENTAL=0: every Mapper::add rebuilds the whole index
   uint64_t stats_index_builds = 0, stats_index_updates = 0;
   int time_every = 8;            // every n-th flimo_update runs one launch per pass, each timed with CUDA events (0 = never)
@@ -243,8 +243,8 @@ int fill_params(flimo_handle h, const double state14[14], MatchParams& P, double
   const int groups = (tiles + 31) / 32;
   const size_t need_part = (size_t)(tiles + groups) * kPartialStride;
   CU(h, grow(&h->partials, &h->partials_cap, need_part));
-  if ((size_t)groups + 1 > h->ticket_cap) {
-    CU(h, grow(&h->ticket, &h->ticket_cap, (size_t)groups + 1));
+  if ((size_t)groups + 1 + kTicketWords > h->ticket_cap) {       // counters + the fixed-point pass accumulators (flimo_dev.cuh)
+    CU(h, grow(&h->ticket, &h->ticket_cap, (size_t)groups + 1 + kTicketWords));
     CU(h, cudaMemsetAsync(h->ticket, 0, h->ticket_cap * sizeof(unsigned int), h->stream));
     CU(h, cudaStreamSynchronize(h->stream));
   }
@@ -271,6 +271,7 @@ int fill_params(flimo_handle h, const double state14[14], MatchParams& P, double
   P.pair_scan = h->pair_scan;
   P.l2_prefetch = h->l2_prefetch;
   P.stage_runs = h->stage_runs;
+  P.fx_reduce = h->fx_reduce;
   P.max_dist_f = ceil_to_float(h->cfg.MAX_DIST_PLANE);
   P.plane_thr = (float)h->cfg.PLANE_THRESHOLD;
   P.estimate_extrinsics = h->cfg.estimate_extrinsics;
@@ -470,6 +471,7 @@ int flimo_create(const flimo_cfg* cfg, int device, flimo_handle* out) {
   if (const char* e = std::getenv("FLIMO_KNN_PERM")) h->scan_perm = std::atoi(e);
   if (const char* e = std::getenv("FLIMO_KNN_PREFETCH")) h->l2_prefetch = std::atoi(e);
   if (const char* e = std::getenv("FLIMO_KNN_STAGE")) h->stage_runs = std::atoi(e);
+  if (const char* e = std::getenv("FLIMO_KNN_FX")) h->fx_reduce = std::atoi(e);
   if (const char* e = std::getenv("FLIMO_INDEX_INCREMENTAL")) h->index_incremental = std::atoi(e);
   CU(h, cudaSetDevice(device));
   CU(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));

@@ -73,6 +73,38 @@ constexpr int kTileQueries = 128;     // queries per CTA tile (== threads per CT
 constexpr int kTriEntries = 91;       // upper triangle of the 13x13 outer product of [row(12), z]
 constexpr int kPartialStride = 96;    // doubles per partial record
 
+// Pass accumulators of the order-free reduction (MatchParams::fx_reduce): they live behind the ticket words,
+//   ticket[0..3]                                   counters
+//   u64 [parity 2][replica kFxReplicas][96][2]     fixed-point sums {units of 2^-18, units of 2^-66}
+// (replicas spread the same-address REDs of tiles that finish together; parity alternates between consecutive passes so
+// that the finisher's zeroing of one set is two passes ahead of its next use).
+constexpr int kFxReplicas = 4;
+constexpr int kTicketWords = 4 + 2 * kFxReplicas * kPartialStride * 2 * 2;
+#ifdef __CUDACC__
+__device__ __forceinline__ unsigned long long* fx_slot(unsigned int* ticket, int sel, int rep, int e) {
+  return reinterpret_cast<unsigned long long*>(ticket + 4) + ((size_t)((sel & 1) * kFxReplicas + rep) * kPartialStride + (size_t)e) * 2;
+}
+// Sum of entry e over the replicas as float64 (one rounding); the slots are cleared for their next use.
+__device__ __forceinline__ double fx_collect(unsigned int* ticket, int sel, int e) {
+  long long hi = 0, lo = 0;
+  unsigned long long v[2 * kFxReplicas];
+#pragma unroll
+  for (int r = 0; r < kFxReplicas; ++r) {
+    const unsigned long long* a = fx_slot(ticket, sel, r, e);
+    v[2 * r] = __ldcg(a);
+    v[2 * r + 1] = __ldcg(a + 1);
+  }
+#pragma unroll
+  for (int r = 0; r < kFxReplicas; ++r) {
+    hi += (long long)v[2 * r];
+    lo += (long long)v[2 * r + 1];
+    unsigned long long* a = fx_slot(ticket, sel, r, e);
+    __stcg(reinterpret_cast<ulonglong2*>(a), make_ulonglong2(0ull, 0ull));
+  }
+  return (double)hi * 0x1p-18 + (double)lo * 0x1p-66;
+}
+#endif
+
 struct MatchParams {
   const float4* scan;          // packed body-frame points; .w carries the original scan index (bit pattern)
   // Unpacked scan (scan == nullptr): the caller's strided xyz array is read in place.  Stored position j of
@@ -93,6 +125,7 @@ struct MatchParams {
   int pair_scan;               // 1 = two lanes per query in the first scan (adjacent 32-byte loads share a wavefront)
   int l2_prefetch;             // 1 = request the whole run with prefetch.global.L2 right after the probe
   int stage_runs;              // 1 = one-launch-per-pass kernel stages the runs in shared memory with cp.async.bulk (TMA) + mbarrier
+  int fx_reduce;               // 1 = tile sums are accumulated with 64-bit fixed-point REDs (one ticket round), 0 = two-level float64 tree
   float max_dist_f;            // smallest float >= MAX_DIST_PLANE  (d2_5 < MAX_DIST_PLANE test)
   float plane_thr;             // (float)PLANE_THRESHOLD
   int estimate_extrinsics;

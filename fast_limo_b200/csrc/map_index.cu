@@ -157,6 +157,186 @@ __global__ void __launch_bounds__(256) boundaries_kernel(const uint32_t* __restr
   if (i == 0 || keys[i - 1] != k) cell_start[k] = (uint32_t)i;
 }
 
+// ---- gapped super-rows ---------------------------------------------------------------------------------------
+// Every super-row (iy, iz) of a level owns a segment [row_base[r], row_base[r + 1]) of the entry array with head-room
+// behind its entries, and nx + 1 slots of the prefix table (slot j = absolute start of cell j, slot nx = end of the row's
+// entries).  A query's run [cell_start[row + ix - 1], cell_start[row + ix + 2]) never leaves its row, so the gaps are
+// invisible to the search — and Mapper::add only has to rewrite the rows a batch touches instead of merging the whole level.
+
+// capacity of row r: its entries + 25 % + 8, even (the search reads 32-byte pairs)
+__global__ void __launch_bounds__(256) row_caps_kernel(const uint32_t* __restrict__ tmp_start, int nx, size_t n_rows, uint32_t* __restrict__ row_cap) {
+  const size_t r = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (r > n_rows) return;
+  if (r == n_rows) {
+    row_cap[r] = 0u;
+    return;
+  }
+  const uint32_t cnt = tmp_start[(r + 1) * (size_t)nx] - tmp_start[r * (size_t)nx];
+  row_cap[r] = (cnt + (cnt >> 2) + 9u) & ~1u;
+}
+
+// prefix table of the gapped layout from the dense one of the sorted array
+__global__ void __launch_bounds__(256) row_table_kernel(const uint32_t* __restrict__ tmp_start, const uint32_t* __restrict__ row_base, int nx,
+                                                        size_t n_rows, uint32_t* __restrict__ cell_start) {
+  const size_t id = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  const size_t n_slots = n_rows * (size_t)(nx + 1);
+  if (id >= n_slots) return;
+  const size_t r = id / (size_t)(nx + 1);
+  const int j = (int)(id - r * (size_t)(nx + 1));
+  cell_start[id] = row_base[r] + (tmp_start[r * (size_t)nx + j] - tmp_start[r * (size_t)nx]);
+}
+
+// sorted (cell key, id) pairs -> entries at their place inside their row's segment
+__global__ void __launch_bounds__(256) row_scatter_kernel(const float4* __restrict__ src, const uint32_t* __restrict__ order,
+                                                          const uint32_t* __restrict__ sorted_keys, size_t n, const uint32_t* __restrict__ tmp_start,
+                                                          const uint32_t* __restrict__ row_base, int nx, uint32_t n_cells, float4* __restrict__ dst) {
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t k = sorted_keys[i];
+  if (k >= n_cells) return;                               // rows outside the grid are not stored
+  const uint32_t r = k / (uint32_t)nx;
+  const float4 v = src[order[i]];
+  dst[row_base[r] + ((uint32_t)i - tmp_start[(size_t)r * nx])] = make_float4(v.x, v.y, v.z, __uint_as_float(k));
+}
+
+// ---- incremental update: all levels in one pass over 54 entries per new point -------------------------------------
+struct LevelDev {
+  float4* pts;
+  uint32_t* cell_start;
+  uint32_t* row_base;      // segment of every row ...
+  uint32_t* row_cap;       // ... and its capacity (rows that outgrow it move to the free tail of the array)
+  uint32_t* tail;          // first free entry behind all segments
+  uint32_t cap_entries;
+  GridDesc g;
+  uint32_t n_cells;
+};
+struct UpdLevels {
+  LevelDev lv[kMaxLevels];
+  int n_levels;
+};
+struct RowJob {          // one touched row of one level
+  uint32_t level, row, begin, end;   // [begin, end) = its new entries in the sorted update arrays
+  uint32_t cnt, off;                 // entries the row holds now, their offset in the scratch copy (rows merged in place)
+  uint32_t new_base, new_cap;        // new_cap != 0: the row moves to [new_base, new_base + new_cap)
+};
+
+__global__ void __launch_bounds__(256) upd_keys_kernel(const float4* __restrict__ p, size_t m, UpdLevels U, uint32_t id_base,
+                                                       unsigned long long* __restrict__ keys, uint32_t* __restrict__ vals) {
+  const size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  const size_t per_level = 9 * m;
+  if (e >= per_level * (size_t)U.n_levels) return;
+  const int l = (int)(e / per_level);
+  const size_t q = e - (size_t)l * per_level;
+  const size_t i = q / 9;
+  const int c = (int)(q - 9 * i);
+  const GridDesc& g = U.lv[l].g;
+  const float4 v = p[i];
+  const int ix = cell_coord(v.x, g.ox, g.inv_cell, g.nx);
+  const int iy = cell_coord(v.y, g.oy, g.inv_cell, g.ny) + (c % 3 - 1);
+  const int iz = cell_coord(v.z, g.oz, g.inv_cell, g.nz) + (c / 3 - 1);
+  const bool ok = iy >= 0 && iy < g.ny && iz >= 0 && iz < g.nz;
+  const uint32_t key = ok ? (uint32_t)((iz * g.ny + iy) * g.nx + ix) : 0xFFFFFFFFu;      // outside the grid: sorted behind the level's rows
+  keys[e] = ((unsigned long long)l << 32) | key;
+  vals[e] = id_base + (uint32_t)i;
+}
+
+__global__ void __launch_bounds__(256) upd_gather_kernel(const float4* __restrict__ src, const uint32_t* __restrict__ order,
+                                                         const unsigned long long* __restrict__ keys, size_t n, float4* __restrict__ dst) {
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 v = src[order[i]];
+  dst[i] = make_float4(v.x, v.y, v.z, __uint_as_float((uint32_t)keys[i]));
+}
+
+// first new entry of every (level, row) group -> a job; checks the row's head-room
+__global__ void __launch_bounds__(256) upd_jobs_kernel(const unsigned long long* __restrict__ keys, uint32_t n, UpdLevels U, RowJob* __restrict__ jobs,
+                                                       uint32_t* __restrict__ counters /* [0] jobs, [1] scratch entries, [2] overflow */) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const unsigned long long k = keys[i];
+  const uint32_t l = (uint32_t)(k >> 32), ck = (uint32_t)k;
+  if (ck == 0xFFFFFFFFu) return;
+  const uint32_t nx = (uint32_t)U.lv[l].g.nx, r = ck / nx;
+  if (i > 0) {
+    const unsigned long long kp = keys[i - 1];
+    if ((uint32_t)(kp >> 32) == l && (uint32_t)kp != 0xFFFFFFFFu && (uint32_t)kp / nx == r) return;   // not the head of its group
+  }
+  const unsigned long long limit = ((unsigned long long)l << 32) | (unsigned long long)(r + 1u) * nx;   // first key of the next row
+  uint32_t lo = i + 1, hi = n;
+  while (lo < hi) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (keys[mid] < limit) lo = mid + 1; else hi = mid;
+  }
+  const uint32_t base = U.lv[l].row_base[r], cap = U.lv[l].row_cap[r];
+  const uint32_t cnt = U.lv[l].cell_start[(size_t)r * (nx + 1) + nx] - base;
+  const uint32_t need = cnt + (lo - i);
+  RowJob j;
+  j.level = l; j.row = r; j.begin = i; j.end = lo; j.cnt = cnt;
+  j.off = 0u; j.new_base = 0u; j.new_cap = 0u;
+  if (need > cap) {                                        // the row outgrows its segment: it moves to the tail with room to double
+    j.new_cap = (2u * need + 33u) & ~1u;
+    j.new_base = atomicAdd(U.lv[l].tail, j.new_cap);
+    if ((unsigned long long)j.new_base + j.new_cap + 8ull > (unsigned long long)U.lv[l].cap_entries) counters[2] = 1u;   // array full: rebuild (compacts)
+  } else {
+    j.off = atomicAdd(&counters[1], cnt);
+  }
+  jobs[atomicAdd(&counters[0], 1u)] = j;
+}
+
+// One CTA per touched row: copy the row aside, merge it with its new entries by cell key (old entries first among
+// equal keys) back into the row's segment, move the row's table slots up by the new entries in front of them.
+__global__ void __launch_bounds__(128) upd_merge_kernel(const RowJob* __restrict__ jobs, UpdLevels U, const float4* __restrict__ new_pts,
+                                                        float4* __restrict__ scratch) {
+  const RowJob j = jobs[blockIdx.x];
+  const LevelDev& L = U.lv[j.level];
+  const uint32_t nx = (uint32_t)L.g.nx, base = L.row_base[j.row];
+  const bool moves = j.new_cap != 0u;
+  float4* row = L.pts + (moves ? j.new_base : base);
+  const float4* old = moves ? L.pts + base : scratch + j.off;           // a moving row is read where it lies
+  const float4* nw = new_pts + j.begin;
+  const uint32_t n_new = j.end - j.begin;
+  if (!moves) {
+    float4* keep = scratch + j.off;
+    for (uint32_t i = threadIdx.x; i < j.cnt; i += blockDim.x) keep[i] = row[i];
+    __syncthreads();
+  }
+  for (uint32_t i = threadIdx.x; i < j.cnt; i += blockDim.x) {          // old entry i: behind the new entries with a SMALLER key
+    const float4 v = old[i];
+    const uint32_t key = __float_as_uint(v.w);
+    uint32_t lo = 0, hi = n_new;
+    while (lo < hi) {
+      const uint32_t mid = (lo + hi) >> 1;
+      if (__float_as_uint(nw[mid].w) < key) lo = mid + 1; else hi = mid;
+    }
+    row[i + lo] = v;
+  }
+  for (uint32_t i = threadIdx.x; i < n_new; i += blockDim.x) {          // new entry i: behind the old entries with a key <= its own
+    const float4 v = nw[i];
+    const uint32_t key = __float_as_uint(v.w);
+    uint32_t lo = 0, hi = j.cnt;
+    while (lo < hi) {
+      const uint32_t mid = (lo + hi) >> 1;
+      if (__float_as_uint(old[mid].w) <= key) lo = mid + 1; else hi = mid;
+    }
+    row[i + lo] = v;
+  }
+  uint32_t* slots = L.cell_start + (size_t)j.row * (nx + 1);
+  const uint32_t first_key = j.row * nx;
+  const uint32_t shift = moves ? j.new_base - base : 0u;               // (modular arithmetic: new_base may lie below base)
+  for (uint32_t c = threadIdx.x; c <= nx; c += blockDim.x) {            // slot c moves up by the new entries of cells < c
+    uint32_t lo = 0, hi = n_new;
+    while (lo < hi) {
+      const uint32_t mid = (lo + hi) >> 1;
+      if (__float_as_uint(nw[mid].w) < first_key + c) lo = mid + 1; else hi = mid;
+    }
+    slots[c] += lo + shift;
+  }
+  if (moves && threadIdx.x == 0) {
+    L.row_base[j.row] = j.new_base;
+    L.row_cap[j.row] = j.new_cap;
+  }
+}
+
 __global__ void __launch_bounds__(256) pack_points_kernel(const unsigned char* __restrict__ src, size_t n, size_t stride,
                                                           float4* __restrict__ dst, unsigned int* __restrict__ count) {
   const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;

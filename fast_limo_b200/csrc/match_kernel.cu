@@ -37,7 +37,13 @@ constexpr int kGroupTiles = 32;   // tiles per first-level reduction group
 struct Top5 {
   float d[5];
   uint32_t i[5];
+  uint32_t sl;     // 3 bits per neighbour: its slot in the thread's neighbour stash (see kStashStride)
 };
+// Neighbour stash: the exact re-ranking loads the coordinates of (up to) six candidates anyway; they are parked in
+// shared memory (slot j of lane l of a warp at [j * 32 + l], conflict-free for any per-lane slot) so that the plane fit
+// reads the five winners from there instead of fetching them from the map a second time.
+constexpr int kStashStride = 32;
+constexpr uint32_t kStashIdentity = 0u | (1u << 3) | (2u << 6) | (3u << 9) | (4u << 12);
 
 // Sorted insertion; on equal distance the earlier candidate stays in front and a candidate equal
 // to the current worst is rejected (Octree.hpp:72-87).  Branch free; NaN is never inserted.
@@ -163,7 +169,7 @@ __device__ __forceinline__ void rank4(float (&k)[6], const Pair& p0, const Pair&
 // relative to it), a = absolute position of ordinal 0.
 template <int kSrc = 1>
 __device__ __forceinline__ bool finish_private(const float (&k)[6], const float4* __restrict__ pts, uint32_t a, float qx, float qy,
-                                               float qz, Top5& t) {
+                                               float qz, Top5& t, float4* stash) {
   const uint32_t low = kKeyLow;
   const float inf = __int_as_float(0x7f800000);
   // exact re-ranking of the (up to) six kept candidates: sort (exact d2 bits, ordinal) pairs
@@ -174,8 +180,12 @@ __device__ __forceinline__ bool finish_private(const float (&k)[6], const float4
     const bool have = kb < 0x7f800000u;
     const uint32_t ord = kb & low;
     float d = inf;
-    if (have) d = sqdist(qx, qy, qz, kSrc == 2 ? pts[ord] : __ldg(&pts[ord]));
-    ek[j] = ((unsigned long long)__float_as_uint(d) << 32) | (have ? ord : 0xFFFFFFFFu);
+    if (have) {
+      const float4 p = kSrc == 2 ? pts[ord] : __ldg(&pts[ord]);
+      stash[j * kStashStride] = p;
+      d = sqdist(qx, qy, qz, p);
+    }
+    ek[j] = ((unsigned long long)__float_as_uint(d) << 32) | (have ? ((ord << 3) | (uint32_t)j) : 0xFFFFFFFFu);   // ties: by ordinal
   }
   cmpswap64(ek[0], ek[5]); cmpswap64(ek[1], ek[3]); cmpswap64(ek[2], ek[4]);
   cmpswap64(ek[1], ek[2]); cmpswap64(ek[3], ek[4]);
@@ -183,9 +193,12 @@ __device__ __forceinline__ bool finish_private(const float (&k)[6], const float4
   cmpswap64(ek[0], ek[1]); cmpswap64(ek[2], ek[3]); cmpswap64(ek[4], ek[5]);
   cmpswap64(ek[1], ek[2]); cmpswap64(ek[3], ek[4]);
 #pragma unroll
+  t.sl = 0u;
+#pragma unroll
   for (int j = 0; j < 5; ++j) {
     t.d[j] = __uint_as_float((uint32_t)(ek[j] >> 32));
-    t.i[j] = a + (uint32_t)(ek[j] & 0xFFFFFFFFu);
+    t.i[j] = a + ((uint32_t)(ek[j] & 0xFFFFFFFFu) >> 3);
+    t.sl |= ((uint32_t)ek[j] & 7u) << (3 * j);
   }
   // Acceptance.  Every candidate that was not kept has a ranking key >= k5 (the sixth smallest), hence a
   // ranking distance >= bucket_floor(k5) and an exact distance within 4 ulp of that.  If k5's bucket
@@ -203,7 +216,7 @@ __device__ __forceinline__ bool finish_private(const float (&k)[6], const float4
 // the (at most one) leading entry before s is masked, trailing entries are never ranked.
 template <int kWide>
 __device__ __forceinline__ bool block_scan_private(const LevelView& L, uint32_t s, uint32_t e, float qx, float qy, float qz,
-                                                   Top5& t, const float4* staged = nullptr) {
+                                                   Top5& t, float4* stash, const float4* staged = nullptr) {
   const uint32_t total = e - s;
 #pragma unroll
   for (int j = 0; j < 5; ++j) {
@@ -251,7 +264,7 @@ __device__ __forceinline__ bool block_scan_private(const LevelView& L, uint32_t 
   if (n + 1 < tot) keys6_insert(k, pack_key(sqdist_rank(qx, qy, qz, a0.bx, a0.by, a0.bz), low, n + 1));
   if (n + 2 < tot) keys6_insert(k, pack_key(sqdist_rank(qx, qy, qz, a1.ax, a1.ay, a1.az), low, n + 2));
 
-  return finish_private<kWide>(k, pts, a, qx, qy, qz, t);
+  return finish_private<kWide>(k, pts, a, qx, qy, qz, t, stash);
 }
 
 // ---- two lanes per query (P.pair_scan) ------------------------------------------------------------------
@@ -335,8 +348,19 @@ __device__ __forceinline__ void block_scan_team(const LevelView& L, int T, int t
     mine.i[j] = 0xFFFFFFFFu;
   }
   const float4* __restrict__ pts = L.pts;
+  // four loads in flight per lane (the offers form one dependent chain; the loads do not depend on it)
+  uint32_t i = s + tl;
+  const uint32_t T4 = 4u * (uint32_t)T;
 #pragma unroll 1
-  for (uint32_t i = s + tl; i < e; i += T) top5_offer(mine, sqdist(qx, qy, qz, __ldg(&pts[i])), i);
+  for (; i + 3u * (uint32_t)T < e; i += T4) {
+    const float4 p0 = __ldg(&pts[i]), p1 = __ldg(&pts[i + T]), p2 = __ldg(&pts[i + 2 * T]), p3 = __ldg(&pts[i + 3 * T]);
+    top5_offer(mine, sqdist(qx, qy, qz, p0), i);
+    top5_offer(mine, sqdist(qx, qy, qz, p1), i + T);
+    top5_offer(mine, sqdist(qx, qy, qz, p2), i + 2 * T);
+    top5_offer(mine, sqdist(qx, qy, qz, p3), i + 3 * T);
+  }
+#pragma unroll 1
+  for (; i < e; i += T) top5_offer(mine, sqdist(qx, qy, qz, __ldg(&pts[i])), i);
 #pragma unroll
   for (int round = 0; round < 5; ++round) {
     const uint32_t db = __float_as_uint(mine.d[0]);
@@ -496,7 +520,7 @@ struct StageCtx {
 template <bool kWide, bool kPair, bool kStage = false>
 __device__ __forceinline__ void knn_search(const MatchParams& P, int lane, bool active, float qx, float qy, float qz, Top5& t,
                                            int& lvl, int& first_lvl, uint32_t& first_cnt, unsigned long long& t_priv, unsigned long long& t_probe,
-                                           const StageCtx stage = StageCtx{nullptr, nullptr, nullptr}) {
+                                           float4* stash, const StageCtx stage = StageCtx{nullptr, nullptr, nullptr}) {
   const unsigned int full = 0xffffffffu;
   lvl = 0;
   first_lvl = 0;
@@ -529,7 +553,7 @@ __device__ __forceinline__ void knn_search(const MatchParams& P, int lane, bool 
       hx0 = pr.hx; hy0 = pr.hy; hz0 = pr.hz;
     }
     if (!kPair && !kStage) {
-      const bool exact_here = block_scan_private<kWide ? 1 : 0>(P.lv[lvl], pr.s, pr.e, qx, qy, qz, t);
+      const bool exact_here = block_scan_private<kWide ? 1 : 0>(P.lv[lvl], pr.s, pr.e, qx, qy, qz, t, stash);
       if (!exact_here) {
         pending = true;                                          // redo this level cooperatively
       } else if (!block_is_final(P.lv[lvl].g, P.max_dist_f, qx, qy, qz, pr.hx, pr.hy, pr.hz, t.d[4])) {
@@ -560,8 +584,8 @@ __device__ __forceinline__ void knn_search(const MatchParams& P, int lane, bool 
     }
     if (active) {
       const int top = P.n_levels - 1;
-      const bool exact_here = staged ? block_scan_private<2>(P.lv[lvl], scan_s, scan_e, qx, qy, qz, t, stage.lane_slice)
-                                     : block_scan_private<kWide ? 1 : 0>(P.lv[lvl], scan_s, scan_e, qx, qy, qz, t);
+      const bool exact_here = staged ? block_scan_private<2>(P.lv[lvl], scan_s, scan_e, qx, qy, qz, t, stash, stage.lane_slice)
+                                     : block_scan_private<kWide ? 1 : 0>(P.lv[lvl], scan_s, scan_e, qx, qy, qz, t, stash);
       if (!exact_here) {
         pending = true;
       } else if (!block_is_final(P.lv[lvl].g, P.max_dist_f, qx, qy, qz, hx0, hy0, hz0, t.d[4])) {
@@ -602,7 +626,7 @@ __device__ __forceinline__ void knn_search(const MatchParams& P, int lane, bool 
       bool exact_here = total_own == 0u;                         // empty block: exact (nothing there)
       if (do_scan) {
         const uint32_t a = scan_s & ~3u;
-        exact_here = finish_private(kk, P.lv[lvl].pts + a, a, qx, qy, qz, t);
+        exact_here = finish_private(kk, P.lv[lvl].pts + a, a, qx, qy, qz, t, stash);
       }
       if (!exact_here) {
         pending = true;
@@ -616,10 +640,12 @@ __device__ __forceinline__ void knn_search(const MatchParams& P, int lane, bool 
     __syncwarp();
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_priv));
   }
+  bool teamed = false;
 #pragma unroll 1
   for (;;) {
     const unsigned int todo = __ballot_sync(full, pending);
     if (todo == 0) break;
+    teamed = teamed || pending;
     // Split the warp into G = pow2ceil(#pending) teams of T = 32/G lanes; team g serves the pending
     // lane of rank g.  Few stragglers => wide teams (short, parallel scans); many => T = 1, which is
     // the thread-per-query regime with every lane busy.
@@ -653,6 +679,12 @@ __device__ __forceinline__ void knn_search(const MatchParams& P, int lane, bool 
       if (block_is_final(L.g, P.max_dist_f, qx, qy, qz, hx, hy, hz, t.d[4]) || lvl + 1 >= P.n_levels) pending = false;
       else lvl = next_level(P, lvl, t.d[4]);
     }
+  }
+  if (teamed) {                                                  // a team's answer: its five points go to the stash now
+    const float4* __restrict__ src = P.lv[lvl].pts;
+#pragma unroll
+    for (int j = 0; j < 5; ++j) stash[j * kStashStride] = __ldg(&src[t.i[j]]);
+    t.sl = kStashIdentity;
   }
 }
 
@@ -840,6 +872,20 @@ __device__ __forceinline__ void tri13(int e, int& i, int& j) {
   j = r + (e - base);
 }
 
+// pack: 13x13 triangle entry e=(i,j) -> [0..77] HTH tri (12x12), [78..89] HTh, [91] sum z^2 (flimo.h layout)
+__device__ __forceinline__ int packed_slot13(int e) {
+  if (e < kTriEntries) {
+    int i, j;
+    tri13(e, i, j);
+    if (j < 12) return i * 12 - (i * (i - 1)) / 2 + (j - i);
+    if (i < 12) return 78 + i;
+    return 91;
+  }
+  if (e == 91) return 92;     // n_valid
+  if (e == 92) return 90;     // n_rows
+  return e;                   // 93,94,95 reserved (zero)
+}
+
 __device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p) {
   unsigned long long v;
   asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
@@ -870,7 +916,7 @@ struct TileShared {
 template <bool kWide, bool kPair, bool kExternalFinal = false, bool kStage = false>
 __device__ __forceinline__ bool match_tile(const MatchParams& P, const PoseConsts& pc, TileShared& sh, const int tile_idx,
                                            const int n_tiles, const uint32_t orig_limit, const bool reuse_rows = false,
-                                           const StageCtx stage = StageCtx{nullptr, nullptr, nullptr}) {
+                                           const StageCtx stage = StageCtx{nullptr, nullptr, nullptr}, const int acc_sel = 0) {
   auto& tile = sh.tile;
   auto& wsum = sh.wsum;
   int& s_last = sh.s_last;
@@ -932,24 +978,24 @@ __device__ __forceinline__ bool match_tile(const MatchParams& P, const PoseConst
       t.d[j] = __int_as_float(0x7f800000);
       t.i[j] = 0;
     }
+    t.sl = kStashIdentity;
     if (P.timing) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tm0));
-    knn_search<kWide, kPair, kStage>(P, lane, in_range, g[0], g[1], g[2], t, lvl, first_lvl, first_cnt, t_priv, t_probe, stage);      // warp-converged call
+    float4* stash = reinterpret_cast<float4*>(&tile[warp][0][0]) + lane;   // the warp's row block is free until its rows are written below
+    knn_search<kWide, kPair, kStage>(P, lane, in_range, g[0], g[1], g[2], t, lvl, first_lvl, first_cnt, t_priv, t_probe, stash, stage);      // warp-converged call
     if (P.timing) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tm1));
 
     if (in_range) {
-      const float4* __restrict__ src = P.lv[lvl].pts;             // storage t.i[] indexes into
       float n4[4] = {0.f, 0.f, 0.f, 0.f};
       float dist = 0.f;
       // Plane::enough_points + close_enough: an empty slot is +inf and fails the strict '<'.
       if (t.d[4] < P.max_dist_f) {
         float A[5][3];
-        float4 nb[5];
   #pragma unroll
         for (int j = 0; j < 5; ++j) {
-          nb[j] = __ldg(&src[t.i[j]]);
-          A[j][0] = nb[j].x;
-          A[j][1] = nb[j].y;
-          A[j][2] = nb[j].z;
+          const float4 nbj = stash[((t.sl >> (3 * j)) & 7u) * kStashStride];
+          A[j][0] = nbj.x;
+          A[j][1] = nbj.y;
+          A[j][2] = nbj.z;
         }
         float x[3];
         plane_qr_solve(A, x);
@@ -961,7 +1007,8 @@ __device__ __forceinline__ bool match_tile(const MatchParams& P, const PoseConst
         bool ok = true;
   #pragma unroll
         for (int j = 0; j < 5; ++j) {
-          const float res = ((n4[0] * nb[j].x + n4[1] * nb[j].y) + n4[2] * nb[j].z) + n4[3];
+          const float4 nbj = stash[((t.sl >> (3 * j)) & 7u) * kStashStride];   // (re-read: cheaper than 15 registers across the QR)
+          const float res = ((n4[0] * nbj.x + n4[1] * nbj.y) + n4[2] * nbj.z) + n4[3];
           if (fabsf(res) > P.plane_thr) ok = false;
         }
         accepted = ok;
@@ -1081,6 +1128,47 @@ __device__ __forceinline__ bool match_tile(const MatchParams& P, const PoseConst
     (void)__ballot_sync(0xffffffffu, lvl != first_lvl);
     (void)__reduce_max_sync(0xffffffffu, first_cnt);
   }
+  // ---- CTA partial -> order-free exact accumulation (P.fx_reduce) ------------------------------------
+  // The tile's 96 sums are split into two 64-bit fixed-point words (units 2^-18 and 2^-66) and added to the pass
+  // accumulators with integer REDs: integer addition is associative, so the pass sum is the same whatever order the
+  // tiles finish in — deterministic like the tree below, but ONE ticket round instead of two (the finisher converts
+  // the 96 sums back to float64 with a single rounding each).  Range: |tile sum| < 2^44, up to 2^15 tiles.
+  if (P.fx_reduce) {
+    if (threadIdx.x < kPartialStride) {
+      double s = 0.0;
+#pragma unroll
+      for (int w = 0; w < kTileQueries / 32; ++w) s += wsum[w][threadIdx.x];
+      const double hi_d = rint(s * 0x1p18);
+      const long long hi = (long long)hi_d;
+      const long long lo = __double2ll_rn((s - hi_d * 0x1p-18) * 0x1p66);
+      unsigned long long* a = fx_slot(P.ticket, acc_sel, tile_idx & (kFxReplicas - 1), threadIdx.x);
+      if (hi != 0) atomicAdd(a, (unsigned long long)hi);
+      if (lo != 0) atomicAdd(a + 1, (unsigned long long)lo);
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const unsigned int prev = atomicAdd(&P.ticket[0], 1u);
+      s_last = (prev == (unsigned int)(n_tiles - 1)) ? 1 : 0;
+    }
+    if (kExternalFinal) return false;   // the filter kernel waits for ticket[0] == n_tiles and reads the accumulators itself
+    __syncthreads();
+    if (!s_last) return false;
+    __threadfence();
+    if (threadIdx.x < kPartialStride) {
+      const double s = fx_collect(P.ticket, acc_sel, threadIdx.x);
+      wsum[0][packed_slot13(threadIdx.x)] = s;                 // stage in packed order
+    }
+    if (threadIdx.x == 0) P.ticket[0] = 0u;                  // self reset for the next pass / launch
+    __threadfence();
+    __syncthreads();
+    if (P.timing && threadIdx.x == 0) {
+      unsigned long long te;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(te));
+      P.timing[(size_t)n_tiles * (kTileQueries / 32) * 8] = te;
+    }
+    return true;
+  }
   // ---- CTA partial, then a deterministic two-level tree over tiles ----------------------------------
   const int n_groups = (n_tiles + kGroupTiles - 1) / kGroupTiles;
   const int group = tile_idx / kGroupTiles;
@@ -1097,7 +1185,7 @@ __device__ __forceinline__ bool match_tile(const MatchParams& P, const PoseConst
   if (threadIdx.x == 0) {
     const int g_first = group * kGroupTiles;
     const int g_count = min(kGroupTiles, n_tiles - g_first);
-    const unsigned int prev = atomicAdd(&P.ticket[1 + group], 1u);
+    const unsigned int prev = atomicAdd(&P.ticket[kTicketWords + group], 1u);
     s_last = (prev == (unsigned int)(g_count - 1)) ? 1 : 0;
   }
   __syncthreads();
@@ -1122,7 +1210,7 @@ __device__ __forceinline__ bool match_tile(const MatchParams& P, const PoseConst
   __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) {
-    P.ticket[1 + group] = 0u;   // self reset for the next launch
+    P.ticket[kTicketWords + group] = 0u;   // self reset for the next launch
     const unsigned int prev = atomicAdd(&P.ticket[0], 1u);
     s_last = (prev == (unsigned int)(n_groups - 1)) ? 1 : 0;
   }
@@ -1141,19 +1229,7 @@ __device__ __forceinline__ bool match_tile(const MatchParams& P, const PoseConst
 #pragma unroll
       for (int u = 0; u < 32; ++u) s += v[u];
     }
-    // pack: 13x13 triangle entry e=(i,j) -> [0..77] HTH tri (12x12), [78..89] HTh, [91] sum z^2
-    int out_idx;
-    const int e = threadIdx.x;
-    if (e < kTriEntries) {
-      int i, j;
-      tri13(e, i, j);
-      if (j < 12) out_idx = i * 12 - (i * (i - 1)) / 2 + (j - i);
-      else if (i < 12) out_idx = 78 + i;
-      else out_idx = 91;
-    } else if (e == 91) out_idx = 92;     // n_valid
-    else if (e == 92) out_idx = 90;       // n_rows
-    else out_idx = e;                     // 93,94,95 reserved (zero)
-    wsum[0][out_idx] = s;                                  // stage in packed order
+    wsum[0][packed_slot13((int)threadIdx.x)] = s;           // stage in packed order
   }
   if (threadIdx.x == 0) P.ticket[0] = 0u;                  // self reset for the next pass / launch
   __syncthreads();
@@ -1187,7 +1263,8 @@ __device__ __forceinline__ void publish_result(const MatchParams& P, TileShared&
 template <bool kWide, bool kPair>
 __global__ void __launch_bounds__(kTileQueries, 7) match_reduce_kernel(const __grid_constant__ MatchParams P) {
   __shared__ TileShared sh;
-  if (match_tile<kWide, kPair>(P, P.pc, sh, (int)blockIdx.x, (int)gridDim.x, P.orig_limit)) publish_result(P, sh, P.seq, 0ull);
+  if (match_tile<kWide, kPair>(P, P.pc, sh, (int)blockIdx.x, (int)gridDim.x, P.orig_limit, false, StageCtx{nullptr, nullptr, nullptr}, (int)(P.seq & 1ull)))
+    publish_result(P, sh, P.seq, 0ull);
 }
 
 // One launch = one pass, runs staged in shared memory by bulk asynchronous copies (see StageCtx above).
@@ -1201,7 +1278,7 @@ __global__ void __launch_bounds__(kTileQueries, 2) match_reduce_staged_kernel(co
   __syncthreads();
   uint32_t phase = 0u;
   const StageCtx stage{s_stage + ((size_t)warp * 32 + lane) * kStageStride, &s_bar[warp], &phase};
-  if (match_tile<true, false, false, true>(P, P.pc, sh, (int)blockIdx.x, (int)gridDim.x, P.orig_limit, false, stage)) publish_result(P, sh, P.seq, 0ull);
+  if (match_tile<true, false, false, true>(P, P.pc, sh, (int)blockIdx.x, (int)gridDim.x, P.orig_limit, false, stage, (int)(P.seq & 1ull))) publish_result(P, sh, P.seq, 0ull);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -1272,7 +1349,8 @@ __global__ void __launch_bounds__(kTileQueries, 7) match_persistent_kernel(const
     __syncthreads();
     if (s_ctl.cmd != 0u) return;
     for (int t = (int)blockIdx.x; t < n_tiles; t += (int)gridDim.x)
-      if (match_tile<kWide, kPair>(P, s_ctl.pc, sh, t, n_tiles, s_ctl.orig_limit)) publish_result(P, sh, want, s_ctl.t_begin);
+      if (match_tile<kWide, kPair>(P, s_ctl.pc, sh, t, n_tiles, s_ctl.orig_limit, false, StageCtx{nullptr, nullptr, nullptr}, (int)(want & 1ull)))
+        publish_result(P, sh, want, s_ctl.t_begin);
     __syncthreads();
   }
 }
@@ -1325,7 +1403,8 @@ __global__ void __launch_bounds__(kTileQueries, 7) registration_tiles_kernel(con
     // cmd 3 = the pass is repeated with the same pose and a row limit: a CTA that owns exactly one tile re-selects the rows
     // it still holds in shared memory instead of matching the tile again
     const bool reuse = s_ctl.cmd == 3u && (int)gridDim.x >= n_tiles;
-    for (int t = (int)blockIdx.x; t < n_tiles; t += (int)gridDim.x) match_tile<kWide, kPair, true>(P, s_ctl.pc, sh, t, n_tiles, s_ctl.orig_limit, reuse);
+    for (int t = (int)blockIdx.x; t < n_tiles; t += (int)gridDim.x)
+      match_tile<kWide, kPair, true>(P, s_ctl.pc, sh, t, n_tiles, s_ctl.orig_limit, reuse, StageCtx{nullptr, nullptr, nullptr}, (int)(cmd_no & 1ull));
     __syncthreads();
   }
 }

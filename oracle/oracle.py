@@ -65,6 +65,7 @@ def lib():
         L.orc_match.restype = C.c_long
         L.orc_match.argtypes = [C.c_void_p, C.POINTER(OrcCfg), f64p, f32p, C.c_size_t, C.c_size_t,
                                 u8p, f32p, f32p, f32p, f32p, f64p, f64p, f64p, f64p, i64p]
+        L.orc_scan_to_world.argtypes = [f64p, f32p, C.c_size_t, C.c_size_t, f32p]
         L.orc_update.restype = C.c_int
         L.orc_update.argtypes = [C.c_void_p, C.POINTER(OrcCfg), f64p, f64p, C.c_int, f64p, C.c_double, C.c_double,
                                  f32p, C.c_size_t, C.c_size_t, f64p, C.c_int]
@@ -175,6 +176,15 @@ class OracleMap:
                                   _p(lim, C.c_double), float(R), float(D), _p(scan, C.c_float), scan.shape[0],
                                   scan.shape[1], _p(trace, C.c_double), trace.shape[0])
         return st, Pm, unpack_trace(trace[:passes])
+
+
+def scan_to_world(state14, scan):
+    """pcl::transformPointCloud(pc2match, final_scan, state.get_RT()) (Localizer.cpp:361): (n, 3) float32 world points."""
+    scan = _xyz(scan)
+    st = np.ascontiguousarray(state14, np.float64)
+    out = np.zeros((scan.shape[0], 3), np.float32)
+    lib().orc_scan_to_world(_p(st, C.c_double), _p(scan, C.c_float), scan.shape[0], scan.shape[1], _p(out, C.c_float))
+    return out
 
 
 def unpack_trace(tr):

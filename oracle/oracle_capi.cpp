@@ -114,6 +114,14 @@ void orc_plane_fit(const float* pts, int k, float out[4]) {
   out[3] = static_cast<float>(1.0 / static_cast<double>(nrm));
 }
 
+// pcl::transformPointCloud(*pc2match, *final_scan, state.get_RT()) of Localizer.cpp:361 — the same float evaluation of
+// T * (x, y, z, 1) as the per-point transform of Mapper::match (Mapper.cpp:71-72).  out: 3 floats per point.
+void orc_scan_to_world(const double* state14, const float* scan, size_t n, size_t stride, float* out) {
+  FState s;
+  s.prepare(state14, state14 + 3, state14 + 7, state14 + 11);
+  for (size_t i = 0; i < n; ++i) affine_apply(s.R_wb, s.t_wb, scan + i * stride, out + 3 * i);
+}
+
 // One measurement pass (h_share_model): Mapper::match + Localizer::calculate_H + HTH/HTh.
 // state14 = pos[3], rot[4] (x,y,z,w), offset_R_L_I[4], offset_T_L_I[3].
 // Per-query outputs (may be null) are sized n_q = min(n, max_pc2match).
