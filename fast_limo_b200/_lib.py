@@ -77,6 +77,9 @@ class FlimoStats(C.Structure):
         ("map_bytes", C.c_uint64),
         ("persist_ms_total", C.c_double),
         ("persist_passes", C.c_uint64),
+        ("index_builds", C.c_uint64),
+        ("index_updates", C.c_uint64),
+        ("index_rows_moved", C.c_uint64),
     ]
 
 

@@ -259,6 +259,7 @@ int fill_params(flimo_handle h, const double state14[14], MatchParams& P, double
   for (int l = 0; l < kMaxLevels; ++l) {
     P.lv[l].pts = h->map.lv[l].pts;
     P.lv[l].cell_start = h->map.lv[l].cell_start;
+    P.lv[l].row_stride = h->map.lv[l].g.nx + 1;
     P.lv[l].g = h->map.lv[l].g;
   }
   make_pose(state14, P.pc);
@@ -621,12 +622,14 @@ int flimo_get_stats(flimo_handle h, flimo_stats* out) {
   h->stats.table_bytes = 0;
   h->stats.map_bytes = h->map.n_pts * sizeof(float4);
   for (int l = 0; l < h->map.n_levels; ++l) {
-    h->stats.table_bytes += (h->map.lv[l].n_cells + 2) * sizeof(uint32_t);
-    // super-row entries (16 bytes each), plus their ping-pong partner once the incremental merge has been used
-    h->stats.map_bytes += h->map.lv[l].cap_entries * (h->map.lv[l].pts_alt ? 2 : 1) * sizeof(float4);
+    h->stats.table_bytes += (h->map.lv[l].cap_slots + 2 * h->map.lv[l].cap_rows) * sizeof(uint32_t);
+    h->stats.map_bytes += h->map.lv[l].cap_entries * sizeof(float4);   // super-row entries (16 bytes each) incl. the rows' head-room
   }
   h->stats.persist_ms_total = h->persist_ns_total * 1e-6;
   h->stats.persist_passes = h->persist_passes;
+  h->stats.index_builds = h->stats_index_builds;
+  h->stats.index_updates = h->stats_index_updates;
+  h->stats.index_rows_moved = h->map.rows_moved;
   *out = h->stats;
   return FLIMO_OK;
 }
@@ -685,7 +688,7 @@ int flimo_map_add_device(flimo_handle h, const void* d_xyz, size_t n, size_t str
   // 3. accept / drop per point, append the accepted ones to the canonical list, update the counts
   const auto ta1 = std::chrono::steady_clock::now();
   unsigned int accepted = 0;
-  CU(h, map_insert_batch(h->lattice, h->counts, h->batch, kept, h->cfg.octree_downsampling, first, h->map.pts + old_n,
+  CU(h, map_insert_batch(h->lattice, h->counts, h->batch, kept, old_n, h->cfg.octree_downsampling, first, h->map.pts + old_n,
                          h->d_count, h->batch_keys, h->batch_accept, &accepted, h->stream, &h->stats.kernel_launches));
   const size_t total = old_n + accepted;
   h->map_exists = true;                                         // the tree exists even if this batch was dropped entirely
@@ -699,12 +702,18 @@ int flimo_map_add_device(flimo_handle h, const void* d_xyz, size_t n, size_t str
   const float coarsest = (float)(std::sqrt(std::max(h->cfg.MAX_DIST_PLANE, 1e-6)) * 1.0001 + 1e-4);
   if (h->index_incremental && !first && map_index_can_update(h->map, old_n, lo, hi)) {
     // merge the accepted points into every level (the arrays end up identical to a rebuild)
-    CU(h, map_index_update(h->map, old_n, h->stream, &h->stats.kernel_launches));
+    bool full = false;
+    CU(h, map_index_update(h->map, old_n, h->stream, &h->stats.kernel_launches, &full));
     for (int a = 0; a < 3; ++a) {
       h->map.lo[a] = std::min(h->map.lo[a], lo[a]);
       h->map.hi[a] = std::max(h->map.hi[a], hi[a]);
     }
     h->stats_index_updates++;
+    if (full) {                                                  // no room left behind a level's segments: rebuild (compacts)
+      CU(h, map_index_build(h->map, h->cfg.knn_cell, h->cfg.knn_level_ratio, coarsest, max_cells, h->stream,
+                            &h->stats.kernel_launches));
+      h->stats_index_builds++;
+    }
   } else {
     CU(h, map_index_build(h->map, h->cfg.knn_cell, h->cfg.knn_level_ratio, coarsest, max_cells, h->stream,
                           &h->stats.kernel_launches));

@@ -30,9 +30,10 @@ struct GridDesc {
 constexpr int kMaxLevels = 12;
 
 struct LevelView {
-  const float4* pts;           // super-row storage (9x duplicated), sorted by (row, ix)
-  const uint32_t* cell_start;  // nx*ny*nz + 1 prefix offsets into pts
+  const float4* pts;           // super-row storage (9x duplicated): one gapped segment per row, sorted by ix inside it
+  const uint32_t* cell_start;  // [ny*nz rows][nx + 1]: slot ix = absolute start of cell ix of the row, slot nx = end of the row's entries
   GridDesc g;
+  int row_stride;              // nx + 1
 };
 
 // Constants of one measurement pass.  Built on the host from the double filter state exactly the
@@ -178,11 +179,12 @@ struct RegParams {
 
 // map_index.cu
 struct LevelIndex {
-  float4* pts = nullptr;        // duplicated, sorted by super-row cell key (kept in .w)
-  float4* pts_alt = nullptr;            // ping-pong partner of pts for the incremental merge
-  uint32_t* cell_start = nullptr;
+  float4* pts = nullptr;        // super-row entries (cell key kept in .w), one segment with head-room per row (map_index.cu)
+  uint32_t* cell_start = nullptr;   // (nx + 1) slots per row
+  uint32_t* row_base = nullptr;     // [n_rows + 1] segment start of every row
+  uint32_t* row_cap = nullptr;      // [n_rows + 1] segment capacity; row_cap[n_rows + 1] = the tail pointer (first free entry)
   size_t n_entries = 0, cap_entries = 0;
-  size_t n_cells = 0, cap_cells = 0;
+  size_t n_cells = 0, n_rows = 0, cap_slots = 0, cap_rows = 0;
   GridDesc g{};
 };
 
@@ -193,9 +195,13 @@ struct MapIndex {
   int n_levels = 0;
   float lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};   // bounding box of the map
   float glo[3] = {0, 0, 0}, ghi[3] = {0, 0, 0}; // box the grids were laid out for (bounding box + margin)
-  // incremental update scratch (new entries of one level)
-  float4* upd_pts = nullptr;
-  size_t upd_cap = 0;
+  // incremental update scratch (new entries of all levels): sorted 64-bit (level, cell) keys, point ids, entries, row jobs
+  void* upd_buf = nullptr;
+  size_t upd_bytes = 0;
+  uint32_t* upd_counters = nullptr;   // [0] jobs, [1] rows moved to the tail, [2] a level's array is full
+  uint32_t* row_first = nullptr;      // build scratch: first sorted entry of every row
+  size_t row_first_cap = 0;
+  uint64_t rows_moved = 0;            // statistics
   // scratch
   uint32_t *keys = nullptr, *keys_alt = nullptr, *vals = nullptr, *vals_alt = nullptr;
   size_t cap_scratch = 0;       // entries (9 per point)
@@ -210,11 +216,12 @@ struct MapIndex {
 cudaError_t map_index_build(MapIndex& idx, float cell0, float ratio, float coarsest_min, size_t max_cells,
                             cudaStream_t st, uint64_t* launches);
 cudaError_t map_index_reserve(MapIndex& idx, size_t n_pts);
-// Incremental form for Mapper::add: the points idx.pts[old_n..idx.n_pts) are merged into every level (sort of
-// the 9*m new entries + one merge pass + table shift) — the arrays end up identical to a full rebuild.
+// Incremental form for Mapper::add: the points idx.pts[old_n..idx.n_pts) are merged into the rows they touch, all levels
+// in one pass (sort of the 9*m*levels new entries, one CTA per touched row).  Answers are identical to a full rebuild's.
 // Precondition (map_index_can_update): same grids, capacity in place, batch inside the grid box.
+// *full = true: a level ran out of room behind its segments — the caller rebuilds (which compacts) before the next search.
 bool map_index_can_update(const MapIndex& idx, size_t old_n, const float batch_lo[3], const float batch_hi[3]);
-cudaError_t map_index_update(MapIndex& idx, size_t old_n, cudaStream_t st, uint64_t* launches);
+cudaError_t map_index_update(MapIndex& idx, size_t old_n, cudaStream_t st, uint64_t* launches, bool* full);
 void map_index_free(MapIndex& idx);
 
 // Packs strided xyz (device) into float4 with w = 0, dropping NaN points; writes the count.
@@ -264,7 +271,7 @@ struct CountTable {                    // open-addressing hash: cell key -> numb
 void lattice_init(OctreeLattice& L, const float lo[3], const float hi[3], float min_extent);
 void lattice_grow(OctreeLattice& L, const float boundary[3]);
 void table_free(CountTable& T);
-cudaError_t map_insert_batch(OctreeLattice& L, CountTable& T, const float4* d_batch, size_t n, int downsample, bool first_batch,
+cudaError_t map_insert_batch(OctreeLattice& L, CountTable& T, const float4* d_batch, size_t n, size_t map_points, int downsample, bool first_batch,
                              float4* d_dst, unsigned int* d_counter, unsigned long long* d_cell_keys, uint8_t* d_accept,
                              unsigned int* n_accepted, cudaStream_t st, uint64_t* launches);
 // bounding box (lo[3], hi[3]) of n float4 points on the device -> host (synchronises the stream)

@@ -19,7 +19,6 @@
 #include <cmath>
 #include <cstdio>
 
-#include <cub/device/device_merge.cuh>
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 #include <thrust/iterator/reverse_iterator.h>
@@ -158,53 +157,68 @@ __global__ void __launch_bounds__(256) boundaries_kernel(const uint32_t* __restr
 }
 
 // ---- gapped super-rows ---------------------------------------------------------------------------------------
-// Every super-row (iy, iz) of a level owns a segment [row_base[r], row_base[r + 1]) of the entry array with head-room
-// behind its entries, and nx + 1 slots of the prefix table (slot j = absolute start of cell j, slot nx = end of the row's
-// entries).  A query's run [cell_start[row + ix - 1], cell_start[row + ix + 2]) never leaves its row, so the gaps are
-// invisible to the search — and Mapper::add only has to rewrite the rows a batch touches instead of merging the whole level.
+// Every super-row (iy, iz) of a level owns a segment [row_base[r], row_base[r] + row_cap[r]) of the entry array with
+// head-room behind its entries, and nx + 1 slots of the prefix table (slot j = absolute start of cell j, slot nx = end of
+// the row's entries).  A query's run [slot[ix - 1], slot[ix + 2]) never leaves its row, so the gaps are invisible to the
+// search — and Mapper::add only rewrites the rows a batch touches instead of merging the whole level.
 
-// capacity of row r: its entries + 25 % + 8, even (the search reads 32-byte pairs)
-__global__ void __launch_bounds__(256) row_caps_kernel(const uint32_t* __restrict__ tmp_start, int nx, size_t n_rows, uint32_t* __restrict__ row_cap) {
-  const size_t r = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+// row_first[r] = first sorted position whose key is >= r * nx  (r == n_rows: first out-of-grid sentinel)
+__global__ void __launch_bounds__(256) row_first_kernel(const uint32_t* __restrict__ keys, uint32_t n, int nx, uint32_t n_rows,
+                                                        uint32_t* __restrict__ row_first) {
+  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r > n_rows) return;
+  const unsigned long long target = (unsigned long long)r * (unsigned long long)nx;
+  uint32_t lo = 0, hi = n;
+  while (lo < hi) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if ((unsigned long long)keys[mid] < target) lo = mid + 1; else hi = mid;
+  }
+  row_first[r] = lo;
+}
+
+// capacity of row r: its entries + 1/8 + 8, even (the search reads 32-byte pairs)
+__device__ __host__ __forceinline__ uint32_t row_capacity(uint32_t cnt) { return (cnt + (cnt >> 3) + 9u) & ~1u; }
+
+__global__ void __launch_bounds__(256) row_caps_kernel(const uint32_t* __restrict__ row_first, uint32_t n_rows, uint32_t* __restrict__ row_cap) {
+  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r > n_rows) return;
+  row_cap[r] = (r == n_rows) ? 0u : row_capacity(row_first[r + 1] - row_first[r]);
+}
+
+// slot nx of every row = end of its entries; the tail pointer = end of the last segment
+__global__ void __launch_bounds__(256) row_ends_kernel(const uint32_t* __restrict__ row_first, const uint32_t* __restrict__ row_base, int nx,
+                                                       uint32_t n_rows, uint32_t* __restrict__ cell_start, uint32_t* __restrict__ tail) {
+  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r > n_rows) return;
   if (r == n_rows) {
-    row_cap[r] = 0u;
+    *tail = row_base[n_rows];
     return;
   }
-  const uint32_t cnt = tmp_start[(r + 1) * (size_t)nx] - tmp_start[r * (size_t)nx];
-  row_cap[r] = (cnt + (cnt >> 2) + 9u) & ~1u;
+  cell_start[(size_t)r * (nx + 1) + nx] = row_base[r] + (row_first[r + 1] - row_first[r]);
 }
 
-// prefix table of the gapped layout from the dense one of the sorted array
-__global__ void __launch_bounds__(256) row_table_kernel(const uint32_t* __restrict__ tmp_start, const uint32_t* __restrict__ row_base, int nx,
-                                                        size_t n_rows, uint32_t* __restrict__ cell_start) {
-  const size_t id = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-  const size_t n_slots = n_rows * (size_t)(nx + 1);
-  if (id >= n_slots) return;
-  const size_t r = id / (size_t)(nx + 1);
-  const int j = (int)(id - r * (size_t)(nx + 1));
-  cell_start[id] = row_base[r] + (tmp_start[r * (size_t)nx + j] - tmp_start[r * (size_t)nx]);
-}
-
-// sorted (cell key, id) pairs -> entries at their place inside their row's segment
+// first entry of every occupied cell -> its slot; entries -> their place inside their row's segment
 __global__ void __launch_bounds__(256) row_scatter_kernel(const float4* __restrict__ src, const uint32_t* __restrict__ order,
-                                                          const uint32_t* __restrict__ sorted_keys, size_t n, const uint32_t* __restrict__ tmp_start,
-                                                          const uint32_t* __restrict__ row_base, int nx, uint32_t n_cells, float4* __restrict__ dst) {
+                                                          const uint32_t* __restrict__ sorted_keys, size_t n, const uint32_t* __restrict__ row_first,
+                                                          const uint32_t* __restrict__ row_base, int nx, uint32_t n_cells,
+                                                          uint32_t* __restrict__ cell_start, float4* __restrict__ dst) {
   const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (i >= n) return;
   const uint32_t k = sorted_keys[i];
   if (k >= n_cells) return;                               // rows outside the grid are not stored
   const uint32_t r = k / (uint32_t)nx;
+  const uint32_t at = row_base[r] + ((uint32_t)i - row_first[r]);
+  if (i == 0 || sorted_keys[i - 1] != k) cell_start[(size_t)r * (nx + 1) + (k - r * (uint32_t)nx)] = at;
   const float4 v = src[order[i]];
-  dst[row_base[r] + ((uint32_t)i - tmp_start[(size_t)r * nx])] = make_float4(v.x, v.y, v.z, __uint_as_float(k));
+  dst[at] = make_float4(v.x, v.y, v.z, __uint_as_float(k));
 }
 
-// ---- incremental update: all levels in one pass over 54 entries per new point -------------------------------------
+// ---- incremental update: all levels in one pass over 9 entries per new point and level -------------------------
 struct LevelDev {
   float4* pts;
   uint32_t* cell_start;
   uint32_t* row_base;      // segment of every row ...
-  uint32_t* row_cap;       // ... and its capacity (rows that outgrow it move to the free tail of the array)
+  uint32_t* row_cap;       // ... and its capacity (a row that outgrows it moves to the free tail of the array)
   uint32_t* tail;          // first free entry behind all segments
   uint32_t cap_entries;
   GridDesc g;
@@ -216,8 +230,9 @@ struct UpdLevels {
 };
 struct RowJob {          // one touched row of one level
   uint32_t level, row, begin, end;   // [begin, end) = its new entries in the sorted update arrays
-  uint32_t cnt, off;                 // entries the row holds now, their offset in the scratch copy (rows merged in place)
+  uint32_t cnt;                      // entries the row holds now
   uint32_t new_base, new_cap;        // new_cap != 0: the row moves to [new_base, new_base + new_cap)
+  uint32_t skip;                     // the array is full: the host rebuilds the index
 };
 
 __global__ void __launch_bounds__(256) upd_keys_kernel(const float4* __restrict__ p, size_t m, UpdLevels U, uint32_t id_base,
@@ -250,7 +265,7 @@ __global__ void __launch_bounds__(256) upd_gather_kernel(const float4* __restric
 
 // first new entry of every (level, row) group -> a job; checks the row's head-room
 __global__ void __launch_bounds__(256) upd_jobs_kernel(const unsigned long long* __restrict__ keys, uint32_t n, UpdLevels U, RowJob* __restrict__ jobs,
-                                                       uint32_t* __restrict__ counters /* [0] jobs, [1] scratch entries, [2] overflow */) {
+                                                       uint32_t* __restrict__ counters /* [0] jobs, [1] rows moved, [2] overflow */) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const unsigned long long k = keys[i];
@@ -261,79 +276,102 @@ __global__ void __launch_bounds__(256) upd_jobs_kernel(const unsigned long long*
     const unsigned long long kp = keys[i - 1];
     if ((uint32_t)(kp >> 32) == l && (uint32_t)kp != 0xFFFFFFFFu && (uint32_t)kp / nx == r) return;   // not the head of its group
   }
-  const unsigned long long limit = ((unsigned long long)l << 32) | (unsigned long long)(r + 1u) * nx;   // first key of the next row
+  const unsigned long long limit = ((unsigned long long)l << 32) | ((unsigned long long)(r + 1u) * nx);   // first key of the next row (<= 2^32 - 1 for the last one)
   uint32_t lo = i + 1, hi = n;
   while (lo < hi) {
     const uint32_t mid = (lo + hi) >> 1;
-    if (keys[mid] < limit) lo = mid + 1; else hi = mid;
+    const unsigned long long km = keys[mid];
+    if (km < limit && (uint32_t)km != 0xFFFFFFFFu) lo = mid + 1; else hi = mid;
   }
   const uint32_t base = U.lv[l].row_base[r], cap = U.lv[l].row_cap[r];
   const uint32_t cnt = U.lv[l].cell_start[(size_t)r * (nx + 1) + nx] - base;
   const uint32_t need = cnt + (lo - i);
   RowJob j;
   j.level = l; j.row = r; j.begin = i; j.end = lo; j.cnt = cnt;
-  j.off = 0u; j.new_base = 0u; j.new_cap = 0u;
+  j.new_base = 0u; j.new_cap = 0u; j.skip = 0u;
   if (need > cap) {                                        // the row outgrows its segment: it moves to the tail with room to double
     j.new_cap = (2u * need + 33u) & ~1u;
     j.new_base = atomicAdd(U.lv[l].tail, j.new_cap);
-    if ((unsigned long long)j.new_base + j.new_cap + 8ull > (unsigned long long)U.lv[l].cap_entries) counters[2] = 1u;   // array full: rebuild (compacts)
-  } else {
-    j.off = atomicAdd(&counters[1], cnt);
+    atomicAdd(&counters[1], 1u);
+    if ((unsigned long long)j.new_base + j.new_cap > (unsigned long long)U.lv[l].cap_entries) {   // array full: rebuild (compacts)
+      counters[2] = 1u;
+      j.skip = 1u;
+    }
   }
   jobs[atomicAdd(&counters[0], 1u)] = j;
 }
 
-// One CTA per touched row: copy the row aside, merge it with its new entries by cell key (old entries first among
-// equal keys) back into the row's segment, move the row's table slots up by the new entries in front of them.
-__global__ void __launch_bounds__(128) upd_merge_kernel(const RowJob* __restrict__ jobs, UpdLevels U, const float4* __restrict__ new_pts,
-                                                        float4* __restrict__ scratch) {
-  const RowJob j = jobs[blockIdx.x];
-  const LevelDev& L = U.lv[j.level];
-  const uint32_t nx = (uint32_t)L.g.nx, base = L.row_base[j.row];
-  const bool moves = j.new_cap != 0u;
-  float4* row = L.pts + (moves ? j.new_base : base);
-  const float4* old = moves ? L.pts + base : scratch + j.off;           // a moving row is read where it lies
-  const float4* nw = new_pts + j.begin;
-  const uint32_t n_new = j.end - j.begin;
-  if (!moves) {
-    float4* keep = scratch + j.off;
-    for (uint32_t i = threadIdx.x; i < j.cnt; i += blockDim.x) keep[i] = row[i];
+__device__ __forceinline__ uint32_t lower_bound_w(const float4* __restrict__ a, uint32_t n, uint32_t key) {   // #entries with cell key < key
+  uint32_t lo = 0, hi = n;
+  while (lo < hi) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (__float_as_uint(a[mid].w) < key) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+// One CTA per touched row (grid-stride over the job list): the row's entries move up by the number of new entries with a
+// smaller cell key — in place, back to front in CTA-wide chunks (a chunk's destinations lie at or behind its own sources,
+// never in front of a chunk that has not been read yet) — the new entries drop into the holes (old entries stay in front
+// among equal keys), and the row's table slots move up by the new entries in front of them.
+__global__ void __launch_bounds__(256) upd_merge_kernel(const RowJob* __restrict__ jobs, const uint32_t* __restrict__ counters, UpdLevels U,
+                                                        const float4* __restrict__ new_pts) {
+  const uint32_t n_jobs = counters[0];
+  const uint32_t B = blockDim.x, tid = threadIdx.x;
+  for (uint32_t job = blockIdx.x; job < n_jobs; job += gridDim.x) {
+    const RowJob j = jobs[job];
+    if (j.skip) continue;
+    const LevelDev& L = U.lv[j.level];
+    const uint32_t nx = (uint32_t)L.g.nx, base = L.row_base[j.row];
+    const bool moves = j.new_cap != 0u;
+    const float4* __restrict__ nw = new_pts + j.begin;
+    const uint32_t n_new = j.end - j.begin, cnt = j.cnt;
+    uint32_t* slots = L.cell_start + (size_t)j.row * (nx + 1);
+    const uint32_t first_key = j.row * nx;
+    if (moves) {
+      const float4* src = L.pts + base;
+      float4* dst = L.pts + j.new_base;
+      for (uint32_t i = tid; i < cnt; i += B) {
+        const float4 v = src[i];
+        dst[i + lower_bound_w(nw, n_new, __float_as_uint(v.w))] = v;
+      }
+    } else {
+      float4* row = L.pts + base;
+      // entries in front of the first new entry's cell stay where they are
+      const uint32_t keep = slots[__float_as_uint(nw[0].w) - first_key] - base;
+      const uint32_t span = cnt - keep;
+      for (uint32_t c = (span + B - 1) / B; c-- > 0;) {
+        const uint32_t i = keep + c * B + tid;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        uint32_t lo = 0;
+        if (i < cnt) {
+          v = row[i];
+          lo = lower_bound_w(nw, n_new, __float_as_uint(v.w));
+        }
+        __syncthreads();
+        if (i < cnt && lo) row[i + lo] = v;
+        __syncthreads();
+      }
+    }
     __syncthreads();
-  }
-  for (uint32_t i = threadIdx.x; i < j.cnt; i += blockDim.x) {          // old entry i: behind the new entries with a SMALLER key
-    const float4 v = old[i];
-    const uint32_t key = __float_as_uint(v.w);
-    uint32_t lo = 0, hi = n_new;
-    while (lo < hi) {
-      const uint32_t mid = (lo + hi) >> 1;
-      if (__float_as_uint(nw[mid].w) < key) lo = mid + 1; else hi = mid;
+    {
+      float4* dst = L.pts + (moves ? j.new_base : base);
+      for (uint32_t i = tid; i < n_new; i += B) {              // new entry i: behind the old entries of its own and all earlier cells
+        const float4 v = nw[i];
+        dst[i + (slots[__float_as_uint(v.w) - first_key + 1u] - base)] = v;
+      }
     }
-    row[i + lo] = v;
-  }
-  for (uint32_t i = threadIdx.x; i < n_new; i += blockDim.x) {          // new entry i: behind the old entries with a key <= its own
-    const float4 v = nw[i];
-    const uint32_t key = __float_as_uint(v.w);
-    uint32_t lo = 0, hi = j.cnt;
-    while (lo < hi) {
-      const uint32_t mid = (lo + hi) >> 1;
-      if (__float_as_uint(old[mid].w) <= key) lo = mid + 1; else hi = mid;
+    __syncthreads();
+    const uint32_t shift = moves ? j.new_base - base : 0u;   // (modular arithmetic: new_base may lie below base)
+    for (uint32_t c = tid; c <= nx; c += B) {                  // slot c moves up by the new entries of cells < c
+      const uint32_t lo = lower_bound_w(nw, n_new, first_key + c);
+      if (lo | shift) slots[c] += lo + shift;
     }
-    row[i + lo] = v;
-  }
-  uint32_t* slots = L.cell_start + (size_t)j.row * (nx + 1);
-  const uint32_t first_key = j.row * nx;
-  const uint32_t shift = moves ? j.new_base - base : 0u;               // (modular arithmetic: new_base may lie below base)
-  for (uint32_t c = threadIdx.x; c <= nx; c += blockDim.x) {            // slot c moves up by the new entries of cells < c
-    uint32_t lo = 0, hi = n_new;
-    while (lo < hi) {
-      const uint32_t mid = (lo + hi) >> 1;
-      if (__float_as_uint(nw[mid].w) < first_key + c) lo = mid + 1; else hi = mid;
+    if (moves && tid == 0) {
+      L.row_base[j.row] = j.new_base;
+      L.row_cap[j.row] = j.new_cap;
     }
-    slots[c] += lo + shift;
-  }
-  if (moves && threadIdx.x == 0) {
-    L.row_base[j.row] = j.new_base;
-    L.row_cap[j.row] = j.new_cap;
+    __syncthreads();
   }
 }
 
@@ -537,10 +575,13 @@ void map_index_free(MapIndex& idx) {
   cudaFree(idx.pts);
   for (auto& l : idx.lv) {
     cudaFree(l.pts);
-    cudaFree(l.pts_alt);
     cudaFree(l.cell_start);
+    cudaFree(l.row_base);
+    cudaFree(l.row_cap);
   }
-  cudaFree(idx.upd_pts);
+  cudaFree(idx.upd_buf);
+  cudaFree(idx.upd_counters);
+  cudaFree(idx.row_first);
   cudaFree(idx.keys);
   cudaFree(idx.cub_tmp);
   cudaFree(idx.bbox);
@@ -574,46 +615,86 @@ static GridDesc make_grid(const float lo[3], const float hi[3], float cell) {
   return g;
 }
 
-static cudaError_t build_level(MapIndex& idx, LevelIndex& L, const GridDesc& g, cudaStream_t st, uint64_t* launches) {
+static cudaError_t build_level(MapIndex& idx, LevelIndex& L, const GridDesc& g, cudaStream_t st, uint64_t* launches, double* alloc_us = nullptr) {
+  const auto t_alloc0 = std::chrono::steady_clock::now();
   const size_t n = idx.n_pts, n9 = 9 * n;
   const size_t n_cells = (size_t)g.nx * g.ny * g.nz;
-  if (n_cells + 2 > L.cap_cells) {
+  const size_t n_rows = (size_t)g.ny * g.nz, n_slots = n_rows * (size_t)(g.nx + 1);
+  if (n_slots + 2 > L.cap_slots) {
+    const bool had = L.cell_start != nullptr;
     if (L.cell_start) cudaFree(L.cell_start);
     L.cell_start = nullptr;
-    L.cap_cells = 0;
-    const size_t cap = std::max(n_cells + n_cells / 2 + 1024, (size_t)1 << 22);   // the grid grows with the map's bounding box
+    L.cap_slots = 0;
+    // the grid grows with the map's bounding box: exact the first time (floor 16 M slots), doubled when it has to grow
+    const size_t cap = std::max((had ? 2 * n_slots : n_slots) + 1024, (size_t)1 << 24);
     FL_TRY(cudaMalloc(&L.cell_start, cap * sizeof(uint32_t)));
-    L.cap_cells = cap;
+    L.cap_slots = cap;
   }
-  if (n9 > L.cap_entries) {
+  if (n_rows + 2 > L.cap_rows) {
+    cudaFree(L.row_base);
+    cudaFree(L.row_cap);
+    L.row_base = L.row_cap = nullptr;
+    L.cap_rows = 0;
+    const size_t cap = n_rows + n_rows / 2 + 1024;
+    FL_TRY(cudaMalloc(&L.row_base, cap * sizeof(uint32_t)));
+    FL_TRY(cudaMalloc(&L.row_cap, cap * sizeof(uint32_t)));
+    L.cap_rows = cap;
+  }
+  if (n_rows + 2 > idx.row_first_cap) {
+    cudaFree(idx.row_first);
+    idx.row_first = nullptr;
+    idx.row_first_cap = 0;
+    const size_t cap = n_rows + n_rows / 2 + 1024;
+    FL_TRY(cudaMalloc(&idx.row_first, cap * sizeof(uint32_t)));
+    idx.row_first_cap = cap;
+  }
+  // Room for the entries with every row's head-room (entries + 1/8 + 10 per row), plus a free tail of 1/8 for rows that
+  // outgrow their segment — all of it below 2^32 entries.  The first allocation is exact (a static map wastes nothing); a
+  // map that has outgrown its arrays once will grow again, so a re-allocation takes 2.5 x: the free tail then absorbs ~40 % of
+  // growth (moved rows leave holes behind) before the next rebuild compacts the level.
+  // (Maps below a million points are given the room of a million: allocation is the expensive part of a rebuild.)
+  const size_t segs = n9 + n9 / 8 + 10 * n_rows;
+  const size_t need = segs + std::max(segs / 8, (size_t)1 << 16);
+  const size_t floor_entries = 9 * std::min(idx.cap_pts, (size_t)1 << 20) * 5 / 4 + 10 * n_rows;
+  if (need >= 0xFFFFFFF0ull / 3) return cudaErrorInvalidValue;
+  if (need > L.cap_entries) {
+    const size_t want = std::max(L.pts ? 2 * need + need / 2 : need, floor_entries);
     if (L.pts) cudaFree(L.pts);
     L.pts = nullptr;
     L.cap_entries = 0;
-    if (L.pts_alt) cudaFree(L.pts_alt);
-    L.pts_alt = nullptr;
-    const size_t cap = 9 * idx.cap_pts;
-    FL_TRY(cudaMalloc(&L.pts, (cap + 8) * sizeof(float4)));     // + slack: the search reads whole 32-byte pairs
-    L.cap_entries = cap;                                        // the ping-pong partner is allocated by the first incremental update
+    FL_TRY(cudaMalloc(&L.pts, (want + 8) * sizeof(float4)));     // + slack: the search reads whole 32-byte pairs
+    L.cap_entries = want;
   }
   L.g = g;
   L.n_cells = n_cells;
+  L.n_rows = n_rows;
+  if (alloc_us) *alloc_us = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_alloc0).count();
   keys9_kernel<<<nblk(n9), 256, 0, st>>>(idx.pts, n, g, (uint32_t)n_cells, idx.keys, idx.vals);
   int bits = 1;
   while (bits < 32 && ((size_t)1 << bits) <= n_cells) ++bits;      // keys go up to n_cells inclusive
   cub::DoubleBuffer<uint32_t> dk(idx.keys, idx.keys_alt), dv(idx.vals, idx.vals_alt);
-  size_t bytes = 0, bytes2 = 0;
+  size_t bytes = 0, bytes2 = 0, bytes3 = 0;
   FL_TRY(cub::DeviceRadixSort::SortPairs(nullptr, bytes, dk, dv, (int)n9, 0, bits, st));
-  auto rb = thrust::make_reverse_iterator(L.cell_start + n_cells + 2);
-  FL_TRY(cub::DeviceScan::InclusiveScan(nullptr, bytes2, rb, rb, cub::Min(), (int)(n_cells + 2), st));
-  if (bytes2 > bytes) bytes = bytes2;
+  auto rb = thrust::make_reverse_iterator(L.cell_start + n_slots);
+  FL_TRY(cub::DeviceScan::InclusiveScan(nullptr, bytes2, rb, rb, cub::Min(), (long long)n_slots, st));
+  FL_TRY(cub::DeviceScan::ExclusiveSum(nullptr, bytes3, L.row_cap, L.row_base, (int)(n_rows + 1), st));
+  bytes = std::max(bytes, std::max(bytes2, bytes3));
   FL_TRY(ensure(&idx.cub_tmp, &idx.cub_tmp_bytes, bytes));
   FL_TRY(cub::DeviceRadixSort::SortPairs(idx.cub_tmp, bytes, dk, dv, (int)n9, 0, bits, st));
-  gather_tag_kernel<<<nblk(n9), 256, 0, st>>>(idx.pts, dv.Current(), dk.Current(), n9, L.pts);
-  FL_TRY(cudaMemsetAsync(L.cell_start, 0xFF, (n_cells + 2) * sizeof(uint32_t), st));
-  boundaries_kernel<<<nblk(n9), 256, 0, st>>>(dk.Current(), n9, n_cells, L.cell_start);
-  FL_TRY(cub::DeviceScan::InclusiveScan(idx.cub_tmp, bytes, rb, rb, cub::Min(), (int)(n_cells + 2), st));
+  // rows: first sorted entry, capacity, segment start (exclusive sum of the capacities)
+  const unsigned int rblk = nblk(n_rows + 1);
+  row_first_kernel<<<rblk, 256, 0, st>>>(dk.Current(), (uint32_t)n9, g.nx, (uint32_t)n_rows, idx.row_first);
+  row_caps_kernel<<<rblk, 256, 0, st>>>(idx.row_first, (uint32_t)n_rows, L.row_cap);
+  FL_TRY(cub::DeviceScan::ExclusiveSum(idx.cub_tmp, bytes, L.row_cap, L.row_base, (int)(n_rows + 1), st));
+  // table: occupied cells and row ends are written, empty cells take the next start (suffix minimum: the segments of a
+  // fresh build lie in row order)
+  FL_TRY(cudaMemsetAsync(L.cell_start, 0xFF, n_slots * sizeof(uint32_t), st));
+  row_ends_kernel<<<rblk, 256, 0, st>>>(idx.row_first, L.row_base, g.nx, (uint32_t)n_rows, L.cell_start, L.row_cap + n_rows + 1);
+  row_scatter_kernel<<<nblk(n9), 256, 0, st>>>(idx.pts, dv.Current(), dk.Current(), n9, idx.row_first, L.row_base, g.nx, (uint32_t)n_cells,
+                                                L.cell_start, L.pts);
+  FL_TRY(cub::DeviceScan::InclusiveScan(idx.cub_tmp, bytes, rb, rb, cub::Min(), (long long)n_slots, st));
   L.n_entries = n9;
-  if (launches) *launches += 10;
+  if (launches) *launches += 12;
   return cudaGetLastError();
 }
 
@@ -654,13 +735,15 @@ cudaError_t map_index_build(MapIndex& idx, float cell0, float ratio, float coars
   for (;;) {
     if (nl == kMaxLevels - 1 && cell < coarsest_min) cell = coarsest_min;   // force termination
     const auto t0 = std::chrono::steady_clock::now();
-    FL_TRY(build_level(idx, idx.lv[nl], make_grid(idx.glo, idx.ghi, cell), st, launches));
+    double alloc_us = 0.0;
+    FL_TRY(build_level(idx, idx.lv[nl], make_grid(idx.glo, idx.ghi, cell), st, launches, &alloc_us));
     if (prof) {
       const auto t1 = std::chrono::steady_clock::now();
       cudaStreamSynchronize(st);
       const auto t2 = std::chrono::steady_clock::now();
-      std::fprintf(stderr, "[index] level %d cell %.3f n %zu cells %zu: host %.0f us, +sync %.0f us\n", nl, cell, n, idx.lv[nl].n_cells,
-                   std::chrono::duration<double, std::micro>(t1 - t0).count(), std::chrono::duration<double, std::micro>(t2 - t1).count());
+      std::fprintf(stderr, "[index] level %d cell %.3f n %zu cells %zu entries cap %zu: host %.0f us (allocation %.0f us), +sync %.0f us\n", nl, cell, n,
+                   idx.lv[nl].n_cells, idx.lv[nl].cap_entries, std::chrono::duration<double, std::micro>(t1 - t0).count(), alloc_us,
+                   std::chrono::duration<double, std::micro>(t2 - t1).count());
     }
     ++nl;
     if (cell >= coarsest_min || nl == kMaxLevels) break;
@@ -676,56 +759,64 @@ bool map_index_can_update(const MapIndex& idx, size_t old_n, const float batch_l
   const size_t m = idx.n_pts - old_n;
   if (4 * m > old_n) return false;                                  // a large batch: the full rebuild is as cheap
   if (idx.n_pts > idx.cap_pts) return false;
+  if (9 * m * (size_t)idx.n_levels >= 0x7FFFFFF0ull) return false;
   for (int a = 0; a < 3; ++a)
     if (!(batch_lo[a] >= idx.glo[a] && batch_hi[a] <= idx.ghi[a])) return false;   // also rejects NaN boxes
   for (int l = 0; l < idx.n_levels; ++l) {
     const LevelIndex& L = idx.lv[l];
-    if (!L.pts || 9 * idx.n_pts > L.cap_entries || L.n_entries != 9 * old_n) return false;
+    if (!L.pts || !L.row_base || L.n_entries != 9 * old_n) return false;
   }
   return true;
 }
 
-struct LessCell {   // super-row entries are ordered by their cell key (.w); entries of one cell are equivalent
-  __device__ bool operator()(const float4& a, const float4& b) const { return __float_as_uint(a.w) < __float_as_uint(b.w); }
-};
-
-cudaError_t map_index_update(MapIndex& idx, size_t old_n, cudaStream_t st, uint64_t* launches) {
-  const size_t n = idx.n_pts, m = n - old_n, m9 = 9 * m, n9_old = 9 * old_n;
-  if (m9 > idx.upd_cap) {
-    cudaFree(idx.upd_pts);
-    idx.upd_pts = nullptr;
-    idx.upd_cap = 0;
-    const size_t cap = m9 + m9 / 2 + 4096;
-    FL_TRY(cudaMalloc(&idx.upd_pts, cap * sizeof(float4)));
-    idx.upd_cap = cap;
-  }
+cudaError_t map_index_update(MapIndex& idx, size_t old_n, cudaStream_t st, uint64_t* launches, bool* full) {
+  const size_t n = idx.n_pts, m = n - old_n, E = 9 * m * (size_t)idx.n_levels;
+  *full = false;
+  // scratch: keys (2 x u64), ids (2 x u32), entries (float4), jobs
+  const size_t off_keys = 0, off_vals = off_keys + 2 * E * sizeof(unsigned long long), off_pts = (off_vals + 2 * E * sizeof(uint32_t) + 15) & ~(size_t)15,
+               off_jobs = off_pts + E * sizeof(float4), total = off_jobs + E * sizeof(RowJob);
+  FL_TRY(ensure(&idx.upd_buf, &idx.upd_bytes, total));
+  if (!idx.upd_counters) FL_TRY(cudaMalloc(&idx.upd_counters, 4 * sizeof(uint32_t)));
+  unsigned char* buf = static_cast<unsigned char*>(idx.upd_buf);
+  unsigned long long* k0 = reinterpret_cast<unsigned long long*>(buf + off_keys);
+  uint32_t* v0 = reinterpret_cast<uint32_t*>(buf + off_vals);
+  float4* upd_pts = reinterpret_cast<float4*>(buf + off_pts);
+  RowJob* jobs = reinterpret_cast<RowJob*>(buf + off_jobs);
+  UpdLevels U{};
+  U.n_levels = idx.n_levels;
   for (int l = 0; l < idx.n_levels; ++l) {
     LevelIndex& L = idx.lv[l];
-    const GridDesc& g = L.g;
-    if (!L.pts_alt) FL_TRY(cudaMalloc(&L.pts_alt, (L.cap_entries + 8) * sizeof(float4)));
-    // 1. the nine (super-row key, id) pairs of every new point, sorted (stable radix sort => (key, id) order)
-    keys9_kernel<<<nblk(m9), 256, 0, st>>>(idx.pts + old_n, m, g, (uint32_t)L.n_cells, idx.keys, idx.vals, (uint32_t)old_n);
-    int bits = 1;
-    while (bits < 32 && ((size_t)1 << bits) <= L.n_cells) ++bits;
-    cub::DoubleBuffer<uint32_t> dk(idx.keys, idx.keys_alt), dv(idx.vals, idx.vals_alt);
-    size_t bytes = 0, bytes2 = 0;
-    FL_TRY(cub::DeviceRadixSort::SortPairs(nullptr, bytes, dk, dv, (int)m9, 0, bits, st));
-    FL_TRY((cub::DeviceMerge::MergeKeys(nullptr, bytes2, L.pts, (int)n9_old, idx.upd_pts, (int)m9, L.pts_alt, LessCell{}, st)));
-    if (bytes2 > bytes) bytes = bytes2;
-    FL_TRY(ensure(&idx.cub_tmp, &idx.cub_tmp_bytes, bytes));
-    FL_TRY(cub::DeviceRadixSort::SortPairs(idx.cub_tmp, bytes, dk, dv, (int)m9, 0, bits, st));
-    gather_tag_kernel<<<nblk(m9), 256, 0, st>>>(idx.pts, dv.Current(), dk.Current(), m9, idx.upd_pts);
-    // 2. one merge pass by cell key.  Entries of the same cell are equivalent for the merge (it is not stable), so their
-    //    order inside a cell may differ from a full rebuild's; the search is exact for any order inside a run (ties in
-    //    distance, which only duplicate points produce, are broken by position either way).
-    FL_TRY((cub::DeviceMerge::MergeKeys(idx.cub_tmp, bytes, L.pts, (int)n9_old, idx.upd_pts, (int)m9, L.pts_alt, LessCell{}, st)));
-    std::swap(L.pts, L.pts_alt);
-    // 3. prefix table: every start moves up by the number of new entries in front of it
-    const size_t n_slots = L.n_cells + 2;
-    table_shift_kernel<<<(unsigned int)((n_slots + 1023) / 1024), 256, 0, st>>>(L.cell_start, n_slots, dk.Current(), (uint32_t)m9);
-    L.n_entries = n9_old + m9;
-    if (launches) *launches += 8;
+    U.lv[l].pts = L.pts;
+    U.lv[l].cell_start = L.cell_start;
+    U.lv[l].row_base = L.row_base;
+    U.lv[l].row_cap = L.row_cap;
+    U.lv[l].tail = L.row_cap + L.n_rows + 1;
+    U.lv[l].cap_entries = (uint32_t)L.cap_entries;
+    U.lv[l].g = L.g;
+    U.lv[l].n_cells = (uint32_t)L.n_cells;
   }
+  FL_TRY(cudaMemsetAsync(idx.upd_counters, 0, 4 * sizeof(uint32_t), st));
+  // 1. the nine (level, super-row cell) keys of every new point on every level, sorted (stable: (key, id) order)
+  upd_keys_kernel<<<nblk(E), 256, 0, st>>>(idx.pts + old_n, m, U, (uint32_t)old_n, k0, v0);
+  int lbits = 1;
+  while ((1 << lbits) < idx.n_levels) ++lbits;
+  cub::DoubleBuffer<unsigned long long> dk(k0, k0 + E);
+  cub::DoubleBuffer<uint32_t> dv(v0, v0 + E);
+  size_t bytes = 0;
+  FL_TRY(cub::DeviceRadixSort::SortPairs(nullptr, bytes, dk, dv, (int)E, 0, 32 + lbits, st));
+  FL_TRY(ensure(&idx.cub_tmp, &idx.cub_tmp_bytes, bytes));
+  FL_TRY(cub::DeviceRadixSort::SortPairs(idx.cub_tmp, bytes, dk, dv, (int)E, 0, 32 + lbits, st));
+  upd_gather_kernel<<<nblk(E), 256, 0, st>>>(idx.pts, dv.Current(), dk.Current(), E, upd_pts);
+  // 2. one job per touched row, 3. one CTA per job
+  upd_jobs_kernel<<<nblk(E), 256, 0, st>>>(dk.Current(), (uint32_t)E, U, jobs, idx.upd_counters);
+  upd_merge_kernel<<<148 * 8, 256, 0, st>>>(jobs, idx.upd_counters, U, upd_pts);
+  uint32_t hc[4] = {0, 0, 0, 0};
+  FL_TRY(cudaMemcpyAsync(hc, idx.upd_counters, sizeof(hc), cudaMemcpyDeviceToHost, st));
+  FL_TRY(cudaStreamSynchronize(st));
+  for (int l = 0; l < idx.n_levels; ++l) idx.lv[l].n_entries = 9 * n;
+  idx.rows_moved += hc[1];
+  *full = hc[2] != 0u;
+  if (launches) *launches += 9;
   return cudaGetLastError();
 }
 

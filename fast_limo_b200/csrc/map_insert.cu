@@ -243,8 +243,8 @@ static void lattice_desc(const OctreeLattice& L, LatticeDesc& d) {
 
 static cudaError_t table_reserve(CountTable& T, size_t need_entries, cudaStream_t st) {
   size_t want = T.cap ? T.cap : (1u << 22);      // start large: growing means a rehash and two large (de)allocations
-  while (want < 2 * need_entries) want <<= 1;
-  if (want == T.cap) return cudaSuccess;
+  if (want >= 2 * need_entries) return cudaSuccess;   // load <= 1/2: keep the table
+  while (want < 4 * need_entries) want <<= 1;          // grow to load <= 1/4, so that the next growth is a doubling of the map away
   unsigned long long* nk = nullptr;
   uint32_t* nv = nullptr;
   FL_TRY(cudaMalloc(&nk, want * sizeof(unsigned long long)));
@@ -272,12 +272,13 @@ void table_free(CountTable& T) {
 // Applies the insert rule to `n` packed batch points (float4, NaN already removed) and appends the
 // accepted ones to dst[0..); *n_accepted receives their number.  Every call adds at most 2n table
 // entries, so the table is grown up front.
-cudaError_t map_insert_batch(OctreeLattice& L, CountTable& T, const float4* d_batch, size_t n, int downsample, bool first_batch,
+cudaError_t map_insert_batch(OctreeLattice& L, CountTable& T, const float4* d_batch, size_t n, size_t map_points, int downsample, bool first_batch,
                              float4* d_dst, unsigned int* d_counter, unsigned long long* d_cell_keys, uint8_t* d_accept,
                              unsigned int* n_accepted, cudaStream_t st, uint64_t* launches) {
   *n_accepted = 0;
   if (n == 0) return cudaSuccess;
-  T.used_bound += 2 * n;
+  // occupied slots <= distinct min-level cells + distinct parents <= 2 x map points (only accepted points add entries)
+  T.used_bound = 2 * (map_points + n);
   FL_TRY(table_reserve(T, T.used_bound, st));
   LatticeDesc d;
   lattice_desc(L, d);

@@ -192,7 +192,6 @@ __device__ __forceinline__ bool finish_private(const float (&k)[6], const float4
   cmpswap64(ek[0], ek[3]); cmpswap64(ek[2], ek[5]);
   cmpswap64(ek[0], ek[1]); cmpswap64(ek[2], ek[3]); cmpswap64(ek[4], ek[5]);
   cmpswap64(ek[1], ek[2]); cmpswap64(ek[3], ek[4]);
-#pragma unroll
   t.sl = 0u;
 #pragma unroll
   for (int j = 0; j < 5; ++j) {
@@ -337,7 +336,7 @@ __device__ __forceinline__ void block_scan_team(const LevelView& L, int T, int t
   if (valid) {
     const int hx = cell_coord(qx, G.ox, G.inv_cell, G.nx), hy = cell_coord(qy, G.oy, G.inv_cell, G.ny),
               hz = cell_coord(qz, G.oz, G.inv_cell, G.nz);
-    const int row = (hz * G.ny + hy) * G.nx;
+    const size_t row = (size_t)(hz * G.ny + hy) * (size_t)L.row_stride;
     s = __ldg(&L.cell_start[row + max(hx - 1, 0)]);
     e = __ldg(&L.cell_start[row + min(hx + 1, G.nx - 1) + 1]);
   }
@@ -421,7 +420,7 @@ __device__ __forceinline__ void probe_level(const LevelView& L, float qx, float 
   p.hx = cell_coord(qx, G.ox, G.inv_cell, G.nx);
   p.hy = cell_coord(qy, G.oy, G.inv_cell, G.ny);
   p.hz = cell_coord(qz, G.oz, G.inv_cell, G.nz);
-  const int row = (p.hz * G.ny + p.hy) * G.nx;
+  const size_t row = (size_t)(p.hz * G.ny + p.hy) * (size_t)L.row_stride;
   p.s = __ldg(&L.cell_start[row + max(p.hx - 1, 0)]);
   p.e = __ldg(&L.cell_start[row + min(p.hx + 1, G.nx - 1) + 1]);
 }

@@ -297,9 +297,11 @@ typedef struct {
   float knn_cell;               /* finest grid cell in use */
   int32_t grid_nx, grid_ny, grid_nz;
   int32_t n_levels;
-  uint64_t table_bytes, map_bytes;   /* device memory of the prefix tables / of the point + key arrays (all levels, incl. ping-pong copies) */
+  uint64_t table_bytes, map_bytes;   /* device memory of the prefix tables / of the canonical points + super-row entries (all levels, incl. head-room) */
   double persist_ms_total;      /* in-kernel device time (%globaltimer) of the passes run by the persistent kernel */
   uint64_t persist_passes;      /* number of such passes */
+  uint64_t index_builds, index_updates;   /* Mapper::add calls that rebuilt the search index / merged the batch into the touched rows */
+  uint64_t index_rows_moved;    /* rows that outgrew their segment during those merges and moved to the free tail */
 } flimo_stats;
 int flimo_get_stats(flimo_handle h, flimo_stats* out);
 void* flimo_stream(flimo_handle h);   /* the handle's cudaStream_t */

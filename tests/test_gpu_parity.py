@@ -427,6 +427,45 @@ def test_incremental_index_equals_rebuild(oracle, flimo_lib):
     check_per_point(m_inc.match_debug(case.init), ref)
 
 
+def test_incremental_index_growth_stress(oracle, flimo_lib):
+    """A map that grows by a factor of 20 in small batches wandering through the grid box: rows outgrow their segments and
+    move to the free tail, the tail runs out (rebuild) — after every few batches the answers must equal those of an index
+    rebuilt from scratch at every add, and at the end the oracle's."""
+    case = synth.make_case("c1")
+    order = np.argsort(case.map_pts[:, 0] + 0.3 * case.map_pts[:, 1], kind="stable")       # sweep through the world
+    pts = case.map_pts[order]
+    corners = np.float32([[-45, -45, -3], [45, 45, 28]])                                    # fixes the grid box up front
+    base = np.concatenate([corners, pts[::20]])                                            # a thin sample everywhere
+    rest = np.delete(pts, np.arange(0, len(pts), 20), axis=0)
+    os.environ["FLIMO_INDEX_INCREMENTAL"] = "0"
+    try:
+        m_full = mapper(octree_downsampling=False)
+    finally:
+        del os.environ["FLIMO_INDEX_INCREMENTAL"]
+    m_inc = mapper(octree_downsampling=False)
+    om = oracle.OracleMap(downsample=False)
+    for m in (m_full, m_inc):
+        m.add(base, 0.0)
+        m.set_scan(case.scan)
+    om.add(base)
+    n_b = 48
+    step = len(rest) // n_b
+    for k in range(n_b):
+        b = rest[k * step: (k + 1) * step] if k + 1 < n_b else rest[k * step:]
+        for m in (m_full, m_inc):
+            m.add(b, float(k + 1))
+        om.add(b)
+        if k % 6 == 5 or k + 1 == n_b:
+            assert m_full.size() == m_inc.size() == om.size()
+            a, c = m_full.match_debug(case.init), m_inc.match_debug(case.init)
+            for key in ("good", "plane", "dist", "nn_d2"):
+                assert np.array_equal(a[key], c[key]), (k, key)
+    st = m_inc.stats()
+    assert st["index_updates"] >= n_b // 2 and st["index_rows_moved"] > 0, st       # the incremental path ran and rows did move
+    ocfg = oracle.make_cfg(max_pc2match=BIG, max_matches=BIG, num_threads=4)
+    check_per_point(m_inc.match_debug(case.init), om.match(ocfg, case.init[:14], case.scan))
+
+
 @pytest.mark.parametrize("tag", ["a", "b", "c"])
 def test_against_reference_octree_golden(flimo_lib, tag):
     """The CUDA path against vectors produced by the REFERENCE's own octree (tests/golden/ref_octree_*.npz,
