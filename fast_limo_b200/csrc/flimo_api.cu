@@ -25,7 +25,6 @@ using namespace flimo;
 
 // Index ladder defaults (tools/tune_knn.py sweeps on the 5 M-point headline map, B200): finest cell 0.25 m,
 // cells grow 1.5x per level, a query starts on the finest level whose block holds >= 8 candidates.
-constexpr float kDefaultCell = 0.25f;
 constexpr float kDefaultRatio = 1.5f;
 constexpr int kDefaultTau = 8;
 
@@ -457,7 +456,7 @@ int flimo_create(const flimo_cfg* cfg, int device, flimo_handle* out) {
   if (const char* e = std::getenv("FLIMO_KNN_CELL")) h->cfg.knn_cell = (float)std::atof(e);
   if (const char* e = std::getenv("FLIMO_KNN_RATIO")) h->cfg.knn_level_ratio = (float)std::atof(e);
   if (const char* e = std::getenv("FLIMO_KNN_TAU")) h->cfg.knn_tau = std::atoi(e);
-  if (!(h->cfg.knn_cell > 0.f)) h->cfg.knn_cell = kDefaultCell;
+  if (!(h->cfg.knn_cell > 0.f)) h->cfg.knn_cell = 0.f;         // 0 = chosen from the map's density at every full index build (map_index_build)
   if (!(h->cfg.knn_level_ratio > 1.05f)) h->cfg.knn_level_ratio = kDefaultRatio;
   if (h->cfg.knn_tau <= 0) h->cfg.knn_tau = kDefaultTau;
   h->knn_tau = h->cfg.knn_tau;

@@ -213,6 +213,24 @@ __global__ void __launch_bounds__(256) row_scatter_kernel(const float4* __restri
   dst[at] = make_float4(v.x, v.y, v.z, __uint_as_float(k));
 }
 
+// Sum over every `step`-th map point of the size of the 3x3x3 block around its own cell (= the run a query at that point
+// would scan): the density measure behind the automatic choice of the finest cell.
+__global__ void __launch_bounds__(256) block_size_kernel(const float4* __restrict__ p, size_t n, size_t step, GridDesc g,
+                                                         const uint32_t* __restrict__ cell_start, unsigned long long* __restrict__ sum) {
+  const size_t j = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  const size_t i = j * step;
+  unsigned int len = 0;
+  if (i < n) {
+    const float4 v = p[i];
+    const int ix = cell_coord(v.x, g.ox, g.inv_cell, g.nx), iy = cell_coord(v.y, g.oy, g.inv_cell, g.ny), iz = cell_coord(v.z, g.oz, g.inv_cell, g.nz);
+    const size_t row = (size_t)(iz * g.ny + iy) * (size_t)(g.nx + 1);
+    len = cell_start[row + min(ix + 1, g.nx - 1) + 1] - cell_start[row + max(ix - 1, 0)];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) len += __shfl_xor_sync(0xffffffffu, len, o);
+  if ((threadIdx.x & 31) == 0 && len) atomicAdd(sum, (unsigned long long)len);
+}
+
 // ---- incremental update: all levels in one pass over 9 entries per new point and level -------------------------
 struct LevelDev {
   float4* pts;
@@ -615,7 +633,8 @@ static GridDesc make_grid(const float lo[3], const float hi[3], float cell) {
   return g;
 }
 
-static cudaError_t build_level(MapIndex& idx, LevelIndex& L, const GridDesc& g, cudaStream_t st, uint64_t* launches, double* alloc_us = nullptr) {
+static cudaError_t build_level(MapIndex& idx, LevelIndex& L, const GridDesc& g, cudaStream_t st, uint64_t* launches, double* alloc_us = nullptr,
+                               unsigned long long* d_block_sum = nullptr, size_t sample_step = 1) {
   const auto t_alloc0 = std::chrono::steady_clock::now();
   const size_t n = idx.n_pts, n9 = 9 * n;
   const size_t n_cells = (size_t)g.nx * g.ny * g.nz;
@@ -693,6 +712,10 @@ static cudaError_t build_level(MapIndex& idx, LevelIndex& L, const GridDesc& g, 
   row_scatter_kernel<<<nblk(n9), 256, 0, st>>>(idx.pts, dv.Current(), dk.Current(), n9, idx.row_first, L.row_base, g.nx, (uint32_t)n_cells,
                                                 L.cell_start, L.pts);
   FL_TRY(cub::DeviceScan::InclusiveScan(idx.cub_tmp, bytes, rb, rb, cub::Min(), (long long)n_slots, st));
+  if (d_block_sum) {
+    FL_TRY(cudaMemsetAsync(d_block_sum, 0, sizeof(unsigned long long), st));
+    block_size_kernel<<<nblk((n + sample_step - 1) / sample_step), 256, 0, st>>>(idx.pts, n, sample_step, g, L.cell_start, d_block_sum);
+  }
   L.n_entries = n9;
   if (launches) *launches += 12;
   return cudaGetLastError();
@@ -722,13 +745,22 @@ cudaError_t map_index_build(MapIndex& idx, float cell0, float ratio, float coars
     idx.glo[a] = idx.lo[a] - margin;
     idx.ghi[a] = idx.hi[a] + margin;
   }
-  if (!(cell0 > 0.f)) cell0 = 0.25f;
+  // cell0 <= 0: the finest cell is chosen from the map's density.  Level 0 is built with 0.25 m; if the 3x3x3 block around a
+  // map point then holds more than 45 candidates on average (every query scans long runs) it is rebuilt once with a cell
+  // that brings the average back to ~28 (surfaces: candidates scale with the cell's area).  Results never depend on the
+  // cells (the search is exact for any grid); this is a speed choice only.
+  bool auto_cell = !(cell0 > 0.f);
+  if (auto_cell) cell0 = 0.25f;
   if (!(ratio > 1.05f)) ratio = 1.5f;
-  for (;;) {   // finest level must fit the table budget
-    const GridDesc g = make_grid(idx.glo, idx.ghi, cell0);
-    if ((double)g.nx * g.ny * g.nz <= (double)max_cells) break;
-    cell0 *= 1.25992105f;
-  }
+  auto fit_budget = [&](float c) {
+    for (;;) {   // finest level must fit the table budget
+      const GridDesc g = make_grid(idx.glo, idx.ghi, c);
+      if ((double)g.nx * g.ny * (g.nz + 1.0) <= (double)max_cells) return c;
+      c *= 1.25992105f;
+    }
+  };
+  cell0 = fit_budget(cell0);
+  if (!idx.upd_counters) FL_TRY(cudaMalloc(&idx.upd_counters, 8 * sizeof(uint32_t)));   // [0..3] update counters, [4..5] density sum (u64)
   int nl = 0;
   float cell = cell0;
   static const bool prof = std::getenv("FLIMO_PROFILE_INDEX") != nullptr;
@@ -736,7 +768,26 @@ cudaError_t map_index_build(MapIndex& idx, float cell0, float ratio, float coars
     if (nl == kMaxLevels - 1 && cell < coarsest_min) cell = coarsest_min;   // force termination
     const auto t0 = std::chrono::steady_clock::now();
     double alloc_us = 0.0;
-    FL_TRY(build_level(idx, idx.lv[nl], make_grid(idx.glo, idx.ghi, cell), st, launches, &alloc_us));
+    const bool probe_density = auto_cell && nl == 0;
+    const size_t sample_step = std::max<size_t>(1, n >> 18);   // ~260 k samples
+    FL_TRY(build_level(idx, idx.lv[nl], make_grid(idx.glo, idx.ghi, cell), st, launches, &alloc_us,
+                       probe_density ? reinterpret_cast<unsigned long long*>(idx.upd_counters + 4) : nullptr, sample_step));
+    if (probe_density) {
+      auto_cell = false;                                     // one retry at most
+      unsigned long long block_sum = 0;
+      FL_TRY(cudaMemcpyAsync(&block_sum, idx.upd_counters + 4, sizeof(block_sum), cudaMemcpyDeviceToHost, st));
+      FL_TRY(cudaStreamSynchronize(st));
+      const double mean = (double)block_sum / (double)((n + sample_step - 1) / sample_step);
+      if (prof) std::fprintf(stderr, "[index] %.1f candidates per 3x3x3 block around a map point at %.3f m\n", mean, cell0);
+      if (mean > 45.0) {
+        const float finer = fit_budget(std::max(0.125f, cell0 * (float)std::sqrt(28.0 / mean)));
+        if (finer < 0.9f * cell0) {
+          if (prof) std::fprintf(stderr, "[index] %.1f candidates per 3x3x3 block at %.3f m: finest cell -> %.3f m\n", mean, cell0, finer);
+          cell0 = cell = finer;
+          continue;                                          // rebuild level 0
+        }
+      }
+    }
     if (prof) {
       const auto t1 = std::chrono::steady_clock::now();
       cudaStreamSynchronize(st);
@@ -776,7 +827,7 @@ cudaError_t map_index_update(MapIndex& idx, size_t old_n, cudaStream_t st, uint6
   const size_t off_keys = 0, off_vals = off_keys + 2 * E * sizeof(unsigned long long), off_pts = (off_vals + 2 * E * sizeof(uint32_t) + 15) & ~(size_t)15,
                off_jobs = off_pts + E * sizeof(float4), total = off_jobs + E * sizeof(RowJob);
   FL_TRY(ensure(&idx.upd_buf, &idx.upd_bytes, total));
-  if (!idx.upd_counters) FL_TRY(cudaMalloc(&idx.upd_counters, 4 * sizeof(uint32_t)));
+  if (!idx.upd_counters) FL_TRY(cudaMalloc(&idx.upd_counters, 8 * sizeof(uint32_t)));
   unsigned char* buf = static_cast<unsigned char*>(idx.upd_buf);
   unsigned long long* k0 = reinterpret_cast<unsigned long long*>(buf + off_keys);
   uint32_t* v0 = reinterpret_cast<uint32_t*>(buf + off_vals);

@@ -242,9 +242,9 @@ static void lattice_desc(const OctreeLattice& L, LatticeDesc& d) {
 }
 
 static cudaError_t table_reserve(CountTable& T, size_t need_entries, cudaStream_t st) {
+  if (T.cap && T.cap >= 2 * need_entries) return cudaSuccess;   // load <= 1/2: keep the table
   size_t want = T.cap ? T.cap : (1u << 22);      // start large: growing means a rehash and two large (de)allocations
-  if (want >= 2 * need_entries) return cudaSuccess;   // load <= 1/2: keep the table
-  while (want < 4 * need_entries) want <<= 1;          // grow to load <= 1/4, so that the next growth is a doubling of the map away
+  while (want < 4 * need_entries) want <<= 1;    // (re)size to load <= 1/4, so that the next growth is a doubling of the map away
   unsigned long long* nk = nullptr;
   uint32_t* nv = nullptr;
   FL_TRY(cudaMalloc(&nk, want * sizeof(unsigned long long)));
