@@ -328,7 +328,12 @@ __device__ __forceinline__ void pair_scan_round(const float4* __restrict__ pts, 
 // and the lists are merged inside the team by five rounds of (d2 bits, position) arg-min built from
 // xor-shuffles of width T.  Results are identical in all lanes of a team.  A team with nothing to do
 // passes valid = false.
-__device__ __forceinline__ void block_scan_team(const LevelView& L, int T, int tl, bool valid, float qx, float qy, float qz,
+// `bound`: an upper bound of the query's true 5th squared distance (the exact 5th distance inside a smaller block that was
+// scanned before, +inf if none): candidates beyond it cannot be among the five nearest and skip the insertion.
+__device__ __forceinline__ void team_offer(Top5& mine, float d, uint32_t i, float bound) {
+  if (d <= bound && d < mine.d[4]) top5_offer(mine, d, i);
+}
+__device__ __forceinline__ void block_scan_team(const LevelView& L, int T, int tl, bool valid, float qx, float qy, float qz, float bound,
                                                 float (&rd)[5], uint32_t (&ri)[5]) {
   const unsigned int full = 0xffffffffu;
   const GridDesc& G = L.g;
@@ -353,13 +358,13 @@ __device__ __forceinline__ void block_scan_team(const LevelView& L, int T, int t
 #pragma unroll 1
   for (; i + 3u * (uint32_t)T < e; i += T4) {
     const float4 p0 = __ldg(&pts[i]), p1 = __ldg(&pts[i + T]), p2 = __ldg(&pts[i + 2 * T]), p3 = __ldg(&pts[i + 3 * T]);
-    top5_offer(mine, sqdist(qx, qy, qz, p0), i);
-    top5_offer(mine, sqdist(qx, qy, qz, p1), i + T);
-    top5_offer(mine, sqdist(qx, qy, qz, p2), i + 2 * T);
-    top5_offer(mine, sqdist(qx, qy, qz, p3), i + 3 * T);
+    team_offer(mine, sqdist(qx, qy, qz, p0), i, bound);
+    team_offer(mine, sqdist(qx, qy, qz, p1), i + T, bound);
+    team_offer(mine, sqdist(qx, qy, qz, p2), i + 2 * T, bound);
+    team_offer(mine, sqdist(qx, qy, qz, p3), i + 3 * T, bound);
   }
 #pragma unroll 1
-  for (; i < e; i += T) top5_offer(mine, sqdist(qx, qy, qz, __ldg(&pts[i])), i);
+  for (; i < e; i += T) team_offer(mine, sqdist(qx, qy, qz, __ldg(&pts[i])), i, bound);
 #pragma unroll
   for (int round = 0; round < 5; ++round) {
     const uint32_t db = __float_as_uint(mine.d[0]);
@@ -525,6 +530,7 @@ __device__ __forceinline__ void knn_search(const MatchParams& P, int lane, bool 
   first_lvl = 0;
   first_cnt = 0;
   bool pending = false;
+  float ub = __int_as_float(0x7f800000);       // upper bound of the true 5th squared distance known so far (see block_scan_team)
   uint32_t scan_s = 0, scan_e = 0;
   int hx0 = 0, hy0 = 0, hz0 = 0;
   if (active) {
@@ -558,6 +564,7 @@ __device__ __forceinline__ void knn_search(const MatchParams& P, int lane, bool 
       } else if (!block_is_final(P.lv[lvl].g, P.max_dist_f, qx, qy, qz, pr.hx, pr.hy, pr.hz, t.d[4])) {
         pending = lvl < top;
         if (pending) lvl = next_level(P, lvl, t.d[4]);
+        ub = t.d[4];
       }
     }
     if (kStage) {
@@ -590,6 +597,7 @@ __device__ __forceinline__ void knn_search(const MatchParams& P, int lane, bool 
       } else if (!block_is_final(P.lv[lvl].g, P.max_dist_f, qx, qy, qz, hx0, hy0, hz0, t.d[4])) {
         pending = lvl < top;
         if (pending) lvl = next_level(P, lvl, t.d[4]);
+        ub = t.d[4];
       }
     }
     __syncwarp();                                                // the slices are free again (next tile of a resident kernel)
@@ -632,6 +640,7 @@ __device__ __forceinline__ void knn_search(const MatchParams& P, int lane, bool 
       } else if (!block_is_final(P.lv[lvl].g, P.max_dist_f, qx, qy, qz, hx0, hy0, hz0, t.d[4])) {
         pending = lvl < top;
         if (pending) lvl = next_level(P, lvl, t.d[4]);
+        ub = t.d[4];
       }
     }
   }
@@ -658,7 +667,8 @@ __device__ __forceinline__ void knn_search(const MatchParams& P, int lane, bool 
     const int bl = __shfl_sync(full, lvl, src_lane);
     float rd[5];
     uint32_t ri[5];
-    block_scan_team(P.lv[bl], T, tl, valid, bx, by, bz, rd, ri);
+    const float bb = __shfl_sync(full, ub, src_lane);
+    block_scan_team(P.lv[bl], T, tl, valid, bx, by, bz, bb, rd, ri);
     // hand the results back: pending lane of rank r reads from the first lane of team r
     const int my_rank = __popc(todo & ((1u << lane) - 1u));
     const int from = pending ? my_rank * T : lane;
@@ -677,6 +687,7 @@ __device__ __forceinline__ void knn_search(const MatchParams& P, int lane, bool 
                 hz = cell_coord(qz, L.g.oz, L.g.inv_cell, L.g.nz);
       if (block_is_final(L.g, P.max_dist_f, qx, qy, qz, hx, hy, hz, t.d[4]) || lvl + 1 >= P.n_levels) pending = false;
       else lvl = next_level(P, lvl, t.d[4]);
+      ub = t.d[4];
     }
   }
   if (teamed) {                                                  // a team's answer: its five points go to the stash now
