@@ -17,6 +17,8 @@
   repeats  : the timed loop of --steps steps is run --repeats times (default 9) after ONE warm-up; the median repeat is
              reported (value, ms_per_step, e2e), min / max beside it — a 20-step loop is 3 ms long and a single one is noisy
   caps_kitti : e2e scans/s with the reference's shipped caps (config/kitti.yaml: 10 000 queried points, 5 000 rows, 4 passes)
+  streams  : BASELINE configs c3 / c5 in small (--stream-scans each): the whole per-scan sequence raw message -> filters / deskew /
+             voxel grid -> update -> Mapper::add with map growth; scans/s, latency p50 / p99, Mapper::add time, index statistics
   c4       : (at --gpus 8, or --c4) 300 000-point rosette scan against a 20 M-point map, scan sharded over the ranks
 
 N > 1 (torchrun): the scan is sharded across ranks (replicated map); every rank runs the whole update on its device, the 96
@@ -170,6 +172,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--repeats", type=int, default=9, help="the timed loop of --steps steps is repeated; the MEDIAN repeat is reported")
     ap.add_argument("--no-extra", action="store_true", help="skip the caps_kitti / c4 legs")
+    ap.add_argument("--stream-scans", type=int, default=70, help="scans of the c3 / c5 stream replays (streams field)")
     ap.add_argument("--c4", action="store_true", help="also run config c4 (300k-pt rosette scan, 20M-pt map); default at --gpus 8")
     ap.add_argument("--exchange", choices=["peer", "shm", "nccl"], default="peer",
                     help="N>1: how the 96 doubles per pass are summed over ranks (peer: NVLink peer stores from inside the "
@@ -335,6 +338,7 @@ def main():
                     m.match(st)
             kernel_where = "one launch per pass on this rank's shard right after the timed region (8 scans x 3 poses)"
         st_k1 = m.stats()
+    st_end = m.stats()
     pose_err = arm.pose_err(x, args.steps)
     n_pts, lo, hi = arm.n_pts, arm.lo, arm.hi
     map_gb = st1["map_bytes"] / 1e9
@@ -355,6 +359,17 @@ def main():
                                "passes_incl_repeats_per_scan": (s1["match_launches"] - s0["match_launches"]) / n_upd,
                                "pose_err_m": k_arm.pose_err(kx, min(args.steps, 500))}
         k_arm.close()
+    if not args.no_extra and world == 1:
+        # (1b) BASELINE configs c3 / c5 in small: stream replays through the whole per-scan sequence (raw message -> filters / deskew /
+        #      voxel grid -> update -> Mapper::add with map growth); generation of the synthetic messages is not counted
+        from fast_limo_b200 import replay as R
+        c3 = R.replay(args.stream_scans, rings=64, az=2048, dt=0.1, imu_hz=200.0, speed=10.0, leaf=0.5, max_iter=3)
+        c5 = R.replay(args.stream_scans, rings=32, az=1024, dt=0.02, imu_hz=400.0, speed=12.0, leaf=0.5, max_iter=3, premap=2_000_000)
+        extra["streams"] = {
+            "c3": dict(c3, workload="c3: 64x2048-pt HDL-64E-shaped sweeps at 10 m/s, map grows from empty (kitti-style pipeline, caps raised)"),
+            "c5": dict(c5, workload="c5: 32x1024-pt sweeps at 50 Hz with deskew against a pre-built 2M-pt map that keeps growing; "
+                                    "latency = raw message -> pose on the host"),
+            "note": "scans_per_s = 1 / (prep + update + Mapper::add) per scan through the public API, host buffers in, pose out; first 10 scans untimed"}
     if not args.no_extra and (args.c4 or world == 8):
         if True:
             # (2) BASELINE config c4: 300 000-point rosette scan against a 20 M-point map (index >> L2), scan sharded over the ranks
@@ -403,7 +418,8 @@ def main():
             "details": {"arithmetic": "float32 per point (kNN, plane fit, residual, Jacobian row), float64 normal equations and filter algebra",
                         "parallelism": "scan-shard x%d (replicated map, 96 doubles summed per pass via %s)" % (world, exch if world > 1 else "no exchange"),
                         "update": "device-resident: tiles kernel + filter CTA, no host between passes; every 8th scan one launch per pass (event-timed)",
-                        "passes_per_scan": passes, "map_index_gb": map_gb, "pose_err_m": pose_err, "knn_cell": st1["knn_cell"], "levels": st1["n_levels"]},
+                        "passes_per_scan": passes, "map_index_gb": map_gb, "pose_err_m": pose_err, "knn_cell": st1["knn_cell"], "levels": st1["n_levels"],
+                        "update_stalls": int(st_end["update_stalls"])},
             "e2e": {"value": args.steps / (ms_e2e / 1e3), "unit": "scans/s", "h2d_bytes_per_step": n_pts * 16,   # summed over ranks
                     "d2h_bytes_per_step": 160 * 16},
             # kernels launched during ONE timed loop of `steps` steps (counted over warm-up + all repeats, scaled)

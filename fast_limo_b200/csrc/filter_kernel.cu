@@ -90,13 +90,13 @@ __device__ __forceinline__ bool peer_exchange_sums(const RegParams& RP, FilterSh
   if (t < kPartialStride) {
     const double mine = fs.sums[0][t];
     for (int r = 0; r < RP.world; ++r) st_record(inbox_slot(RP.inbox[r], xs, RP.rank, t), mine, xs);
-    const unsigned long long t0 = gtime_ns();
+    const long long w0 = watch_start();
     double sum = 0.0;
     for (int r = 0; r < RP.world; ++r) {                 // fixed rank order: identical sums on every rank
       const double* slot = inbox_slot(RP.inbox[RP.rank], xs, r, t);
       ulonglong2 rec = ld_record(slot);
       while (rec.y != xs) {
-        if (gtime_ns() - t0 > RP.peer_timeout_ns) {
+        if (watch_expired(w0, RP.peer_timeout_ns)) {
           fs.flag = 0;
           break;
         }
@@ -147,10 +147,10 @@ __device__ __forceinline__ uint32_t first_n_limit(const RegParams& RP, FilterSha
     __syncthreads();
     if (t < RP.world) st_record(inbox_slot(RP.inbox[t], xs, RP.rank, 96), (double)n_words, xs);
     if (t < RP.world) {
-      const unsigned long long t0 = gtime_ns();
+      const long long w0 = watch_start();
       const double* slot = inbox_slot(RP.inbox[RP.rank], xs, t, 96);
       while (ld_record(slot).y != xs)
-        if (gtime_ns() - t0 > RP.peer_timeout_ns) {
+        if (watch_expired(w0, RP.peer_timeout_ns)) {
           s_i[131] = 0;
           break;
         }
@@ -217,6 +217,8 @@ __global__ void __launch_bounds__(kFilterThreads, 1) filter_kernel(const __grid_
   PassCtl* dctl = P.dev_ctl;
   ekf::UpdState& st = *RP.st;
   ekf::StepShared& ss = fs.step;
+  // the dependent launch (the tiles kernel, next in this stream) may be dispatched from here on: this CTA is resident
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const unsigned long long t_kernel = gtime_ns();
 
   // the inputs of the update: mapped host block -> device memory (one PCIe round trip, all loads in flight at once)
@@ -258,23 +260,30 @@ __global__ void __launch_bounds__(kFilterThreads, 1) filter_kernel(const __grid_
     need_pre = false;
     // ---- wait for the last group of this pass, sum the group partials in a fixed order -------------------
     if (tid == 0) {
-      const unsigned long long t0 = gtime_ns();
+      const long long w0 = watch_start();
       unsigned int naps = 0;
       fs.flag = 1;
       const unsigned int n_arrivals = P.fx_reduce ? (unsigned int)n_tiles : (unsigned int)n_groups;   // tiles (order-free sums) or groups (tree)
       while (ld_acquire_u32(&P.ticket[0]) != n_arrivals) {
         __nanosleep(20);
-        if ((++naps & 1023u) == 0u && gtime_ns() - t0 > P.watchdog_ns) {
+        if ((++naps & 1023u) == 0u && watch_expired(w0, P.watchdog_ns)) {
           fs.flag = 0;
           break;
         }
       }
+      if (!fs.flag) {                                      // diagnostics of a pass that never completed (flimo_update prints them)
+        dctl->pad[0] = ld_acquire_u32(&P.ticket[0]);
+        dctl->pad[1] = (uint32_t)(fs.stamps[14] / 1000ull);      // when the command of this pass was posted
+        dctl->pad[2] = (uint32_t)(gtime_ns() / 1000ull);
+        P.ticket[2] = ld_acquire_u32(&P.ticket[1]);
+      }
+      P.ticket[1] = 0u;
       P.ticket[0] = 0u;                                    // for the next pass (its groups start after the next command)
       fs.stamps[15] = gtime_ns();
     }
     __syncthreads();
     bool ok = fs.flag != 0;
-    const double pass_ns = (double)(fs.stamps[15] - fs.stamps[14]);      // command posted -> pass sums complete
+    const double pass_ns = timer_span_ns(fs.stamps[15], fs.stamps[14]);  // command posted -> pass sums complete
     const int pass_idx = ss.passes;                                      // (only post_step_rest changes it, barriers away)
     if (ok && P.fx_reduce) {
       __threadfence();
@@ -364,7 +373,7 @@ __global__ void __launch_bounds__(kFilterThreads, 1) filter_kernel(const __grid_
         if (tid == 27) tr[27] = fs.sums[0][90];
         if (tid == 28) tr[28] = pass_ns;
         if (tid == 29) tr[29] = (double)cur_limit;
-        if (tid >= 32 && tid < 40) st.phase_ns[pass_idx][tid - 32] = (double)(fs.stamps[tid - 32] - fs.stamps[15]);
+        if (tid >= 32 && tid < 40) st.phase_ns[pass_idx][tid - 32] = timer_span_ns(fs.stamps[tid - 32], fs.stamps[15]);
       }
     }
     __syncthreads();
@@ -382,7 +391,7 @@ __global__ void __launch_bounds__(kFilterThreads, 1) filter_kernel(const __grid_
           else if (i < kResSums + kPartialStride) v = fs.sums[0][i - kResSums];
           else if (i == kResPasses) v = (double)ss.passes;
           else if (i == kResFailed) v = (double)ss.failed;
-          else if (i == kResDevNs) v = (double)(gtime_ns() - t_kernel);
+          else if (i == kResDevNs) v = timer_span_ns(gtime_ns(), t_kernel);
           else if (i == kResRedone) v = (double)redone;
           else if (i >= kResXDev && i < kResXDev + 26) v = ss.x[i - kResXDev];
           st_record(RP.host_res + 2 * (size_t)i, v, RP.res_seq);

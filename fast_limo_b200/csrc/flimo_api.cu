@@ -105,7 +105,10 @@ struct flimo_ctx {
   int probe_mode = 1, wide_loads = 1, pair_scan = 0;
   int interleave = 0, scan_perm = 1, l2_prefetch = 0, stage_runs = 0, fx_reduce = 1;
   int index_incremental = 1;     // FLIMO_INDEX_INCREMENTAL=0: every Mapper::add rebuilds the whole index
-  uint64_t stats_index_builds = 0, stats_index_updates = 0;
+  uint64_t stats_index_builds = 0, stats_index_updates = 0, stats_update_stalls = 0;
+  uint4* cta_trace = nullptr;     // FLIMO_DEBUG_CTA_TRACE=1: per-CTA progress records of the registration tiles kernel (diagnostics)
+  bool pdl = true;                // FLIMO_PDL=0: filter and tiles kernels on two streams instead of a programmatic dependent launch
+  int debug_stall_every = 0;      // FLIMO_DEBUG_STALL_EVERY: fault injection for the stall recovery of flimo_update (tests)
   int time_every = 8;            // every n-th flimo_update runs one launch per pass, each timed with CUDA events (0 = never)
   // persistent kernel (one launch per flimo_update)
   PassCtlWire* h_ctl = nullptr;  // mapped pinned host control block (tagged 16-byte records)
@@ -282,6 +285,7 @@ int fill_params(flimo_handle h, const double state14[14], MatchParams& P, double
   P.dbg16 = dbg;
   P.valid_by_orig = valid;
   P.timing = h->timing;
+  P.cta_trace = h->cta_trace;
   P.host_out96 = nullptr;
   P.host_out_alt = 0;
   P.seq = 0;
@@ -473,6 +477,9 @@ int flimo_create(const flimo_cfg* cfg, int device, flimo_handle* out) {
   if (const char* e = std::getenv("FLIMO_KNN_STAGE")) h->stage_runs = std::atoi(e);
   if (const char* e = std::getenv("FLIMO_KNN_FX")) h->fx_reduce = std::atoi(e);
   if (const char* e = std::getenv("FLIMO_INDEX_INCREMENTAL")) h->index_incremental = std::atoi(e);
+  if (const char* e = std::getenv("FLIMO_DEBUG_STALL_EVERY")) h->debug_stall_every = std::atoi(e);
+  if (const char* e = std::getenv("FLIMO_PDL")) h->pdl = std::atoi(e) != 0;
+  const bool want_cta_trace = std::getenv("FLIMO_DEBUG_CTA_TRACE") != nullptr;
   CU(h, cudaSetDevice(device));
   CU(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   CU(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
@@ -488,6 +495,10 @@ int flimo_create(const flimo_cfg* cfg, int device, flimo_handle* out) {
   CU(h, cudaHostAlloc(&h->h_ctl, sizeof(PassCtlWire), cudaHostAllocMapped));
   std::memset(h->h_ctl, 0, sizeof(PassCtlWire));
   CU(h, cudaHostGetDevicePointer(reinterpret_cast<void**>(&h->d_h_ctl), h->h_ctl, 0));
+  if (want_cta_trace) {
+    CU(h, cudaMalloc(&h->cta_trace, 4096 * sizeof(uint4)));
+    CU(h, cudaMemset(h->cta_trace, 0, 4096 * sizeof(uint4)));
+  }
   CU(h, cudaMalloc(&h->dev_ctl, sizeof(PassCtl)));
   CU(h, cudaMemset(h->dev_ctl, 0, sizeof(PassCtl)));
   h->persist_capacity = match_persistent_capacity();
@@ -554,6 +565,7 @@ void flimo_destroy(flimo_handle h) {
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   if (h->ev_prefetch) cudaEventDestroy(h->ev_prefetch);
   cudaFree(h->dev_ctl);
+  cudaFree(h->cta_trace);
   cudaFree(h->upd_state);
   cudaFreeHost(h->h_in);
   cudaFree(h->dev_in);
@@ -629,6 +641,7 @@ int flimo_get_stats(flimo_handle h, flimo_stats* out) {
   h->stats.index_builds = h->stats_index_builds;
   h->stats.index_updates = h->stats_index_updates;
   h->stats.index_rows_moved = h->map.rows_moved;
+  h->stats.update_stalls = h->stats_update_stalls;
   *out = h->stats;
   return FLIMO_OK;
 }
@@ -1356,7 +1369,9 @@ static int update_device(flimo_handle h, double state26[26], double P529[529], i
   RP.rank = exchange ? h->peer_rank : 0;
   for (int r = 0; r < kMaxPeers; ++r) RP.inbox[r] = exchange ? h->peer_inbox[r] : nullptr;
   RP.peer_timeout_ns = 2000ull * 1000ull * 1000ull;
-  RP.m.watchdog_ns = 4000ull * 1000ull * 1000ull;       // hang protection only: tiles without a filter kernel (or vice versa) give up
+  // hang protection only: tiles without a filter kernel (or vice versa) give up.  One GPU: a pass takes well under a
+  // millisecond, and a stalled update is redone with one launch per pass (flimo_update); several ranks may enter late.
+  RP.m.watchdog_ns = (exchange ? 4000ull : 250ull) * 1000ull * 1000ull;
   const int max_cmds = 2 * (max_iter + 2) + 2;          // every pass may be repeated once (first-N rule) + stop
   RP.xseq = h->peer_xseq + 1;
   h->peer_xseq += (unsigned long long)max_cmds;
@@ -1375,8 +1390,17 @@ static int update_device(flimo_handle h, double state26[26], double P529[529], i
   const int tiles = match_num_tiles((int)n);
   const int grid = std::min(tiles, h->reg_capacity);
   // the filter CTA first (its own stream: it has to run beside the tiles), then the tiles
-  CU(h, launch_filter(RP, h->filter_stream));
-  CU(h, launch_registration_tiles(RP.m, grid, h->stream));
+  // (h->pdl: both on the handle's stream, the tiles as a programmatic dependent of the filter kernel — see
+  //  launch_registration_tiles; FLIMO_PDL=0: the round-2 arrangement on two streams, ordered by launch time only)
+  CU(h, launch_filter(RP, h->pdl ? h->stream : h->filter_stream));
+  if (h->debug_stall_every > 0 && (h->device_updates + 1) % (uint64_t)h->debug_stall_every == 0) {
+    // fault injection (tests): these tiles listen for the wrong command numbers, i.e. they go silent after the first pass
+    MatchParams deaf = RP.m;
+    deaf.ctl_seq += 1000000ull;
+    CU(h, launch_registration_tiles(deaf, grid, h->stream, h->pdl));
+  } else {
+    CU(h, launch_registration_tiles(RP.m, grid, h->stream, h->pdl));
+  }
   h->stats.kernel_launches += 2;
   if (h->pref_idx >= 0 && !h->pref_issued) {               // the requested copy of the next scan overlaps the update
     rc = issue_prefetch(h);
@@ -1412,9 +1436,48 @@ static int update_device(flimo_handle h, double state26[26], double P529[529], i
   }
   if (failed) {
     // the kernels may have stopped in the middle of a pass: drain them and clear the last-CTA-done counters
+    const cudaError_t qf = cudaStreamQuery(h->filter_stream), qt = cudaStreamQuery(h->stream);
     cudaStreamSynchronize(h->filter_stream);
     cudaStreamSynchronize(h->stream);
+    if (failed == 2) {                                           // diagnostics of a pass that never completed
+      unsigned int tk[4] = {0, 0, 0, 0};
+      PassCtl dc{};
+      if (h->ticket) cudaMemcpy(tk, h->ticket, sizeof(tk), cudaMemcpyDeviceToHost);
+      if (h->dev_ctl) cudaMemcpy(&dc, h->dev_ctl, sizeof(dc), cudaMemcpyDeviceToHost);
+      std::fprintf(stderr, "[flimo] at the time-out: %u tiles had delivered, %u CTAs had begun the pass\n", dc.pad[0], tk[2]);
+      if (h->cta_trace) {
+        std::vector<uint4> tr((size_t)grid);
+        cudaMemcpy(tr.data(), h->cta_trace, tr.size() * sizeof(uint4), cudaMemcpyDeviceToHost);
+        int by_state[16][12] = {};
+        for (const uint4& r : tr) by_state[r.x & 15u][((r.x >> 8) & 255u) < 12u ? ((r.x >> 8) & 255u) : 11u]++;
+        for (int pss = 0; pss < 16; ++pss)
+          for (int ph = 0; ph < 12; ++ph)
+            if (by_state[pss][ph]) std::fprintf(stderr, "[flimo]   %d CTAs: pass %d phase %d (1 waiting, 2 running, 3 delivered, 9 gave up)\n", by_state[pss][ph], pss, ph);
+        std::fprintf(stderr, "[flimo]   command posted at %u us, filter time-out at %u us\n", dc.pad[1], dc.pad[2]);
+        int shown = 0;
+        for (size_t b = 0; b < tr.size() && shown < 10; ++b)
+          if (((tr[b].x >> 8) & 255u) == 9u && (tr[b].x & 15u) == 1u) {
+            std::fprintf(stderr, "[flimo]   CTA %zu on SM %u gave up after %u polls and %u k cycles, last saw %u\n", b, tr[b].x >> 16, tr[b].z, tr[b].w, tr[b].y);
+            ++shown;
+          }
+        shown = 0;
+        for (size_t b = 0; b < tr.size() && shown < 4; ++b)
+          if ((tr[b].x & 15u) == 2u) {
+            std::fprintf(stderr, "[flimo]   CTA %zu on SM %u (ran the pass): phase %u, then waited for command %u from %u us, last saw %u\n", b, tr[b].x >> 16,
+                         (tr[b].x >> 8) & 255u, tr[b].z, tr[b].w, tr[b].y);
+            ++shown;
+          }
+      }
+      std::fprintf(stderr, "[flimo] update %llu: pass sums never completed: ticket[0]=%u of %d tiles (grid %d), device command seq=%llu cmd=%u, "
+                           "first command of this update %llu, passes done %d, streams at failure: filter %s, tiles %s\n",
+                   (unsigned long long)h->device_updates, tk[0], tiles, grid, (unsigned long long)dc.seq, dc.cmd, (unsigned long long)RP.m.ctl_seq, passes,
+                   cudaGetErrorName(qf), cudaGetErrorName(qt));
+    }
     if (h->ticket) cudaMemset(h->ticket, 0, h->ticket_cap * sizeof(unsigned int));
+  }
+  if (failed == 2 && !exchange) {                         // own kernels only: the caller redoes the update with one launch per pass
+    h->stats_update_stalls++;
+    return 2;
   }
   if (failed == 2) return fail(h, FLIMO_ERR_STATE, "a peer rank (or this rank's tile kernel) did not deliver its pass sums in time");
   if (failed) return fail(h, FLIMO_ERR_STATE, "singular or non-finite normal equations: state left at the prediction");
@@ -1591,14 +1654,16 @@ int flimo_update(flimo_handle h, double state26[26], double P529[529], int max_i
   const bool classic = !h->persistent || h->device < 0 || h->persist_capacity <= 0 || !flimo_map_exists(h) ||
                        h->shard_end <= h->shard_begin || h->timing != nullptr ||
                        (h->time_every > 0 && (h->update_calls % (uint64_t)h->time_every) == 0);
+  bool stalled = false;
   if (!classic && h->device_ekf) {                        // the whole update on the device
     NEED_GPU(h);
     const int rc = update_device(h, state26, P529, max_iter, limit23, R_noise, D_degeneracy, passes_out, false);
     if (rc <= 0) return rc;
+    stalled = rc == 2;                                     // the resident kernels stopped answering: one launch per pass below
   }
   u.begin(state26, P529, max_iter, limit23, R_noise, D_degeneracy);
   double x[26], HTH[144], HTh[12];
-  if (!classic && !u.done()) {
+  if (!classic && !stalled && !u.done()) {
     const int rc = update_persistent(h, u, false);
     if (rc < 0) return rc;
   }

@@ -55,7 +55,7 @@ struct PassCtl {
   uint32_t cmd;                // 0 = run the pass, 1 = stop (kernel exits), 3 = run it again with the same pose and a row limit
   uint32_t orig_limit;         // first-N cap on contributing rows
   PoseConsts pc;
-  uint32_t pad[1];
+  uint32_t pad[3];             // diagnostics of a stalled pass: tiles delivered at the time-out, time the command was posted, time of the time-out (us, low 32 bits)
 };
 static_assert(sizeof(PassCtl) % 8 == 0, "PassCtl must be a whole number of 8-byte words");
 // Wire format of the HOST control block: the 56 payload words of a PassCtl (cmd, orig_limit, pose) in 19
@@ -79,6 +79,22 @@ constexpr int kPartialStride = 96;    // doubles per partial record
 //   u64 [parity 2][replica kFxReplicas][96][2]     fixed-point sums {units of 2^-18, units of 2^-66}
 // (replicas spread the same-address REDs of tiles that finish together; parity alternates between consecutive passes so
 // that the finisher's zeroing of one set is two passes ahead of its next use).
+#ifdef __CUDACC__
+// Watchdogs count SM cycles (clock64), not %globaltimer: the global timer is re-synchronised now and then and can step
+// BACKWARDS by a few hundred microseconds (measured on B200: every few seconds; all SMs at once).  An unsigned
+// `globaltimer - t0 > limit` then turns true at once — about one update in 20 000 ended by a watchdog that way.
+// The cycle counter of an SM is monotonic; 2.25 cycles per nanosecond is above any B200 clock, so a limit never fires early.
+__device__ __forceinline__ long long watch_start() { return clock64(); }
+__device__ __forceinline__ bool watch_expired(long long c0, unsigned long long limit_ns) {
+  return (unsigned long long)(clock64() - c0) > 2ull * limit_ns + (limit_ns >> 2);
+}
+// elapsed %globaltimer time for statistics: a negative difference (timer stepped back in between) counts as zero
+__device__ __forceinline__ double timer_span_ns(unsigned long long t1, unsigned long long t0) {
+  const long long d = (long long)(t1 - t0);
+  return d > 0 ? (double)d : 0.0;
+}
+#endif
+
 constexpr int kFxReplicas = 4;
 constexpr int kTicketWords = 4 + 2 * kFxReplicas * kPartialStride * 2 * 2;
 #ifdef __CUDACC__
@@ -140,6 +156,7 @@ struct MatchParams {
   unsigned int host_out_alt;   // doubles between the two alternating host result blocks (block = seq & 1); 0 = one block
   unsigned long long seq;      // sequence number stored with every record
   unsigned long long* timing;  // optional per-warp timestamps (profiling builds of the tools only)
+  uint4* cta_trace;            // optional: per-CTA progress record of the registration tiles kernel {pass, phase, last seq seen (lo), smid}
   // persistent kernel only
   const PassCtlWire* host_ctl; // device alias of the host control block
   PassCtl* dev_ctl;            // device copy
@@ -280,7 +297,7 @@ cudaError_t points_bbox(const float4* d_pts, size_t n, float* d_scratch8, float 
 // match_kernel.cu
 cudaError_t launch_match(const MatchParams& p, cudaStream_t st);
 cudaError_t launch_match_persistent(const MatchParams& p, int grid, cudaStream_t st);
-cudaError_t launch_registration_tiles(const MatchParams& p, int grid, cudaStream_t st);
+cudaError_t launch_registration_tiles(const MatchParams& p, int grid, cudaStream_t st, bool after_primary);
 cudaError_t launch_filter(const RegParams& p, cudaStream_t st);
 int match_persistent_capacity();
 int registration_capacity();

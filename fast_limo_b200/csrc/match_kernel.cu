@@ -1255,7 +1255,7 @@ __device__ __forceinline__ bool match_tile(const MatchParams& P, const PoseConst
 // mapped pinned host copy.
 __device__ __forceinline__ void publish_result(const MatchParams& P, TileShared& sh, const unsigned long long seq,
                                                const unsigned long long t_begin) {
-  if (threadIdx.x == 93 && t_begin != 0ull) sh.wsum[0][93] = (double)(globaltimer_ns() - t_begin);   // persistent kernel: device time of the pass (ns)
+  if (threadIdx.x == 93 && t_begin != 0ull) sh.wsum[0][93] = timer_span_ns(globaltimer_ns(), t_begin);   // persistent kernel: device time of the pass (ns)
   if (threadIdx.x < kPartialStride) {
     const double v = sh.wsum[0][threadIdx.x];
     P.out96[threadIdx.x] = v;
@@ -1316,13 +1316,13 @@ __global__ void __launch_bounds__(kTileQueries, 7) match_persistent_kernel(const
       const uint32_t tag = (uint32_t)ctl;
       uint32_t r0 = 0, r1 = 0, r2 = 0, r3 = tag;
       bool ok = false;
-      const unsigned long long t0 = globaltimer_ns();
+      const long long w0 = watch_start();
       for (;;) {
         if (lane < kCtlRecords)
           asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "l"(&hctl->rec[lane][0]) : "memory");
         ok = __all_sync(0xffffffffu, r3 == tag);
         if (ok) break;
-        if (__any_sync(0xffffffffu, globaltimer_ns() - t0 > P.watchdog_ns)) break;
+        if (__any_sync(0xffffffffu, watch_expired(w0, P.watchdog_ns))) break;
       }
       if (ok) {
         uint32_t* dst = reinterpret_cast<uint32_t*>(&dctl->cmd);          // cmd, orig_limit, pose words follow each other
@@ -1391,16 +1391,28 @@ __global__ void __launch_bounds__(kTileQueries, 7) registration_tiles_kernel(con
     } else {
       const unsigned long long want = P.ctl_seq + cmd_no - 1ull;
       if (tid == 0) {
-        const unsigned long long t0 = globaltimer_ns();
+        const unsigned long long t0 = globaltimer_ns();   // (diagnostics only)
+        const long long w0 = watch_start();
         unsigned int naps = 0;
-        while (ld_acquire_u64(&dctl->seq) != want) {
+        unsigned int smid = 0;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        const uint32_t tag = (uint32_t)cmd_no | (smid << 16);
+        if (P.cta_trace) P.cta_trace[blockIdx.x] = make_uint4(tag | (1u << 8), 0u, (uint32_t)want, (uint32_t)(t0 / 1000ull));
+        unsigned long long seen;
+        while ((seen = ld_acquire_u64(&dctl->seq)) != want) {
           __nanosleep(32);
-          if ((++naps & 1023u) == 0u && globaltimer_ns() - t0 > P.watchdog_ns) {   // the filter kernel is gone
-            s_ctl.cmd = 2u;
-            break;
+          if ((++naps & 1023u) == 0u) {
+            if (P.cta_trace) P.cta_trace[blockIdx.x] = make_uint4(tag | (1u << 8), (uint32_t)seen, (uint32_t)want, (uint32_t)(t0 / 1000ull));
+            if (watch_expired(w0, P.watchdog_ns)) {        // the filter kernel is gone
+              s_ctl.cmd = 2u;
+              break;
+            }
           }
         }
         if (s_ctl.cmd != 2u) s_ctl.cmd = 0u;
+        if (P.cta_trace)
+          P.cta_trace[blockIdx.x] = s_ctl.cmd == 2u ? make_uint4(tag | (9u << 8), (uint32_t)seen, naps, (uint32_t)((clock64() - w0) >> 10))
+                                                    : make_uint4(tag | (2u << 8), (uint32_t)seen, (uint32_t)want, (uint32_t)(t0 / 1000ull));
       }
       __syncthreads();
       if (s_ctl.cmd == 2u) return;
@@ -1410,12 +1422,14 @@ __global__ void __launch_bounds__(kTileQueries, 7) registration_tiles_kernel(con
     }
     __syncthreads();
     if (s_ctl.cmd != 0u && s_ctl.cmd != 3u) return;
+    if (tid == 0 && P.cta_trace) atomicAdd(&P.ticket[1], 1u);   // diagnostics (FLIMO_DEBUG_CTA_TRACE): CTAs that began this pass
     // cmd 3 = the pass is repeated with the same pose and a row limit: a CTA that owns exactly one tile re-selects the rows
     // it still holds in shared memory instead of matching the tile again
     const bool reuse = s_ctl.cmd == 3u && (int)gridDim.x >= n_tiles;
     for (int t = (int)blockIdx.x; t < n_tiles; t += (int)gridDim.x)
       match_tile<kWide, kPair, true>(P, s_ctl.pc, sh, t, n_tiles, s_ctl.orig_limit, reuse, StageCtx{nullptr, nullptr, nullptr}, (int)(cmd_no & 1ull));
     __syncthreads();
+    if (tid == 0 && P.cta_trace) P.cta_trace[blockIdx.x].x = (P.cta_trace[blockIdx.x].x & ~0xFF00u) | (3u << 8);   // delivered
   }
 }
 
@@ -1441,13 +1455,27 @@ int match_persistent_capacity() {
   return sms * per_sm;
 }
 
-cudaError_t launch_registration_tiles(const MatchParams& p, int grid, cudaStream_t st) {
+// `after_primary`: programmatic dependent launch — the tiles follow the filter kernel IN THE SAME STREAM and may start as soon
+// as the filter CTA has executed griddepcontrol.launch_dependents (its first instruction), not when it completes.  That is
+// the residency guarantee of the pair: the filter CTA wants an SM of its own, and tile CTAs dispatched before it would fill
+// every SM and never leave (they wait for the filter's commands) — measured: about one update in 20 000 when the two
+// kernels were launched on two streams in the right order.
+cudaError_t launch_registration_tiles(const MatchParams& p, int grid, cudaStream_t st, bool after_primary) {
   const int n = p.q_end - p.q_begin;
   if (n <= 0 || grid <= 0) return cudaErrorInvalidValue;
-  if (p.pair_scan) registration_tiles_kernel<true, true><<<grid, kTileQueries, 0, st>>>(p);
-  else if (p.wide_loads) registration_tiles_kernel<true, false><<<grid, kTileQueries, 0, st>>>(p);
-  else registration_tiles_kernel<false, false><<<grid, kTileQueries, 0, st>>>(p);
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned int)grid);
+  cfg.blockDim = dim3(kTileQueries);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = after_primary ? 1 : 0;
+  if (p.pair_scan) return cudaLaunchKernelEx(&cfg, registration_tiles_kernel<true, true>, p);
+  if (p.wide_loads) return cudaLaunchKernelEx(&cfg, registration_tiles_kernel<true, false>, p);
+  return cudaLaunchKernelEx(&cfg, registration_tiles_kernel<false, false>, p);
 }
 
 // CUDA loads kernels lazily at their first launch, and that load can wait for the device to drain — which never

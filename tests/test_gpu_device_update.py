@@ -181,3 +181,23 @@ def test_peer_exchange_two_processes(flimo_lib, mm):
     if mm == 400:
         g = np.load(os.path.join(G, "tiny_m400.npz"))
         assert np.allclose(out[0][0][0], g["x_final"], atol=1e-9)
+
+
+def test_stalled_resident_update_is_redone_per_pass(oracle, flimo_lib):
+    """The resident kernels of an update wait for each other (tiles for the next pose, the filter CTA for the pass sums); a
+    watchdog ends a stalled pair and flimo_update then redoes the update with one launch per pass.  Fault injection
+    (FLIMO_DEBUG_STALL_EVERY): every third update's tiles go deaf after their first pass.  Results must not change."""
+    case = synth.make_case("tiny")
+    P0 = synth.default_P0()
+    m = mapper()
+    m.add(case.map_pts, 0.0)
+    m.set_scan(case.scan)
+    x_ref, P_ref, p_ref = m.update(case.init, P0, 2, 0.0)
+    mf = mapper(env={"FLIMO_DEBUG_STALL_EVERY": "3", "FLIMO_TIME_EVERY": "0"})
+    mf.add(case.map_pts, 0.0)
+    mf.set_scan(case.scan)
+    for k in range(7):
+        x, P, passes = mf.update(case.init, P0, 2, 0.0)
+        assert passes == p_ref == 3
+        assert np.abs(x - x_ref).max() <= 1e-9 and np.allclose(P, P_ref, rtol=1e-4, atol=1e-11), k      # device vs host filter step: libm last bits
+    assert mf.stats()["update_stalls"] == 2 and m.stats()["update_stalls"] == 0
