@@ -80,10 +80,10 @@ constexpr int kPartialStride = 96;    // doubles per partial record
 // (replicas spread the same-address REDs of tiles that finish together; parity alternates between consecutive passes so
 // that the finisher's zeroing of one set is two passes ahead of its next use).
 #ifdef __CUDACC__
-// Watchdogs count SM cycles (clock64), not %globaltimer: the global timer is re-synchronised now and then and can step
-// BACKWARDS by a few hundred microseconds (measured on B200: every few seconds; all SMs at once).  An unsigned
-// `globaltimer - t0 > limit` then turns true at once — about one update in 20 000 ended by a watchdog that way.
-// The cycle counter of an SM is monotonic; 2.25 cycles per nanosecond is above any B200 clock, so a limit never fires early.
+// Watchdogs count SM cycles (clock64), not %globaltimer: the cycle counter of an SM is monotonic whatever happens to the
+// global timer (an unsigned `globaltimer - t0 > limit` turns true at once if the timer is ever set back), and %globaltimer
+// values of different SMs were found not to be comparable at the 100 us level.  2.25 cycles per nanosecond is above any
+// B200 clock, so a limit never fires early (at 1.965 GHz it fires 15 % late).
 __device__ __forceinline__ long long watch_start() { return clock64(); }
 __device__ __forceinline__ bool watch_expired(long long c0, unsigned long long limit_ns) {
   return (unsigned long long)(clock64() - c0) > 2ull * limit_ns + (limit_ns >> 2);
