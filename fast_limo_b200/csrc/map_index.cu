@@ -672,11 +672,15 @@ static cudaError_t build_level(MapIndex& idx, LevelIndex& L, const GridDesc& g, 
   // map that has outgrown its arrays once will grow again, so a re-allocation takes 2.5 x: the free tail then absorbs ~40 % of
   // growth (moved rows leave holes behind) before the next rebuild compacts the level.
   // (Maps below a million points are given the room of a million: allocation is the expensive part of a rebuild.)
+  // A rebuild after growth keeps the arrays as long as the segments plus a small tail (1/32) still fit: the rebuild compacts
+  // (rows that moved left holes behind), so a map that was allocated exactly and then grows by a few per cent is not
+  // re-allocated — (de)allocating gigabytes took hundreds of milliseconds in the stream replays.
   const size_t segs = n9 + n9 / 8 + 10 * n_rows;
   const size_t need = segs + std::max(segs / 8, (size_t)1 << 16);
+  const size_t min_need = segs + std::max(segs / 32, (size_t)1 << 14);
   const size_t floor_entries = 9 * std::min(idx.cap_pts, (size_t)1 << 20) * 5 / 4 + 10 * n_rows;
   if (need >= 0xFFFFFFF0ull / 3) return cudaErrorInvalidValue;
-  if (need > L.cap_entries) {
+  if (min_need > L.cap_entries) {
     const size_t want = std::max(L.pts ? 2 * need + need / 2 : need, floor_entries);
     if (L.pts) cudaFree(L.pts);
     L.pts = nullptr;
