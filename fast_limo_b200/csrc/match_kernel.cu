@@ -913,6 +913,7 @@ __device__ __forceinline__ int match_num_tiles_dev(int n_queries) { return (n_qu
 struct TileShared {
   __align__(16) float tile[kTileQueries / 32][32][24];   // rows of [row(12), z] as floats; stride 24: conflict-free fragment reads
   double wsum[kTileQueries / 32][kPartialStride];
+  float4 held[kTileQueries];   // resident kernel, one tile per CTA: the tile's scan points (x, y, z, original index) stay here over the passes
   int s_last;
 };
 
@@ -926,7 +927,8 @@ struct TileShared {
 template <bool kWide, bool kPair, bool kExternalFinal = false, bool kStage = false>
 __device__ __forceinline__ bool match_tile(const MatchParams& P, const PoseConsts& pc, TileShared& sh, const int tile_idx,
                                            const int n_tiles, const uint32_t orig_limit, const bool reuse_rows = false,
-                                           const StageCtx stage = StageCtx{nullptr, nullptr, nullptr}, const int acc_sel = 0) {
+                                           const StageCtx stage = StageCtx{nullptr, nullptr, nullptr}, const int acc_sel = 0,
+                                           const int held_mode = 0 /* 1: keep the scan points in sh.held, 2: take them from there */) {
   auto& tile = sh.tile;
   auto& wsum = sh.wsum;
   int& s_last = sh.s_last;
@@ -961,7 +963,11 @@ __device__ __forceinline__ bool match_tile(const MatchParams& P, const PoseConst
     float g[3] = {0.f, 0.f, 0.f};
     if (in_range) {
       float sx, sy, sz;
-      if (P.scan != nullptr) {
+      if (held_mode == 2) {                                  // the same tile as in the previous pass of this registration
+        const float4 sp = sh.held[threadIdx.x];
+        orig = __float_as_uint(sp.w);
+        sx = sp.x; sy = sp.y; sz = sp.z;
+      } else if (P.scan != nullptr) {
         const float4 sp = __ldg(&P.scan[q]);
         orig = __float_as_uint(sp.w);
         sx = sp.x; sy = sp.y; sz = sp.z;
@@ -980,6 +986,7 @@ __device__ __forceinline__ bool match_tile(const MatchParams& P, const PoseConst
           sx = __ldg(sf); sy = __ldg(sf + 1); sz = __ldg(sf + 2);
         }
       }
+      if (held_mode == 1) sh.held[threadIdx.x] = make_float4(sx, sy, sz, __uint_as_float(orig));
       affine_apply(pc.R_wb, pc.t_wb, sx, sy, sz, g);
     }
     Top5 t;
@@ -1425,9 +1432,12 @@ __global__ void __launch_bounds__(kTileQueries, 7) registration_tiles_kernel(con
     if (tid == 0 && P.cta_trace) atomicAdd(&P.ticket[1], 1u);   // diagnostics (FLIMO_DEBUG_CTA_TRACE): CTAs that began this pass
     // cmd 3 = the pass is repeated with the same pose and a row limit: a CTA that owns exactly one tile re-selects the rows
     // it still holds in shared memory instead of matching the tile again
-    const bool reuse = s_ctl.cmd == 3u && (int)gridDim.x >= n_tiles;
+    const bool one_tile = (int)gridDim.x >= n_tiles;          // this CTA owns exactly one tile: its scan points are loaded once
+    const bool reuse = s_ctl.cmd == 3u && one_tile;
+    const int held_mode = one_tile ? (cmd_no == 0 ? 1 : 2) : 0;
     for (int t = (int)blockIdx.x; t < n_tiles; t += (int)gridDim.x)
-      match_tile<kWide, kPair, true>(P, s_ctl.pc, sh, t, n_tiles, s_ctl.orig_limit, reuse, StageCtx{nullptr, nullptr, nullptr}, (int)(cmd_no & 1ull));
+      match_tile<kWide, kPair, true>(P, s_ctl.pc, sh, t, n_tiles, s_ctl.orig_limit, reuse, StageCtx{nullptr, nullptr, nullptr}, (int)(cmd_no & 1ull),
+                                     held_mode);
     __syncthreads();
     if (tid == 0 && P.cta_trace) P.cta_trace[blockIdx.x].x = (P.cta_trace[blockIdx.x].x & ~0xFF00u) | (3u << 8);   // delivered
   }
