@@ -406,6 +406,7 @@ def main():
         # -> filter step -> next command, i.e. everything between two poses; N > 1: includes the wait for the slowest rank)
         pp = st1["persist_passes"] - st0["persist_passes"]
         k1_in_ms = (st1["persist_ms_total"] - st0["persist_ms_total"]) / pp if pp else None
+        xch_us = (st1["exchange_ms_total"] - st0["exchange_ms_total"]) / pp * 1e3 if pp else None
         peak, peak_src = _peaks()
         achieved = (hi - lo) * A_PM / (k1_ms * 1e-3) / 1e9
         exch = {"peer": "NVLink peer stores inside the filter kernel", "shm": "fused host-segment exchange", "nccl": "NCCL all-reduce"}[args.exchange]
@@ -419,7 +420,9 @@ def main():
                         "parallelism": "scan-shard x%d (replicated map, 96 doubles summed per pass via %s)" % (world, exch if world > 1 else "no exchange"),
                         "update": "device-resident: tiles kernel + filter CTA, no host between passes; every 8th scan one launch per pass (event-timed)",
                         "passes_per_scan": passes, "map_index_gb": map_gb, "pose_err_m": pose_err, "knn_cell": st1["knn_cell"], "levels": st1["n_levels"],
-                        "update_stalls": int(st_end["update_stalls"])},
+                        "update_stalls": int(st_end["update_stalls"]),
+                        # per pass on rank 0: own tiles complete -> sums of all ranks in hand (collect; N > 1: + NVLink peer stores + wait for the slowest rank)
+                        "exchange_us_per_pass": xch_us},
             "e2e": {"value": args.steps / (ms_e2e / 1e3), "unit": "scans/s", "h2d_bytes_per_step": n_pts * 16,   # summed over ranks
                     "d2h_bytes_per_step": 160 * 16},
             # kernels launched during ONE timed loop of `steps` steps (counted over warm-up + all repeats, scaled)

@@ -80,6 +80,7 @@ class FlimoStats(C.Structure):
         ("index_builds", C.c_uint64),
         ("index_updates", C.c_uint64),
         ("index_rows_moved", C.c_uint64),
+        ("exchange_ms_total", C.c_double),
         ("update_stalls", C.c_uint64),
     ]
 

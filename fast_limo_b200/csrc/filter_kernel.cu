@@ -60,6 +60,7 @@ struct FilterShared {
   double sums[2][kPartialStride];       // packed pass sums: [0] = the ones the step uses, [1] = scratch of the exchange
   int scratch[kFilterThreads + 8];
   unsigned long long stamps[16];
+  double xch_ns;                        // sum over the passes: own tiles complete -> sums of ALL ranks in hand (collect + peer exchange)
   int flag;
 };
 
@@ -246,7 +247,10 @@ __global__ void __launch_bounds__(kFilterThreads, 1) filter_kernel(const __grid_
   ekf::CtaExec ex{tid, kFilterThreads, fs.stamps};
   bool need_pre = true;
   int redone = 0;
-  if (tid == 0) fs.stamps[14] = t_kernel;                   // when the current command was posted
+  if (tid == 0) {
+    fs.stamps[14] = t_kernel;                               // when the current command was posted
+    fs.xch_ns = 0.0;
+  }
   for (unsigned long long cmd_no = 0;; ++cmd_no) {
     // The pass that exhausts MAX_NUM_ITERS is known to be the last one before it starts: its sums go straight to the host,
     // which forms the final state and covariance (IteratedUpdate::finish) — nothing to prepare or to solve here.
@@ -305,6 +309,7 @@ __global__ void __launch_bounds__(kFilterThreads, 1) filter_kernel(const __grid_
     const unsigned long long xs = RP.xseq + cmd_no;
     if (ok && RP.world > 1) ok = peer_exchange_sums(RP, fs, xs);
     ex.stamp(0);
+    if (tid == 0) fs.xch_ns += timer_span_ns(fs.stamps[0], fs.stamps[15]);
 
     uint32_t next_cmd = 0u, next_limit = 0xFFFFFFFFu;
     bool stepped = false;
@@ -393,6 +398,7 @@ __global__ void __launch_bounds__(kFilterThreads, 1) filter_kernel(const __grid_
           else if (i == kResFailed) v = (double)ss.failed;
           else if (i == kResDevNs) v = timer_span_ns(gtime_ns(), t_kernel);
           else if (i == kResRedone) v = (double)redone;
+          else if (i == kResXchNs) v = fs.xch_ns;
           else if (i >= kResXDev && i < kResXDev + 26) v = ss.x[i - kResXDev];
           st_record(RP.host_res + 2 * (size_t)i, v, RP.res_seq);
         }

@@ -139,6 +139,7 @@ struct flimo_ctx {
   int peer_rank = 0, peer_world = 0;
   unsigned long long peer_xseq = 0;
   double persist_ns_total = 0;   // in-kernel device time of persistent passes
+  double exchange_ns_total = 0;  // of it: own tiles complete -> sums of all ranks in hand (device-resident updates)
   uint64_t persist_passes = 0;
   uint64_t update_calls = 0;
   int test_stall_pass = -1;      // FLIMO_TEST_STALL_PASS=k: the host sleeps 60 ms before command k of every update (watchdog test)
@@ -637,6 +638,7 @@ int flimo_get_stats(flimo_handle h, flimo_stats* out) {
     h->stats.map_bytes += h->map.lv[l].cap_entries * sizeof(float4);   // super-row entries (16 bytes each) incl. the rows' head-room
   }
   h->stats.persist_ms_total = h->persist_ns_total * 1e-6;
+  h->stats.exchange_ms_total = h->exchange_ns_total * 1e-6;
   h->stats.persist_passes = h->persist_passes;
   h->stats.index_builds = h->stats_index_builds;
   h->stats.index_updates = h->stats_index_updates;
@@ -1416,6 +1418,7 @@ static int update_device(flimo_handle h, double state26[26], double P529[529], i
   const uint64_t redone = (uint64_t)std::llround(res[kResRedone]);
   h->stats.match_launches += (uint64_t)passes + redone;
   h->persist_ns_total += res[kResDevNs];
+  h->exchange_ns_total += res[kResXchNs];
   h->persist_passes += (uint64_t)passes + redone;
   h->device_updates++;
   h->device_redone += redone;

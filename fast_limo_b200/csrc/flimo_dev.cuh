@@ -169,7 +169,7 @@ struct MatchParams {
 constexpr int kResRecords = 160;      // host result block: records {double value, u64 seq}
 // x_eval = state the LAST pass was evaluated at, sums = its 96 packed sums (the host forms the final state and
 // covariance from them, IteratedUpdate::finish), x_dev = the device's own state after the last pass (tests)
-constexpr int kResXEval = 0, kResSums = 26, kResPasses = 122, kResFailed = 123, kResDevNs = 124, kResRedone = 125, kResXDev = 128;
+constexpr int kResXEval = 0, kResSums = 26, kResPasses = 122, kResFailed = 123, kResDevNs = 124, kResRedone = 125, kResXchNs = 126, kResXDev = 128;
 constexpr int kMaxPeers = 8;
 // Peer inbox (device memory of every rank, mapped by all ranks of the node through CUDA IPC):
 //   records : [parity 2][source rank 8][128] x {double value, u64 seq}   (0..95 pass sums, 96 = "flag words stored")

@@ -302,6 +302,7 @@ typedef struct {
   uint64_t persist_passes;      /* number of such passes */
   uint64_t index_builds, index_updates;   /* Mapper::add calls that rebuilt the search index / merged the batch into the touched rows */
   uint64_t index_rows_moved;    /* rows that outgrew their segment during those merges and moved to the free tail */
+  double exchange_ms_total;     /* device-resident updates: time from "own tiles complete" to "pass sums of all ranks in hand" (collect + NVLink peer exchange + wait for the slowest rank), summed over the persist_passes */
   uint64_t update_stalls;       /* flimo_update calls whose resident kernels stopped answering (watchdog) and that were redone with one launch per pass */
 } flimo_stats;
 int flimo_get_stats(flimo_handle h, flimo_stats* out);
