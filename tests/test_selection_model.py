@@ -219,3 +219,92 @@ def test_scan_permutation_model():
         magic = ((1 << 64) - 1) // n
         for prod in ((n - 1) * (n - 1), (n - 1) * (n - 2), n * (n - 1) - 1, n - 1, n, 0):
             assert _barrett(prod, n, magic) == prod % n
+
+
+# ---- round 2: order-free pass sums, team-rescan pruning, in-place row merge (numpy / pure-Python models) ----------------
+def _fx_split(s):
+    """match_kernel.cu (fx_reduce): a float64 tile sum as two fixed-point integers, units 2^-18 and 2^-66."""
+    hi = int(np.rint(s * 2.0 ** 18))
+    lo = int(np.rint((s - hi * 2.0 ** -18) * 2.0 ** 66))
+    return hi, lo
+
+
+def test_fixed_point_pass_sums_are_exact_and_order_free():
+    """The tiles add (hi, lo) with integer REDs; the finisher returns hi * 2^-18 + lo * 2^-66.  Integer addition is
+    associative, so any arrival order gives the same bits, and the result is the correctly rounded exact sum up to the
+    2^-66 granularity of a tile — closer to it than a float64 tree."""
+    import math
+    rng = np.random.default_rng(3)
+    for scale in (1e-6, 1.0, 4.0e4, 3.0e9):                          # sum z^2 ... sum of 150 m lever arms squared
+        tiles = (rng.standard_normal(2344) * scale).astype(np.float64)
+        tiles[::7] *= 1e-9
+        parts = [_fx_split(float(t)) for t in tiles]
+        for hi, lo in parts:
+            assert abs(hi) < 2 ** 62 and abs(lo) <= 2 ** 47          # rem <= 2^-19 -> lo <= 2^47: 2^15 tiles stay below 2^63
+        ref = None
+        for _ in range(5):
+            order = rng.permutation(len(parts))
+            H = sum(parts[i][0] for i in order)
+            L = sum(parts[i][1] for i in order)
+            assert -2 ** 63 <= H < 2 ** 63 and -2 ** 63 <= L < 2 ** 63
+            got = float(H) * 2.0 ** -18 + float(L) * 2.0 ** -66
+            ref = got if ref is None else ref
+            assert got == ref                                         # bit-identical whatever the order
+        exact = math.fsum(tiles.tolist())
+        assert abs(ref - exact) <= 2344 * 2.0 ** -66 + abs(exact) * 2.0 ** -52
+
+
+def test_team_rescan_bound_keeps_the_exact_answer():
+    """block_scan_team: candidates with d2 > bound skip the insertion, where bound = the exact 5th squared distance inside a
+    smaller block scanned before (an upper bound of the true one).  The five nearest of the larger block are unchanged."""
+    rng = np.random.default_rng(11)
+    for _ in range(300):
+        big = rng.random((int(rng.integers(6, 200)), 3)).astype(np.float32)
+        q = rng.random(3).astype(np.float32)
+        d2 = ((big - q) ** 2).sum(1)
+        small = rng.choice(len(big), size=int(rng.integers(5, len(big) + 1)), replace=False)     # the block scanned first
+        bound = np.sort(d2[small])[4]
+        keep = d2 <= bound
+        full = np.lexsort((np.arange(len(big)), d2))[:5]
+        pruned_idx = np.flatnonzero(keep)
+        pruned = pruned_idx[np.lexsort((pruned_idx, d2[keep]))[:5]]
+        assert np.array_equal(full, pruned)
+
+
+def _merge_row_in_place(row, cnt, new, cap, B=8):
+    """upd_merge_kernel (map_index.cu), in place: row[:cnt] old entries (key, id) sorted by key, `new` sorted by key.
+    Old entries move up by the number of new entries with a SMALLER key, back to front in chunks of B 'threads'
+    (reads of a chunk complete before its writes); the new entries drop into the holes behind the old entries of their own
+    and all earlier cells."""
+    keys_new = [k for k, _ in new]
+    import bisect
+    first_new = keys_new[0]
+    keep = bisect.bisect_left([k for k, _ in row[:cnt]], first_new)     # = slot[first new cell] - base
+    old_keys = [k for k, _ in row[:cnt]]                               # (the kernel reads these from the table slots)
+    span = cnt - keep
+    for c in reversed(range((span + B - 1) // B)):
+        idx = [keep + c * B + t for t in range(B) if keep + c * B + t < cnt]
+        vals = [row[i] for i in idx]                                   # all reads of the chunk ...
+        for i, v in zip(idx, vals):                                    # ... then all writes
+            lo = bisect.bisect_left(keys_new, v[0])
+            if lo:
+                assert i + lo < cap
+                row[i + lo] = v
+    for i, v in enumerate(new):
+        row[i + bisect.bisect_right(old_keys, v[0])] = v               # old entries with key <= own key stay in front
+    return cnt + len(new)
+
+
+def test_in_place_row_merge_model():
+    rng = np.random.default_rng(5)
+    for _ in range(400):
+        nx = int(rng.integers(3, 40))
+        cnt, k = int(rng.integers(0, 120)), int(rng.integers(1, 60))
+        old = sorted((int(rng.integers(0, nx)), 1000 + i) for i in range(cnt))
+        old = sorted(old, key=lambda e: e[0])
+        new = sorted(((int(rng.integers(0, nx)), 5000 + i) for i in range(k)), key=lambda e: e[0])
+        cap = cnt + k + int(rng.integers(0, 9))
+        row = old + [(-1, -1)] * (cap - cnt)
+        n = _merge_row_in_place(row, cnt, new, cap, B=int(rng.choice([1, 4, 8, 32])))
+        want = sorted(old + new, key=lambda e: (e[0], e[1] >= 5000))   # by cell; old entries first inside a cell, orders kept
+        assert n == cnt + k and row[:n] == want
