@@ -92,21 +92,37 @@ __device__ __forceinline__ bool peer_exchange_sums(const RegParams& RP, FilterSh
     const double mine = fs.sums[0][t];
     for (int r = 0; r < RP.world; ++r) st_record(inbox_slot(RP.inbox[r], xs, RP.rank, t), mine, xs);
     const long long w0 = watch_start();
-    double sum = 0.0;
-    for (int r = 0; r < RP.world; ++r) {                 // fixed rank order: identical sums on every rank
-      const double* slot = inbox_slot(RP.inbox[RP.rank], xs, r, t);
-      ulonglong2 rec = ld_record(slot);
-      while (rec.y != xs) {
-        if (watch_expired(w0, RP.peer_timeout_ns)) {
-          fs.flag = 0;
-          break;
+    // the records of all ranks are polled TOGETHER (eight independent loads in flight per round): polling them one rank after
+    // the other cost one memory latency per rank — 5.5 us per pass at eight ranks against 3.0 at two
+    double* const my_inbox = RP.inbox[RP.rank];
+    ulonglong2 rec[kMaxPeers];
+#pragma unroll
+    for (int r = 0; r < kMaxPeers; ++r) rec[r] = make_ulonglong2(0ull, xs);
+#pragma unroll
+    for (int r = 0; r < kMaxPeers; ++r)
+      if (r < RP.world) rec[r] = ld_record(inbox_slot(my_inbox, xs, r, t));
+    for (;;) {
+      bool all = true;
+#pragma unroll
+      for (int r = 0; r < kMaxPeers; ++r)
+        if (r < RP.world && rec[r].y != xs) {
+          rec[r] = ld_record(inbox_slot(my_inbox, xs, r, t));
+          all = false;                                     // (checked again in the next round)
         }
-        rec = ld_record(slot);
+      if (all) break;
+      if (watch_expired(w0, RP.peer_timeout_ns)) {
+        fs.flag = 0;
+        break;
       }
-      double v = __longlong_as_double((long long)rec.x);
-      if (t >= 93) v = 0.0;                              // slots 93.. are per-rank bookkeeping
-      sum += v;
     }
+    double sum = 0.0;
+#pragma unroll
+    for (int r = 0; r < kMaxPeers; ++r)                    // fixed rank order: identical sums on every rank
+      if (r < RP.world) {
+        double v = __longlong_as_double((long long)rec[r].x);
+        if (t >= 93) v = 0.0;                              // slots 93.. are per-rank bookkeeping
+        sum += v;
+      }
     fs.sums[1][t] = sum;
   }
   __syncthreads();
